@@ -1,0 +1,410 @@
+/*
+ * dmfb_oracle.c — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Scalar CPU restatement of the DMFB environment step of jesselasse/MARL-DMFB
+ * (env/DMFB/dmfb.py).  It exists only so that tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference leg can check (and time) the
+ * CUDA path against something that follows the reference line by line.  The
+ * product (marl-dmfb_b200/) never links, imports or calls it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py replays every trace under
+ * tests/golden/ (npz files) — recorded from the unmodified Python reference by
+ * tests/golden/make_golden.py — through this file and requires bit equality
+ * of positions, observations, dones, constraints, success, usage, health and
+ * of the float64 rewards.
+ *
+ * Each function cites the reference lines it restates (paths relative to the
+ * reference repo root).  One chip is handled at a time with the same loop
+ * structure as the reference; batching is a plain loop over chips (optionally
+ * OpenMP for the timing legs).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct orc_dmfb_cfg {
+    int32_t width, length, n_agents, fov, stall, b_degrade;
+} orc_dmfb_cfg;
+
+#define MAXA 64
+
+/* Droplet.move + Action (dmfb.py:26-31,103-124) */
+static int orc_move(int *x, int *y, int action, int width, int length)
+{
+    switch (action) {
+    case 0: break;            /* STALL */
+    case 4: *y += 1; break;   /* UP    */
+    case 3: *y -= 1; break;   /* DOWN  */
+    case 2: *x -= 1; break;   /* LEFT  */
+    case 1: *x += 1; break;   /* RIGHT */
+    default: return -1;       /* TypeError('action is illegal') */
+    }
+    if (*x > width - 1) *x = width - 1; else if (*x < 0) *x = 0;
+    if (*y > length - 1) *y = length - 1; else if (*y < 0) *y = 0;
+    return 0;
+}
+
+/* RoutingTaskManager._isinvalidaction (dmfb.py:310-323): any pair of droplets
+ * at squared distance 0 (the Gram-matrix EDM of :200-205 is exact on small ints). */
+static int orc_any_pair_equal(const int *x, const int *y, int n)
+{
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++)
+            if (i != j) {
+                int dx = x[i] - x[j], dy = y[i] - y[j];
+                if (dx * dx + dy * dy == 0) return 1;
+            }
+    return 0;
+}
+
+/* RoutingTaskManager.getOneObs (dmfb.py:395-457) + DMFBenv.getOneObs (:614-620):
+ * int8 (3,fov,fov) flattened, then the 2-byte direction vector. */
+static void orc_one_obs(const orc_dmfb_cfg *c, const int *x, const int *y, const int *gx, const int *gy,
+                        int agent, int8_t *obs)
+{
+    const int fov = c->fov, hf = fov / 2, n = c->n_agents;
+    const int f2 = fov * fov;
+    memset(obs, 0, (size_t)(3 * f2 + 2));
+    const int cx = x[agent], cy = y[agent];
+    const int ox = cx - fov / 2, oy = cy - fov / 2;
+    /* layer 0: every droplet inside the window (:410-413) */
+    for (int idx = 0; idx < n; idx++) {
+        int rx = x[idx] - ox, ry = y[idx] - oy;
+        if (0 <= rx && rx < fov && 0 <= ry && ry < fov) obs[0 * f2 + rx * fov + ry] = (int8_t)(idx + 1);
+    }
+    /* layer 1: goals of the other visible droplets, clipped into the window (:416-420);
+     * abs(d) < fov/2 is a true division in the reference -> compare 2*abs(d) < fov */
+    for (int idx = 0; idx < n; idx++) {
+        if (idx != agent && 2 * abs(x[idx] - cx) < fov && 2 * abs(y[idx] - cy) < fov) {
+            int rx = gx[idx] - ox, ry = gy[idx] - oy;
+            if (rx < 0) rx = 0; if (rx > fov - 1) rx = fov - 1;
+            if (ry < 0) ry = 0; if (ry > fov - 1) ry = fov - 1;
+            obs[1 * f2 + rx * fov + ry] = (int8_t)(idx + 1);
+        }
+    }
+    /* layer 2: blocks (none: n_blocks == 0 in every supported config) + off-chip boundary (:428-439) */
+    int leftbound = hf - cx, rightbound = hf - (c->width - 1 - cx);
+    if (leftbound > 0) {
+        for (int r = 0; r < leftbound && r < fov; r++)
+            for (int q = 0; q < fov; q++) obs[2 * f2 + r * fov + q] = 1;
+    } else if (rightbound > 0) {
+        for (int r = (fov - rightbound < 0 ? 0 : fov - rightbound); r < fov; r++)
+            for (int q = 0; q < fov; q++) obs[2 * f2 + r * fov + q] = 1;
+    }
+    int upbound = hf - cy, downbound = hf - (c->length - 1 - cy);
+    if (upbound > 0) {
+        for (int r = 0; r < fov; r++)
+            for (int q = 0; q < upbound && q < fov; q++) obs[2 * f2 + r * fov + q] = 1;
+    } else if (downbound > 0) {
+        for (int r = 0; r < fov; r++)
+            for (int q = (fov - downbound < 0 ? 0 : fov - downbound); q < fov; q++) obs[2 * f2 + r * fov + q] = 1;
+    }
+    /* direction vector (:442-454): python round() == round-half-even on the double == rint() */
+    int drx = gx[agent] - cx, dry = gy[agent] - cy;
+    if (abs(drx) > hf) {
+        double scale = (double)(c->width - hf) / (double)(10 - hf);
+        if (drx > 0) drx = (int)rint((double)(drx - hf) / scale) + hf;
+        else drx = (int)rint((double)(drx + hf) / scale) - hf;
+    }
+    if (abs(dry) > hf) {
+        double scale = (double)(c->length - hf) / (double)(10 - hf);
+        if (dry > 0) dry = (int)rint((double)(dry - hf) / scale) + hf;
+        else dry = (int)rint((double)(dry + hf) / scale) - hf;
+    }
+    obs[3 * f2 + 0] = (int8_t)drx;
+    obs[3 * f2 + 1] = (int8_t)dry;
+}
+
+static void orc_load(const orc_dmfb_cfg *c, const uint8_t *drop, int *x, int *y, int *gx, int *gy)
+{
+    for (int i = 0; i < c->n_agents; i++) {
+        x[i] = drop[4 * i + 0]; y[i] = drop[4 * i + 1];
+        gx[i] = drop[4 * i + 2]; gy[i] = drop[4 * i + 3];
+    }
+}
+
+/* DMFBenv.getObs (dmfb.py:622-626) for chip state `drop` */
+static void orc_all_obs(const orc_dmfb_cfg *c, const uint8_t *drop, int8_t *obs)
+{
+    int x[MAXA], y[MAXA], gx[MAXA], gy[MAXA];
+    orc_load(c, drop, x, y, gx, gy);
+    const int D = 3 * c->fov * c->fov + 2;
+    for (int i = 0; i < c->n_agents; i++) orc_one_obs(c, x, y, gx, gy, i, obs + (size_t)i * D);
+}
+
+/* DMFBenv.step (dmfb.py:560-587) -> RoutingTaskManager.moveDroplets (:253-299) ->
+ * moveOneDroplet (:325-359) -> addUsage (:459-463), for ONE chip.
+ * Returns -1 on an illegal action. */
+static int orc_step_one(const orc_dmfb_cfg *c, uint8_t *drop, int32_t *step_count, int32_t *cum_constraints,
+                        double *usage, const double *health, const int8_t *actions, const double *u,
+                        int record, int8_t *obs, double *reward, uint8_t *done, int32_t *constraints_out,
+                        uint8_t *success_out)
+{
+    const int n = c->n_agents, W = c->width, L = c->length;
+    int x[MAXA], y[MAXA], gx[MAXA], gy[MAXA], dist[MAXA];
+    int px[MAXA], py[MAXA], cxs[MAXA], cys[MAXA], pre_done[MAXA], sta[MAXA], dyn[MAXA];
+    double rew[MAXA];
+    orc_load(c, drop, x, y, gx, gy);
+    for (int i = 0; i < n; i++) dist[i] = abs(x[i] - gx[i]) + abs(y[i] - gy[i]); /* Droplet.distance :93-95 */
+
+    *step_count += 1;                                     /* :561 */
+    int success = 0;
+    for (int i = 0; i < n; i++) pre_done[i] = (dist[i] == 0); /* getTaskStatus :278,365-366 */
+    for (int i = 0; i < n; i++) {                          /* moveOneDroplet :325-359 */
+        int ox = x[i], oy = y[i];
+        double r;
+        if (c->stall && dist[i] == 0) {
+            r = 0.0;
+        } else {
+            double prob = health ? health[(size_t)x[i] * L + y[i]] : 1.0; /* getMoveProb :361-363 */
+            double draw = u ? u[i] : 0.0;
+            if (draw <= prob) {                            /* random.random() <= prob :335 */
+                if (orc_move(&x[i], &y[i], actions[i], W, L)) return -1;
+                /* _isTouchingBlocks: no blocks */
+                if (orc_any_pair_equal(x, y, n)) { x[i] = ox; y[i] = oy; } /* :341-343 */
+            }
+            int nd = abs(x[i] - gx[i]) + abs(y[i] - gy[i]);
+            if (nd == dist[i] && dist[i] == 0) r = -0.1;
+            else if (nd == dist[i] && actions[i] == 0) r = -0.25;
+            else if (nd < dist[i]) r = -0.1;
+            else r = -0.4;
+            dist[i] = nd;
+        }
+        rew[i] = r; px[i] = ox; py[i] = oy; cxs[i] = x[i]; cys[i] = y[i];
+    }
+    /* comflic_static (:254-261): norm(cur_i-cur_j) < 2, each unordered pair counted to both */
+    for (int i = 0; i < n; i++) { sta[i] = 0; dyn[i] = 0; }
+    for (int i = 0; i < n - 1; i++)
+        for (int j = i + 1; j < n; j++) {
+            int dx = cxs[i] - cxs[j], dy = cys[i] - cys[j];
+            if (dx * dx + dy * dy < 4) { sta[i]++; sta[j]++; }
+        }
+    /* comflic_dynamic (:263-271): norm(past_i-cur_j) < 2 over ordered pairs, counted to both */
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++)
+            if (i != j) {
+                int dx = px[i] - cxs[j], dy = py[i] - cys[j];
+                if (dx * dx + dy * dy < 4) { dyn[i]++; dyn[j]++; }
+            }
+    int constraints = 0;
+    for (int i = 0; i < n; i++) constraints += sta[i] + dyn[i];          /* :287 */
+    for (int i = 0; i < n; i++) rew[i] = (rew[i] - (double)(2 * sta[i])) - (double)(2 * dyn[i]); /* :288 */
+    if (c->stall)
+        for (int i = 0; i < n; i++) if (pre_done[i]) rew[i] = 0.0;      /* :289-292 */
+    int all_done = 1;
+    for (int i = 0; i < n; i++) if (dist[i] != 0) all_done = 0;
+    if (all_done) {                                                        /* :293-296 */
+        for (int i = 0; i < n; i++) rew[i] = rew[i] + 10.0;
+        if (constraints == 0) for (int i = 0; i < n; i++) rew[i] = rew[i] + 10.0;
+    }
+    if (record && usage)                                                   /* addUsage :459-463 */
+        for (int i = 0; i < n; i++) if (dist[i] != 0) usage[(size_t)x[i] * L + y[i]] += 1.0;
+    *cum_constraints += constraints;                                       /* :572 */
+    for (int i = 0; i < n; i++) { drop[4 * i + 0] = (uint8_t)x[i]; drop[4 * i + 1] = (uint8_t)y[i]; }
+    if (obs) orc_all_obs(c, drop, obs);                                    /* :576 */
+    if (*step_count < 2 * (W + L)) {                                       /* :577-585, max_step :508 */
+        if (all_done && *cum_constraints == 0) success = 1;
+        for (int i = 0; i < n; i++) done[i] = (uint8_t)(dist[i] == 0);
+    } else {
+        for (int i = 0; i < n; i++) done[i] = 1;
+    }
+    for (int i = 0; i < n; i++) reward[i] = rew[i];
+    *constraints_out = constraints;
+    *success_out = (uint8_t)success;
+    return 0;
+}
+
+/* RoutingTaskManager.updateHealth (dmfb.py:465-471) */
+static void orc_update_health(const orc_dmfb_cfg *c, double *usage, double *health, const double *degrade)
+{
+    const int cells = c->width * c->length;
+    for (int k = 0; k < cells; k++)
+        if (usage[k] > 50.0) {
+            if (health) health[k] = health[k] * (degrade ? degrade[k] : 1.0);
+            usage[k] = 0.0;
+        }
+}
+
+/* ------------------------------------------------------------ batch API -- */
+
+int orc_dmfb_step(const orc_dmfb_cfg *c, int n_envs, uint8_t *drop, int32_t *step_count, int32_t *cum_constraints,
+                  double *usage, const double *health, const int8_t *actions, const double *u, int record,
+                  int8_t *obs, double *reward, uint8_t *done, int32_t *constraints, uint8_t *success)
+{
+    const int A = c->n_agents, cells = c->width * c->length, D = 3 * c->fov * c->fov + 2;
+    int err = 0;
+    for (int e = 0; e < n_envs; e++) {
+        int rc = orc_step_one(c, drop + (size_t)e * A * 4, step_count + e, cum_constraints + e,
+                              usage ? usage + (size_t)e * cells : NULL, health ? health + (size_t)e * cells : NULL,
+                              actions + (size_t)e * A, u ? u + (size_t)e * A : NULL, record,
+                              obs ? obs + (size_t)e * A * D : NULL, reward + (size_t)e * A, done + (size_t)e * A,
+                              constraints + e, success + e);
+        if (rc) err |= 1;
+    }
+    return err ? -1 : 0;
+}
+
+/* DMFBenv.reset(new) (dmfb.py:589-597) with the task (layout) injected:
+ * refresh (:174-183): new task; new -> health=1, usage=0, degrade redrawn (injected);
+ * else updateHealth.  Then getObs. */
+int orc_dmfb_reset(const orc_dmfb_cfg *c, int n_envs, const uint8_t *mask, int new_task, const uint8_t *layouts,
+                   const double *degrade_in, uint8_t *drop, int32_t *step_count, int32_t *cum_constraints,
+                   double *usage, double *health, double *degrade, int8_t *obs)
+{
+    const int A = c->n_agents, cells = c->width * c->length, D = 3 * c->fov * c->fov + 2;
+    for (int e = 0; e < n_envs; e++) {
+        if (mask && !mask[e]) continue;
+        step_count[e] = 0;
+        cum_constraints[e] = 0;
+        memcpy(drop + (size_t)e * A * 4, layouts + (size_t)e * A * 4, (size_t)A * 4);
+        if (new_task) {
+            for (int k = 0; k < cells; k++) {
+                if (health) health[(size_t)e * cells + k] = 1.0;
+                if (usage) usage[(size_t)e * cells + k] = 0.0;
+                if (degrade) degrade[(size_t)e * cells + k] = degrade_in ? degrade_in[(size_t)e * cells + k] : 1.0;
+            }
+        } else if (usage) {
+            orc_update_health(c, usage + (size_t)e * cells, health ? health + (size_t)e * cells : NULL,
+                              degrade ? degrade + (size_t)e * cells : NULL);
+        }
+        if (obs) orc_all_obs(c, drop + (size_t)e * A * 4, obs + (size_t)e * A * D);
+    }
+    return 0;
+}
+
+int orc_dmfb_observe(const orc_dmfb_cfg *c, int n_envs, const uint8_t *drop, int8_t *obs)
+{
+    const int A = c->n_agents, D = 3 * c->fov * c->fov + 2;
+    for (int e = 0; e < n_envs; e++) orc_all_obs(c, drop + (size_t)e * A * 4, obs + (size_t)e * A * D);
+    return 0;
+}
+
+/* RoutingTaskManager.getglobalobs (dmfb.py:368-392) as int8 [3,W,L] per chip */
+int orc_dmfb_global_state(const orc_dmfb_cfg *c, int n_envs, const uint8_t *drop, int8_t *out)
+{
+    const int A = c->n_agents, W = c->width, L = c->length;
+    for (int e = 0; e < n_envs; e++) {
+        int8_t *g = out + (size_t)e * 3 * W * L;
+        memset(g, 0, (size_t)3 * W * L);
+        const uint8_t *d = drop + (size_t)e * A * 4;
+        for (int i = 0; i < A; i++) {
+            g[0 * W * L + d[4 * i + 0] * L + d[4 * i + 1]] = (int8_t)(i + 1);
+            g[1 * W * L + d[4 * i + 2] * L + d[4 * i + 3]] = (int8_t)(i + 1);
+        }
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------- task generator -- */
+/* splitmix64: only the *distribution* of generated tasks has to match the reference
+ * (its own generator is numpy's global Mersenne Twister, dmfb.py:209-210). */
+static inline uint64_t orc_splitmix(uint64_t *s)
+{
+    uint64_t z = (*s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+/* _Generate_Start_End (dmfb.py:207-226): 2A uniform cells; the whole set is redrawn until the
+ * minimum pairwise squared distance is > 2.  layout = [A][4] (x,y,gx,gy). */
+void orc_dmfb_gen_layout(const orc_dmfb_cfg *c, uint64_t *rng, uint8_t *layout)
+{
+    const int A = c->n_agents, m = 2 * A;
+    int px[2 * MAXA], py[2 * MAXA];
+    for (;;) {
+        for (int k = 0; k < m; k++) py[k] = (int)(orc_splitmix(rng) % (uint64_t)c->length);
+        for (int k = 0; k < m; k++) px[k] = (int)(orc_splitmix(rng) % (uint64_t)c->width);
+        int ok = 1;
+        for (int i = 0; i < m && ok; i++)
+            for (int j = i + 1; j < m; j++) {
+                int dx = px[i] - px[j], dy = py[i] - py[j];
+                if (dx * dx + dy * dy <= 2) { ok = 0; break; }
+            }
+        if (ok) break;
+    }
+    for (int i = 0; i < A; i++) {
+        layout[4 * i + 0] = (uint8_t)px[i]; layout[4 * i + 1] = (uint8_t)py[i];
+        layout[4 * i + 2] = (uint8_t)px[A + i]; layout[4 * i + 3] = (uint8_t)py[A + i];
+    }
+}
+
+/* CPU-baseline driver (bench.py cpu_baseline / --impl reference): n_envs chips, `steps` lock-step
+ * env steps with uniform random actions, auto-reset when an episode ends (all done or step limit),
+ * degradation draws uniform.  Every step writes the full observation tensor, like the GPU path.
+ * Chips are split over n_threads POSIX threads (the reference itself is single-threaded Python;
+ * independent chips are its only parallelism).  Returns the number of agent-steps executed;
+ * *checksum defeats dead-code elimination. */
+#include <pthread.h>
+
+typedef struct {
+    const orc_dmfb_cfg *c;
+    int e0, e1, steps;
+    uint64_t seed, total;
+    int8_t *obs;
+} orc_roll_job;
+
+static void *orc_dmfb_roll_thread(void *arg)
+{
+    orc_roll_job *job = (orc_roll_job *)arg;
+    const orc_dmfb_cfg *c = job->c;
+    const int A = c->n_agents, cells = c->width * c->length, D = 3 * c->fov * c->fov + 2;
+    double *usage = (double *)calloc((size_t)cells, sizeof(double));
+    double *health = (double *)malloc((size_t)cells * sizeof(double));
+    double *degrade = (double *)malloc((size_t)cells * sizeof(double));
+    uint64_t total = 0;
+    for (int e = job->e0; e < job->e1; e++) {
+        uint64_t rng = job->seed * 0x100000001B3ull + (uint64_t)e;
+        uint8_t drop[4 * MAXA];
+        int8_t acts[MAXA];
+        double u[MAXA], rew[MAXA];
+        uint8_t done[MAXA], succ;
+        int32_t sc = 0, cc = 0, cons;
+        int8_t *obs = job->obs + (size_t)e * A * D;
+        for (int k = 0; k < cells; k++) {
+            usage[k] = 0.0; health[k] = 1.0;
+            degrade[k] = c->b_degrade ? (double)(orc_splitmix(&rng) >> 11) * (1.0 / 9007199254740992.0) * 0.4 + 0.6 : 1.0;
+        }
+        orc_dmfb_gen_layout(c, &rng, drop);
+        for (int t = 0; t < job->steps; t++) {
+            for (int i = 0; i < A; i++) {
+                acts[i] = (int8_t)(orc_splitmix(&rng) % 5u);
+                u[i] = (double)(orc_splitmix(&rng) >> 11) * (1.0 / 9007199254740992.0);
+            }
+            orc_step_one(c, drop, &sc, &cc, usage, c->b_degrade ? health : NULL, acts, u, 1, obs, rew, done,
+                         &cons, &succ);
+            int all = 1;
+            for (int i = 0; i < A; i++) { all &= done[i]; total += (uint64_t)(rew[i] < 0.0); }
+            if (all) {
+                sc = 0; cc = 0;
+                orc_dmfb_gen_layout(c, &rng, drop);
+                orc_update_health(c, usage, health, degrade);
+                orc_all_obs(c, drop, obs);
+            }
+        }
+    }
+    free(usage); free(health); free(degrade);
+    job->total = total;
+    return NULL;
+}
+
+int64_t orc_dmfb_rollout(const orc_dmfb_cfg *c, int n_envs, int steps, uint64_t seed, int8_t *obs /* [n_envs,A,D] */,
+                         int n_threads, uint64_t *checksum)
+{
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 1024) n_threads = 1024;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    orc_roll_job *jobs = (orc_roll_job *)malloc(sizeof(orc_roll_job) * (size_t)n_threads);
+    for (int t = 0; t < n_threads; t++) {
+        jobs[t].c = c; jobs[t].steps = steps; jobs[t].seed = seed; jobs[t].obs = obs; jobs[t].total = 0;
+        jobs[t].e0 = (int)((int64_t)n_envs * t / n_threads);
+        jobs[t].e1 = (int)((int64_t)n_envs * (t + 1) / n_threads);
+        pthread_create(&th[t], NULL, orc_dmfb_roll_thread, &jobs[t]);
+    }
+    uint64_t total = 0;
+    for (int t = 0; t < n_threads; t++) { pthread_join(th[t], NULL); total += jobs[t].total; }
+    free(th); free(jobs);
+    if (checksum) *checksum = total;
+    return (int64_t)n_envs * steps * c->n_agents;
+}

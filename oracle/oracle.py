@@ -1,0 +1,120 @@
+"""ctypes binding of the CPU oracle (oracle/*.c) — TEST INFRASTRUCTURE ONLY.
+
+The arrays mirror the product's struct-of-arrays boundary (include/dmfb_b200.h) so that parity
+tests can compare buffers directly, but the usage matrix is float64 here, as in the reference
+(dmfb.py:148), not uint16.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    """gcc the oracle into oracle/liboracle.so (idempotent)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".c")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liboracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.orc_dmfb_rollout.restype = C.c_int64
+        if hasattr(_LIB, "orc_meda_rollout"):
+            _LIB.orc_meda_rollout.restype = C.c_int64
+    return _LIB
+
+
+class _DmfbCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("width", "length", "n_agents", "fov", "stall", "b_degrade")]
+
+
+def _p(a, ct=None):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleDMFB:
+    """N independent DMFB chips stepped by the C restatement of env/DMFB/dmfb.py."""
+
+    def __init__(self, n_envs, width, length, n_agents, fov=9, stall=True, b_degrade=False):
+        self.N, self.W, self.L, self.A, self.fov = n_envs, width, length, n_agents, fov
+        self.D = 3 * fov * fov + 2
+        self.cfg = _DmfbCfg(width, length, n_agents, fov, int(stall), int(b_degrade))
+        self.b_degrade = bool(b_degrade)
+        N, A = n_envs, n_agents
+        self.drop = np.zeros((N, A, 4), np.uint8)
+        self.step_count = np.zeros(N, np.int32)
+        self.constraints = np.zeros(N, np.int32)
+        self.usage = np.zeros((N, width, length), np.float64)
+        self.health = np.ones((N, width, length), np.float64)
+        self.degrade = np.ones((N, width, length), np.float64)
+
+    def reset(self, layouts, new=False, degrade=None, mask=None):
+        obs = np.zeros((self.N, self.A, self.D), np.int8)
+        layouts = np.ascontiguousarray(layouts, np.uint8)
+        if degrade is not None:
+            degrade = np.ascontiguousarray(degrade, np.float64)
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+        lib().orc_dmfb_reset(C.byref(self.cfg), self.N, _p(mask), int(new), _p(layouts), _p(degrade),
+                             _p(self.drop), _p(self.step_count), _p(self.constraints), _p(self.usage),
+                             _p(self.health), _p(self.degrade), _p(obs))
+        return obs
+
+    def step(self, actions, draws=None, record=True, want_obs=True):
+        N, A = self.N, self.A
+        actions = np.ascontiguousarray(actions, np.int8)
+        if draws is not None:
+            draws = np.ascontiguousarray(draws, np.float64)
+        obs = np.zeros((N, A, self.D), np.int8) if want_obs else None
+        reward = np.zeros((N, A), np.float64)
+        done = np.zeros((N, A), np.uint8)
+        cons = np.zeros(N, np.int32)
+        succ = np.zeros(N, np.uint8)
+        rc = lib().orc_dmfb_step(C.byref(self.cfg), N, _p(self.drop), _p(self.step_count), _p(self.constraints),
+                                 _p(self.usage), _p(self.health) if self.b_degrade else None, _p(actions),
+                                 _p(draws), int(record), _p(obs), _p(reward), _p(done), _p(cons), _p(succ))
+        if rc:
+            raise TypeError("action is illegal")
+        return obs, reward, done, cons, succ
+
+    def observe(self):
+        obs = np.zeros((self.N, self.A, self.D), np.int8)
+        lib().orc_dmfb_observe(C.byref(self.cfg), self.N, _p(self.drop), _p(obs))
+        return obs
+
+    def global_state(self):
+        out = np.zeros((self.N, 3, self.W, self.L), np.int8)
+        lib().orc_dmfb_global_state(C.byref(self.cfg), self.N, _p(self.drop), _p(out))
+        return out
+
+    def gen_layouts(self, seed):
+        """Reference-distributed random tasks (dmfb.py:207-226) for all N chips."""
+        out = np.zeros((self.N, self.A, 4), np.uint8)
+        for e in range(self.N):
+            s = C.c_uint64((seed << 20) + e)
+            lib().orc_dmfb_gen_layout(C.byref(self.cfg), C.byref(s), _p(out[e]))
+        return out
+
+
+def dmfb_rollout(width, length, n_agents, fov, stall, b_degrade, n_envs, steps, seed=1, threads=1):
+    """Timed CPU leg: returns agent-steps executed (see orc_dmfb_rollout)."""
+    cfg = _DmfbCfg(width, length, n_agents, fov, int(stall), int(b_degrade))
+    obs = np.zeros((n_envs, n_agents, 3 * fov * fov + 2), np.int8)
+    chk = C.c_uint64(0)
+    n = lib().orc_dmfb_rollout(C.byref(cfg), n_envs, steps, C.c_uint64(seed), _p(obs), int(threads), C.byref(chk))
+    return int(n), int(chk.value)
