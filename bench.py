@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — env agent-steps/sec of the batched DMFB env.step on B200 (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps 400 --warmup 40            # own arm, one JSON line on stdout
+  python bench.py --impl reference --steps 3 --warmup 1       # CPU arm: the oracle port on all host threads
+  torchrun --nproc-per-node N ... bench.py --gpus N ...       # one rank per GPU, envs sharded, no collective
+
+Workload (config.workload): DMFB 10x10 chip, 4 droplets, fov 9, 65,536 envs per GPU, uniform random
+actions (pre-generated, resident in HBM), auto-reset when an episode ends (all done or 40 steps), every
+step's observation written to a rotating [41, N, A, 245] int8 episode buffer (2.6 GB > L2, so the stores
+really reach HBM; no separate L2 flush).  One "step" = DMFBenv.step on all envs of the GPU = the step
+kernel + the masked auto-reset kernel.
+
+value     whole-job agent-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
+e2e       same metric through the HOST-buffer C ABI (dmfb_host_step): actions H2D from pinned memory,
+          obs / reward / done / info D2H, every step, inside the timed region
+roofline  step kernel alone: algorithmic bytes per launch / CUDA-event duration vs the measured HBM peak
+cpu_baseline  the C oracle port of the reference env (oracle/) on this box's host threads
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, L, A, FOV = 10, 10, 4, 9
+N_PER_GPU = 65536
+D = 3 * FOV * FOV + 2
+EP_LEN = 2 * (W + L)
+METRIC = "env agent-steps/sec (DMFB 10x10 4d fov9, 64K envs/GPU)"
+UNIT = "agent-steps/s"
+# algorithmic bytes per env-step for C1 (obs 980 + reward 16 + team 4 + done 4 +
+# avail 20 + info 5 + actions 4 + pos R/W 16 + goals 8 + counters R/W 12)
+ALG_BYTES_PER_ENV_STEP = 1069
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=400)
+    p.add_argument("--warmup", type=int, default=40)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--envs", type=int, default=N_PER_GPU, help="envs per GPU (default 65536)")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------ helpers --
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline(seconds, threads=None):
+    """The C oracle port of DMFBenv.step (oracle/dmfb_oracle.c) on the host cores: bounded sample of the
+    same workload (same chip, droplets, fov, random actions, auto-reset, full obs written every step)."""
+    import oracle
+    oracle.build()
+    threads = threads or os.cpu_count() or 1
+    n_envs = 256 * threads
+    # calibrate: ~0.3 s probe, then size the real sample to `seconds`
+    t0 = time.perf_counter()
+    n, _ = oracle.dmfb_rollout(W, L, A, FOV, True, False, n_envs, 40, seed=1, threads=threads)
+    dt = time.perf_counter() - t0
+    steps = max(40, int(40 * seconds / max(dt, 1e-3)))
+    steps = min(steps, 400000)
+    t0 = time.perf_counter()
+    n, _ = oracle.dmfb_rollout(W, L, A, FOV, True, False, n_envs, steps, seed=2, threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_envs} envs x {steps} lock-step env-steps, C oracle port of the reference env "
+                      f"(the reference itself is single-threaded Python, ~8e3 agent-steps/s/core; see BASELINE.md), "
+                      f"{dt:.1f} s wall"}
+
+
+# ------------------------------------------------------------ reference arm --
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    threads = os.cpu_count() or 1
+    n_envs = 256 * threads
+    steps_per = 40  # one bench "step" here = 40 lock-step env steps over the sample (one episode length)
+    for _ in range(max(args.warmup, 1)):
+        oracle.dmfb_rollout(W, L, A, FOV, True, False, n_envs, steps_per, seed=3, threads=threads)
+    t0 = time.perf_counter()
+    total = 0
+    for k in range(args.steps):
+        n, _ = oracle.dmfb_rollout(W, L, A, FOV, True, False, n_envs, steps_per, seed=10 + k, threads=threads)
+        total += n
+    dt = time.perf_counter() - t0
+    value = total / dt
+    sample = (f"each step = {n_envs} envs x {steps_per} env-steps of the C oracle port of the reference env on "
+              f"{threads} host threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "DMFB 10x10 chip, 4 droplets, fov 9, random actions, auto-reset", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ own arm --
+def run_b200(args, rank, world, local_rank):
+    import torch
+    pkg = importlib.import_module("marl-dmfb_b200")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = pkg._native.load()
+    N = args.envs
+    env = pkg.BatchedDMFB(N, W, L, A, fov=FOV, stall=True, b_degrade=False, device=dev, seed=1234,
+                          env_base=rank * N)
+    slots = EP_LEN
+    obs_buf = torch.empty(slots + 1, N, A, D, dtype=torch.int8, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    actions = torch.randint(0, 5, (slots, N, A), device=dev, generator=gen, dtype=torch.int8)
+    env.reset(out=obs_buf[0])
+    stream = torch.cuda.Stream(device=dev)
+
+    def do_steps(t0, k):
+        for t in range(t0, t0 + k):
+            s = t % slots
+            env.step(actions[s], auto_reset=True, out=obs_buf[s + 1])
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- capture `chunk` consecutive steps in one CUDA graph (launch-bound otherwise: ~15 us kernels) ----
+    chunk = min(args.steps, slots) if not args.no_graph else 0
+    graph = None
+    with torch.cuda.stream(stream):
+        do_steps(0, max(args.warmup, 3))  # warm-up (also triggers cudaFuncSetAttribute / module load)
+        stream.synchronize()
+        if chunk:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                do_steps(0, chunk)
+            graph.replay()
+            stream.synchronize()
+
+    def timed_region():
+        n_graph = (args.steps // chunk) if chunk else 0
+        rem = args.steps - n_graph * chunk
+        for _ in range(n_graph):
+            graph.replay()
+        if rem:
+            do_steps(n_graph * chunk, rem)
+
+    barrier()
+    launches0 = lib.dmfb_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            timed_region()
+            ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    n_graph = (args.steps // chunk) if chunk else 0
+    gpu_launches = 2 * args.steps  # step kernel + masked auto-reset kernel per step (graph replays included)
+    _ = lib.dmfb_launch_count() - launches0
+    t_all = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    ms_max = float(t_all.item())
+    value = world * N * A * args.steps / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel: the step kernel alone, CUDA events on its stream ----
+    roof = None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        reps = 200
+        with torch.cuda.stream(stream):
+            for t in range(5):
+                env.step(actions[t % slots], out=obs_buf[t % slots + 1])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, stream=stream):
+                for t in range(slots):
+                    env.step(actions[t], out=obs_buf[t + 1])
+            g2.replay()
+            stream.synchronize()
+            e0.record(stream)
+            for _ in range(reps // slots):
+                g2.replay()
+            e1.record(stream)
+            stream.synchronize()
+        per_launch_s = e0.elapsed_time(e1) * 1e-3 / ((reps // slots) * slots)
+        alg_bytes = ALG_BYTES_PER_ENV_STEP * N
+        achieved = alg_bytes / per_launch_s / 1e9
+        roof = {"bound": "hbm", "kernel": "dmfb_step_kernel<9>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6}
+        tr = os.path.join(ROOT, "profiles", "traffic_step_kernel.json")
+        if os.path.exists(tr):
+            try:
+                with open(tr) as f:
+                    roof["traffic"] = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+    env.reset()
+
+    # ---- e2e: host-buffer C ABI, H2D actions + D2H results every step ----
+    e2e = None
+    if not args.no_e2e:
+        import numpy as np
+        del obs_buf
+        torch.cuda.empty_cache()
+        henv = pkg.HostDMFB(N, W, L, A, fov=FOV, device=local_rank, seed=1234, env_base=rank * N, n_chunks=8)
+        henv.reset()
+        rng = np.random.default_rng(5 + rank)
+        host_actions = [rng.integers(0, 5, (N, A)).astype(np.int8) for _ in range(4)]
+        k_e2e = max(10, min(args.steps, 60))
+        for t in range(3):
+            henv.step(host_actions[t % 4], auto_reset=True)
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(k_e2e):
+            henv.step(host_actions[t % 4], auto_reset=True)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * N * A * k_e2e / float(t_e.item()), "unit": UNIT,
+               "h2d_bytes_per_step": henv.h2d_bytes_per_step, "d2h_bytes_per_step": henv.d2h_bytes_per_step,
+               "steps": k_e2e, "ms_per_step": float(t_e.item()) / k_e2e * 1e3,
+               "api": "dmfb_host_step (host buffers, 8 chunk streams, pinned staging)"}
+        henv.close()
+
+    if rank == 0:
+        cpu = None if args.no_cpu else cpu_baseline(args.cpu_seconds)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"DMFB {W}x{L} chip, {A} droplets, fov {FOV}, {N} envs/GPU, random actions, "
+                                       f"auto-reset, obs to rotating [{slots + 1},N,A,{D}] buffer",
+                           "envs_per_gpu": N, "parallelism": f"env-shard x{world} (no collective)",
+                           "l2": f"outputs rotate over {(slots + 1) * N * A * D / 1e9:.2f} GB > L2 (no explicit flush)",
+                           "cuda_graph_steps": chunk},
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": gpu_launches,
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

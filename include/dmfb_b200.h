@@ -55,6 +55,10 @@ enum dmfb_status {
 #define DMFB_STEP_RECORD_USAGE 1u  /* DMFBenv.step(record=True): addUsage, dmfb.py:570-571 */
 #define DMFB_STEP_FREEZE_TERM 2u   /* lock-step rollouts: envs whose `terminated` flag was already set
                                       are not stepped and emit the zero padding of rollout.py:131-141 */
+#define DMFB_STEP_AUTO_RESET 4u    /* vectorised rollouts: envs that terminate in this step (all done or step
+                                      limit) get DMFBenv.reset(new=False) right after it; their obs rows then hold
+                                      the first observation of the new episode, reward/done/info those of the
+                                      finished step */
 
 /* ------------------------------------------------------------------ DMFB -- */
 
@@ -112,6 +116,7 @@ typedef struct dmfb_out {
     uint8_t* success;       /* [N]             info['success'], dmfb.py:579-580 */
     uint8_t* terminated;    /* [N]             all(dones), rollout.py:34-35 */
     uint8_t* padded;        /* [N]             1 when the env was frozen (DMFB_STEP_FREEZE_TERM) */
+    int32_t* status;        /* [1]             sticky bit 0: an illegal action was applied (TypeError, dmfb.py:115-116) */
 } dmfb_out_t;
 
 /* Validate arguments like DMFBenv.__init__/RoutingTaskManager.__init__ (dmfb.py:128-155,
@@ -203,6 +208,7 @@ typedef struct meda_out {
     uint8_t* success;       /* [N] */
     uint8_t* terminated;    /* [N] */
     uint8_t* padded;        /* [N] */
+    int32_t* status;        /* [1] sticky bit 0: action outside 0..8 seen */
 } meda_out_t;
 
 int meda_cfg_init(meda_cfg_t* cfg, int width, int length, int n_agents, int fov, int b_degrade,

@@ -1,0 +1,157 @@
+// common.cuh — shared device/host helpers for the sm_100a DMFB / MEDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "dmfb_b200.h"
+
+namespace dmfb {
+
+// ---------------------------------------------------------------- host side --
+extern thread_local char g_last_error[256];
+extern std::atomic<uint64_t> g_launches;
+
+inline int cuda_fail(cudaError_t e, const char* what)
+{
+    snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
+    return DMFB_ERR_CUDA;
+}
+#define DMFB_CUDA_TRY(expr)                                      \
+    do {                                                         \
+        cudaError_t _e = (expr);                                 \
+        if (_e != cudaSuccess) return dmfb::cuda_fail(_e, #expr); \
+    } while (0)
+
+inline int gcd_int(int a, int b)
+{
+    while (b) { int t = a % b; a = b; b = t; }
+    return a;
+}
+
+// Smallest number of envs whose rows (row_bytes each) form a span that is a multiple of 16 bytes,
+// scaled up to roughly `target_bytes` per tile.  Tiles of that many envs start 16-byte aligned when
+// the tensor base is, which is what the TMA bulk store needs.
+inline int pick_tile_envs(int row_bytes, int target_bytes, int max_envs)
+{
+    int unit = 16 / gcd_int(16, row_bytes);
+    int e = unit;
+    while (e * 2 <= max_envs && (e * 2) * row_bytes <= target_bytes) e *= 2;
+    return e;
+}
+
+// -------------------------------------------------------------- device side --
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// Make this thread's generic-proxy shared-memory writes visible to the async (TMA) proxy.
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// TMA 1-D bulk store shared -> global (UBLKCP in SASS).  dst/src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// Wait until the bulk stores of all committed groups have finished READING shared memory.
+__device__ __forceinline__ void tma_store_wait_read_all()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// Philox4x32-10 (Salmon et al. 2011) — counter-based, so a draw is a pure function of
+// (seed, env, episode, step, agent) and does not depend on how envs are sharded over GPUs.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+// 53-bit uniform in [0,1), built like CPython's random.random(): (a>>5, b>>6) -> (a*2^26+b)/2^53
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b)
+{
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+enum : uint32_t { kStreamMove = 1, kStreamLayout = 2, kStreamDegrade = 3 };
+
+__device__ __forceinline__ uint4 env_random(uint64_t seed, uint32_t stream, int64_t env, uint32_t episode,
+                                            uint32_t a, uint32_t b)
+{
+    const uint2 key = make_uint2((uint32_t)seed ^ (stream * 0x85EBCA6Bu), (uint32_t)(seed >> 32) ^ (uint32_t)(env >> 32));
+    return philox4x32_10(make_uint4((uint32_t)env, episode, a, b), key);
+}
+
+__device__ __forceinline__ int load_action(const void* actions, int elem_size, size_t idx)
+{
+    if (elem_size == 1) return (int)static_cast<const int8_t*>(actions)[idx];
+    if (elem_size == 4) return (int)static_cast<const int32_t*>(actions)[idx];
+    return (int)static_cast<const long long*>(actions)[idx];
+}
+
+// Cooperative store of a finished shared-memory tile to global memory.
+//  - fast path: global address 16-byte aligned -> one TMA bulk store for the 16-byte multiple part
+//    (issued by thread 0) + at most 15 tail bytes by ordinary stores;
+//  - slow path (unaligned tensor base): byte stores.
+// Must be called by all threads of the CTA after their last write to the tile; contains the
+// proxy fence + barrier, and thread 0 returns only after the TMA has finished reading smem.
+__device__ __forceinline__ void store_tile(int8_t* __restrict__ gdst, const int8_t* tile, uint32_t nbytes)
+{
+    const bool aligned = ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
+    if (aligned) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        const uint32_t bulk = nbytes & ~15u;
+        if (threadIdx.x == 0 && bulk) {
+            tma_store_1d(gdst, tile, bulk);
+            tma_store_commit();
+        }
+        for (uint32_t b = bulk + threadIdx.x; b < nbytes; b += blockDim.x) gdst[b] = tile[b];
+        if (threadIdx.x == 0 && bulk) tma_store_wait_read_all();
+    } else {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < nbytes; b += blockDim.x) gdst[b] = tile[b];
+    }
+}
+
+// Store only the rows (row_bytes each) whose flag is set; used by masked resets.
+__device__ __forceinline__ void store_rows_masked(int8_t* __restrict__ gdst, const int8_t* tile, int n_rows,
+                                                  int row_bytes, const uint8_t* row_flag)
+{
+    __syncthreads();
+    const bool w4 = ((reinterpret_cast<uintptr_t>(gdst) & 3) == 0) && (row_bytes % 4 == 0);
+    for (int r = 0; r < n_rows; ++r) {
+        if (!row_flag[r]) continue;
+        const int8_t* src = tile + (size_t)r * row_bytes;
+        int8_t* dst = gdst + (size_t)r * row_bytes;
+        if (w4) {
+            for (int k = threadIdx.x; k < row_bytes / 4; k += blockDim.x)
+                reinterpret_cast<uint32_t*>(dst)[k] = reinterpret_cast<const uint32_t*>(src)[k];
+        } else {
+            for (int k = threadIdx.x; k < row_bytes; k += blockDim.x) dst[k] = src[k];
+        }
+    }
+}
+
+#endif  // __CUDACC__
+}  // namespace dmfb

@@ -1,0 +1,344 @@
+"""Host-side mirror of the reference DMFB env interface (env/DMFB/dmfb.py) over GPU-resident state.
+
+* ``BatchedDMFB`` — N independent chips in HBM, stepped in lock step by the sm_100a kernels through
+  the C ABI (include/dmfb_b200.h).  Tensors in, tensors out, no host synchronisation inside ``step``.
+* ``DMFBenv``     — N = 1 adapter returning the reference's exact Python types (lists of np.int8
+  arrays, {"player_i": float} dicts, info dict) so that the reference's own
+  ``common/rollout.py:Evaluator`` / ``RolloutWorker`` can drive it unmodified.
+
+PyTorch is used only for device memory and streams.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedDMFB:
+    """N chips x A droplets.  Mirrors DMFBenv (dmfb.py:474-640) with a leading env dimension.
+
+    reset(mask=None, new=False, layouts=None, degrade=None) -> obs[N,A,D] int8
+    step(actions[N,A]) -> obs, reward[N,A] f32, done[N,A] bool, info{constraints, success, terminated, team_reward}
+    get_obs() / get_state() / get_avail_actions() / get_env_info()
+    """
+
+    n_actions = 5
+
+    def __init__(self, n_envs, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False,
+                 per_degrade=0.1, device="cuda", seed=0, env_base=0, track_usage=None, reward_f64=False,
+                 degrade=None, layouts=None):
+        self.lib = nat.load()
+        self.cfg = nat.DmfbCfg()
+        nat.check(self.lib.dmfb_cfg_init(C.byref(self.cfg), width, length, n_agents, n_blocks, fov, int(bool(stall)),
+                                         int(bool(b_degrade)), float(per_degrade)), "dmfb_cfg_init")
+        if n_blocks != 0:
+            raise NotImplementedError("n_blocks > 0 is not supported (every shipped config uses 0 blocks)")
+        self.cfg.env_base = int(env_base)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedDMFB needs a CUDA device: there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.N, self.W, self.L, self.A, self.fov = int(n_envs), width, length, n_agents, fov
+        self.D = self.cfg.obs_dim
+        self.max_step = self.cfg.max_step
+        self.stall, self.b_degrade, self.per_degrade = bool(stall), bool(b_degrade), float(per_degrade)
+        self.seed = int(seed)
+        self.agents = ["player_{}".format(i) for i in range(n_agents)]
+        N, A, dev = self.N, self.A, self.device
+        if track_usage is None:
+            track_usage = self.b_degrade
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+        # ---- state (struct of arrays over N) ----
+        self.drop = z(N, A, 4, dtype=torch.uint8)
+        self.start = z(N, A, 2, dtype=torch.uint8)
+        self.step_count = z(N, dtype=torch.int32)
+        self.constraints_cum = z(N, dtype=torch.int32)
+        self.terminated = z(N, dtype=torch.uint8)
+        self.episode = z(N, dtype=torch.int32)
+        self.usage = z(N, width, length, dtype=torch.int16) if track_usage else None  # uint16 bit pattern
+        self.health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
+        self.degrade = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
+        self.state = nat.DmfbState(
+            n_envs=N, drop=self.drop.data_ptr(), start=self.start.data_ptr(), step_count=self.step_count.data_ptr(),
+            constraints=self.constraints_cum.data_ptr(), terminated=self.terminated.data_ptr(),
+            episode=self.episode.data_ptr(), usage=self.usage.data_ptr() if track_usage else None,
+            health=self.health.data_ptr() if self.b_degrade else None,
+            degrade=self.degrade.data_ptr() if self.b_degrade else None, blocks=None)
+        # ---- per-step outputs ----
+        self.obs = z(N, A, self.D, dtype=torch.int8)
+        self.reward = z(N, A, dtype=torch.float32)
+        self.reward_f64 = z(N, A, dtype=torch.float64) if reward_f64 else None
+        self.team_reward = z(N, dtype=torch.float32)
+        self.done = z(N, A, dtype=torch.uint8)
+        self.avail = torch.ones(N, A, self.n_actions, dtype=torch.uint8, device=dev)
+        self.constraints = z(N, dtype=torch.int32)
+        self.success = z(N, dtype=torch.uint8)
+        self.term_out = z(N, dtype=torch.uint8)
+        self.padded = z(N, dtype=torch.uint8)
+        self.status = z(1, dtype=torch.int32)
+        self._out = self._make_out(self.obs)
+        # the reference constructor draws the degradation matrix and a first task (dmfb.py:151-155)
+        self.reset(new=True, layouts=layouts, degrade=degrade)
+
+    # ------------------------------------------------------------------ helpers --
+    def _make_out(self, obs):
+        return nat.DmfbOut(
+            obs=obs.data_ptr(), reward=self.reward.data_ptr(),
+            reward_f64=self.reward_f64.data_ptr() if self.reward_f64 is not None else None,
+            team_reward=self.team_reward.data_ptr(), done=self.done.data_ptr(), avail=self.avail.data_ptr(),
+            constraints=self.constraints.data_ptr(), success=self.success.data_ptr(),
+            terminated=self.term_out.data_ptr(), padded=self.padded.data_ptr(), status=self.status.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _as(self, t, dtype, shape, name):
+        if t is None:
+            return None
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(np.ascontiguousarray(t))
+        t = t.to(device=self.device, dtype=dtype).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    # ---------------------------------------------------------------------- API --
+    def reset(self, mask=None, new=False, layouts=None, degrade=None, out=None):
+        """DMFBenv.reset(new) (dmfb.py:589-597) for the envs selected by ``mask`` (None = all).
+
+        layouts: optional [N,A,4] (x, y, goal_x, goal_y) injected tasks; default: on-device generator
+        equivalent to _Generate_Start_End (dmfb.py:207-226).  degrade: optional [N,W,L] float64 factors
+        (only used with new=True)."""
+        mask_t = self._as(mask, torch.uint8, (self.N,), "mask")
+        lay_t = self._as(layouts, torch.uint8, (self.N, self.A, 4), "layouts")
+        deg_t = self._as(degrade, torch.float64, (self.N, self.W, self.L), "degrade")
+        obs = self.obs if out is None else out
+        with torch.cuda.device(self.device):
+            rc = self.lib.dmfb_reset(C.byref(self.cfg), C.byref(self.state), _ptr(mask_t), int(bool(new)), _ptr(lay_t),
+                                     _ptr(deg_t), self.seed, _ptr(obs), self._stream())
+        nat.check(rc, "dmfb_reset")
+        return obs
+
+    def restart(self, mask=None):
+        """DMFBenv.restart (dmfb.py:599-605)."""
+        mask_t = self._as(mask, torch.uint8, (self.N,), "mask")
+        with torch.cuda.device(self.device):
+            rc = self.lib.dmfb_restart(C.byref(self.cfg), C.byref(self.state), _ptr(mask_t), _ptr(self.obs),
+                                       self._stream())
+        nat.check(rc, "dmfb_restart")
+        return self.obs
+
+    def step(self, actions, draws=None, record=True, freeze_terminated=False, auto_reset=False, out=None):
+        """DMFBenv.step (dmfb.py:560-587) on every env.
+
+        actions: [N,A] integer tensor (int8 / int32 / int64) on this device.
+        draws:   optional [N,A] float64 move-success draws replacing random.random() (dmfb.py:335).
+        freeze_terminated: lock-step episodes — finished envs are not stepped and emit zero padding.
+        auto_reset: envs that terminate in this step are reset (new task, updateHealth) right after it;
+                 their obs rows hold the first observation of the next episode.
+        out:     optional int8 [N,A,D] tensor that receives the observation (e.g. a slice of an
+                 episode buffer) instead of ``self.obs``."""
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.ascontiguousarray(actions))
+        if actions.device != self.device:
+            actions = actions.to(self.device)
+        if actions.dtype not in (torch.int8, torch.uint8, torch.int32, torch.int64):
+            actions = actions.to(torch.int64)
+        actions = actions.contiguous()
+        if tuple(actions.shape) != (self.N, self.A):
+            raise RuntimeError("The number of actions is not the same as n_droplets")  # dmfb.py:272-274
+        draws_t = self._as(draws, torch.float64, (self.N, self.A), "draws")
+        flags = ((nat.STEP_RECORD_USAGE if record else 0) | (nat.STEP_FREEZE_TERM if freeze_terminated else 0)
+                 | (nat.STEP_AUTO_RESET if auto_reset else 0))
+        if out is None:
+            obs, o = self.obs, self._out
+        else:
+            obs, o = out, self._make_out(out)
+        with torch.cuda.device(self.device):
+            rc = self.lib.dmfb_step(C.byref(self.cfg), C.byref(self.state), _ptr(actions), actions.element_size(),
+                                    _ptr(draws_t), self.seed, flags, C.byref(o), self._stream())
+        nat.check(rc, "dmfb_step")
+        info = {"constraints": self.constraints, "success": self.success, "terminated": self.term_out.view(torch.bool),
+                "team_reward": self.team_reward, "padded": self.padded.view(torch.bool)}
+        return obs, self.reward, self.done.view(torch.bool), info
+
+    def get_obs(self, out=None):
+        """getObs() of the current state (dmfb.py:622-626), recomputed from the droplet positions."""
+        obs = self.obs if out is None else out
+        with torch.cuda.device(self.device):
+            rc = self.lib.dmfb_observe(C.byref(self.cfg), C.byref(self.state), _ptr(obs), self._stream())
+        nat.check(rc, "dmfb_observe")
+        return obs
+
+    def get_state(self, out=None):
+        """getglobalobs() (dmfb.py:368-392) as int8 [N,3,W,L]."""
+        if out is None:
+            out = torch.empty(self.N, 3, self.W, self.L, dtype=torch.int8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.dmfb_global_state(C.byref(self.cfg), C.byref(self.state), _ptr(out), self._stream())
+        nat.check(rc, "dmfb_global_state")
+        return out
+
+    def get_avail_actions(self):
+        """[N,A,n_actions] mask: all ones (rollout.py:22), zeros for padded steps (rollout.py:138-139)."""
+        return self.avail
+
+    def get_env_info(self):
+        """dmfb.py:633-640."""
+        return {"n_actions": self.n_actions, "n_agents": self.A,
+                "obs_shape": (3, self.fov, self.fov, 2, self.D), "episode_limit": self.max_step}
+
+    def check_actions(self):
+        """Raises the reference's TypeError if an illegal action was applied since the last check
+        (device -> host sync; dmfb.py:115-116)."""
+        if int(self.status.item()) & 1:
+            self.status.zero_()
+            raise TypeError("action is illegal")
+
+    # convenience views
+    @property
+    def positions(self):
+        return self.drop[:, :, 0:2]
+
+    @property
+    def goals(self):
+        return self.drop[:, :, 2:4]
+
+    def usage_counts(self):
+        """m_usage as an integer tensor (stored as uint16)."""
+        return None if self.usage is None else (self.usage.to(torch.int32) & 0xFFFF)
+
+
+class _RoutingManagerView:
+    """The attributes of RoutingTaskManager that callers read (evaDegre.py:21; dmfb.py:194-195)."""
+
+    def __init__(self, env):
+        self._e = env
+
+    @property
+    def m_health(self):
+        b = self._e._b
+        return np.ones((b.W, b.L)) if b.health is None else b.health[0].cpu().numpy()
+
+    @property
+    def m_degrade(self):
+        b = self._e._b
+        return np.ones((b.W, b.L)) if b.degrade is None else b.degrade[0].cpu().numpy()
+
+    @property
+    def m_usage(self):
+        b = self._e._b
+        return np.zeros((b.W, b.L)) if b.usage is None else b.usage_counts()[0].cpu().numpy().astype(np.float64)
+
+    @property
+    def starts(self):
+        return self._e._b.start[0].cpu().numpy().astype(int)
+
+    @property
+    def ends(self):
+        return self._e._b.drop[0, :, 2:4].cpu().numpy().astype(int)
+
+    @property
+    def distances(self):
+        d = self._e._b.drop[0].cpu().numpy().astype(int)
+        return np.abs(d[:, 0] - d[:, 2]) + np.abs(d[:, 1] - d[:, 3])
+
+    def getTaskStatus(self):
+        return [bool(x == 0) for x in self.distances]
+
+
+class DMFBenv:
+    """Drop-in for env.DMFB.dmfb.DMFBenv (dmfb.py:474-640) on top of a 1-env GPU batch.
+
+    Same constructor signature, same return types: reset() -> list of np.int8 arrays of length
+    3*fov*fov+2; step(list|dict) -> (obs list, rewards dict, dones dict, info dict)."""
+
+    metadata = {"render.modes": ["human", "rgb_array"]}
+
+    def __init__(self, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False, per_degrade=0.1,
+                 show=False, savemp4=False, device="cuda", seed=None, layouts=None, degrade=None):
+        assert width >= 5 and length >= 5
+        assert n_agents > 0
+        if seed is None:
+            seed = int(np.random.randint(0, 2**31 - 1))  # the reference seeds from the wall clock (dmfb.py:154)
+        self._b = BatchedDMFB(1, width, length, n_agents, n_blocks, fov=fov, stall=stall, b_degrade=b_degrade,
+                              per_degrade=per_degrade, device=device, seed=seed, track_usage=True, reward_f64=True,
+                              layouts=None if layouts is None else np.asarray(layouts)[None],
+                              degrade=None if degrade is None else np.asarray(degrade)[None])
+        self.mode = None  # rendering is out of scope (dmfb.py:642-720)
+        self.agents = list(self._b.agents)
+        self.possible_agents = self.agents[:]
+        self.width, self.length = width, length
+        self.max_step = self._b.max_step
+        self.rewards = {a: 0.0 for a in self.agents}
+        self.dones = {a: False for a in self.agents}
+        self.routing_manager = _RoutingManagerView(self)
+
+    @property
+    def step_count(self):
+        return int(self._b.step_count[0].item())
+
+    @property
+    def constraints(self):
+        return int(self._b.constraints_cum[0].item())
+
+    def _obs_list(self, obs):
+        o = obs[0].cpu().numpy()
+        return [o[i].copy() for i in range(len(self.agents))]
+
+    def step(self, actions, record=True):
+        if isinstance(actions, dict):
+            acts = [actions[a] for a in self.agents]
+        elif isinstance(actions, list):
+            acts = actions
+        else:
+            raise TypeError("wrong actions")                     # dmfb.py:563-568
+        if len(acts) != len(self.agents):
+            raise RuntimeError("The number of actions is not the same as n_droplets")
+        a = torch.as_tensor(np.asarray([int(x) for x in acts], dtype=np.int64)[None])
+        obs, _, done, info = self._b.step(a, record=record)
+        self._b.check_actions()
+        r = self._b.reward_f64[0].cpu().numpy()
+        d = done[0].cpu().numpy()
+        for k, name in enumerate(self.agents):
+            self.rewards[name] = r[k]
+            self.dones[name] = bool(d[k])
+        out_info = {"constraints": int(info["constraints"][0].item()), "success": int(info["success"][0].item())}
+        return self._obs_list(obs), self.rewards, self.dones, out_info
+
+    def reset(self, new=False, layouts=None):
+        self.rewards = {a: 0 for a in self.agents}
+        self.dones = {a: False for a in self.agents}
+        obs = self._b.reset(new=new, layouts=None if layouts is None else np.asarray(layouts)[None])
+        return self._obs_list(obs)
+
+    def restart(self, index=None):
+        self.rewards = {a: 0.0 for a in self.agents}
+        self.dones = {a: False for a in self.agents}
+        return self._obs_list(self._b.restart())
+
+    def seed(self, seed=None):
+        pass                                                     # dmfb.py:607-608
+
+    def close(self):
+        pass
+
+    def render(self, close=False):
+        return None                                              # mode is None (dmfb.py:643-644)
+
+    def getOneObs(self, agent):
+        index = int(agent[-1]) if isinstance(agent, str) else agent  # dmfb.py:614-620
+        return self._obs_list(self._b.get_obs())[index]
+
+    def getObs(self):
+        return self._obs_list(self._b.get_obs())
+
+    def get_env_info(self):
+        return self._b.get_env_info()

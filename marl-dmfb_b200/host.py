@@ -1,0 +1,87 @@
+"""HostDMFB — the DMFB hot path behind HOST buffers (dmfb_host_* of include/dmfb_b200.h).
+
+Same call shape as the reference env (actions in host memory in, observations / rewards / dones /
+info in host memory out, env/DMFB/dmfb.py:560-587), batched over N chips.  The handle owns the device
+state; each call moves its inputs H2D and its results D2H.  This is the path bench.py reports as `e2e`."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+
+
+class _Pinned:
+    """numpy array over cudaHostAlloc'ed memory (freed with the object)."""
+
+    def __init__(self, lib, shape, dtype):
+        self._lib = lib
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._ptr = lib.dmfb_host_alloc_pinned(max(nbytes, 16))
+        if not self._ptr:
+            raise MemoryError("cudaHostAlloc failed")
+        buf = (C.c_uint8 * max(nbytes, 16)).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            self._lib.dmfb_host_free_pinned(self._ptr)
+        except Exception:
+            pass
+
+
+class HostDMFB:
+    def __init__(self, n_envs, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False,
+                 per_degrade=0.1, device=0, seed=0, env_base=0, n_chunks=8):
+        self.lib = nat.load()
+        self.cfg = nat.DmfbCfg()
+        nat.check(self.lib.dmfb_cfg_init(C.byref(self.cfg), width, length, n_agents, n_blocks, fov, int(bool(stall)),
+                                         int(bool(b_degrade)), float(per_degrade)), "dmfb_cfg_init")
+        self.cfg.env_base = int(env_base)
+        self.N, self.A, self.D = int(n_envs), n_agents, self.cfg.obs_dim
+        self.seed = int(seed)
+        self._h = C.c_void_p()
+        nat.check(self.lib.dmfb_host_create(C.byref(self.cfg), self.N, int(device), int(n_chunks), C.byref(self._h)),
+                  "dmfb_host_create")
+        N, A = self.N, self.A
+        self._pins = {k: _Pinned(self.lib, s, d) for k, (s, d) in dict(
+            actions=((N, A), np.int8), obs=((N, A, self.D), np.int8), reward=((N, A), np.float32),
+            done=((N, A), np.uint8), constraints=((N,), np.int32), success=((N,), np.uint8)).items()}
+        self.actions = self._pins["actions"].array   # write your actions here (pinned) or pass an array to step()
+        self.obs = self._pins["obs"].array
+        self.reward = self._pins["reward"].array
+        self.done = self._pins["done"].array
+        self.constraints = self._pins["constraints"].array
+        self.success = self._pins["success"].array
+        self.h2d_bytes_per_step = N * A
+        self.d2h_bytes_per_step = N * A * self.D + N * A * 4 + N * A + N * 4 + N
+
+    def _p(self, a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    def reset(self, new=False, layouts=None, degrade=None):
+        lay = None if layouts is None else np.ascontiguousarray(layouts, np.uint8)
+        deg = None if degrade is None else np.ascontiguousarray(degrade, np.float64)
+        nat.check(self.lib.dmfb_host_reset(self._h, int(bool(new)), self._p(lay), self._p(deg), self.seed,
+                                           self._p(self.obs)), "dmfb_host_reset")
+        return self.obs
+
+    def step(self, actions=None, draws=None, record=True, auto_reset=False):
+        if actions is not None and actions is not self.actions:
+            self.actions[...] = actions
+        u = None if draws is None else np.ascontiguousarray(draws, np.float64)
+        flags = (nat.STEP_RECORD_USAGE if record else 0) | (nat.STEP_AUTO_RESET if auto_reset else 0)
+        nat.check(self.lib.dmfb_host_step(self._h, self._p(self.actions), self._p(u), self.seed, flags,
+                                          self._p(self.obs), self._p(self.reward), self._p(self.done),
+                                          self._p(self.constraints), self._p(self.success)), "dmfb_host_step")
+        return self.obs, self.reward, self.done.view(np.bool_), {"constraints": self.constraints, "success": self.success}
+
+    def close(self):
+        if self._h:
+            self.lib.dmfb_host_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,232 @@
+"""GPU parity for the DMFB hot path: CUDA kernels (through the C ABI) vs
+ (1) golden traces recorded from the unmodified reference env, and
+ (2) the CPU oracle on seeded random inputs at sizes the oracle finishes in seconds,
+ (3) size-independent properties at the full 64K-env size.
+Bit-exact for every integer/byte tensor and for the float64 rewards; float32 rewards within 1e-6 rel."""
+import importlib
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def pkg():
+    return importlib.import_module("marl-dmfb_b200")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", golden_names("dmfb"))
+def test_dmfb_cuda_matches_reference_trace(name):
+    g = load_golden(name)
+    K, A, W, L = g["K"], g["A"], g["W"], g["L"]
+    env = pkg().BatchedDMFB(K, W, L, A, fov=g["fov"], stall=bool(g["stall"]), b_degrade=bool(g["b_degrade"]),
+                            per_degrade=g["per_degrade"], device="cuda:0", track_usage=True, reward_f64=True,
+                            degrade=g["degrade"] if g["b_degrade"] else None, layouts=g["layouts"][0])
+    obs_t, state_t = list(g["obs_t"]), list(g["state_t"])
+    for ep in range(g["n_ep"]):
+        obs = env.reset(new=False, layouts=g["layouts"][ep])
+        np.testing.assert_array_equal(_np(obs), g["obs_reset"][ep], err_msg=f"{name} reset obs ep{ep}")
+        if g["b_degrade"]:
+            np.testing.assert_array_equal(_np(env.health), g["health_reset"][ep], err_msg=f"health ep{ep}")
+        np.testing.assert_array_equal(_np(env.usage_counts()), g["usage_reset"][ep], err_msg=f"usage ep{ep}")
+        for t in range(g["T"]):
+            acts = torch.as_tensor(g["actions"][ep, t], device="cuda:0")
+            obs, rew, done, info = env.step(acts, draws=g["draws"][ep, t])
+            msg = f"{name} ep{ep} t{t}"
+            np.testing.assert_array_equal(_np(env.positions), g["pos"][ep, t], err_msg=msg + " pos")
+            np.testing.assert_array_equal(_np(env.reward_f64), g["reward"][ep, t], err_msg=msg + " reward f64")
+            np.testing.assert_allclose(_np(rew), g["reward"][ep, t], rtol=1e-6, atol=0, err_msg=msg + " reward f32")
+            np.testing.assert_allclose(_np(info["team_reward"]), g["reward"][ep, t].sum(-1) / A, rtol=1e-6, atol=1e-7)
+            np.testing.assert_array_equal(_np(done).astype(np.uint8), g["done"][ep, t], err_msg=msg + " done")
+            np.testing.assert_array_equal(_np(info["constraints"]), g["constraints"][ep, t], err_msg=msg + " constraints")
+            np.testing.assert_array_equal(_np(info["success"]), g["success"][ep, t], err_msg=msg + " success")
+            np.testing.assert_array_equal(_np(info["terminated"]), g["done"][ep, t].all(-1), err_msg=msg + " terminated")
+            if t in obs_t:
+                np.testing.assert_array_equal(_np(obs), g["obs"][ep, obs_t.index(t)], err_msg=msg + " obs")
+                np.testing.assert_array_equal(_np(env.get_obs(out=torch.empty_like(obs))), _np(obs))
+            if t in state_t:
+                np.testing.assert_array_equal(_np(env.get_state()), g["state"][ep, state_t.index(t)],
+                                              err_msg=msg + " state")
+        np.testing.assert_array_equal(_np(env.usage_counts()), g["usage_end"][ep], err_msg=f"usage end ep{ep}")
+    if g["b_degrade"]:
+        np.testing.assert_array_equal(_np(env.health), g["health_final"])
+    assert _np(env.get_avail_actions()).min() == 1
+
+
+CASES = [
+    # N, W, L, A, fov, stall, degrade
+    (1000, 10, 10, 4, 9, True, True),
+    (333, 20, 20, 10, 9, True, False),
+    (130, 50, 50, 10, 9, True, True),
+    (257, 12, 15, 6, 7, False, True),
+    (64, 16, 11, 3, 8, True, False),
+    (97, 30, 30, 7, 11, True, True),
+    (40, 25, 40, 5, 13, True, True),
+    (33, 9, 9, 2, 9, True, False),
+    (31, 40, 40, 12, 19, True, True),
+    (1, 10, 10, 4, 9, True, True),
+]
+
+
+@pytest.mark.parametrize("N,W,L,A,fov,stall,deg", CASES)
+def test_dmfb_cuda_matches_oracle_random(oracle_lib, N, W, L, A, fov, stall, deg):
+    rng = np.random.default_rng(N * 7 + W)
+    ref = oracle_lib.OracleDMFB(N, W, L, A, fov=fov, stall=stall, b_degrade=deg)
+    degrade = rng.random((N, W, L)) * 0.4 + 0.6 if deg else None
+    layouts = ref.gen_layouts(seed=N)
+    env = pkg().BatchedDMFB(N, W, L, A, fov=fov, stall=stall, b_degrade=deg, per_degrade=1.0, device="cuda:0",
+                            track_usage=True, reward_f64=True, degrade=degrade, layouts=layouts)
+    if deg:
+        ref.degrade[...] = degrade
+        # pre-age the chips so that health < 1 matters from the first step
+        ref.health[...] = rng.random((N, W, L)) * 0.7 + 0.3
+        env.health.copy_(torch.as_tensor(ref.health))
+    T = min(2 * (W + L) + 3, 70)
+    for ep in range(3):
+        layouts = ref.gen_layouts(seed=1000 * ep + N)
+        if ep == 1:  # masked reset: only even envs get a new task
+            mask = (np.arange(N) % 2 == 0).astype(np.uint8)
+        else:
+            mask = None
+        o_ref = ref.reset(layouts, mask=mask)
+        buf = env.obs.clone()
+        o_gpu = env.reset(layouts=layouts, mask=mask)
+        sel = slice(None) if mask is None else mask.astype(bool)
+        np.testing.assert_array_equal(_np(o_gpu)[sel], o_ref[sel], err_msg=f"reset obs ep{ep}")
+        if mask is not None:  # rows of unselected envs must be untouched
+            np.testing.assert_array_equal(_np(o_gpu)[~sel], _np(buf)[~sel])
+        np.testing.assert_array_equal(_np(env.drop), ref.drop)
+        for t in range(T):
+            # goal-biased actions so that arrivals, collisions and the +10/+10 bonus all occur
+            d = ref.drop.astype(np.int32)
+            dx, dy = d[..., 2] - d[..., 0], d[..., 3] - d[..., 1]
+            toward = np.where(np.abs(dx) >= np.abs(dy), np.where(dx > 0, 1, 2), np.where(dy > 0, 4, 3))
+            toward = np.where((dx == 0) & (dy == 0), 0, toward)
+            acts = np.where(rng.random((N, A)) < 0.7, toward, rng.integers(0, 5, (N, A))).astype(np.int8)
+            draws = rng.random((N, A))
+            obs, rew, done, cons, succ = ref.step(acts, draws)
+            g_obs, g_rew, g_done, info = env.step(torch.as_tensor(acts.astype(np.int64), device="cuda:0"), draws=draws)
+            msg = f"ep{ep} t{t}"
+            np.testing.assert_array_equal(_np(env.drop), ref.drop, err_msg=msg + " drop")
+            np.testing.assert_array_equal(_np(g_obs), obs, err_msg=msg + " obs")
+            np.testing.assert_array_equal(_np(env.reward_f64), rew, err_msg=msg + " reward")
+            np.testing.assert_allclose(_np(g_rew), rew, rtol=1e-6, atol=0)
+            np.testing.assert_array_equal(_np(g_done).astype(np.uint8), done, err_msg=msg + " done")
+            np.testing.assert_array_equal(_np(info["constraints"]), cons, err_msg=msg + " constraints")
+            np.testing.assert_array_equal(_np(info["success"]), succ, err_msg=msg + " success")
+            np.testing.assert_array_equal(_np(env.step_count), ref.step_count)
+            np.testing.assert_array_equal(_np(env.constraints_cum), ref.constraints)
+        np.testing.assert_array_equal(_np(env.usage_counts()), ref.usage, err_msg=f"usage ep{ep}")
+        np.testing.assert_array_equal(_np(env.get_state()), ref.global_state())
+        if deg:
+            np.testing.assert_array_equal(_np(env.health), ref.health)
+
+
+def test_dmfb_known_answers():
+    """Constructed layouts with known answers from the reference."""
+    P = pkg()
+
+    def run(layout, acts, steps=1, **kw):
+        env = P.DMFBenv(10, 10, len(layout), fov=9, layouts=layout, **kw)
+        env.reset(layouts=layout)
+        out = None
+        for _ in range(steps):
+            out = env.step(list(acts))
+        return out
+
+    # adjacent move: droplet 0 moves right next to droplet 1 which stalls
+    obs, r, d, info = run([(2, 2, 8, 2), (4, 2, 4, 9)], [1, 0])
+    assert info["constraints"] == 4 and np.allclose([r["player_0"], r["player_1"]], [-4.1, -4.25], rtol=1e-12)
+    # move into an occupied cell -> reverted
+    obs, r, d, info = run([(2, 2, 8, 2), (3, 2, 3, 9)], [1, 0])
+    assert info["constraints"] == 6 and np.allclose([r["player_0"], r["player_1"]], [-6.4, -6.25], rtol=1e-12)
+    # wall clamp
+    obs, r, d, info = run([(0, 0, 5, 5), (9, 9, 4, 4)], [2, 0])
+    assert info["constraints"] == 0 and np.allclose([r["player_0"], r["player_1"]], [-0.4, -0.25], rtol=1e-12)
+    # both arrive in the same step without constraints: -0.1 + 10 + 10, success
+    obs, r, d, info = run([(1, 1, 2, 1), (7, 7, 7, 8)], [1, 4])
+    assert info["success"] == 1 and np.allclose([r["player_0"], r["player_1"]], [19.9, 19.9], rtol=1e-12)
+    assert d == {"player_0": True, "player_1": True}
+    # the step after everybody is done: 0 + 10 + 10
+    obs, r, d, info = run([(1, 1, 2, 1), (7, 7, 7, 8)], [1, 4], steps=2)
+    assert np.allclose([r["player_0"], r["player_1"]], [20.0, 20.0], rtol=1e-12)
+    assert all(o.dtype == np.int8 and o.shape == (245,) for o in obs)
+
+
+def test_dmfb_ctor_errors():
+    P = pkg()
+    with pytest.raises(RuntimeError, match="Fov is too large"):
+        P.BatchedDMFB(4, 8, 8, 2, fov=9)
+    with pytest.raises(TypeError, match="Too many droplets"):
+        P.BatchedDMFB(4, 5, 5, 5, fov=5)
+    with pytest.raises(AssertionError):
+        P.DMFBenv(4, 10, 2)
+    env = P.DMFBenv(10, 10, 4, fov=9)
+    with pytest.raises(TypeError):
+        env.step([0, 1, 2, 7])
+    with pytest.raises(TypeError, match="wrong actions"):
+        env.step((0, 1, 2, 3))
+    with pytest.raises(RuntimeError):
+        env.step([0, 1])
+
+
+def test_dmfb_freeze_terminated_pads_like_rollout():
+    """DMFB_STEP_FREEZE_TERM: a finished env emits the zero padding of rollout.py:131-141."""
+    P = pkg()
+    layouts = np.array([[(1, 1, 2, 1), (7, 7, 7, 8)], [(1, 1, 9, 9), (7, 7, 0, 0)]], np.uint8)
+    env = P.BatchedDMFB(2, 10, 10, 2, fov=9, device="cuda:0", layouts=layouts)
+    env.reset(layouts=layouts)
+    a = torch.tensor([[1, 4], [0, 0]], device="cuda:0")
+    obs, rew, done, info = env.step(a, freeze_terminated=True)
+    assert _np(info["terminated"]).tolist() == [True, False]
+    pos = _np(env.positions).copy()
+    obs, rew, done, info = env.step(a, freeze_terminated=True)
+    assert _np(info["padded"]).tolist() == [True, False]
+    assert not _np(obs)[0].any() and _np(obs)[1].any()
+    assert _np(rew)[0].tolist() == [0.0, 0.0] and _np(env.get_avail_actions())[0].max() == 0
+    assert _np(env.get_avail_actions())[1].min() == 1
+    np.testing.assert_array_equal(_np(env.positions)[0], pos[0])
+    assert int(env.step_count[0]) == 1 and int(env.step_count[1]) == 2
+
+
+def test_dmfb_device_generator_and_full_size_properties():
+    """64K envs (the benchmark size): on-device task generator obeys the reference's rejection rule
+    (dmfb.py:220: every pairwise squared distance among the 2A points > 2) and the step keeps the
+    invariants the reference guarantees: no two droplets share a cell, positions stay on chip,
+    obs layer-0 centre byte equals own index + 1, sharded generation equals the unsharded one."""
+    P = pkg()
+    N, W, L, A, fov = 65536, 10, 10, 4, 9
+    env = P.BatchedDMFB(N, W, L, A, fov=fov, device="cuda:0", seed=1234)
+    obs = env.reset()
+    d = env.drop.to(torch.int32)
+    pts = torch.cat([d[:, :, 0:2], d[:, :, 2:4]], dim=1)  # [N,2A,2]
+    diff = pts[:, :, None, :] - pts[:, None, :, :]
+    d2 = (diff * diff).sum(-1) + torch.eye(2 * A, device="cuda:0", dtype=torch.int32)[None] * 1000
+    assert int(d2.min()) > 2
+    assert int(d[:, :, 0].max()) < W and int(d[:, :, 1].max()) < L
+    # roughly uniform starts
+    hist = torch.bincount((d[:, :, 0] * L + d[:, :, 1]).flatten(), minlength=W * L).float()
+    assert hist.min() > 0.5 * hist.mean() and hist.max() < 1.6 * hist.mean()
+    # sharded generation == unsharded, env for env
+    lo, hi = P.shard_range(N, 1, 4)
+    shard = P.BatchedDMFB(hi - lo, W, L, A, fov=fov, device="cuda:0", seed=1234, env_base=lo)
+    shard.reset()
+    assert torch.equal(shard.drop, env.drop[lo:hi])
+    gen = torch.Generator(device="cuda:0").manual_seed(5)
+    for t in range(45):
+        acts = torch.randint(0, 5, (N, A), device="cuda:0", generator=gen, dtype=torch.int8)
+        obs, rew, done, info = env.step(acts)
+        p = env.drop[:, :, 0].to(torch.int32) * L + env.drop[:, :, 1].to(torch.int32)
+        srt = p.sort(dim=1).values
+        assert bool((srt[:, 1:] != srt[:, :-1]).all()), "two droplets share a cell"
+        centre = obs.view(N, A, -1)[:, :, (fov // 2) * fov + fov // 2]
+        assert torch.equal(centre, torch.arange(1, A + 1, device="cuda:0", dtype=torch.int8).expand(N, A))
+    assert bool(done.all()) and int(env.step_count.min()) == 45  # past max_step: dones forced True
+    assert int(info["success"].sum()) == 0
