@@ -8,8 +8,8 @@
 Workload (config.workload): DMFB 10x10 chip, 4 droplets, fov 9, 65,536 envs per GPU, uniform random
 actions (pre-generated, resident in HBM), auto-reset when an episode ends (all done or 40 steps), every
 step's observation written to a rotating [41, N, A, 245] int8 episode buffer (2.6 GB > L2, so the stores
-really reach HBM; no separate L2 flush).  One "step" = DMFBenv.step on all envs of the GPU = the step
-kernel + the masked auto-reset kernel.
+really reach HBM; no separate L2 flush).  One "step" = DMFBenv.step on all envs of the GPU = one launch of the
+step kernel (auto-reset fused).
 
 value     whole-job agent-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
 e2e       same metric through the HOST-buffer C ABI (dmfb_host_step): actions H2D from pinned memory,
@@ -224,7 +224,7 @@ def run_b200(args, rank, world, local_rank):
         barrier()
     ms = ev0.elapsed_time(ev1)
     n_graph = (args.steps // chunk) if chunk else 0
-    gpu_launches = 2 * args.steps  # step kernel + masked auto-reset kernel per step (graph replays included)
+    gpu_launches = args.steps  # one fused step(+auto-reset) kernel per step (graph replays included)
     _ = lib.dmfb_launch_count() - launches0
     t_all = torch.tensor([ms], device=dev, dtype=torch.float64)
     if dist is not None:

@@ -30,17 +30,21 @@ constexpr int kThreads = 128;
 struct TileLayout {
     int E, A, SA, D, nw, ncodes;
     uint32_t tile_bytes;
-    uint32_t off_drop, off_past, off_rew, off_flag, off_donemask, off_l2row, off_l2col, off_dirx, off_diry, total;
+    uint32_t off_drop, off_past, off_rew, off_flag, off_donemask, off_l2row, off_l2col, off_dirx, off_diry;
+    uint32_t off_f64, off_i32, off_act, total;
     __host__ __device__ TileLayout(const dmfb_cfg_t& c, int E_) {
         E = E_; A = c.n_agents; SA = A | 1; D = c.obs_dim; nw = c.l2_words; ncodes = 2 * (c.fov / 2) + 1;
         tile_bytes = ((uint32_t)(E * A * D) + 15u) & ~15u;
         uint32_t o = tile_bytes;
+        off_f64 = o; o += (uint32_t)(E * A) * 8u * 2u;   // staged draws + health probabilities (float64)
         off_drop = o; o += (uint32_t)(E * SA) * 4u;
         off_past = o; o += (uint32_t)(E * SA) * 4u;
         off_rew = o; o += (uint32_t)(E * SA) * 4u;
         off_donemask = o; o += (uint32_t)E * 4u;
+        off_i32 = o; o += (uint32_t)E * 4u * 8u;          // per-env scalars, see EnvScalar
         off_l2row = o; o += (uint32_t)(ncodes * nw) * 4u;
         off_l2col = o; o += (uint32_t)(ncodes * nw) * 4u;
+        off_act = o; o += ((uint32_t)(E * A) + 3u) & ~3u;
         off_flag = o; o += ((uint32_t)E + 3u) & ~3u;
         off_dirx = o; o += ((uint32_t)(2 * c.width) + 3u) & ~3u;
         off_diry = o; o += ((uint32_t)(2 * c.length) + 3u) & ~3u;
@@ -48,25 +52,42 @@ struct TileLayout {
     }
 };
 
+// per-env scalars staged in smem: [slot][E] int32
+enum EnvScalar { kStepIn = 0, kCumIn, kEpisode, kStepOut, kCumOut, kCons, kMisc /* success | term<<8 | padded<<16 | reset<<24 */, kTeam, kNumScalars };
+static_assert(kNumScalars == 8, "TileLayout reserves 8 scalar slots");
+
+// S.flag values
+constexpr uint8_t kFlagFrozen = 1;    // padded step: zero observation
+constexpr uint8_t kFlagSkip = 2;      // masked reset: env not selected
+constexpr uint8_t kFlagNewTask = 4;   // auto-reset: a new task was generated, updateHealth still to run
+
 struct TileSmem {
     int8_t* tile;
+    double* draw;        // [E*A]
+    double* prob;        // [E*A]
     uint32_t* drop;      // [E][SA] packed x | y<<8 | gx<<16 | gy<<24
     uint32_t* past;      // [E][SA] past x | y<<8 | sta<<16 | dyn<<24
     float* rew;          // [E][SA]
     uint32_t* donemask;  // [E]
+    int32_t* sc;         // [kNumScalars][E]
     uint32_t* l2row;     // [ncodes][nw]
     uint32_t* l2col;
-    uint8_t* flag;       // [E] 0 = live, 1 = frozen/padded (zero obs), 2 = not selected (masked reset)
+    int8_t* act;         // [E*A]
+    uint8_t* flag;       // [E]
     int8_t* dirx;
     int8_t* diry;
     __device__ TileSmem(unsigned char* base, const TileLayout& L) {
         tile = reinterpret_cast<int8_t*>(base);
+        draw = reinterpret_cast<double*>(base + L.off_f64);
+        prob = draw + L.E * L.A;
         drop = reinterpret_cast<uint32_t*>(base + L.off_drop);
         past = reinterpret_cast<uint32_t*>(base + L.off_past);
         rew = reinterpret_cast<float*>(base + L.off_rew);
         donemask = reinterpret_cast<uint32_t*>(base + L.off_donemask);
+        sc = reinterpret_cast<int32_t*>(base + L.off_i32);
         l2row = reinterpret_cast<uint32_t*>(base + L.off_l2row);
         l2col = reinterpret_cast<uint32_t*>(base + L.off_l2col);
+        act = reinterpret_cast<int8_t*>(base + L.off_act);
         flag = reinterpret_cast<uint8_t*>(base + L.off_flag);
         dirx = reinterpret_cast<int8_t*>(base + L.off_dirx);
         diry = reinterpret_cast<int8_t*>(base + L.off_diry);
@@ -113,7 +134,7 @@ __device__ __forceinline__ void paint_agents(const dmfb_cfg_t& cfg, const TileLa
     const int W = cfg.width, Lc = cfg.length;
     for (int g = threadIdx.x; g < e_valid * A; g += blockDim.x) {
         const int e = g / A, i = g - e * A;
-        if (S.flag[e]) continue;
+        if (S.flag[e] & (kFlagFrozen | kFlagSkip)) continue;
         const uint32_t* drop = S.drop + e * SA;
         const uint32_t me = drop[i];
         const int x = me & 255u, y = (me >> 8) & 255u, gx = (me >> 16) & 255u, gy = me >> 24;
@@ -175,40 +196,67 @@ __device__ __forceinline__ void paint_agents(const dmfb_cfg_t& cfg, const TileLa
     }
 }
 
-// One env of DMFBenv.step; executed by one thread.  Results that other threads need go to smem.
-__device__ __forceinline__ void step_one_env(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const TileLayout& L,
-                                             const TileSmem& S, int e, int64_t n, const void* actions, int aes,
-                                             const double* __restrict__ u, uint64_t seed, uint32_t flags,
-                                             const dmfb_out_t& out)
+// _Generate_Start_End (dmfb.py:207-226): 2A uniform cells, whole set redrawn until every pairwise squared
+// distance is > 2.  Drawing point by point and restarting at the first conflict accepts exactly the same
+// sets with the same probabilities.
+__device__ __noinline__ void generate_layout(const dmfb_cfg_t& cfg, uint64_t seed, int64_t env, uint32_t episode,
+                                             uint32_t* drop)
 {
-    const int A = L.A, SA = L.SA, W = cfg.width, Lc = cfg.length;
+    const int A = cfg.n_agents, m = 2 * A;
+    uint8_t px[2 * DMFB_MAX_AGENTS], py[2 * DMFB_MAX_AGENTS];
+    uint32_t attempt = 0;
+    for (;;) {
+        bool ok = true;
+        for (int k = 0; k < m && ok; k += 2) {
+            const uint4 r = env_random(seed, kStreamLayout, env, episode, attempt, (uint32_t)k);
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+            for (int q = 0; q < 2 && k + q < m && ok; ++q) {
+                const int x = (int)__umulhi(rr[2 * q], (uint32_t)cfg.width);
+                const int y = (int)__umulhi(rr[2 * q + 1], (uint32_t)cfg.length);
+                for (int j = 0; j < k + q; ++j) {
+                    const int dx = x - px[j], dy = y - py[j];
+                    if (dx * dx + dy * dy <= 2) { ok = false; break; }
+                }
+                px[k + q] = (uint8_t)x;
+                py[k + q] = (uint8_t)y;
+            }
+        }
+        if (ok) break;
+        ++attempt;
+    }
+    for (int i = 0; i < A; ++i)
+        drop[i] = (uint32_t)px[i] | ((uint32_t)py[i] << 8) | ((uint32_t)px[A + i] << 16) | ((uint32_t)py[A + i] << 24);
+}
+
+// One env of DMFBenv.step; executed by one thread on inputs already staged in shared memory.
+// Everything it produces goes back to shared memory; the CTA writes it out coalesced afterwards.
+__device__ __forceinline__ void step_one_env(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const TileLayout& L,
+                                             const TileSmem& S, int e, int64_t n, bool have_prob, bool have_draw,
+                                             uint64_t seed, uint32_t flags, const dmfb_out_t& out)
+{
+    const int A = L.A, SA = L.SA, E = L.E, W = cfg.width, Lc = cfg.length;
     uint32_t* drop = S.drop + e * SA;
     uint32_t* past = S.past + e * SA;
     float* rew = S.rew + e * SA;
     const uint32_t all_mask = (A >= 32) ? 0xFFFFFFFFu : ((1u << A) - 1u);
-    const uint32_t* gdrop = reinterpret_cast<const uint32_t*>(st.drop) + (size_t)n * A;
-    for (int i = 0; i < A; ++i) drop[i] = gdrop[i];
 
-    if ((flags & DMFB_STEP_FREEZE_TERM) && st.terminated[n]) {
+    if (S.flag[e] & kFlagFrozen) {
         // lock-step padding (rollout.py:131-141): zero obs / reward / avail, terminated = padded = 1
-        S.flag[e] = 1;
         S.donemask[e] = all_mask;
         for (int i = 0; i < A; ++i) {
             rew[i] = 0.f;
             if (out.reward_f64) out.reward_f64[(size_t)n * A + i] = 0.0;
         }
-        if (out.team_reward) out.team_reward[n] = 0.f;
-        if (out.constraints) out.constraints[n] = 0;
-        if (out.success) out.success[n] = 0;
-        if (out.terminated) out.terminated[n] = 1;
-        if (out.padded) out.padded[n] = 1;
+        S.sc[kStepOut * E + e] = S.sc[kStepIn * E + e];
+        S.sc[kCumOut * E + e] = S.sc[kCumIn * E + e];
+        S.sc[kCons * E + e] = 0;
+        S.sc[kMisc * E + e] = (1 << 8) | (1 << 16);
+        S.sc[kTeam * E + e] = __float_as_int(0.f);
         return;
     }
-    S.flag[e] = 0;
 
-    const int sc = st.step_count[n] + 1;                         // dmfb.py:561
-    const double* health = st.health ? st.health + (size_t)n * W * Lc : nullptr;
-    const uint32_t episode = st.episode ? st.episode[n] : 0u;
+    const int sc = S.sc[kStepIn * E + e] + 1;                    // dmfb.py:561
+    const uint32_t episode = (uint32_t)S.sc[kEpisode * E + e];
     uint32_t pre_done = 0;                                        // getTaskStatus before the moves (:278)
     uint64_t base_code = 0;                                       // 2 bits per droplet: 0 -> 0.0, 1 -> -0.1, 2 -> -0.25, 3 -> -0.4
     bool illegal = false;
@@ -223,13 +271,13 @@ __device__ __forceinline__ void step_one_env(const dmfb_cfg_t& cfg, const dmfb_s
         if (cfg.stall && od == 0) {
             code = 0;                                             // reward 0, no move, no draw (:331-332)
         } else {
-            const int a = load_action(actions, aes, (size_t)n * A + i);
+            const int a = S.act[e * A + i];
             bool move = true;
-            if (health) {
-                const double prob = health[x * Lc + y];           // getMoveProb (:361-363)
+            if (have_prob) {
+                const double prob = S.prob[e * A + i];            // getMoveProb (:361-363), cell = position at step start
                 double draw;
-                if (u) {
-                    draw = u[(size_t)n * A + i];
+                if (have_draw) {
+                    draw = S.draw[e * A + i];
                 } else {
                     const uint4 r = env_random(seed, kStreamMove, cfg.env_base + n, episode, (uint32_t)sc, (uint32_t)i);
                     draw = u53(r.x, r.y);
@@ -300,9 +348,8 @@ __device__ __forceinline__ void step_one_env(const dmfb_cfg_t& cfg, const dmfb_s
                 *cell = (uint16_t)(v + (v != 0xFFFFu));
             }
     }
-    const int cum = st.constraints[n] + constraints;              // (:572)
-    st.constraints[n] = cum;
-    st.step_count[n] = sc;
+    int cum = S.sc[kCumIn * E + e] + constraints;                 // (:572)
+    int sc_out = sc;
     uint32_t done_mask;
     int success = 0;
     if (sc < cfg.max_step) {                                      // (:577-585)
@@ -312,13 +359,26 @@ __device__ __forceinline__ void step_one_env(const dmfb_cfg_t& cfg, const dmfb_s
         done_mask = all_mask;
     }
     S.donemask[e] = done_mask;
-    const uint8_t term = (done_mask == all_mask) ? 1 : 0;
-    st.terminated[n] = term;
-    if (out.team_reward) out.team_reward[n] = (float)(sum / (double)A);  // rollout.py:33
-    if (out.constraints) out.constraints[n] = constraints;
-    if (out.success) out.success[n] = (uint8_t)success;
-    if (out.terminated) out.terminated[n] = term;
-    if (out.padded) out.padded[n] = 0;
+    const int term = (done_mask == all_mask) ? 1 : 0;
+    int did_reset = 0;
+    if (term && (flags & DMFB_STEP_AUTO_RESET)) {
+        // DMFBenv.reset(new=False) (:589-597) fused into the step: new task now, updateHealth by the CTA later
+        const uint32_t ep2 = episode + 1u;
+        generate_layout(cfg, seed, cfg.env_base + n, ep2, drop);
+        if (st.episode) st.episode[n] = ep2;
+        if (st.start)
+            for (int i = 0; i < A; ++i)
+                reinterpret_cast<uint16_t*>(st.start)[(size_t)n * A + i] = (uint16_t)(drop[i] & 0xFFFFu);
+        sc_out = 0;
+        cum = 0;
+        did_reset = 1;
+        S.flag[e] = kFlagNewTask;
+    }
+    S.sc[kStepOut * E + e] = sc_out;
+    S.sc[kCumOut * E + e] = cum;
+    S.sc[kCons * E + e] = constraints;
+    S.sc[kMisc * E + e] = success | (term << 8) | (did_reset << 24);
+    S.sc[kTeam * E + e] = __float_as_int((float)(sum / (double)A));  // rollout.py:33
     if (illegal && out.status) atomicOr(out.status, 1);
 }
 
@@ -332,28 +392,84 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     const TileSmem S(smem_raw, L);
     const int64_t n0 = (int64_t)blockIdx.x * E;
     const int e_valid = (int)min((int64_t)E, (int64_t)st.n_envs - n0);
-    const int A = L.A;
+    const int A = L.A, SA = L.SA;
+    const int W = cfg.width, Lc = cfg.length;
+    const bool have_prob = st.health != nullptr;
+    const bool have_draw = have_prob && (u != nullptr);
 
+    // ---- phase A: every global input of the tile is fetched coalesced, in one round trip ----------
+    {
+        const uint32_t* gdrop = reinterpret_cast<const uint32_t*>(st.drop) + (size_t)n0 * A;
+        const size_t gbase = (size_t)n0 * A;
+        for (int j = threadIdx.x; j < e_valid * A; j += blockDim.x) {
+            const int e = j / A, i = j - e * A;
+            const uint32_t d = gdrop[j];
+            S.drop[e * SA + i] = d;
+            S.act[j] = (int8_t)load_action(actions, aes, gbase + j);
+            if (have_prob) {
+                S.prob[j] = st.health[((size_t)(n0 + e) * W + (d & 255u)) * Lc + ((d >> 8) & 255u)];
+                if (have_draw) S.draw[j] = u[gbase + j];
+            }
+        }
+        for (int e = threadIdx.x; e < e_valid; e += blockDim.x) {
+            S.sc[kStepIn * E + e] = st.step_count[n0 + e];
+            S.sc[kCumIn * E + e] = st.constraints[n0 + e];
+            S.sc[kEpisode * E + e] = st.episode ? (int32_t)st.episode[n0 + e] : 0;
+            S.flag[e] = ((flags & DMFB_STEP_FREEZE_TERM) && st.terminated[n0 + e]) ? kFlagFrozen : 0;
+        }
+    }
     load_tables(cfg, L, S);
     zero_tile(L, S);
-    if ((int)threadIdx.x < e_valid)
-        step_one_env(cfg, st, L, S, threadIdx.x, n0 + threadIdx.x, actions, aes, u, seed, flags, out);
     __syncthreads();
 
-    // coalesced write-back of the staged small tensors
+    // ---- phase B: dynamics, one thread per env, shared memory only ---------------------------------
+    if ((int)threadIdx.x < e_valid)
+        step_one_env(cfg, st, L, S, threadIdx.x, n0 + threadIdx.x, have_prob, have_draw, seed, flags, out);
+    __syncthreads();
+
+    // ---- phase C: coalesced write-back of state and of the small outputs ---------------------------
     {
         uint32_t* gdrop = reinterpret_cast<uint32_t*>(st.drop) + (size_t)n0 * A;
         const size_t gbase = (size_t)n0 * A;
         for (int j = threadIdx.x; j < e_valid * A; j += blockDim.x) {
             const int e = j / A, i = j - e * A;
-            gdrop[j] = S.drop[e * L.SA + i];
-            if (out.reward) out.reward[gbase + j] = S.rew[e * L.SA + i];
+            gdrop[j] = S.drop[e * SA + i];
+            if (out.reward) out.reward[gbase + j] = S.rew[e * SA + i];
             if (out.done) out.done[gbase + j] = (uint8_t)((S.donemask[e] >> i) & 1u);
         }
         if (out.avail) {
             const int per_env = A * cfg.n_actions;
             uint8_t* gav = out.avail + (size_t)n0 * per_env;
-            for (int j = threadIdx.x; j < e_valid * per_env; j += blockDim.x) gav[j] = S.flag[j / per_env] ? 0 : 1;
+            for (int j = threadIdx.x; j < e_valid * per_env; j += blockDim.x)
+                gav[j] = (S.flag[j / per_env] & kFlagFrozen) ? 0 : 1;
+        }
+        for (int e = threadIdx.x; e < e_valid; e += blockDim.x) {
+            const int64_t n = n0 + e;
+            const int misc = S.sc[kMisc * E + e];
+            const int term = (misc >> 8) & 1, did_reset = (misc >> 24) & 1;
+            st.step_count[n] = S.sc[kStepOut * E + e];
+            st.constraints[n] = S.sc[kCumOut * E + e];
+            st.terminated[n] = (uint8_t)(term & !did_reset);
+            if (out.team_reward) out.team_reward[n] = __int_as_float(S.sc[kTeam * E + e]);
+            if (out.constraints) out.constraints[n] = S.sc[kCons * E + e];
+            if (out.success) out.success[n] = (uint8_t)(misc & 1);
+            if (out.terminated) out.terminated[n] = (uint8_t)term;
+            if (out.padded) out.padded[n] = (uint8_t)((misc >> 16) & 1);
+        }
+        // fused auto-reset: updateHealth (dmfb.py:465-471) of the envs that just got a new task
+        if ((flags & DMFB_STEP_AUTO_RESET) && st.usage) {
+            const int cells = W * Lc;
+            for (int e = 0; e < e_valid; ++e) {
+                if (!(S.flag[e] & kFlagNewTask)) continue;
+                uint16_t* usage = st.usage + (size_t)(n0 + e) * cells;
+                double* health = st.health ? st.health + (size_t)(n0 + e) * cells : nullptr;
+                const double* degrade = st.degrade ? st.degrade + (size_t)(n0 + e) * cells : nullptr;
+                for (int k = threadIdx.x; k < cells; k += blockDim.x)
+                    if (usage[k] > 50) {
+                        if (health) health[k] = health[k] * (degrade ? degrade[k] : 1.0);
+                        usage[k] = 0;
+                    }
+            }
         }
     }
     paint_agents<FOV_T>(cfg, L, S, e_valid);
@@ -361,37 +477,6 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
 }
 
 // --------------------------------------------------------------------- reset --
-
-// _Generate_Start_End (dmfb.py:207-226): 2A uniform cells, whole set redrawn until every pairwise squared
-// distance is > 2.  Drawing point by point and restarting at the first conflict accepts exactly the same
-// sets with the same probabilities.
-__device__ void generate_layout(const dmfb_cfg_t& cfg, uint64_t seed, int64_t env, uint32_t episode, uint32_t* drop)
-{
-    const int A = cfg.n_agents, m = 2 * A;
-    uint8_t px[2 * DMFB_MAX_AGENTS], py[2 * DMFB_MAX_AGENTS];
-    uint32_t attempt = 0;
-    for (;;) {
-        bool ok = true;
-        for (int k = 0; k < m && ok; k += 2) {
-            const uint4 r = env_random(seed, kStreamLayout, env, episode, attempt, (uint32_t)k);
-            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-            for (int q = 0; q < 2 && k + q < m && ok; ++q) {
-                const int x = (int)__umulhi(rr[2 * q], (uint32_t)cfg.width);
-                const int y = (int)__umulhi(rr[2 * q + 1], (uint32_t)cfg.length);
-                for (int j = 0; j < k + q; ++j) {
-                    const int dx = x - px[j], dy = y - py[j];
-                    if (dx * dx + dy * dy <= 2) { ok = false; break; }
-                }
-                px[k + q] = (uint8_t)x;
-                py[k + q] = (uint8_t)y;
-            }
-        }
-        if (ok) break;
-        ++attempt;
-    }
-    for (int i = 0; i < A; ++i)
-        drop[i] = (uint32_t)px[i] | ((uint32_t)py[i] << 8) | ((uint32_t)px[A + i] << 16) | ((uint32_t)py[A + i] << 24);
-}
 
 // mode 0: reset (new task), mode 1: restart (back to start cells), mode 2: observe only
 template <int FOV_T>
@@ -408,14 +493,16 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
     const int A = L.A, SA = L.SA;
     const int cells = cfg.width * cfg.length;
 
+    int selected = 0;
+    if ((int)threadIdx.x < e_valid) selected = (mask == nullptr) || (mask[n0 + threadIdx.x] != 0);
+    const int n_selected = __syncthreads_count(selected);
+    if (n_selected == 0) return;  // nothing to reset in this tile (the common case of a masked auto-reset)
     load_tables(cfg, L, S);
     if (obs) zero_tile(L, S);
-    int selected = 0;
     if ((int)threadIdx.x < e_valid) {
         const int e = threadIdx.x;
         const int64_t n = n0 + e;
-        selected = (mask == nullptr) || (mask[n] != 0);
-        S.flag[e] = selected ? 0 : 2;
+        S.flag[e] = selected ? 0 : kFlagSkip;
         uint32_t* drop = S.drop + e * SA;
         uint32_t* gdrop = reinterpret_cast<uint32_t*>(st.drop) + (size_t)n * A;
         if (selected && mode != 2) {
@@ -443,7 +530,7 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
             for (int i = 0; i < A; ++i) drop[i] = gdrop[i];
         }
     }
-    const int n_selected = __syncthreads_count(selected);
+    __syncthreads();
 
     // refresh(new) (dmfb.py:174-183): new -> health=1, usage=0, degrade redrawn; else updateHealth (:465-471)
     if (mode == 0 && (st.usage || st.health || st.degrade)) {
@@ -647,9 +734,7 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
 #undef LAUNCH_STEP
     g_launches.fetch_add(1);
     DMFB_CUDA_TRY(cudaGetLastError());
-    if (flags & DMFB_STEP_AUTO_RESET)
-        return launch_reset(cfg, state, state->terminated, 0, 0, nullptr, nullptr, seed, out->obs, stream);
-    return DMFB_OK;
+    return DMFB_OK;  // DMFB_STEP_AUTO_RESET is fused into the step kernel
 }
 
 static int launch_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t* mask, int mode, int new_task,

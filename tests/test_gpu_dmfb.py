@@ -230,3 +230,42 @@ def test_dmfb_device_generator_and_full_size_properties():
         assert torch.equal(centre, torch.arange(1, A + 1, device="cuda:0", dtype=torch.int8).expand(N, A))
     assert bool(done.all()) and int(env.step_count.min()) == 45  # past max_step: dones forced True
     assert int(info["success"].sum()) == 0
+
+
+@pytest.mark.parametrize("W,L,A,fov,deg", [(10, 10, 4, 9, True), (20, 20, 10, 9, False), (12, 15, 6, 7, True)])
+def test_dmfb_fused_auto_reset_equals_step_plus_masked_reset(W, L, A, fov, deg):
+    """step(auto_reset=True) == step() followed by reset(mask=terminated) with the same new tasks."""
+    P = pkg()
+    N = 3000
+    kw = dict(fov=fov, b_degrade=deg, per_degrade=1.0, device="cuda:0", seed=77, track_usage=True)
+    e1 = P.BatchedDMFB(N, W, L, A, **kw)
+    e2 = P.BatchedDMFB(N, W, L, A, **kw)
+    assert torch.equal(e1.drop, e2.drop)
+    if deg:  # age the chips so that health matters and usage crosses the threshold quickly
+        e1.usage.fill_(49); e2.usage.fill_(49)
+    gen = torch.Generator(device="cuda:0").manual_seed(3)
+    n_resets = 0
+    for t in range(2 * (W + L) + 25):
+        d = e1.drop.to(torch.int32)
+        dx, dy = d[..., 2] - d[..., 0], d[..., 3] - d[..., 1]
+        toward = torch.where(dx.abs() >= dy.abs(), torch.where(dx > 0, 1, 2), torch.where(dy > 0, 4, 3))
+        toward = torch.where((dx == 0) & (dy == 0), 0, toward)
+        rnd = torch.randint(0, 5, (N, A), device="cuda:0", generator=gen)
+        acts = torch.where(torch.rand(N, A, device="cuda:0", generator=gen) < 0.8, toward, rnd).to(torch.int8)
+        draws = torch.rand(N, A, device="cuda:0", generator=gen, dtype=torch.float64)
+        o1, r1, d1, i1 = e1.step(acts, draws=draws, auto_reset=True)
+        term1 = i1["terminated"].clone()
+        o2, r2, d2, i2 = e2.step(acts, draws=draws)
+        assert torch.equal(i2["terminated"], term1) and torch.equal(r1, r2) and torch.equal(d1, d2)
+        assert torch.equal(i1["success"], i2["success"]) and torch.equal(i1["constraints"], i2["constraints"])
+        e2.reset(mask=term1.to(torch.uint8), layouts=e1.drop)
+        n_resets += int(term1.sum())
+        assert torch.equal(e1.drop, e2.drop) and torch.equal(o1, e2.obs)
+        assert torch.equal(e1.step_count, e2.step_count) and torch.equal(e1.constraints_cum, e2.constraints_cum)
+        assert torch.equal(e1.terminated, e2.terminated) and int(e1.terminated.sum()) == 0
+        assert torch.equal(e1.usage, e2.usage) and torch.equal(e1.start, e2.start)
+        if deg:
+            assert torch.equal(e1.health, e2.health)
+    assert n_resets > N  # every env finished at least one episode
+    if deg:
+        assert float(e1.health.min()) < 1.0
