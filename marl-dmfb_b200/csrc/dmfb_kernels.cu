@@ -9,11 +9,13 @@
 //  * one CTA per tile of E consecutive envs; E is chosen so that the tile's observation span
 //    E*A*(3*fov^2+2) bytes is a multiple of 16 -> the CTA's output is one contiguous, 16-byte aligned
 //    range of the [N,A,D] int8 tensor even though a single 245-byte row is not;
-//  * the tile is staged in shared memory: 16-byte zero fill, boundary layer expanded from per-agent
+//  * one THREAD PER DROPLET, G = next power of two >= A lanes per env: the sequential, order dependent
+//    move/revert loop of the reference runs as A rounds of shuffle + ballot inside the lane group; the
+//    pairwise fluidic-constraint counts, rewards, dones and the usage update are per lane, per-env
+//    scalars are handled by the group leader; droplet state lives in registers from load to store;
+//  * the observation tile is staged in shared memory: 16-byte zero fill, boundary layer expanded from
 //    bit masks (4 output bytes per multiply), sparse byte scatter for droplet ids / clipped goals /
 //    direction bytes, then ONE TMA bulk store (cp.async.bulk.global.shared::cta) per tile;
-//  * dynamics (sequential, order dependent moves) run one thread per env on packed (x,y,gx,gy)
-//    words held in shared memory; all small outputs are staged and written coalesced;
 //  * HBM-bound integer/byte work: no tensor cores.
 #include "common.cuh"
 
@@ -24,27 +26,19 @@ std::atomic<uint64_t> g_launches{0};
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kMaxThreads = 512;
+constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // Shared-memory carve-up of one tile, computed identically on host and device.
 struct TileLayout {
-    int E, A, SA, D, nw, ncodes;
-    uint32_t tile_bytes;
-    uint32_t off_drop, off_past, off_rew, off_flag, off_donemask, off_l2row, off_l2col, off_dirx, off_diry;
-    uint32_t off_f64, off_i32, off_act, total;
+    int E, A, D, nw, ncodes;
+    uint32_t tile_bytes, off_l2row, off_l2col, off_flag, off_dirx, off_diry, total;
     __host__ __device__ TileLayout(const dmfb_cfg_t& c, int E_) {
-        E = E_; A = c.n_agents; SA = A | 1; D = c.obs_dim; nw = c.l2_words; ncodes = 2 * (c.fov / 2) + 1;
+        E = E_; A = c.n_agents; D = c.obs_dim; nw = c.l2_words; ncodes = 2 * (c.fov / 2) + 1;
         tile_bytes = ((uint32_t)(E * A * D) + 15u) & ~15u;
         uint32_t o = tile_bytes;
-        off_f64 = o; o += (uint32_t)(E * A) * 8u * 2u;   // staged draws + health probabilities (float64)
-        off_drop = o; o += (uint32_t)(E * SA) * 4u;
-        off_past = o; o += (uint32_t)(E * SA) * 4u;
-        off_rew = o; o += (uint32_t)(E * SA) * 4u;
-        off_donemask = o; o += (uint32_t)E * 4u;
-        off_i32 = o; o += (uint32_t)E * 4u * 8u;          // per-env scalars, see EnvScalar
         off_l2row = o; o += (uint32_t)(ncodes * nw) * 4u;
         off_l2col = o; o += (uint32_t)(ncodes * nw) * 4u;
-        off_act = o; o += ((uint32_t)(E * A) + 3u) & ~3u;
         off_flag = o; o += ((uint32_t)E + 3u) & ~3u;
         off_dirx = o; o += ((uint32_t)(2 * c.width) + 3u) & ~3u;
         off_diry = o; o += ((uint32_t)(2 * c.length) + 3u) & ~3u;
@@ -52,42 +46,21 @@ struct TileLayout {
     }
 };
 
-// per-env scalars staged in smem: [slot][E] int32
-enum EnvScalar { kStepIn = 0, kCumIn, kEpisode, kStepOut, kCumOut, kCons, kMisc /* success | term<<8 | padded<<16 | reset<<24 */, kTeam, kNumScalars };
-static_assert(kNumScalars == 8, "TileLayout reserves 8 scalar slots");
-
 // S.flag values
-constexpr uint8_t kFlagFrozen = 1;    // padded step: zero observation
-constexpr uint8_t kFlagSkip = 2;      // masked reset: env not selected
-constexpr uint8_t kFlagNewTask = 4;   // auto-reset: a new task was generated, updateHealth still to run
+constexpr uint8_t kFlagSelected = 1;  // masked reset: env selected (row must be stored)
+constexpr uint8_t kFlagNewTask = 4;   // a new task was generated for the env: updateHealth still to run
 
 struct TileSmem {
     int8_t* tile;
-    double* draw;        // [E*A]
-    double* prob;        // [E*A]
-    uint32_t* drop;      // [E][SA] packed x | y<<8 | gx<<16 | gy<<24
-    uint32_t* past;      // [E][SA] past x | y<<8 | sta<<16 | dyn<<24
-    float* rew;          // [E][SA]
-    uint32_t* donemask;  // [E]
-    int32_t* sc;         // [kNumScalars][E]
-    uint32_t* l2row;     // [ncodes][nw]
+    uint32_t* l2row;  // [ncodes][nw]
     uint32_t* l2col;
-    int8_t* act;         // [E*A]
-    uint8_t* flag;       // [E]
+    uint8_t* flag;    // [E]
     int8_t* dirx;
     int8_t* diry;
     __device__ TileSmem(unsigned char* base, const TileLayout& L) {
         tile = reinterpret_cast<int8_t*>(base);
-        draw = reinterpret_cast<double*>(base + L.off_f64);
-        prob = draw + L.E * L.A;
-        drop = reinterpret_cast<uint32_t*>(base + L.off_drop);
-        past = reinterpret_cast<uint32_t*>(base + L.off_past);
-        rew = reinterpret_cast<float*>(base + L.off_rew);
-        donemask = reinterpret_cast<uint32_t*>(base + L.off_donemask);
-        sc = reinterpret_cast<int32_t*>(base + L.off_i32);
         l2row = reinterpret_cast<uint32_t*>(base + L.off_l2row);
         l2col = reinterpret_cast<uint32_t*>(base + L.off_l2col);
-        act = reinterpret_cast<int8_t*>(base + L.off_act);
         flag = reinterpret_cast<uint8_t*>(base + L.off_flag);
         dirx = reinterpret_cast<int8_t*>(base + L.off_dirx);
         diry = reinterpret_cast<int8_t*>(base + L.off_diry);
@@ -110,65 +83,128 @@ __device__ __forceinline__ void zero_tile(const TileLayout& L, const TileSmem& S
 {
     uint4* t4 = reinterpret_cast<uint4*>(S.tile);
     const int n16 = (int)(L.tile_bytes >> 4);
-    for (int k = threadIdx.x; k < n16; k += blockDim.x) t4[k] = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    int k = threadIdx.x;
+    const int stride = blockDim.x;
+    for (; k + 3 * stride < n16; k += 4 * stride) {
+        t4[k] = z; t4[k + stride] = z; t4[k + 2 * stride] = z; t4[k + 3 * stride] = z;
+    }
+    for (; k < n16; k += stride) t4[k] = z;
 }
 
+// |ax-bx| <= 1 && |ay-by| <= 1 on packed (x | y<<8) cells.  On the integer grid this is both
+// "Euclid < 2" (dmfb.py:258,268) and "squared distance <= 2" (dmfb.py:220).
 __device__ __forceinline__ int near1(uint32_t a, uint32_t b)
 {
-    // |ax-bx| <= 1 && |ay-by| <= 1  <=>  Euclid < 2 on the integer grid (dmfb.py:258,268)
     const int dx = (int)(a & 255u) - (int)(b & 255u);
     const int dy = (int)((a >> 8) & 255u) - (int)((b >> 8) & 255u);
     return (int)((unsigned)(dx + 1) <= 2u) & (int)((unsigned)(dy + 1) <= 2u);
 }
 
-// getObs() for the live envs of a tile (dmfb.py:395-457, 614-626): one thread per agent.
-// The tile must already be zero filled and S.drop / S.flag valid (barrier before the call).
-template <int FOV_T>
-__device__ __forceinline__ void paint_agents(const dmfb_cfg_t& cfg, const TileLayout& L, const TileSmem& S,
-                                             int e_valid)
+template <int G>
+struct Group {
+    static constexpr unsigned kBits = (G == 32) ? 0xFFFFFFFFu : ((1u << G) - 1u);
+    int lane, base, i;
+    __device__ Group() {
+        lane = threadIdx.x & 31;
+        i = lane & (G - 1);
+        base = lane & ~(G - 1);
+    }
+    // value of lane j of my group (all 32 lanes must call)
+    template <typename T>
+    __device__ __forceinline__ T get(T v, int j) const { return __shfl_sync(kFull, v, base + j); }
+    // bits of my group from a warp ballot
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(kFull, p) >> base) & kBits; }
+    __device__ __forceinline__ int sum(int v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        return v;
+    }
+    __device__ __forceinline__ double sum(double v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        return v;
+    }
+};
+
+// _Generate_Start_End (dmfb.py:207-226): 2A uniform cells, the whole set is redrawn until every pairwise
+// squared distance is > 2.  Lane i draws (start_i, goal_i) from a counter-based RNG keyed by
+// (seed, env, episode, attempt, i); the group rejects the attempt if any two of its 2A points are within
+// one cell of each other.  Every lane of the warp must call; `want` is uniform per group.
+template <int G>
+__device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const Group<G>& g, int A, uint64_t seed,
+                                                    int64_t env, uint32_t episode, bool lane_on, bool want,
+                                                    uint32_t keep)
+{
+    uint32_t word = keep;
+    bool pending = want;
+    uint32_t attempt = 0;
+    while (__any_sync(kFull, pending)) {
+        uint32_t w = 0;
+        if (pending && lane_on) {
+            const uint4 r = env_random(seed, kStreamLayout, env, episode, attempt, (uint32_t)g.i);
+            w = __umulhi(r.x, (uint32_t)cfg.width) | (__umulhi(r.y, (uint32_t)cfg.length) << 8) |
+                (__umulhi(r.z, (uint32_t)cfg.width) << 16) | (__umulhi(r.w, (uint32_t)cfg.length) << 24);
+        }
+        int bad = near1(w, w >> 16);
+        for (int j = 0; j < A; ++j) {
+            const uint32_t o = g.get(w, j);
+            if (j != g.i) bad |= near1(w, o) | near1(w, o >> 16) | near1(w >> 16, o) | near1(w >> 16, o >> 16);
+        }
+        const unsigned gb = g.ballot(bad && lane_on && pending);
+        if (pending && gb == 0u) { word = w; pending = false; }
+        ++attempt;
+    }
+    return word;
+}
+
+// getOneObs (dmfb.py:395-457) of the agent held by this lane, painted into the (zero filled) tile.
+// All lanes of the warp must call (shuffles); only lanes with `on` store.
+template <int FOV_T, int G>
+__device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLayout& L, const TileSmem& S,
+                                            const Group<G>& g, int agent_in_tile, uint32_t me, bool on)
 {
     const int fov = FOV_T ? FOV_T : cfg.fov;
     const int hf = fov >> 1, f2 = fov * fov;
-    const int A = L.A, SA = L.SA, D = L.D;
+    const int A = L.A, D = L.D;
     const int nw = FOV_T ? (FOV_T * FOV_T + 31) / 32 : L.nw;
     const int W = cfg.width, Lc = cfg.length;
-    for (int g = threadIdx.x; g < e_valid * A; g += blockDim.x) {
-        const int e = g / A, i = g - e * A;
-        if (S.flag[e] & (kFlagFrozen | kFlagSkip)) continue;
-        const uint32_t* drop = S.drop + e * SA;
-        const uint32_t me = drop[i];
-        const int x = me & 255u, y = (me >> 8) & 255u, gx = (me >> 16) & 255u, gy = me >> 24;
-        int8_t* rec = S.tile + (size_t)g * D;
+    const int x = me & 255u, y = (me >> 8) & 255u, gx = (me >> 16) & 255u, gy = me >> 24;
+    int8_t* rec = S.tile + (size_t)agent_in_tile * D;
 
-        // ---- layer 2: off-chip boundary (dmfb.py:428-439) expanded from bit masks -------------
-        {
-            const int lb = hf - x, rb = hf - (W - 1 - x);
-            const int ub = hf - y, db = hf - (Lc - 1 - y);
-            const int rc = lb > 0 ? lb : (rb > 0 ? hf + rb : 0);
-            const int cc = ub > 0 ? ub : (db > 0 ? hf + db : 0);
+    // ---- layer 2: off-chip boundary (dmfb.py:428-439) expanded from bit masks ----------------------
+    if (on) {
+        const int lb = hf - x, rb = hf - (W - 1 - x);
+        const int ub = hf - y, db = hf - (Lc - 1 - y);
+        const int rc = lb > 0 ? lb : (rb > 0 ? hf + rb : 0);
+        const int cc = ub > 0 ? ub : (db > 0 ? hf + db : 0);
+        if (rc | cc) {
             const uint32_t* rowm = S.l2row + rc * nw;
             const uint32_t* colm = S.l2col + cc * nw;
-            const int base = g * D + 2 * f2;      // byte offset of the layer inside the tile
-            const int s = base & 3;               // misalignment of the layer start
+            const int base = agent_in_tile * D + 2 * f2;  // byte offset of the layer inside the tile
+            const int s = base & 3;                       // misalignment of the layer start
             uint32_t* wptr = reinterpret_cast<uint32_t*>(S.tile + (base & ~3));
             const int nbits = f2 + s;
-            const int nfull = nbits >> 2;         // whole 4-byte words
-            const int ntail = nbits & 3;          // trailing bytes handled one by one (next agent's bytes follow)
-            if (rc | cc) {
-                uint32_t prev = 0;
-                int k = 0;
+            const int nfull = nbits >> 2;                 // whole 4-byte words (f2/4 or f2/4+1)
+            const int ntail = nbits & 3;                  // trailing bytes: the next agent's bytes follow
+            const int nfull_min = f2 >> 2;
+            uint32_t prev = 0;
 #pragma unroll
-                for (int j = 0; j <= nw; ++j) {
-                    const uint32_t m = (j < nw) ? (rowm[j] | colm[j]) : 0u;
-                    const uint32_t sh = __funnelshift_l(prev, m, s);  // bits of the mask shifted up by s
-                    prev = m;
+            for (int j = 0; j <= nw; ++j) {
+                const uint32_t m = (j < nw) ? (rowm[j] | colm[j]) : 0u;
+                const uint32_t sh = __funnelshift_l(prev, m, s);  // mask bits shifted up by s
+                prev = m;
 #pragma unroll
-                    for (int t = 0; t < 8; ++t, ++k) {
-                        const uint32_t nib = (sh >> (4 * t)) & 0xFu;
-                        if (k < nfull) {
-                            // spread 4 bits to 4 bytes: bit b -> byte b (no carries: 16 distinct partial products)
-                            wptr[k] = (nib * 0x00204081u) & 0x01010101u;
-                        } else if (k == nfull) {
+                for (int t = 0; t < 8; ++t) {
+                    const int k = 8 * j + t;
+                    const uint32_t nib = (sh >> (4 * t)) & 0xFu;
+                    // spread 4 bits to 4 bytes: bit b -> byte b (16 distinct partial products, no carries)
+                    const uint32_t word = (nib * 0x00204081u) & 0x01010101u;
+                    if (k < nfull_min) {
+                        wptr[k] = word;
+                    } else if (k <= nfull_min + 1) {
+                        if (k < nfull) wptr[k] = word;
+                        else if (k == nfull) {
                             int8_t* bp = reinterpret_cast<int8_t*>(wptr + k);
                             for (int b = 0; b < ntail; ++b) bp[b] = (int8_t)((nib >> b) & 1u);
                         }
@@ -176,311 +212,228 @@ __device__ __forceinline__ void paint_agents(const dmfb_cfg_t& cfg, const TileLa
                 }
             }
         }
-        // ---- layers 0 / 1: droplets in the window, clipped goals of visible others (:408-420) ---
-        const int ox = x - hf, oy = y - hf;
-        for (int j = 0; j < A; ++j) {
-            const uint32_t d = drop[j];
-            const int jx = d & 255u, jy = (d >> 8) & 255u;
-            const int rx = jx - ox, ry = jy - oy;
-            if ((unsigned)rx < (unsigned)fov && (unsigned)ry < (unsigned)fov) rec[rx * fov + ry] = (int8_t)(j + 1);
-            if (j != i && 2 * abs(jx - x) < fov && 2 * abs(jy - y) < fov) {
-                int cx = (int)((d >> 16) & 255u) - ox, cy = (int)(d >> 24) - oy;
-                cx = min(max(cx, 0), fov - 1);
-                cy = min(max(cy, 0), fov - 1);
-                rec[f2 + cx * fov + cy] = (int8_t)(j + 1);  // ascending j: later index overwrites
-            }
+    }
+    // ---- layers 0 / 1: droplets in the window, clipped goals of visible others (:408-420) ---------
+    const int ox = x - hf, oy = y - hf;
+    for (int j = 0; j < A; ++j) {
+        const uint32_t d = g.get(me, j);
+        const int jx = d & 255u, jy = (d >> 8) & 255u;
+        const int rx = jx - ox, ry = jy - oy;
+        if (on && (unsigned)rx < (unsigned)fov && (unsigned)ry < (unsigned)fov) rec[rx * fov + ry] = (int8_t)(j + 1);
+        if (on && j != g.i && 2 * abs(jx - x) < fov && 2 * abs(jy - y) < fov) {
+            int cx = (int)((d >> 16) & 255u) - ox, cy = (int)(d >> 24) - oy;
+            cx = min(max(cx, 0), fov - 1);
+            cy = min(max(cy, 0), fov - 1);
+            rec[f2 + cx * fov + cy] = (int8_t)(j + 1);  // ascending j in one thread: later index overwrites
         }
-        // ---- direction bytes (:442-454) from the host-built table ------------------------------
+    }
+    // ---- direction bytes (:442-454) from the host-built table ---------------------------------------
+    if (on) {
         rec[3 * f2] = S.dirx[gx - x + W - 1];
         rec[3 * f2 + 1] = S.diry[gy - y + Lc - 1];
     }
 }
 
-// _Generate_Start_End (dmfb.py:207-226): 2A uniform cells, whole set redrawn until every pairwise squared
-// distance is > 2.  Drawing point by point and restarting at the first conflict accepts exactly the same
-// sets with the same probabilities.
-__device__ __noinline__ void generate_layout(const dmfb_cfg_t& cfg, uint64_t seed, int64_t env, uint32_t episode,
-                                             uint32_t* drop)
+// updateHealth (dmfb.py:465-471) for the envs of the tile flagged kFlagNewTask; whole CTA cooperates.
+__device__ __forceinline__ void update_health_flagged(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const TileSmem& S,
+                                                      int64_t n0, int e_valid)
 {
-    const int A = cfg.n_agents, m = 2 * A;
-    uint8_t px[2 * DMFB_MAX_AGENTS], py[2 * DMFB_MAX_AGENTS];
-    uint32_t attempt = 0;
-    for (;;) {
-        bool ok = true;
-        for (int k = 0; k < m && ok; k += 2) {
-            const uint4 r = env_random(seed, kStreamLayout, env, episode, attempt, (uint32_t)k);
-            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-            for (int q = 0; q < 2 && k + q < m && ok; ++q) {
-                const int x = (int)__umulhi(rr[2 * q], (uint32_t)cfg.width);
-                const int y = (int)__umulhi(rr[2 * q + 1], (uint32_t)cfg.length);
-                for (int j = 0; j < k + q; ++j) {
-                    const int dx = x - px[j], dy = y - py[j];
-                    if (dx * dx + dy * dy <= 2) { ok = false; break; }
-                }
-                px[k + q] = (uint8_t)x;
-                py[k + q] = (uint8_t)y;
+    const int cells = cfg.width * cfg.length;
+    for (int e = 0; e < e_valid; ++e) {
+        if (!(S.flag[e] & kFlagNewTask)) continue;
+        uint16_t* usage = st.usage + (size_t)(n0 + e) * cells;
+        double* health = st.health ? st.health + (size_t)(n0 + e) * cells : nullptr;
+        const double* degrade = st.degrade ? st.degrade + (size_t)(n0 + e) * cells : nullptr;
+        for (int k = threadIdx.x; k < cells; k += blockDim.x)
+            if (usage[k] > 50) {
+                if (health) health[k] = health[k] * (degrade ? degrade[k] : 1.0);
+                usage[k] = 0;
             }
-        }
-        if (ok) break;
-        ++attempt;
     }
-    for (int i = 0; i < A; ++i)
-        drop[i] = (uint32_t)px[i] | ((uint32_t)py[i] << 8) | ((uint32_t)px[A + i] << 16) | ((uint32_t)py[A + i] << 24);
 }
 
-// One env of DMFBenv.step; executed by one thread on inputs already staged in shared memory.
-// Everything it produces goes back to shared memory; the CTA writes it out coalesced afterwards.
-__device__ __forceinline__ void step_one_env(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const TileLayout& L,
-                                             const TileSmem& S, int e, int64_t n, bool have_prob, bool have_draw,
-                                             uint64_t seed, uint32_t flags, const dmfb_out_t& out)
-{
-    const int A = L.A, SA = L.SA, E = L.E, W = cfg.width, Lc = cfg.length;
-    uint32_t* drop = S.drop + e * SA;
-    uint32_t* past = S.past + e * SA;
-    float* rew = S.rew + e * SA;
-    const uint32_t all_mask = (A >= 32) ? 0xFFFFFFFFu : ((1u << A) - 1u);
-
-    if (S.flag[e] & kFlagFrozen) {
-        // lock-step padding (rollout.py:131-141): zero obs / reward / avail, terminated = padded = 1
-        S.donemask[e] = all_mask;
-        for (int i = 0; i < A; ++i) {
-            rew[i] = 0.f;
-            if (out.reward_f64) out.reward_f64[(size_t)n * A + i] = 0.0;
-        }
-        S.sc[kStepOut * E + e] = S.sc[kStepIn * E + e];
-        S.sc[kCumOut * E + e] = S.sc[kCumIn * E + e];
-        S.sc[kCons * E + e] = 0;
-        S.sc[kMisc * E + e] = (1 << 8) | (1 << 16);
-        S.sc[kTeam * E + e] = __float_as_int(0.f);
-        return;
-    }
-
-    const int sc = S.sc[kStepIn * E + e] + 1;                    // dmfb.py:561
-    const uint32_t episode = (uint32_t)S.sc[kEpisode * E + e];
-    uint32_t pre_done = 0;                                        // getTaskStatus before the moves (:278)
-    uint64_t base_code = 0;                                       // 2 bits per droplet: 0 -> 0.0, 1 -> -0.1, 2 -> -0.25, 3 -> -0.4
-    bool illegal = false;
-
-    for (int i = 0; i < A; ++i) {                                 // moveOneDroplet, sequential (:279-283, 325-359)
-        const uint32_t d = drop[i];
-        const int x = d & 255u, y = (d >> 8) & 255u, gx = (d >> 16) & 255u, gy = d >> 24;
-        past[i] = d & 0xFFFFu;
-        const int od = abs(x - gx) + abs(y - gy);
-        if (od == 0) pre_done |= 1u << i;
-        uint32_t code;
-        if (cfg.stall && od == 0) {
-            code = 0;                                             // reward 0, no move, no draw (:331-332)
-        } else {
-            const int a = S.act[e * A + i];
-            bool move = true;
-            if (have_prob) {
-                const double prob = S.prob[e * A + i];            // getMoveProb (:361-363), cell = position at step start
-                double draw;
-                if (have_draw) {
-                    draw = S.draw[e * A + i];
-                } else {
-                    const uint4 r = env_random(seed, kStreamMove, cfg.env_base + n, episode, (uint32_t)sc, (uint32_t)i);
-                    draw = u53(r.x, r.y);
-                }
-                move = draw <= prob;                              // random.random() <= prob (:335)
-            }
-            int nx = x, ny = y;
-            if (move) {
-                if ((unsigned)a > 4u) illegal = true;             // TypeError('action is illegal') (:115-116)
-                nx = x + (a == 1) - (a == 2);                     // Droplet.move (:103-124)
-                ny = y + (a == 4) - (a == 3);
-                nx = min(max(nx, 0), W - 1);
-                ny = min(max(ny, 0), Lc - 1);
-                const uint32_t cand = (uint32_t)nx | ((uint32_t)ny << 8);
-                bool hit = false;                                 // _isinvalidaction (:310-323): cell taken?
-                for (int j = 0; j < A; ++j) hit |= (j != i) & ((drop[j] & 0xFFFFu) == cand);
-                if (hit) { nx = x; ny = y; }
-            }
-            const int nd = abs(nx - gx) + abs(ny - gy);
-            code = (nd == od && od == 0) ? 1u : (nd == od && a == 0) ? 2u : (nd < od) ? 1u : 3u;  // (:345-354)
-            drop[i] = (d & 0xFFFF0000u) | (uint32_t)nx | ((uint32_t)ny << 8);
-        }
-        base_code |= (uint64_t)code << (2 * i);
-    }
-
-    // comflic_static / comflic_dynamic (:254-271) on the final and the saved positions
-    int constraints = 0;
-    uint32_t post_done = 0;
-    for (int k = 0; k < A; ++k) {
-        const uint32_t ck = drop[k], pk = past[k];
-        int sta = 0, dyn = 0;
-        for (int j = 0; j < A; ++j) {
-            if (j == k) continue;
-            const uint32_t cj = drop[j], pj = past[j];
-            sta += near1(ck, cj);
-            dyn += near1(pk, cj) + near1(pj, ck);
-        }
-        constraints += sta + dyn;
-        past[k] = (pk & 0xFFFFu) | ((uint32_t)sta << 16) | ((uint32_t)dyn << 24);
-        if ((ck & 0xFFFFu) == (ck >> 16)) post_done |= 1u << k;
-    }
-    const bool all_done = (post_done == all_mask);               // np.all(getTaskStatus()) after the moves (:293)
-
-    double sum = 0.0;
-    for (int k = 0; k < A; ++k) {
-        const uint32_t code = (uint32_t)(base_code >> (2 * k)) & 3u;
-        double r = code == 0 ? 0.0 : code == 1 ? -0.1 : code == 2 ? -0.25 : -0.4;
-        const uint32_t pk = past[k];
-        r = r - (double)(2 * (int)((pk >> 16) & 255u));           // rewards - 2*sta - 2*dy in float64 (:288)
-        r = r - (double)(2 * (int)(pk >> 24));
-        if (cfg.stall && ((pre_done >> k) & 1u)) r = 0.0;         // (:289-292)
-        if (all_done) {                                           // (:293-296)
-            r = r + 10.0;
-            if (constraints == 0) r = r + 10.0;
-        }
-        rew[k] = (float)r;
-        if (out.reward_f64) out.reward_f64[(size_t)n * A + k] = r;
-        sum += r;
-    }
-
-    if ((flags & DMFB_STEP_RECORD_USAGE) && st.usage) {           // addUsage (:459-463)
-        uint16_t* usage = st.usage + (size_t)n * W * Lc;
-        for (int k = 0; k < A; ++k)
-            if (!((post_done >> k) & 1u)) {
-                const uint32_t ck = drop[k];
-                uint16_t* cell = usage + (ck & 255u) * Lc + ((ck >> 8) & 255u);
-                const uint16_t v = *cell;
-                *cell = (uint16_t)(v + (v != 0xFFFFu));
-            }
-    }
-    int cum = S.sc[kCumIn * E + e] + constraints;                 // (:572)
-    int sc_out = sc;
-    uint32_t done_mask;
-    int success = 0;
-    if (sc < cfg.max_step) {                                      // (:577-585)
-        success = (all_done && cum == 0) ? 1 : 0;
-        done_mask = post_done;
-    } else {
-        done_mask = all_mask;
-    }
-    S.donemask[e] = done_mask;
-    const int term = (done_mask == all_mask) ? 1 : 0;
-    int did_reset = 0;
-    if (term && (flags & DMFB_STEP_AUTO_RESET)) {
-        // DMFBenv.reset(new=False) (:589-597) fused into the step: new task now, updateHealth by the CTA later
-        const uint32_t ep2 = episode + 1u;
-        generate_layout(cfg, seed, cfg.env_base + n, ep2, drop);
-        if (st.episode) st.episode[n] = ep2;
-        if (st.start)
-            for (int i = 0; i < A; ++i)
-                reinterpret_cast<uint16_t*>(st.start)[(size_t)n * A + i] = (uint16_t)(drop[i] & 0xFFFFu);
-        sc_out = 0;
-        cum = 0;
-        did_reset = 1;
-        S.flag[e] = kFlagNewTask;
-    }
-    S.sc[kStepOut * E + e] = sc_out;
-    S.sc[kCumOut * E + e] = cum;
-    S.sc[kCons * E + e] = constraints;
-    S.sc[kMisc * E + e] = success | (term << 8) | (did_reset << 24);
-    S.sc[kTeam * E + e] = __float_as_int((float)(sum / (double)A));  // rollout.py:33
-    if (illegal && out.status) atomicOr(out.status, 1);
-}
-
-template <int FOV_T>
-__global__ void __launch_bounds__(kThreads)
+template <int FOV_T, int G>
+__global__ void __launch_bounds__(kMaxThreads)
 dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, const void* __restrict__ actions,
                  int aes, const double* __restrict__ u, uint64_t seed, uint32_t flags, const dmfb_out_t out, int E)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TileLayout L(cfg, E);
     const TileSmem S(smem_raw, L);
+    const Group<G> g;
+    const int A = L.A, W = cfg.width, Lc = cfg.length;
     const int64_t n0 = (int64_t)blockIdx.x * E;
     const int e_valid = (int)min((int64_t)E, (int64_t)st.n_envs - n0);
-    const int A = L.A, SA = L.SA;
-    const int W = cfg.width, Lc = cfg.length;
-    const bool have_prob = st.health != nullptr;
-    const bool have_draw = have_prob && (u != nullptr);
+    const int e = threadIdx.x / G;                 // env of this lane group inside the tile
+    const int64_t n = n0 + e;
+    const bool env_on = e < e_valid;
+    const bool lane_on = env_on && g.i < A;        // this lane holds droplet g.i of env n
+    const bool leader = env_on && g.i == 0;
+    const size_t ja = (size_t)n * A + g.i;         // index into [N,A] tensors
+    const uint32_t all_mask = (A >= 32) ? 0xFFFFFFFFu : ((1u << A) - 1u);
 
-    // ---- phase A: every global input of the tile is fetched coalesced, in one round trip ----------
-    {
-        const uint32_t* gdrop = reinterpret_cast<const uint32_t*>(st.drop) + (size_t)n0 * A;
-        const size_t gbase = (size_t)n0 * A;
-        for (int j = threadIdx.x; j < e_valid * A; j += blockDim.x) {
-            const int e = j / A, i = j - e * A;
-            const uint32_t d = gdrop[j];
-            S.drop[e * SA + i] = d;
-            S.act[j] = (int8_t)load_action(actions, aes, gbase + j);
-            if (have_prob) {
-                S.prob[j] = st.health[((size_t)(n0 + e) * W + (d & 255u)) * Lc + ((d >> 8) & 255u)];
-                if (have_draw) S.draw[j] = u[gbase + j];
-            }
-        }
-        for (int e = threadIdx.x; e < e_valid; e += blockDim.x) {
-            S.sc[kStepIn * E + e] = st.step_count[n0 + e];
-            S.sc[kCumIn * E + e] = st.constraints[n0 + e];
-            S.sc[kEpisode * E + e] = st.episode ? (int32_t)st.episode[n0 + e] : 0;
-            S.flag[e] = ((flags & DMFB_STEP_FREEZE_TERM) && st.terminated[n0 + e]) ? kFlagFrozen : 0;
-        }
+    // ---- global inputs: one coalesced round trip, issued before the shared-memory work ------------
+    uint32_t d = 0;
+    int a = 0;
+    double prob = 1.0, draw = 0.0;
+    const bool have_prob = st.health != nullptr;
+    if (lane_on) {
+        d = reinterpret_cast<const uint32_t*>(st.drop)[ja];
+        a = load_action(actions, aes, ja);
+        if (have_prob && u) draw = u[ja];
     }
+    int sc_in = 0, cum_in = 0, frozen_i = 0;
+    uint32_t episode = 0;
+    if (leader) {
+        sc_in = st.step_count[n];
+        cum_in = st.constraints[n];
+        if (st.episode) episode = st.episode[n];
+        if (flags & DMFB_STEP_FREEZE_TERM) frozen_i = st.terminated[n];
+    }
+    if (have_prob && lane_on)  // getMoveProb (:361-363): the cell the droplet occupies at the start of the step
+        prob = st.health[((size_t)n * W + (d & 255u)) * Lc + ((d >> 8) & 255u)];
+
     load_tables(cfg, L, S);
     zero_tile(L, S);
-    __syncthreads();
 
-    // ---- phase B: dynamics, one thread per env, shared memory only ---------------------------------
-    if ((int)threadIdx.x < e_valid)
-        step_one_env(cfg, st, L, S, threadIdx.x, n0 + threadIdx.x, have_prob, have_draw, seed, flags, out);
-    __syncthreads();
+    sc_in = g.get(sc_in, 0);
+    cum_in = g.get(cum_in, 0);
+    episode = g.get(episode, 0);
+    const bool frozen = g.get(frozen_i, 0) != 0;   // lock-step padding (rollout.py:131-141)
+    const int sc = sc_in + 1;                      // dmfb.py:561
 
-    // ---- phase C: coalesced write-back of state and of the small outputs ---------------------------
-    {
-        uint32_t* gdrop = reinterpret_cast<uint32_t*>(st.drop) + (size_t)n0 * A;
-        const size_t gbase = (size_t)n0 * A;
-        for (int j = threadIdx.x; j < e_valid * A; j += blockDim.x) {
-            const int e = j / A, i = j - e * A;
-            gdrop[j] = S.drop[e * SA + i];
-            if (out.reward) out.reward[gbase + j] = S.rew[e * SA + i];
-            if (out.done) out.done[gbase + j] = (uint8_t)((S.donemask[e] >> i) & 1u);
-        }
-        if (out.avail) {
-            const int per_env = A * cfg.n_actions;
-            uint8_t* gav = out.avail + (size_t)n0 * per_env;
-            for (int j = threadIdx.x; j < e_valid * per_env; j += blockDim.x)
-                gav[j] = (S.flag[j / per_env] & kFlagFrozen) ? 0 : 1;
-        }
-        for (int e = threadIdx.x; e < e_valid; e += blockDim.x) {
-            const int64_t n = n0 + e;
-            const int misc = S.sc[kMisc * E + e];
-            const int term = (misc >> 8) & 1, did_reset = (misc >> 24) & 1;
-            st.step_count[n] = S.sc[kStepOut * E + e];
-            st.constraints[n] = S.sc[kCumOut * E + e];
-            st.terminated[n] = (uint8_t)(term & !did_reset);
-            if (out.team_reward) out.team_reward[n] = __int_as_float(S.sc[kTeam * E + e]);
-            if (out.constraints) out.constraints[n] = S.sc[kCons * E + e];
-            if (out.success) out.success[n] = (uint8_t)(misc & 1);
-            if (out.terminated) out.terminated[n] = (uint8_t)term;
-            if (out.padded) out.padded[n] = (uint8_t)((misc >> 16) & 1);
-        }
-        // fused auto-reset: updateHealth (dmfb.py:465-471) of the envs that just got a new task
-        if ((flags & DMFB_STEP_AUTO_RESET) && st.usage) {
-            const int cells = W * Lc;
-            for (int e = 0; e < e_valid; ++e) {
-                if (!(S.flag[e] & kFlagNewTask)) continue;
-                uint16_t* usage = st.usage + (size_t)(n0 + e) * cells;
-                double* health = st.health ? st.health + (size_t)(n0 + e) * cells : nullptr;
-                const double* degrade = st.degrade ? st.degrade + (size_t)(n0 + e) * cells : nullptr;
-                for (int k = threadIdx.x; k < cells; k += blockDim.x)
-                    if (usage[k] > 50) {
-                        if (health) health[k] = health[k] * (degrade ? degrade[k] : 1.0);
-                        usage[k] = 0;
-                    }
-            }
+    // ---- moveOneDroplet for all droplets (:325-359) ------------------------------------------------
+    const uint32_t goal = d >> 16;
+    const uint32_t start_cell = d & 0xFFFFu;       // "past" position
+    const int x = d & 255u, y = (d >> 8) & 255u, gx = goal & 255u, gy = goal >> 8;
+    const int od = abs(x - gx) + abs(y - gy);      // Droplet.distance (:93-95)
+    const bool pre_done = (od == 0);               // getTaskStatus before the moves (:278)
+    const bool stalled = cfg.stall && pre_done;    // reward 0, no move, no draw (:331-332)
+    if (have_prob && !u && lane_on && !stalled) {
+        const uint4 r = env_random(seed, kStreamMove, cfg.env_base + n, episode, (uint32_t)sc, (uint32_t)g.i);
+        draw = u53(r.x, r.y);
+    }
+    const bool tries = lane_on && !stalled && !frozen && (draw <= prob);   // random.random() <= prob (:335)
+    uint32_t cand = start_cell;
+    if (tries) {                                   // Droplet.move (:103-124)
+        int nx = x + (a == 1) - (a == 2), ny = y + (a == 4) - (a == 3);
+        nx = min(max(nx, 0), W - 1);
+        ny = min(max(ny, 0), Lc - 1);
+        cand = (uint32_t)nx | ((uint32_t)ny << 8);
+        if ((unsigned)a > 4u && out.status) atomicOr(out.status, 1);       // TypeError('action is illegal') (:115-116)
+    }
+    // Sequential resolution (:279-283): droplet i moves only if its candidate cell is not occupied by any
+    // other droplet at that moment (j < i already moved, j > i still at their old cell) (:341-343).
+    uint32_t cur = lane_on ? start_cell : (0xFF00u | (uint32_t)g.lane);  // idle lanes sit on unique off-chip cells
+    for (int i = 0; i < A; ++i) {
+        const uint32_t ci = g.get(cand, i);
+        const unsigned taken = g.ballot(g.i != i && cur == ci);
+        if (g.i == i && taken == 0u) cur = ci;
+    }
+    const int nx = cur & 255u, ny = cur >> 8;
+    const int nd = abs(nx - gx) + abs(ny - gy);
+    double r;                                      // base reward (:345-354)
+    if (stalled) r = 0.0;
+    else if (nd == od && od == 0) r = -0.1;
+    else if (nd == od && a == 0) r = -0.25;
+    else if (nd < od) r = -0.1;
+    else r = -0.4;
+
+    // ---- comflic_static / comflic_dynamic (:254-271) on the final and the saved positions ---------
+    int sta = 0, dyn = 0;
+    for (int j = 0; j < A; ++j) {
+        const uint32_t cj = g.get(cur, j), pj = g.get(start_cell, j);
+        if (j != g.i) {
+            sta += near1(cur, cj);
+            dyn += near1(start_cell, cj) + near1(pj, cur);
         }
     }
-    paint_agents<FOV_T>(cfg, L, S, e_valid);
+    if (!lane_on) { sta = 0; dyn = 0; }
+    const int constraints = g.sum(sta + dyn);                              // (:287)
+    const bool post_done = (cur == goal);
+    const uint32_t post_mask = g.ballot(lane_on && post_done);
+    const bool all_done = (post_mask == all_mask);                         // np.all(getTaskStatus()) (:293)
+    r = r - (double)(2 * sta);                                             // rewards - 2*sta - 2*dy, float64 (:288)
+    r = r - (double)(2 * dyn);
+    if (cfg.stall && pre_done) r = 0.0;                                    // (:289-292)
+    if (all_done) {                                                        // (:293-296)
+        r = r + 10.0;
+        if (constraints == 0) r = r + 10.0;
+    }
+    if (frozen || !lane_on) r = 0.0;
+    const double team = g.sum(r) / (double)A;                              // rollout.py:33
+
+    // ---- DMFBenv.step bookkeeping (:572-586) --------------------------------------------------------
+    int cum = cum_in + (frozen ? 0 : constraints);
+    int sc_out = frozen ? sc_in : sc;
+    uint32_t done_mask = post_mask;
+    int success = 0;
+    if (sc < cfg.max_step) success = (all_done && cum == 0) ? 1 : 0;
+    else done_mask = all_mask;
+    if (frozen) { done_mask = all_mask; success = 0; }
+    const int term = (done_mask == all_mask) ? 1 : 0;
+
+    if (lane_on && !frozen && (flags & DMFB_STEP_RECORD_USAGE) && st.usage && !post_done) {  // addUsage (:459-463)
+        uint16_t* cell = st.usage + ((size_t)n * W + nx) * Lc + ny;
+        const uint16_t v = *cell;
+        *cell = (uint16_t)(v + (v != 0xFFFFu));
+    }
+
+    // ---- fused auto-reset: DMFBenv.reset(new=False) (:589-597) for envs that just terminated -------
+    uint32_t word = (d & 0xFFFF0000u) | cur;
+    const bool do_reset = (flags & DMFB_STEP_AUTO_RESET) && term && !frozen && env_on;
+    if (flags & DMFB_STEP_AUTO_RESET) {
+        word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n, episode + 1u, lane_on, do_reset, word);
+        if (do_reset) {
+            sc_out = 0;
+            cum = 0;
+            if (lane_on && st.start) reinterpret_cast<uint16_t*>(st.start)[ja] = (uint16_t)(word & 0xFFFFu);
+        }
+    }
+
+    // ---- write-back (coalesced: consecutive lanes -> consecutive agents / envs) ---------------------
+    if (lane_on) {
+        if (!frozen) reinterpret_cast<uint32_t*>(st.drop)[ja] = word;
+        if (out.reward) out.reward[ja] = (float)r;
+        if (out.reward_f64) out.reward_f64[ja] = r;
+        if (out.done) out.done[ja] = (uint8_t)((done_mask >> g.i) & 1u);
+    }
+    if (leader) {
+        st.step_count[n] = sc_out;
+        st.constraints[n] = cum;
+        st.terminated[n] = (uint8_t)(term && !do_reset);
+        if (do_reset && st.episode) st.episode[n] = episode + 1u;
+        if (out.team_reward) out.team_reward[n] = (float)team;
+        if (out.constraints) out.constraints[n] = frozen ? 0 : constraints;
+        if (out.success) out.success[n] = (uint8_t)success;
+        if (out.terminated) out.terminated[n] = (uint8_t)term;
+        if (out.padded) out.padded[n] = (uint8_t)frozen;
+        S.flag[e] = do_reset ? kFlagNewTask : 0;
+    }
+    const int any_frozen = __syncthreads_or(frozen && env_on);   // also the zero-fill / table barrier
+
+    if (out.avail) {  // all ones; zeros for padded envs (rollout.py:22,138-139)
+        const int per_env = A * cfg.n_actions;
+        uint8_t* gav = out.avail + (size_t)n0 * per_env;
+        const int nbytes = e_valid * per_env;
+        if (!any_frozen && (nbytes & 3) == 0 && (reinterpret_cast<uintptr_t>(gav) & 3) == 0) {
+            for (int k = threadIdx.x; k < (nbytes >> 2); k += blockDim.x) reinterpret_cast<uint32_t*>(gav)[k] = 0x01010101u;
+        } else {
+            if (lane_on)
+                for (int k = 0; k < cfg.n_actions; ++k) gav[(e * A + g.i) * cfg.n_actions + k] = frozen ? 0 : 1;
+        }
+    }
+    if ((flags & DMFB_STEP_AUTO_RESET) && st.usage) update_health_flagged(cfg, st, S, n0, e_valid);
+
+    paint_agent<FOV_T, G>(cfg, L, S, g, e * A + g.i, word, lane_on && !frozen);
     store_tile(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
 }
 
 // --------------------------------------------------------------------- reset --
 
 // mode 0: reset (new task), mode 1: restart (back to start cells), mode 2: observe only
-template <int FOV_T>
-__global__ void __launch_bounds__(kThreads)
+template <int FOV_T, int G>
+__global__ void __launch_bounds__(kMaxThreads)
 dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, const uint8_t* __restrict__ mask,
                   int mode, int new_task, const uint8_t* __restrict__ layouts, const double* __restrict__ degrade_in,
                   uint64_t seed, int8_t* __restrict__ obs, int E)
@@ -488,100 +441,93 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TileLayout L(cfg, E);
     const TileSmem S(smem_raw, L);
+    const Group<G> g;
+    const int A = L.A;
     const int64_t n0 = (int64_t)blockIdx.x * E;
     const int e_valid = (int)min((int64_t)E, (int64_t)st.n_envs - n0);
-    const int A = L.A, SA = L.SA;
+    const int e = threadIdx.x / G;
+    const int64_t n = n0 + e;
+    const bool env_on = e < e_valid;
+    const bool lane_on = env_on && g.i < A;
+    const bool leader = env_on && g.i == 0;
+    const size_t ja = (size_t)n * A + g.i;
     const int cells = cfg.width * cfg.length;
 
-    int selected = 0;
-    if ((int)threadIdx.x < e_valid) selected = (mask == nullptr) || (mask[n0 + threadIdx.x] != 0);
-    const int n_selected = __syncthreads_count(selected);
-    if (n_selected == 0) return;  // nothing to reset in this tile (the common case of a masked auto-reset)
+    int sel_i = 0;
+    if (leader) sel_i = (mask == nullptr) || (mask[n] != 0);
+    const int n_selected = __syncthreads_count(sel_i);
+    if (n_selected == 0) return;  // nothing to do in this tile (the common case of a masked reset)
+    const bool selected = g.get(sel_i, 0) != 0;
+
     load_tables(cfg, L, S);
     if (obs) zero_tile(L, S);
-    if ((int)threadIdx.x < e_valid) {
-        const int e = threadIdx.x;
-        const int64_t n = n0 + e;
-        S.flag[e] = selected ? 0 : kFlagSkip;
-        uint32_t* drop = S.drop + e * SA;
-        uint32_t* gdrop = reinterpret_cast<uint32_t*>(st.drop) + (size_t)n * A;
-        if (selected && mode != 2) {
-            if (mode == 0) {
-                const uint32_t episode = st.episode ? st.episode[n] + 1u : 0u;
-                if (st.episode) st.episode[n] = episode;
-                if (layouts) {
-                    const uint32_t* lay = reinterpret_cast<const uint32_t*>(layouts) + (size_t)n * A;
-                    for (int i = 0; i < A; ++i) drop[i] = lay[i];
-                } else {
-                    generate_layout(cfg, seed, cfg.env_base + n, episode, drop);
-                }
-                if (st.start)
-                    for (int i = 0; i < A; ++i)
-                        reinterpret_cast<uint16_t*>(st.start)[(size_t)n * A + i] = (uint16_t)(drop[i] & 0xFFFFu);
-            } else {  // restart: droplets back to their start cells (dmfb.py:185-190)
-                for (int i = 0; i < A; ++i)
-                    drop[i] = (gdrop[i] & 0xFFFF0000u) | reinterpret_cast<const uint16_t*>(st.start)[(size_t)n * A + i];
-            }
-            for (int i = 0; i < A; ++i) gdrop[i] = drop[i];
+
+    uint32_t word = lane_on ? reinterpret_cast<const uint32_t*>(st.drop)[ja] : 0u;
+    if (mode == 0) {
+        uint32_t episode = 0;
+        if (leader && st.episode) episode = st.episode[n] + 1u;
+        episode = g.get(episode, 0);
+        if (layouts) {
+            if (lane_on && selected) word = reinterpret_cast<const uint32_t*>(layouts)[ja];
+        } else {
+            word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n, episode, lane_on, selected && env_on, word);
+        }
+        if (leader && selected && st.episode) st.episode[n] = episode;
+        if (lane_on && selected && st.start) reinterpret_cast<uint16_t*>(st.start)[ja] = (uint16_t)(word & 0xFFFFu);
+    } else if (mode == 1) {  // restart: droplets back to their start cells (dmfb.py:185-190)
+        if (lane_on && selected) word = (word & 0xFFFF0000u) | reinterpret_cast<const uint16_t*>(st.start)[ja];
+    }
+    if (mode != 2 && selected) {
+        if (lane_on) reinterpret_cast<uint32_t*>(st.drop)[ja] = word;
+        if (leader) {
             st.step_count[n] = 0;
             st.constraints[n] = 0;
             st.terminated[n] = 0;
-        } else {
-            for (int i = 0; i < A; ++i) drop[i] = gdrop[i];
         }
     }
+    if (leader) S.flag[e] = selected ? (kFlagSelected | kFlagNewTask) : 0;
     __syncthreads();
 
     // refresh(new) (dmfb.py:174-183): new -> health=1, usage=0, degrade redrawn; else updateHealth (:465-471)
     if (mode == 0 && (st.usage || st.health || st.degrade)) {
-        for (int e = 0; e < e_valid; ++e) {
-            if (S.flag[e]) continue;
-            const int64_t n = n0 + e;
-            uint16_t* usage = st.usage ? st.usage + (size_t)n * cells : nullptr;
-            double* health = st.health ? st.health + (size_t)n * cells : nullptr;
-            double* degrade = st.degrade ? st.degrade + (size_t)n * cells : nullptr;
-            if (new_task) {
-                const uint32_t episode = st.episode ? st.episode[n] : 0u;
+        if (new_task) {
+            for (int ee = 0; ee < e_valid; ++ee) {
+                if (!S.flag[ee]) continue;
+                const int64_t nn = n0 + ee;
+                uint16_t* usage = st.usage ? st.usage + (size_t)nn * cells : nullptr;
+                double* health = st.health ? st.health + (size_t)nn * cells : nullptr;
+                double* degrade = st.degrade ? st.degrade + (size_t)nn * cells : nullptr;
+                const uint32_t episode = st.episode ? st.episode[nn] : 0u;
                 for (int k = threadIdx.x; k < cells; k += blockDim.x) {
                     if (usage) usage[k] = 0;
                     if (health) health[k] = 1.0;
                     if (degrade) {
                         double dg = 1.0;
                         if (degrade_in) {
-                            dg = degrade_in[(size_t)n * cells + k];
+                            dg = degrade_in[(size_t)nn * cells + k];
                         } else if (cfg.b_degrade) {  // _random_health_statue (dmfb.py:157-164)
-                            const uint4 r = env_random(seed, kStreamDegrade, cfg.env_base + n, episode, (uint32_t)k, 0u);
+                            const uint4 r = env_random(seed, kStreamDegrade, cfg.env_base + nn, episode, (uint32_t)k, 0u);
                             dg = u53(r.x, r.y) * 0.4 + 0.6;
                             if (u53(r.z, r.w) < 1.0 - cfg.per_degrade) dg = 1.0;
                         }
                         degrade[k] = dg;
                     }
                 }
-            } else if (usage) {
-                for (int k = threadIdx.x; k < cells; k += blockDim.x) {
-                    if (usage[k] > 50) {
-                        if (health) health[k] = health[k] * (degrade ? degrade[k] : 1.0);
-                        usage[k] = 0;
-                    }
-                }
             }
+        } else if (st.usage) {
+            update_health_flagged(cfg, st, S, n0, e_valid);
         }
     }
     if (obs == nullptr) return;
-    paint_agents<FOV_T>(cfg, L, S, e_valid);
+    paint_agent<FOV_T, G>(cfg, L, S, g, e * A + g.i, word, lane_on && selected);
     int8_t* gobs = obs + (size_t)n0 * A * L.D;
     if (n_selected == e_valid) store_tile(gobs, S.tile, (uint32_t)(e_valid * A * L.D));
-    else if (n_selected > 0) {
-        // flag semantics for store_rows_masked: non-zero = store
-        __syncthreads();
-        if ((int)threadIdx.x < e_valid) S.flag[threadIdx.x] = (S.flag[threadIdx.x] == 0);
-        store_rows_masked(gobs, S.tile, e_valid, A * L.D, S.flag);
-    }
+    else store_rows_masked(gobs, S.tile, e_valid, A * L.D, S.flag);
 }
 
 // ----------------------------------------------------------------- get_state --
 // getglobalobs (dmfb.py:368-392): (3,W,L) per env, int8.  Tile of E2 envs staged in smem.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(128)
 dmfb_global_state_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, int8_t* __restrict__ out,
                          int E2, uint32_t tile_bytes)
 {
@@ -607,12 +553,25 @@ dmfb_global_state_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_stat
     store_tile(out + (size_t)n0 * per_env, tile, (uint32_t)(e_valid * per_env));
 }
 
-int tile_envs_for(const dmfb_cfg_t& cfg)
+int group_size_for(int n_agents)
+{
+    int g = 4;
+    while (g < n_agents) g <<= 1;
+    return g;
+}
+
+// Envs per tile: a multiple of the 16-byte alignment unit, at most kMaxThreads/G lane groups, ~40 KB of smem.
+int tile_envs_for(const dmfb_cfg_t& cfg, int G)
 {
     const int row = cfg.n_agents * cfg.obs_dim;
-    int E = pick_tile_envs(row, 40 * 1024, 64);
-    if (E > kThreads) E = kThreads;
-    return E;
+    int max_envs = kMaxThreads / G;
+    const int cap = G <= 4 ? 32 : 256 / G;  // 128-256 threads per CTA keeps several CTAs resident per SM
+    if (cap >= 16 / gcd_int(16, row) && cap < max_envs) max_envs = cap;
+    if (const char* ev = getenv("DMFB_TILE_ENVS")) {
+        const int v = atoi(ev);
+        if (v > 0 && v * G <= kMaxThreads) return v;
+    }
+    return pick_tile_envs(row, 40 * 1024, max_envs);
 }
 
 template <typename K>
@@ -633,6 +592,69 @@ int check_common(const dmfb_cfg_t* cfg, const dmfb_state_t* st)
         snprintf(g_last_error, sizeof(g_last_error), "n_blocks > 0 is not supported yet");
         return DMFB_ERR_BAD_ARG;
     }
+    return DMFB_OK;
+}
+
+// Calls f.template operator()<FOV_T, G>() with the compile-time specialisation matching (fov, G).
+template <typename F>
+int dispatch(int fov, int G, F&& f)
+{
+#define DMFB_G_CASES(FOVT)                             \
+    switch (G) {                                       \
+    case 4: return f.template operator()<FOVT, 4>();   \
+    case 8: return f.template operator()<FOVT, 8>();   \
+    case 16: return f.template operator()<FOVT, 16>(); \
+    default: return f.template operator()<FOVT, 32>(); \
+    }
+    switch (fov) {
+    case 5: DMFB_G_CASES(5)
+    case 7: DMFB_G_CASES(7)
+    case 9: DMFB_G_CASES(9)
+    default: DMFB_G_CASES(0)
+    }
+#undef DMFB_G_CASES
+}
+
+struct StepLaunch {
+    const dmfb_cfg_t* cfg; const dmfb_state_t* st; const void* actions; int aes; const double* u;
+    uint64_t seed; uint32_t flags; const dmfb_out_t* out; cudaStream_t s; int E, grid; uint32_t smem;
+    template <int FOVT, int G>
+    int operator()() const {
+        int rc = set_smem(dmfb_step_kernel<FOVT, G>, smem);
+        if (rc) return rc;
+        dmfb_step_kernel<FOVT, G><<<grid, E * G, smem, s>>>(*cfg, *st, actions, aes, u, seed, flags, *out, E);
+        return DMFB_OK;
+    }
+};
+
+struct ResetLaunch {
+    const dmfb_cfg_t* cfg; const dmfb_state_t* st; const uint8_t* mask; int mode, new_task; const uint8_t* layouts;
+    const double* degrade; uint64_t seed; int8_t* obs; cudaStream_t s; int E, grid; uint32_t smem;
+    template <int FOVT, int G>
+    int operator()() const {
+        int rc = set_smem(dmfb_reset_kernel<FOVT, G>, smem);
+        if (rc) return rc;
+        dmfb_reset_kernel<FOVT, G><<<grid, E * G, smem, s>>>(*cfg, *st, mask, mode, new_task, layouts, degrade, seed,
+                                                               obs, E);
+        return DMFB_OK;
+    }
+};
+
+int launch_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t* mask, int mode, int new_task,
+                 const uint8_t* layouts, const double* degrade, uint64_t seed, int8_t* obs, void* stream)
+{
+    int rc = check_common(cfg, state);
+    if (rc) return rc;
+    if (state->n_envs == 0) return DMFB_OK;
+    const int G = group_size_for(cfg->n_agents);
+    const int E = tile_envs_for(*cfg, G);
+    const TileLayout L(*cfg, E);
+    ResetLaunch job{cfg, state, mask, mode, new_task, layouts, degrade, seed, obs, static_cast<cudaStream_t>(stream),
+                    E, (state->n_envs + E - 1) / E, L.total};
+    rc = dispatch(cfg->fov, G, job);
+    if (rc) return rc;
+    g_launches.fetch_add(1);
+    DMFB_CUDA_TRY(cudaGetLastError());
     return DMFB_OK;
 }
 
@@ -693,17 +715,6 @@ int dmfb_cfg_init(dmfb_cfg_t* cfg, int width, int length, int n_agents, int n_bl
     return DMFB_OK;
 }
 
-#define DMFB_DISPATCH_FOV(fov, KERNEL, ...)            \
-    switch (fov) {                                     \
-    case 5: KERNEL<5> __VA_ARGS__; break;              \
-    case 7: KERNEL<7> __VA_ARGS__; break;              \
-    case 9: KERNEL<9> __VA_ARGS__; break;              \
-    default: KERNEL<0> __VA_ARGS__; break;             \
-    }
-
-static int launch_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t* mask, int mode, int new_task,
-                        const uint8_t* layouts, const double* degrade, uint64_t seed, int8_t* obs, void* stream);
-
 int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* actions, int action_elem_size,
               const double* u_inject, uint64_t seed, uint32_t flags, const dmfb_out_t* out, void* stream)
 {
@@ -714,56 +725,16 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
         return DMFB_ERR_BAD_ARG;
     }
     if (state->n_envs == 0) return DMFB_OK;
-    const int E = tile_envs_for(*cfg);
+    const int G = group_size_for(cfg->n_agents);
+    const int E = tile_envs_for(*cfg, G);
     const TileLayout L(*cfg, E);
-    const int grid = (state->n_envs + E - 1) / E;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define LAUNCH_STEP(F)                                                                                      \
-    do {                                                                                                    \
-        rc = set_smem(dmfb_step_kernel<F>, L.total);                                                        \
-        if (rc) return rc;                                                                                  \
-        dmfb_step_kernel<F><<<grid, kThreads, L.total, s>>>(*cfg, *state, actions, action_elem_size,        \
-                                                            u_inject, seed, flags, *out, E);                \
-    } while (0)
-    switch (cfg->fov) {
-    case 5: LAUNCH_STEP(5); break;
-    case 7: LAUNCH_STEP(7); break;
-    case 9: LAUNCH_STEP(9); break;
-    default: LAUNCH_STEP(0); break;
-    }
-#undef LAUNCH_STEP
+    StepLaunch job{cfg, state, actions, action_elem_size, u_inject, seed, flags, out, static_cast<cudaStream_t>(stream),
+                   E, (state->n_envs + E - 1) / E, L.total};
+    rc = dispatch(cfg->fov, G, job);
+    if (rc) return rc;
     g_launches.fetch_add(1);
     DMFB_CUDA_TRY(cudaGetLastError());
     return DMFB_OK;  // DMFB_STEP_AUTO_RESET is fused into the step kernel
-}
-
-static int launch_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t* mask, int mode, int new_task,
-                        const uint8_t* layouts, const double* degrade, uint64_t seed, int8_t* obs, void* stream)
-{
-    int rc = check_common(cfg, state);
-    if (rc) return rc;
-    if (state->n_envs == 0) return DMFB_OK;
-    const int E = tile_envs_for(*cfg);
-    const TileLayout L(*cfg, E);
-    const int grid = (state->n_envs + E - 1) / E;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define LAUNCH_RESET(F)                                                                                     \
-    do {                                                                                                    \
-        rc = set_smem(dmfb_reset_kernel<F>, L.total);                                                       \
-        if (rc) return rc;                                                                                  \
-        dmfb_reset_kernel<F><<<grid, kThreads, L.total, s>>>(*cfg, *state, mask, mode, new_task, layouts,   \
-                                                             degrade, seed, obs, E);                        \
-    } while (0)
-    switch (cfg->fov) {
-    case 5: LAUNCH_RESET(5); break;
-    case 7: LAUNCH_RESET(7); break;
-    case 9: LAUNCH_RESET(9); break;
-    default: LAUNCH_RESET(0); break;
-    }
-#undef LAUNCH_RESET
-    g_launches.fetch_add(1);
-    DMFB_CUDA_TRY(cudaGetLastError());
-    return DMFB_OK;
 }
 
 int dmfb_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t* mask, int new_task,
@@ -799,8 +770,8 @@ int dmfb_global_state(const dmfb_cfg_t* cfg, const dmfb_state_t* state, int8_t* 
     rc = set_smem(dmfb_global_state_kernel, tile_bytes);
     if (rc) return rc;
     const int grid = (state->n_envs + E2 - 1) / E2;
-    dmfb_global_state_kernel<<<grid, kThreads, tile_bytes, static_cast<cudaStream_t>(stream)>>>(*cfg, *state, out, E2,
-                                                                                                 tile_bytes);
+    dmfb_global_state_kernel<<<grid, 128, tile_bytes, static_cast<cudaStream_t>(stream)>>>(*cfg, *state, out, E2,
+                                                                                            tile_bytes);
     g_launches.fetch_add(1);
     DMFB_CUDA_TRY(cudaGetLastError());
     return DMFB_OK;
