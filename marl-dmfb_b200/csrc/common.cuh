@@ -95,6 +95,14 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b)
 
 enum : uint32_t { kStreamMove = 1, kStreamLayout = 2, kStreamDegrade = 3 };
 
+// splitmix64 finaliser (Steele/Lea/Flood 2014): cheap counter-based generator for the task sampler
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
 __device__ __forceinline__ uint4 env_random(uint64_t seed, uint32_t stream, int64_t env, uint32_t episode,
                                             uint32_t a, uint32_t b)
 {

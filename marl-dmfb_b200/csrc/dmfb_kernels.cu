@@ -33,17 +33,18 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 struct TileLayout {
     int E, A, D, nw, ncodes;
     uint32_t tile_bytes, off_l2row, off_l2col, off_flag, off_dirx, off_diry, total;
-    __host__ __device__ TileLayout(const dmfb_cfg_t& c, int E_) {
-        E = E_; A = c.n_agents; D = c.obs_dim; nw = c.l2_words; ncodes = 2 * (c.fov / 2) + 1;
+    __host__ __device__ TileLayout(int E_, int A_, int fov, int W, int Lc) {
+        E = E_; A = A_; D = 3 * fov * fov + 2; nw = (fov * fov + 31) / 32; ncodes = 2 * (fov / 2) + 1;
         tile_bytes = ((uint32_t)(E * A * D) + 15u) & ~15u;
         uint32_t o = tile_bytes;
         off_l2row = o; o += (uint32_t)(ncodes * nw) * 4u;
         off_l2col = o; o += (uint32_t)(ncodes * nw) * 4u;
         off_flag = o; o += ((uint32_t)E + 3u) & ~3u;
-        off_dirx = o; o += ((uint32_t)(2 * c.width) + 3u) & ~3u;
-        off_diry = o; o += ((uint32_t)(2 * c.length) + 3u) & ~3u;
+        off_dirx = o; o += ((uint32_t)(2 * W) + 3u) & ~3u;
+        off_diry = o; o += ((uint32_t)(2 * Lc) + 3u) & ~3u;
         total = (o + 15u) & ~15u;
     }
+    __host__ __device__ TileLayout(const dmfb_cfg_t& c, int E_) : TileLayout(E_, c.n_agents, c.fov, c.width, c.length) {}
 };
 
 // S.flag values
@@ -92,6 +93,18 @@ __device__ __forceinline__ void zero_tile(const TileLayout& L, const TileSmem& S
     for (; k < n16; k += stride) t4[k] = z;
 }
 
+// Compile-time sized zero fill: THREADS threads, BYTES % 16 == 0; fully unrolled STS.128 with immediate offsets.
+template <int BYTES, int THREADS>
+__device__ __forceinline__ void zero_tile_static(int8_t* tile)
+{
+    constexpr int n16 = BYTES / 16;
+    uint4* t4 = reinterpret_cast<uint4*>(tile) + threadIdx.x;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int k = 0; k < (n16 + THREADS - 1) / THREADS; ++k)
+        if (k * THREADS + THREADS <= n16 || (int)threadIdx.x + k * THREADS < n16) t4[k * THREADS] = z;
+}
+
 // |ax-bx| <= 1 && |ay-by| <= 1 on packed (x | y<<8) cells.  On the integer grid this is both
 // "Euclid < 2" (dmfb.py:258,268) and "squared distance <= 2" (dmfb.py:220).
 __device__ __forceinline__ int near1(uint32_t a, uint32_t b)
@@ -127,10 +140,17 @@ struct Group {
     }
 };
 
+__device__ __forceinline__ int near_xy(int ax, int ay, int bx, int by)
+{
+    return (int)((unsigned)(ax - bx + 1) <= 2u) & (int)((unsigned)(ay - by + 1) <= 2u);
+}
+
 // _Generate_Start_End (dmfb.py:207-226): 2A uniform cells, the whole set is redrawn until every pairwise
-// squared distance is > 2.  Lane i draws (start_i, goal_i) from a counter-based RNG keyed by
+// squared distance is > 2.  Lane i draws (start_i, goal_i) from a counter-based generator keyed by
 // (seed, env, episode, attempt, i); the group rejects the attempt if any two of its 2A points are within
-// one cell of each other.  Every lane of the warp must call; `want` is uniform per group.
+// one cell of each other — the same accept/reject rule on the same proposal distribution, so the accepted
+// tasks are distributed exactly like the reference's.  Every lane of the warp must call; `want` is uniform
+// per group.
 template <int G>
 __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const Group<G>& g, int A, uint64_t seed,
                                                     int64_t env, uint32_t episode, bool lane_on, bool want,
@@ -138,35 +158,42 @@ __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const
 {
     uint32_t word = keep;
     bool pending = want;
-    uint32_t attempt = 0;
+    // per-lane stream: one splitmix64 sequence per (seed, env, episode, droplet); 128 bits per attempt
+    uint64_t state = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
+    state += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)episode << 32 | (uint32_t)g.i) * 0xDA942042E4DD58B5ull;
+    state = mix64(state);
+    const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
     while (__any_sync(kFull, pending)) {
-        uint32_t w = 0;
+        int sx = 0, sy = 0, tx = 0, ty = 0;
         if (pending && lane_on) {
-            const uint4 r = env_random(seed, kStreamLayout, env, episode, attempt, (uint32_t)g.i);
-            w = __umulhi(r.x, (uint32_t)cfg.width) | (__umulhi(r.y, (uint32_t)cfg.length) << 8) |
-                (__umulhi(r.z, (uint32_t)cfg.width) << 16) | (__umulhi(r.w, (uint32_t)cfg.length) << 24);
+            const uint64_t z0 = mix64(state += 0x9E3779B97F4A7C15ull);
+            const uint64_t z1 = mix64(state += 0x9E3779B97F4A7C15ull);
+            sx = (int)__umulhi((uint32_t)z0, W); sy = (int)__umulhi((uint32_t)(z0 >> 32), Lc);
+            tx = (int)__umulhi((uint32_t)z1, W); ty = (int)__umulhi((uint32_t)(z1 >> 32), Lc);
         }
-        int bad = near1(w, w >> 16);
+        const uint32_t w = (uint32_t)sx | ((uint32_t)sy << 8) | ((uint32_t)tx << 16) | ((uint32_t)ty << 24);
+        int bad = near_xy(sx, sy, tx, ty);
         for (int j = 0; j < A; ++j) {
             const uint32_t o = g.get(w, j);
-            if (j != g.i) bad |= near1(w, o) | near1(w, o >> 16) | near1(w >> 16, o) | near1(w >> 16, o >> 16);
+            const int ox = o & 255u, oy = (o >> 8) & 255u, px = (o >> 16) & 255u, py = o >> 24;
+            if (j != g.i)
+                bad |= near_xy(sx, sy, ox, oy) | near_xy(sx, sy, px, py) | near_xy(tx, ty, ox, oy) | near_xy(tx, ty, px, py);
         }
         const unsigned gb = g.ballot(bad && lane_on && pending);
         if (pending && gb == 0u) { word = w; pending = false; }
-        ++attempt;
     }
     return word;
 }
 
 // getOneObs (dmfb.py:395-457) of the agent held by this lane, painted into the (zero filled) tile.
 // All lanes of the warp must call (shuffles); only lanes with `on` store.
-template <int FOV_T, int G>
+template <int FOV_T, int G, int A_T>
 __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLayout& L, const TileSmem& S,
                                             const Group<G>& g, int agent_in_tile, uint32_t me, bool on)
 {
     const int fov = FOV_T ? FOV_T : cfg.fov;
     const int hf = fov >> 1, f2 = fov * fov;
-    const int A = L.A, D = L.D;
+    const int A = A_T ? A_T : L.A, D = FOV_T ? 3 * FOV_T * FOV_T + 2 : L.D;
     const int nw = FOV_T ? (FOV_T * FOV_T + 31) / 32 : L.nw;
     const int W = cfg.width, Lc = cfg.length;
     const int x = me & 255u, y = (me >> 8) & 255u, gx = (me >> 16) & 255u, gy = me >> 24;
@@ -206,7 +233,9 @@ __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLay
                         if (k < nfull) wptr[k] = word;
                         else if (k == nfull) {
                             int8_t* bp = reinterpret_cast<int8_t*>(wptr + k);
-                            for (int b = 0; b < ntail; ++b) bp[b] = (int8_t)((nib >> b) & 1u);
+                            if (ntail > 0) bp[0] = (int8_t)(nib & 1u);
+                            if (ntail > 1) bp[1] = (int8_t)((nib >> 1) & 1u);
+                            if (ntail > 2) bp[2] = (int8_t)((nib >> 2) & 1u);
                         }
                     }
                 }
@@ -215,6 +244,7 @@ __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLay
     }
     // ---- layers 0 / 1: droplets in the window, clipped goals of visible others (:408-420) ---------
     const int ox = x - hf, oy = y - hf;
+#pragma unroll
     for (int j = 0; j < A; ++j) {
         const uint32_t d = g.get(me, j);
         const int jx = d & 255u, jy = (d >> 8) & 255u;
@@ -252,16 +282,18 @@ __device__ __forceinline__ void update_health_flagged(const dmfb_cfg_t& cfg, con
     }
 }
 
-template <int FOV_T, int G>
-__global__ void __launch_bounds__(kMaxThreads)
+// A_T / E_T: compile-time droplet count and tile size for the shipped configs (0 = run-time values).
+template <int FOV_T, int G, int A_T, int E_T>
+__global__ void __launch_bounds__(E_T ? E_T * G : kMaxThreads)
 dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, const void* __restrict__ actions,
-                 int aes, const double* __restrict__ u, uint64_t seed, uint32_t flags, const dmfb_out_t out, int E)
+                 int aes, const double* __restrict__ u, uint64_t seed, uint32_t flags, const dmfb_out_t out, int E_rt)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const TileLayout L(cfg, E);
+    const int E = E_T ? E_T : E_rt;
+    const int A = A_T ? A_T : cfg.n_agents, W = cfg.width, Lc = cfg.length;
+    const TileLayout L(E, A, FOV_T ? FOV_T : cfg.fov, W, Lc);
     const TileSmem S(smem_raw, L);
     const Group<G> g;
-    const int A = L.A, W = cfg.width, Lc = cfg.length;
     const int64_t n0 = (int64_t)blockIdx.x * E;
     const int e_valid = (int)min((int64_t)E, (int64_t)st.n_envs - n0);
     const int e = threadIdx.x / G;                 // env of this lane group inside the tile
@@ -294,7 +326,10 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
         prob = st.health[((size_t)n * W + (d & 255u)) * Lc + ((d >> 8) & 255u)];
 
     load_tables(cfg, L, S);
-    zero_tile(L, S);
+    if constexpr (FOV_T != 0 && A_T != 0 && E_T != 0)
+        zero_tile_static<((E_T * A_T * (3 * FOV_T * FOV_T + 2) + 15) / 16) * 16, E_T * G>(S.tile);
+    else
+        zero_tile(L, S);
 
     sc_in = g.get(sc_in, 0);
     cum_in = g.get(cum_in, 0);
@@ -325,6 +360,7 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     // Sequential resolution (:279-283): droplet i moves only if its candidate cell is not occupied by any
     // other droplet at that moment (j < i already moved, j > i still at their old cell) (:341-343).
     uint32_t cur = lane_on ? start_cell : (0xFF00u | (uint32_t)g.lane);  // idle lanes sit on unique off-chip cells
+#pragma unroll
     for (int i = 0; i < A; ++i) {
         const uint32_t ci = g.get(cand, i);
         const unsigned taken = g.ballot(g.i != i && cur == ci);
@@ -341,6 +377,7 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
 
     // ---- comflic_static / comflic_dynamic (:254-271) on the final and the saved positions ---------
     int sta = 0, dyn = 0;
+#pragma unroll
     for (int j = 0; j < A; ++j) {
         const uint32_t cj = g.get(cur, j), pj = g.get(start_cell, j);
         if (j != g.i) {
@@ -416,7 +453,10 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
         const int per_env = A * cfg.n_actions;
         uint8_t* gav = out.avail + (size_t)n0 * per_env;
         const int nbytes = e_valid * per_env;
-        if (!any_frozen && (nbytes & 3) == 0 && (reinterpret_cast<uintptr_t>(gav) & 3) == 0) {
+        if (!any_frozen && (nbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(gav) & 15) == 0) {
+            const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+            for (int k = threadIdx.x; k < (nbytes >> 4); k += blockDim.x) reinterpret_cast<uint4*>(gav)[k] = ones;
+        } else if (!any_frozen && (nbytes & 3) == 0 && (reinterpret_cast<uintptr_t>(gav) & 3) == 0) {
             for (int k = threadIdx.x; k < (nbytes >> 2); k += blockDim.x) reinterpret_cast<uint32_t*>(gav)[k] = 0x01010101u;
         } else {
             if (lane_on)
@@ -425,7 +465,7 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     }
     if ((flags & DMFB_STEP_AUTO_RESET) && st.usage) update_health_flagged(cfg, st, S, n0, e_valid);
 
-    paint_agent<FOV_T, G>(cfg, L, S, g, e * A + g.i, word, lane_on && !frozen);
+    paint_agent<FOV_T, G, A_T>(cfg, L, S, g, e * A + g.i, word, lane_on && !frozen);
     store_tile(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
 }
 
@@ -519,7 +559,7 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
         }
     }
     if (obs == nullptr) return;
-    paint_agent<FOV_T, G>(cfg, L, S, g, e * A + g.i, word, lane_on && selected);
+    paint_agent<FOV_T, G, 0>(cfg, L, S, g, e * A + g.i, word, lane_on && selected);
     int8_t* gobs = obs + (size_t)n0 * A * L.D;
     if (n_selected == e_valid) store_tile(gobs, S.tile, (uint32_t)(e_valid * A * L.D));
     else store_rows_masked(gobs, S.tile, e_valid, A * L.D, S.flag);
@@ -618,12 +658,19 @@ int dispatch(int fov, int G, F&& f)
 struct StepLaunch {
     const dmfb_cfg_t* cfg; const dmfb_state_t* st; const void* actions; int aes; const double* u;
     uint64_t seed; uint32_t flags; const dmfb_out_t* out; cudaStream_t s; int E, grid; uint32_t smem;
+    template <int FOVT, int G, int AT, int ET>
+    int go() const {
+        int rc = set_smem(dmfb_step_kernel<FOVT, G, AT, ET>, smem);
+        if (rc) return rc;
+        dmfb_step_kernel<FOVT, G, AT, ET><<<grid, E * G, smem, s>>>(*cfg, *st, actions, aes, u, seed, flags, *out, E);
+        return DMFB_OK;
+    }
     template <int FOVT, int G>
     int operator()() const {
-        int rc = set_smem(dmfb_step_kernel<FOVT, G>, smem);
-        if (rc) return rc;
-        dmfb_step_kernel<FOVT, G><<<grid, E * G, smem, s>>>(*cfg, *st, actions, aes, u, seed, flags, *out, E);
-        return DMFB_OK;
+        // fully specialised instances for the shipped benchmark configs (BASELINE.json C1, C2/C3)
+        if constexpr (FOVT == 9 && G == 4) { if (cfg->n_agents == 4 && E == 32) return go<9, 4, 4, 32>(); }
+        if constexpr (FOVT == 9 && G == 16) { if (cfg->n_agents == 10 && E == 16) return go<9, 16, 10, 16>(); }
+        return go<FOVT, G, 0, 0>();
     }
 };
 
