@@ -26,18 +26,17 @@ std::atomic<uint64_t> g_launches{0};
 
 namespace {
 
-constexpr int kMaxThreads = 512;  // lane groups per CTA * G (the step kernel adds as many helper lanes)
+constexpr int kMaxThreads = 512;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // Shared-memory carve-up of one tile, computed identically on host and device.
 struct TileLayout {
     int E, A, D, nw, ncodes;
-    uint32_t tile_bytes, off_word, off_l2row, off_l2col, off_flag, off_dirx, off_diry, total;
+    uint32_t tile_bytes, off_l2row, off_l2col, off_flag, off_dirx, off_diry, total;
     __host__ __device__ TileLayout(int E_, int A_, int fov, int W, int Lc) {
         E = E_; A = A_; D = 3 * fov * fov + 2; nw = (fov * fov + 31) / 32; ncodes = 2 * (fov / 2) + 1;
         tile_bytes = ((uint32_t)(E * A * D) + 15u) & ~15u;
         uint32_t o = tile_bytes;
-        off_word = o; o += (uint32_t)(E * A) * 4u;
         off_l2row = o; o += (uint32_t)(ncodes * nw) * 4u;
         off_l2col = o; o += (uint32_t)(ncodes * nw) * 4u;
         off_flag = o; o += ((uint32_t)E + 3u) & ~3u;
@@ -50,12 +49,10 @@ struct TileLayout {
 
 // S.flag values
 constexpr uint8_t kFlagSelected = 1;  // masked reset: env selected (row must be stored)
-constexpr uint8_t kFlagFrozen = 2;    // padded step: the env's observation rows stay zero
 constexpr uint8_t kFlagNewTask = 4;   // a new task was generated for the env: updateHealth still to run
 
 struct TileSmem {
     int8_t* tile;
-    uint32_t* word;   // [E][A] packed droplet words (x | y<<8 | gx<<16 | gy<<24) handed to the helper lanes
     uint32_t* l2row;  // [ncodes][nw]
     uint32_t* l2col;
     uint8_t* flag;    // [E]
@@ -63,7 +60,6 @@ struct TileSmem {
     int8_t* diry;
     __device__ TileSmem(unsigned char* base, const TileLayout& L) {
         tile = reinterpret_cast<int8_t*>(base);
-        word = reinterpret_cast<uint32_t*>(base + L.off_word);
         l2row = reinterpret_cast<uint32_t*>(base + L.off_l2row);
         l2col = reinterpret_cast<uint32_t*>(base + L.off_l2col);
         flag = reinterpret_cast<uint8_t*>(base + L.off_flag);
@@ -111,17 +107,9 @@ __device__ __forceinline__ void zero_tile_static(int8_t* tile, int tid)
         if (k * THREADS + THREADS <= n16 || tid + k * THREADS < n16) t4[k * THREADS] = z;
 }
 
-// |ax-bx| <= 1 && |ay-by| <= 1 on packed (x | y<<8) cells.  On the integer grid this is both
-// "Euclid < 2" (dmfb.py:258,268) and "squared distance <= 2" (dmfb.py:220).
-__device__ __forceinline__ int near1(uint32_t a, uint32_t b)
-{
-    const int dx = (int)(a & 255u) - (int)(b & 255u);
-    const int dy = (int)((a >> 8) & 255u) - (int)((b >> 8) & 255u);
-    return (int)((unsigned)(dx + 1) <= 2u) & (int)((unsigned)(dy + 1) <= 2u);
-}
-
 // Two "within one cell" tests in one VABSDIFF4: a and b each pack two cells (x0 | y0<<8 | x1<<16 | y1<<24);
-// bit 0 of the result: cells 0 are neighbours (or equal), bit 1: cells 1 are.
+// bit 0 of the result: cells 0 are neighbours (or equal), bit 1: cells 1 are.  |dx| <= 1 && |dy| <= 1 is, on the
+// integer grid, both "Euclid < 2" (dmfb.py:258,268) and "squared distance <= 2" (dmfb.py:220).
 __device__ __forceinline__ uint32_t near_pair(uint32_t a, uint32_t b)
 {
     const uint32_t t = __vabsdiffu4(a, b) & 0xFEFEFEFEu;   // a byte is zero iff that |difference| <= 1
@@ -155,11 +143,6 @@ struct Group {
         return v;
     }
 };
-
-__device__ __forceinline__ int near_xy(int ax, int ay, int bx, int by)
-{
-    return (int)((unsigned)(ax - bx + 1) <= 2u) & (int)((unsigned)(ay - by + 1) <= 2u);
-}
 
 // _Generate_Start_End (dmfb.py:207-226): 2A uniform cells, the whole set is redrawn until every pairwise
 // squared distance is > 2.  Lane i draws (start_i, goal_i) from a counter-based generator keyed by
@@ -200,39 +183,13 @@ __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const
     return word;
 }
 
-// ---- observation painting (getOneObs, dmfb.py:395-457) into the zero filled tile ---------------------
-// The record of one agent is split between two lanes: layers 0 + direction bytes, and layers 2 + 1.
-// The two halves write disjoint bytes (layer 2's first partial word overlaps only layer 1's tail, which
-// the same lane paints afterwards; its last partial word is written byte by byte).
-
-// Layer 0 (every droplet inside the window, :408-413) and the direction vector (:442-454).
-// get(j) returns the packed word of droplet j of the same env; every lane must call (it may shuffle).
+// ---- observation painting: getOneObs (dmfb.py:395-457) of one agent into the zero filled tile --------
+// get(j) returns the packed word of droplet j of the same env; every lane must call it (it shuffles).
+// Only lanes with `on` store.  Byte ranges of different agents never overlap: layer 2 is written as whole
+// 4-byte words only where the word lies inside this agent's record (its first word may cover the last
+// <= 3 bytes of the agent's own layer 1, which is painted afterwards), the rest byte by byte.
 template <int FOV_T, int A_T, typename GetWord>
-__device__ __forceinline__ void paint_l0_dir(const dmfb_cfg_t& cfg, const TileLayout& L, const TileSmem& S,
-                                             int agent_in_tile, uint32_t me, bool on, GetWord get)
-{
-    const int fov = FOV_T ? FOV_T : cfg.fov;
-    const int hf = fov >> 1, f2 = fov * fov;
-    const int A = A_T ? A_T : L.A, D = FOV_T ? 3 * FOV_T * FOV_T + 2 : L.D;
-    const int x = me & 255u, y = (me >> 8) & 255u, gx = (me >> 16) & 255u, gy = me >> 24;
-    int8_t* rec = S.tile + agent_in_tile * D;
-    const int ox = x - hf, oy = y - hf;
-#pragma unroll
-    for (int j = 0; j < A; ++j) {
-        const uint32_t d = get(j);
-        const int rx = (int)(d & 255u) - ox, ry = (int)((d >> 8) & 255u) - oy;
-        if (on && (unsigned)rx < (unsigned)fov && (unsigned)ry < (unsigned)fov) rec[rx * fov + ry] = (int8_t)(j + 1);
-    }
-    if (on) {
-        rec[3 * f2] = S.dirx[gx - x + cfg.width - 1];
-        rec[3 * f2 + 1] = S.diry[gy - y + cfg.length - 1];
-    }
-}
-
-// Layer 2 (off-chip boundary, :428-439, expanded from bit masks) and layer 1 (goals of the other visible
-// droplets clipped into the window, :416-420).
-template <int FOV_T, int A_T, typename GetWord>
-__device__ __forceinline__ void paint_l2_l1(const dmfb_cfg_t& cfg, const TileLayout& L, const TileSmem& S,
+__device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLayout& L, const TileSmem& S,
                                             int agent_in_tile, int i, uint32_t me, bool on, GetWord get)
 {
     const int fov = FOV_T ? FOV_T : cfg.fov;
@@ -240,9 +197,10 @@ __device__ __forceinline__ void paint_l2_l1(const dmfb_cfg_t& cfg, const TileLay
     const int A = A_T ? A_T : L.A, D = FOV_T ? 3 * FOV_T * FOV_T + 2 : L.D;
     const int nw = FOV_T ? (FOV_T * FOV_T + 31) / 32 : L.nw;
     const int W = cfg.width, Lc = cfg.length;
-    const int x = me & 255u, y = (me >> 8) & 255u;
+    const int x = me & 255u, y = (me >> 8) & 255u, gx = (me >> 16) & 255u, gy = me >> 24;
     int8_t* rec = S.tile + agent_in_tile * D;
 
+    // ---- layer 2: off-chip boundary (:428-439) expanded from bit masks, 4 output bytes per multiply ----
     if (on) {
         const int lb = hf - x, rb = hf - (W - 1 - x);
         const int ub = hf - y, db = hf - (Lc - 1 - y);
@@ -254,48 +212,61 @@ __device__ __forceinline__ void paint_l2_l1(const dmfb_cfg_t& cfg, const TileLay
             const int base = agent_in_tile * D + 2 * f2;  // byte offset of the layer inside the tile
             const int s = base & 3;                       // misalignment of the layer start
             uint32_t* wptr = reinterpret_cast<uint32_t*>(S.tile + (base & ~3));
-            const int nbits = f2 + s;
-            const int nfull = nbits >> 2;                 // whole 4-byte words (f2/4 or f2/4+1)
-            const int ntail = nbits & 3;                  // trailing bytes: the next agent's bytes follow
-            const int nfull_min = f2 >> 2;
+            const int nfull_min = f2 >> 2;                // words that are whole for every alignment
             uint32_t prev = 0;
 #pragma unroll
             for (int j = 0; j <= nw; ++j) {
+                if (8 * j >= nfull_min) break;
                 const uint32_t m = (j < nw) ? (rowm[j] | colm[j]) : 0u;
                 const uint32_t sh = __funnelshift_l(prev, m, s);  // mask bits shifted up by s
                 prev = m;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const int k = 8 * j + t;
-                    const uint32_t nib = (sh >> (4 * t)) & 0xFu;
                     // spread 4 bits to 4 bytes: bit b -> byte b (16 distinct partial products, no carries)
-                    const uint32_t word = (nib * 0x00204081u) & 0x01010101u;
-                    if (k < nfull_min) {
-                        wptr[k] = word;
-                    } else if (k <= nfull_min + 1) {
-                        if (k < nfull) wptr[k] = word;
-                        else if (k == nfull) {
-                            int8_t* bp = reinterpret_cast<int8_t*>(wptr + k);
-                            if (ntail > 0) bp[0] = (int8_t)(nib & 1u);
-                            if (ntail > 1) bp[1] = (int8_t)((nib >> 1) & 1u);
-                            if (ntail > 2) bp[2] = (int8_t)((nib >> 2) & 1u);
-                        }
-                    }
+                    if (k < nfull_min) wptr[k] = (((sh >> (4 * t)) & 0xFu) * 0x00204081u) & 0x01010101u;
                 }
             }
+            // the last (f2 & 3) + s <= 6 bytes: one more whole word if they reach 4, then single bytes
+            const int q0 = 4 * nfull_min - s;             // first layer bit not yet written
+            const int wi = q0 >> 5;
+            const uint32_t lo = (wi < nw) ? (rowm[wi] | colm[wi]) : 0u;
+            const uint32_t hi = (wi + 1 < nw) ? (rowm[wi + 1] | colm[wi + 1]) : 0u;
+            uint32_t rem = __funnelshift_r(lo, hi, q0 & 31);
+            int nrem = f2 - q0;
+            int8_t* bp = reinterpret_cast<int8_t*>(wptr + nfull_min);
+            if (nrem >= 4) {
+                wptr[nfull_min] = ((rem & 0xFu) * 0x00204081u) & 0x01010101u;
+                rem >>= 4; nrem -= 4; bp += 4;
+            }
+            if (nrem > 0) bp[0] = (int8_t)(rem & 1u);
+            if (nrem > 1) bp[1] = (int8_t)((rem >> 1) & 1u);
+            if (nrem > 2) bp[2] = (int8_t)((rem >> 2) & 1u);
         }
     }
+    // ---- layer 0: droplets inside the window (:408-413); layer 1: clipped goals of the other droplets
+    //      with |dx| < fov/2 and |dy| < fov/2 (:416-420) --------------------------------------------------
     const int ox = x - hf, oy = y - hf;
+    const uint32_t vis_bias = (uint32_t)(0x7F - ((fov - 1) >> 1)) * 0x0101u;  // byte + bias sets bit 7 iff byte > (fov-1)/2
 #pragma unroll
     for (int j = 0; j < A; ++j) {
         const uint32_t d = get(j);
-        const int jx = d & 255u, jy = (d >> 8) & 255u;
-        if (on && j != i && 2 * abs(jx - x) < fov && 2 * abs(jy - y) < fov) {
+        const uint32_t ad = __vabsdiffu4(me, d) & 0xFFFFu;            // |dx| | |dy|<<8
+        const bool vis = ((ad + vis_bias) & 0x8080u) == 0u;           // 2|dx| < fov && 2|dy| < fov
+        const int rx = (int)(d & 255u) - ox, ry = (int)((d >> 8) & 255u) - oy;
+        const bool in0 = (fov & 1) ? vis : ((unsigned)rx < (unsigned)fov && (unsigned)ry < (unsigned)fov);
+        if (on && in0) rec[rx * fov + ry] = (int8_t)(j + 1);
+        if (on && vis && j != i) {
             int cx = (int)((d >> 16) & 255u) - ox, cy = (int)(d >> 24) - oy;
             cx = min(max(cx, 0), fov - 1);
             cy = min(max(cy, 0), fov - 1);
             rec[f2 + cx * fov + cy] = (int8_t)(j + 1);  // ascending j in one thread: later index overwrites
         }
+    }
+    // ---- direction bytes (:442-454) from the host-built table -------------------------------------------
+    if (on) {
+        rec[3 * f2] = S.dirx[gx - x + W - 1];
+        rec[3 * f2 + 1] = S.diry[gy - y + Lc - 1];
     }
 }
 
@@ -318,13 +289,10 @@ __device__ __forceinline__ void update_health_flagged(const dmfb_cfg_t& cfg, con
 }
 
 // ------------------------------------------------------------------------ step --
-// CTA = 2 x H threads (H = E*G rounded up to a warp multiple).
-//   agent lanes  [0, H):  lane (e, i) owns droplet i of env e: loads, dynamics, write-back, layer 0 + dir
-//   helper lanes [H, 2H): tables, zero fill, avail mask; after the barrier layer 2 + layer 1 of the same agent
 // A_T / E_T: compile-time droplet count and tile size for the shipped configs (0 = run-time values).
 // DEG_T = false strips the degradation path (health / usage / draws) when the state has none.
 template <int FOV_T, int G, int A_T, int E_T, bool DEG_T>
-__global__ void __launch_bounds__(E_T ? 2 * E_T * G : 2 * kMaxThreads)
+__global__ void __launch_bounds__(E_T ? E_T * G : kMaxThreads)
 dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, const void* __restrict__ actions,
                  int aes, const double* __restrict__ u, uint64_t seed, uint32_t flags, const dmfb_out_t out, int E_rt)
 {
@@ -333,196 +301,183 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     const int A = A_T ? A_T : cfg.n_agents, W = cfg.width, Lc = cfg.length;
     const TileLayout L(E, A, FOV_T ? FOV_T : cfg.fov, W, Lc);
     const TileSmem S(smem_raw, L);
-    const int H = (int)(blockDim.x >> 1);
-    const bool helper = (int)threadIdx.x >= H;
-    const int tid = (int)threadIdx.x - (helper ? H : 0);
+    const int tid = (int)threadIdx.x;
     const Group<G> g(tid);
     const int64_t n0 = (int64_t)blockIdx.x * E;
     const int e_valid = (int)min((int64_t)E, (int64_t)st.n_envs - n0);
     const int e = tid / G;                          // env of this lane group inside the tile
     const int64_t n = n0 + e;
     const bool env_on = e < e_valid;
-    const bool lane_on = env_on && g.i < A;         // this lane is paired with droplet g.i of env n
+    const bool lane_on = env_on && g.i < A;         // this lane holds droplet g.i of env n
+    const bool leader = env_on && g.i == 0;
     const int agent = e * A + g.i;                  // agent index inside the tile
-    uint32_t word = 0;
-    bool frozen = false;
+    const size_t ja = (size_t)n * A + g.i;          // index into [N,A] tensors
+    const uint32_t all_mask = (A >= 32) ? 0xFFFFFFFFu : ((1u << A) - 1u);
 
-    if (helper) {
-        load_tables(cfg, L, S, tid, H);
-        if constexpr (FOV_T != 0 && A_T != 0 && E_T != 0)
-            zero_tile_static<((E_T * A_T * (3 * FOV_T * FOV_T + 2) + 15) / 16) * 16, E_T * G>(S.tile, tid);
-        else
-            zero_tile(L, S, tid, H);
-    } else {
-        const bool leader = env_on && g.i == 0;
-        const size_t ja = (size_t)n * A + g.i;      // index into [N,A] tensors
-        const uint32_t all_mask = (A >= 32) ? 0xFFFFFFFFu : ((1u << A) - 1u);
+    // ---- global inputs: one coalesced round trip, issued before the shared-memory work ------------
+    uint32_t d = 0;
+    int a = 0;
+    double prob = 1.0, draw = 0.0;
+    const bool have_prob = DEG_T && st.health != nullptr;
+    if (lane_on) {
+        d = reinterpret_cast<const uint32_t*>(st.drop)[ja];
+        a = load_action(actions, aes, ja);
+        if (have_prob && u) draw = u[ja];
+    }
+    int sc_in = 0, cum_in = 0, frozen_i = 0;
+    uint32_t episode = 0;
+    if (leader) {
+        sc_in = st.step_count[n];
+        cum_in = st.constraints[n];
+        if (st.episode) episode = st.episode[n];
+        if (flags & DMFB_STEP_FREEZE_TERM) frozen_i = st.terminated[n];
+    }
+    if (have_prob && lane_on)  // getMoveProb (:361-363): the cell occupied at the start of the step
+        prob = st.health[((size_t)n * W + (d & 255u)) * Lc + ((d >> 8) & 255u)];
 
-        // ---- global inputs: one coalesced round trip ------------------------------------------------
-        uint32_t d = 0;
-        int a = 0;
-        double prob = 1.0, draw = 0.0;
-        const bool have_prob = DEG_T && st.health != nullptr;
-        if (lane_on) {
-            d = reinterpret_cast<const uint32_t*>(st.drop)[ja];
-            a = load_action(actions, aes, ja);
-            if (have_prob && u) draw = u[ja];
-        }
-        int sc_in = 0, cum_in = 0, frozen_i = 0;
-        uint32_t episode = 0;
-        if (leader) {
-            sc_in = st.step_count[n];
-            cum_in = st.constraints[n];
-            if (st.episode) episode = st.episode[n];
-            if (flags & DMFB_STEP_FREEZE_TERM) frozen_i = st.terminated[n];
-        }
-        if (have_prob && lane_on)  // getMoveProb (:361-363): the cell occupied at the start of the step
-            prob = st.health[((size_t)n * W + (d & 255u)) * Lc + ((d >> 8) & 255u)];
-        sc_in = g.get(sc_in, 0);
-        cum_in = g.get(cum_in, 0);
-        episode = g.get(episode, 0);
-        frozen = g.get(frozen_i, 0) != 0;           // lock-step padding (rollout.py:131-141)
-        const int sc = sc_in + 1;                   // dmfb.py:561
+    load_tables(cfg, L, S, tid, (int)blockDim.x);
+    if constexpr (FOV_T != 0 && A_T != 0 && E_T != 0)
+        zero_tile_static<((E_T * A_T * (3 * FOV_T * FOV_T + 2) + 15) / 16) * 16, E_T * G>(S.tile, tid);
+    else
+        zero_tile(L, S, tid, (int)blockDim.x);
 
-        // ---- moveOneDroplet for all droplets (:325-359) ---------------------------------------------
-        const uint32_t goal = d >> 16;
-        const uint32_t start_cell = d & 0xFFFFu;    // "past" position
-        const int x = d & 255u, y = (d >> 8) & 255u, gx = goal & 255u, gy = goal >> 8;
-        const int od = abs(x - gx) + abs(y - gy);   // Droplet.distance (:93-95)
-        const bool pre_done = (od == 0);            // getTaskStatus before the moves (:278)
-        const bool stalled = cfg.stall && pre_done; // reward 0, no move, no draw (:331-332)
-        if (have_prob && !u && lane_on && !stalled) {
-            const uint4 r = env_random(seed, kStreamMove, cfg.env_base + n, episode, (uint32_t)sc, (uint32_t)g.i);
-            draw = u53(r.x, r.y);
-        }
-        const bool tries = lane_on && !stalled && !frozen && (draw <= prob);  // random.random() <= prob (:335)
-        uint32_t cand = start_cell;
-        if (tries) {                                // Droplet.move (:103-124)
-            int nx = x + (a == 1) - (a == 2), ny = y + (a == 4) - (a == 3);
-            nx = min(max(nx, 0), W - 1);
-            ny = min(max(ny, 0), Lc - 1);
-            cand = (uint32_t)nx | ((uint32_t)ny << 8);
-            if ((unsigned)a > 4u && out.status) atomicOr(out.status, 1);      // TypeError('action is illegal') (:115-116)
-        }
-        // Sequential resolution (:279-283): droplet i moves only if its candidate cell is not occupied by any
-        // other droplet at that moment (j < i already moved, j > i still at their old cell) (:341-343).
-        uint32_t cur = lane_on ? start_cell : (0xFF00u | (uint32_t)g.lane);  // idle lanes: unique off-chip cells
+    sc_in = g.get(sc_in, 0);
+    cum_in = g.get(cum_in, 0);
+    episode = g.get(episode, 0);
+    const bool frozen = g.get(frozen_i, 0) != 0;    // lock-step padding (rollout.py:131-141)
+    const int sc = sc_in + 1;                       // dmfb.py:561
+
+    // ---- moveOneDroplet for all droplets (:325-359) ------------------------------------------------
+    const uint32_t goal = d >> 16;
+    const uint32_t start_cell = d & 0xFFFFu;        // "past" position
+    const int x = d & 255u, y = (d >> 8) & 255u, gx = goal & 255u, gy = goal >> 8;
+    const int od = abs(x - gx) + abs(y - gy);       // Droplet.distance (:93-95)
+    const bool pre_done = (od == 0);                // getTaskStatus before the moves (:278)
+    const bool stalled = cfg.stall && pre_done;     // reward 0, no move, no draw (:331-332)
+    if (have_prob && !u && lane_on && !stalled) {
+        const uint4 r = env_random(seed, kStreamMove, cfg.env_base + n, episode, (uint32_t)sc, (uint32_t)g.i);
+        draw = u53(r.x, r.y);
+    }
+    const bool tries = lane_on && !stalled && !frozen && (draw <= prob);   // random.random() <= prob (:335)
+    uint32_t cand = start_cell;
+    if (tries) {                                    // Droplet.move (:103-124)
+        int nx = x + (a == 1) - (a == 2), ny = y + (a == 4) - (a == 3);
+        nx = min(max(nx, 0), W - 1);
+        ny = min(max(ny, 0), Lc - 1);
+        cand = (uint32_t)nx | ((uint32_t)ny << 8);
+        if ((unsigned)a > 4u && out.status) atomicOr(out.status, 1);       // TypeError('action is illegal') (:115-116)
+    }
+    // Sequential resolution (:279-283): droplet i moves only if its candidate cell is not occupied by any
+    // other droplet at that moment (j < i already moved, j > i still at their old cell) (:341-343).
+    uint32_t cur = lane_on ? start_cell : (0xFF00u | (uint32_t)g.lane);   // idle lanes: unique off-chip cells
 #pragma unroll
-        for (int i = 0; i < A; ++i) {
-            const uint32_t ci = g.get(cand, i);
-            const unsigned taken = g.ballot(g.i != i && cur == ci);
-            if (g.i == i && taken == 0u) cur = ci;
-        }
-        const int nx = cur & 255u, ny = cur >> 8;
-        const int nd = abs(nx - gx) + abs(ny - gy);
-        double r;                                   // base reward (:345-354)
-        if (stalled) r = 0.0;
-        else if (nd == od && od == 0) r = -0.1;
-        else if (nd == od && a == 0) r = -0.25;
-        else if (nd < od) r = -0.1;
-        else r = -0.4;
+    for (int i = 0; i < A; ++i) {
+        const uint32_t ci = g.get(cand, i);
+        const unsigned taken = g.ballot(g.i != i && cur == ci);
+        if (g.i == i && taken == 0u) cur = ci;
+    }
+    const int nx = cur & 255u, ny = cur >> 8;
+    const int nd = abs(nx - gx) + abs(ny - gy);
+    double r;                                       // base reward (:345-354)
+    if (stalled) r = 0.0;
+    else if (nd == od && od == 0) r = -0.1;
+    else if (nd == od && a == 0) r = -0.25;
+    else if (nd < od) r = -0.1;
+    else r = -0.4;
 
-        // ---- comflic_static / comflic_dynamic (:254-271): final vs final, saved vs final ------------
-        const uint32_t both = cur | (start_cell << 16);        // my (current, past) cells
-        int sta = 0, dyn = 0;
+    // ---- comflic_static / comflic_dynamic (:254-271): final vs final, saved vs final ---------------
+    const uint32_t both = cur | (start_cell << 16); // my (current, past) cells
+    int sta = 0, dyn = 0;
 #pragma unroll
-        for (int j = 0; j < A; ++j) {
-            const uint32_t bj = g.get(both, j);                // (current_j, past_j)
-            const uint32_t h1 = near_pair(both, dup_lo(bj));   // bit0: cur_me~cur_j, bit1: past_me~cur_j
-            const uint32_t h2 = near_pair(both, dup_hi(bj));   // bit0: cur_me~past_j
-            if (j != g.i) {
-                sta += (int)(h1 & 1u);
-                dyn += (int)(h1 >> 1) + (int)(h2 & 1u);
-            }
-        }
-        if (!lane_on) { sta = 0; dyn = 0; }
-        const int constraints = g.sum(sta + dyn);                              // (:287)
-        const bool post_done = (cur == goal);
-        const uint32_t post_mask = g.ballot(lane_on && post_done);
-        const bool all_done = (post_mask == all_mask);                         // np.all(getTaskStatus()) (:293)
-        r = r - (double)(2 * sta);                                             // rewards - 2*sta - 2*dy, float64 (:288)
-        r = r - (double)(2 * dyn);
-        if (cfg.stall && pre_done) r = 0.0;                                    // (:289-292)
-        if (all_done) {                                                        // (:293-296)
-            r = r + 10.0;
-            if (constraints == 0) r = r + 10.0;
-        }
-        if (frozen || !lane_on) r = 0.0;
-        const double team = g.sum(r) / (double)A;                              // rollout.py:33
-
-        // ---- DMFBenv.step bookkeeping (:572-586) ----------------------------------------------------
-        int cum = cum_in + (frozen ? 0 : constraints);
-        int sc_out = frozen ? sc_in : sc;
-        uint32_t done_mask = post_mask;
-        int success = 0;
-        if (sc < cfg.max_step) success = (all_done && cum == 0) ? 1 : 0;
-        else done_mask = all_mask;
-        if (frozen) { done_mask = all_mask; success = 0; }
-        const int term = (done_mask == all_mask) ? 1 : 0;
-
-        if (DEG_T && lane_on && !frozen && (flags & DMFB_STEP_RECORD_USAGE) && st.usage && !post_done) {  // addUsage (:459-463)
-            uint16_t* cell = st.usage + ((size_t)n * W + nx) * Lc + ny;
-            const uint16_t v = *cell;
-            *cell = (uint16_t)(v + (v != 0xFFFFu));
-        }
-
-        // ---- fused auto-reset: DMFBenv.reset(new=False) (:589-597) for envs that just terminated ----
-        word = (d & 0xFFFF0000u) | cur;
-        const bool do_reset = (flags & DMFB_STEP_AUTO_RESET) && term && !frozen && env_on;
-        if (flags & DMFB_STEP_AUTO_RESET) {
-            word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n, episode + 1u, lane_on, do_reset, word);
-            if (do_reset) {
-                sc_out = 0;
-                cum = 0;
-                if (lane_on && st.start) reinterpret_cast<uint16_t*>(st.start)[ja] = (uint16_t)(word & 0xFFFFu);
-            }
-        }
-
-        // ---- write-back (coalesced: consecutive lanes -> consecutive agents / envs) -----------------
-        if (lane_on) {
-            S.word[agent] = word;
-            if (!frozen) reinterpret_cast<uint32_t*>(st.drop)[ja] = word;
-            if (out.reward) out.reward[ja] = (float)r;
-            if (out.reward_f64) out.reward_f64[ja] = r;
-            if (out.done) out.done[ja] = (uint8_t)((done_mask >> g.i) & 1u);
-        }
-        if (leader) {
-            st.step_count[n] = sc_out;
-            st.constraints[n] = cum;
-            st.terminated[n] = (uint8_t)(term && !do_reset);
-            if (do_reset && st.episode) st.episode[n] = episode + 1u;
-            if (out.team_reward) out.team_reward[n] = (float)team;
-            if (out.constraints) out.constraints[n] = frozen ? 0 : constraints;
-            if (out.success) out.success[n] = (uint8_t)success;
-            if (out.terminated) out.terminated[n] = (uint8_t)term;
-            if (out.padded) out.padded[n] = (uint8_t)frozen;
-            S.flag[e] = (uint8_t)((do_reset ? kFlagNewTask : 0) | (frozen ? kFlagFrozen : 0));
+    for (int j = 0; j < A; ++j) {
+        const uint32_t bj = g.get(both, j);                 // (current_j, past_j)
+        const uint32_t h1 = near_pair(both, dup_lo(bj));    // bit0: cur_me~cur_j, bit1: past_me~cur_j
+        const uint32_t h2 = near_pair(both, dup_hi(bj));    // bit0: cur_me~past_j
+        if (j != g.i) {
+            sta += (int)(h1 & 1u);
+            dyn += (int)(h1 >> 1) + (int)(h2 & 1u);
         }
     }
-    const int any_frozen = __syncthreads_or(frozen && env_on);   // tile zeroed, tables + droplet words staged
+    if (!lane_on) { sta = 0; dyn = 0; }
+    const int constraints = g.sum(sta + dyn);                              // (:287)
+    const bool post_done = (cur == goal);
+    const uint32_t post_mask = g.ballot(lane_on && post_done);
+    const bool all_done = (post_mask == all_mask);                         // np.all(getTaskStatus()) (:293)
+    r = r - (double)(2 * sta);                                             // rewards - 2*sta - 2*dy, float64 (:288)
+    r = r - (double)(2 * dyn);
+    if (cfg.stall && pre_done) r = 0.0;                                    // (:289-292)
+    if (all_done) {                                                        // (:293-296)
+        r = r + 10.0;
+        if (constraints == 0) r = r + 10.0;
+    }
+    if (frozen || !lane_on) r = 0.0;
+    const double team = g.sum(r) / (double)A;                              // rollout.py:33
 
+    // ---- DMFBenv.step bookkeeping (:572-586) --------------------------------------------------------
+    int cum = cum_in + (frozen ? 0 : constraints);
+    int sc_out = frozen ? sc_in : sc;
+    uint32_t done_mask = post_mask;
+    int success = 0;
+    if (sc < cfg.max_step) success = (all_done && cum == 0) ? 1 : 0;
+    else done_mask = all_mask;
+    if (frozen) { done_mask = all_mask; success = 0; }
+    const int term = (done_mask == all_mask) ? 1 : 0;
+
+    if (DEG_T && lane_on && !frozen && (flags & DMFB_STEP_RECORD_USAGE) && st.usage && !post_done) {  // addUsage (:459-463)
+        uint16_t* cell = st.usage + ((size_t)n * W + nx) * Lc + ny;
+        const uint16_t v = *cell;
+        *cell = (uint16_t)(v + (v != 0xFFFFu));
+    }
+
+    // ---- fused auto-reset: DMFBenv.reset(new=False) (:589-597) for envs that just terminated -------
+    uint32_t word = (d & 0xFFFF0000u) | cur;
+    const bool do_reset = (flags & DMFB_STEP_AUTO_RESET) && term && !frozen && env_on;
+    if (flags & DMFB_STEP_AUTO_RESET) {
+        word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n, episode + 1u, lane_on, do_reset, word);
+        if (do_reset) {
+            sc_out = 0;
+            cum = 0;
+            if (lane_on && st.start) reinterpret_cast<uint16_t*>(st.start)[ja] = (uint16_t)(word & 0xFFFFu);
+        }
+    }
+
+    // ---- write-back (coalesced: consecutive lanes -> consecutive agents / envs) ---------------------
+    if (lane_on) {
+        if (!frozen) reinterpret_cast<uint32_t*>(st.drop)[ja] = word;
+        if (out.reward) out.reward[ja] = (float)r;
+        if (out.reward_f64) out.reward_f64[ja] = r;
+        if (out.done) out.done[ja] = (uint8_t)((done_mask >> g.i) & 1u);
+    }
+    if (leader) {
+        st.step_count[n] = sc_out;
+        st.constraints[n] = cum;
+        st.terminated[n] = (uint8_t)(term && !do_reset);
+        if (do_reset && st.episode) st.episode[n] = episode + 1u;
+        if (out.team_reward) out.team_reward[n] = (float)team;
+        if (out.constraints) out.constraints[n] = frozen ? 0 : constraints;
+        if (out.success) out.success[n] = (uint8_t)success;
+        if (out.terminated) out.terminated[n] = (uint8_t)term;
+        if (out.padded) out.padded[n] = (uint8_t)frozen;
+        S.flag[e] = (uint8_t)(do_reset ? kFlagNewTask : 0);
+    }
+    const int any_frozen = __syncthreads_or(frozen && env_on);   // also the zero-fill / table barrier
+
+    if (out.avail) {  // all ones; zeros for padded envs (rollout.py:22,138-139)
+        const int per_env = A * cfg.n_actions;
+        uint8_t* gav = out.avail + (size_t)n0 * per_env;
+        const int nbytes = e_valid * per_env;
+        if (!any_frozen && (nbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(gav) & 15) == 0) {
+            const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+            for (int k = tid; k < (nbytes >> 4); k += (int)blockDim.x) reinterpret_cast<uint4*>(gav)[k] = ones;
+        } else if (lane_on) {
+            for (int k = 0; k < cfg.n_actions; ++k) gav[agent * cfg.n_actions + k] = frozen ? 0 : 1;
+        }
+    }
     if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) update_health_flagged(cfg, st, S, n0, e_valid);
 
-    if (helper) {
-        if (out.avail) {  // all ones; zeros for padded envs (rollout.py:22,138-139)
-            const int per_env = A * cfg.n_actions;
-            uint8_t* gav = out.avail + (size_t)n0 * per_env;
-            const int nbytes = e_valid * per_env;
-            if (!any_frozen && (nbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(gav) & 15) == 0) {
-                const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
-                for (int k = tid; k < (nbytes >> 4); k += H) reinterpret_cast<uint4*>(gav)[k] = ones;
-            } else if (lane_on) {
-                const uint8_t v = (S.flag[e] & kFlagFrozen) ? 0 : 1;
-                for (int k = 0; k < cfg.n_actions; ++k) gav[agent * cfg.n_actions + k] = v;
-            }
-        }
-        const bool on = lane_on && !(S.flag[e] & kFlagFrozen);
-        const uint32_t* env_words = S.word + (env_on ? e : 0) * A;
-        const uint32_t me = lane_on ? env_words[g.i] : 0u;
-        paint_l2_l1<FOV_T, A_T>(cfg, L, S, agent, g.i, me, on, [&](int j) { return env_words[j]; });
-    } else {
-        paint_l0_dir<FOV_T, A_T>(cfg, L, S, agent, word, lane_on && !frozen, [&](int j) { return g.get(word, j); });
-    }
+    const bool on = lane_on && !frozen;
+    auto get = [&](int j) { return g.get(word, j); };
+    paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, on, get);
     store_tile(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
 }
 
@@ -619,8 +574,7 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
     if (obs == nullptr) return;
     const bool on = lane_on && selected;
     auto get = [&](int j) { return g.get(word, j); };
-    paint_l2_l1<FOV_T, 0>(cfg, L, S, e * A + g.i, g.i, word, on, get);
-    paint_l0_dir<FOV_T, 0>(cfg, L, S, e * A + g.i, word, on, get);
+    paint_agent<FOV_T, 0>(cfg, L, S, e * A + g.i, g.i, word, on, get);
     int8_t* gobs = obs + (size_t)n0 * A * L.D;
     if (n_selected == e_valid) store_tile(gobs, S.tile, (uint32_t)(e_valid * A * L.D));
     else store_rows_masked(gobs, S.tile, e_valid, A * L.D, S.flag);
@@ -723,8 +677,7 @@ struct StepLaunch {
     int go() const {
         int rc = set_smem(dmfb_step_kernel<FOVT, G, AT, ET, DEG>, smem);
         if (rc) return rc;
-        const int H = ((E * G + 31) / 32) * 32;  // agent lanes; the same number of helper lanes follows
-        dmfb_step_kernel<FOVT, G, AT, ET, DEG><<<grid, 2 * H, smem, s>>>(*cfg, *st, actions, aes, u, seed, flags, *out, E);
+        dmfb_step_kernel<FOVT, G, AT, ET, DEG><<<grid, E * G, smem, s>>>(*cfg, *st, actions, aes, u, seed, flags, *out, E);
         return DMFB_OK;
     }
     template <int FOVT, int G>
