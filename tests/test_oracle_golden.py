@@ -35,3 +35,46 @@ def test_dmfb_oracle_matches_reference_trace(oracle_lib, name):
                                               err_msg=msg + " state")
         np.testing.assert_array_equal(env.usage, g["usage_end"][ep], err_msg=f"usage end ep{ep}")
     np.testing.assert_array_equal(env.health, g["health_final"])
+
+
+@pytest.mark.parametrize("name", golden_names("meda"))
+def test_meda_oracle_matches_reference_trace(oracle_lib, name):
+    g = load_golden(name)
+    K, A, W, L = g["K"], g["A"], g["W"], g["L"]
+    env = oracle_lib.OracleMEDA(K, W, L, A, fov=g["fov"], b_degrade=bool(g["b_degrade"]), obs_version=2)
+    env0 = env.with_version(0)
+    env.degrade[...] = g["degrade"]
+    obs_t = list(g["obs_t"])
+    for ep in range(g["n_ep"]):
+        # the reference updates health AFTER computing the reset observation (meda.py:547-548); the golden
+        # health/usage snapshots are taken after reset() returned
+        obs2 = env.reset(g["layouts"][ep])
+        np.testing.assert_array_equal(obs2, g["obs2_reset"][ep], err_msg=f"v0_2 reset obs ep{ep}")
+        np.testing.assert_array_equal(env0.observe(), g["obs0_reset"][ep], err_msg=f"base reset obs ep{ep}")
+        np.testing.assert_array_equal(env.health, g["health_reset"][ep], err_msg=f"health at reset ep{ep}")
+        np.testing.assert_array_equal(env.usage, g["usage_reset"][ep], err_msg=f"usage at reset ep{ep}")
+        for t in range(g["T"]):
+            obs, rew, done, cons, succ = env.step(g["actions"][ep, t], g["draws"][ep, t])
+            msg = f"{name} ep{ep} t{t}"
+            np.testing.assert_array_equal(env.drop[:, :, 0:2], g["pos"][ep, t], err_msg=msg + " pos")
+            np.testing.assert_array_equal(rew, g["reward"][ep, t], err_msg=msg + " reward")
+            np.testing.assert_array_equal(done, g["done"][ep, t], err_msg=msg + " done")
+            np.testing.assert_array_equal(env.status, g["status"][ep, t], err_msg=msg + " status")
+            np.testing.assert_allclose(-0.6 * cons, g["constraints"][ep, t], rtol=1e-12, atol=1e-12, err_msg=msg)
+            np.testing.assert_array_equal(succ, g["success"][ep, t], err_msg=msg + " success")
+            if t in obs_t:
+                np.testing.assert_array_equal(obs, g["obs2"][ep, obs_t.index(t)], err_msg=msg + " obs v0_2")
+                np.testing.assert_array_equal(env0.observe(), g["obs0"][ep, obs_t.index(t)], err_msg=msg + " obs base")
+        np.testing.assert_array_equal(env.usage, g["usage_end"][ep], err_msg=f"usage end ep{ep}")
+    np.testing.assert_array_equal(env.health, g["health_final"])
+
+
+def test_set_order_emulation_matches_this_cpython(oracle_lib):
+    """oracle's emulation of CPython set iteration order (used for MEDAEnv_v0_2 'observed', meda.py:862-872)
+    against real python sets built the same way, for every subset of 10 agents."""
+    for mask in range(1, 1 << 10):
+        s = set()
+        for i in range(10):
+            if (mask >> i) & 1:
+                s.add(i)
+        assert oracle_lib.cpython_set_order(mask, 10) == list(s), bin(mask)
