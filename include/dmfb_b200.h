@@ -176,9 +176,8 @@ typedef struct meda_cfg {
     /* v0_2 direction vector: dir_y[d+width-1] = round(d/(width/30)), dir_x[d+length-1] = round(d/(length/30)) (meda.py:895) */
     int8_t dir_x[2 * DMFB_MAX_DIM];
     int8_t dir_y[2 * DMFB_MAX_DIM];
-    /* v0_2 "others' goals" write order for A > 8: CPython set iteration order of the observed
-     * indices (meda.py:871-878); set_order[mask][k] for masks over MEDA agents is built on demand by
-     * the host layer, see meda_set_order. */
+    /* v0_2 writes the others' goals in CPython set iteration order of the observed indices (meda.py:871-878);
+     * for A > 8 that is not ascending, see meda_set_order / the `set_order` argument of meda_step. */
 } meda_cfg_t;
 
 typedef struct meda_state {
@@ -189,7 +188,7 @@ typedef struct meda_state {
     uint8_t* status;        /* [N,A] sticky arrival flags (meda.py:159,277) */
     int32_t* step_count;    /* [N] */
     int32_t* fails;         /* [N] episode-cumulative punish count; reference `fails` == -0.6*count (meda.py:521) */
-    uint8_t* done;          /* [N,A] dones dict as of the last step (read by addUsage, meda.py:591-598) */
+    uint8_t* done;          /* reserved (NULL) */
     uint8_t* terminated;    /* [N] */
     uint32_t* episode;      /* [N] */
     uint16_t* usage;        /* [N,W,L] */
@@ -223,6 +222,10 @@ int meda_reset(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t* 
                int8_t* obs, void* stream);
 int meda_observe(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t* set_order,
                  int8_t* obs, void* stream);
+/* Host helper: iteration order of the CPython set {i : bit i of mask_bits} built by ascending insertion
+ * (MEDAEnv_v0_2 iterates such a set, meda.py:862-872).  out[0..n_max) = elements in iteration order, 0xFF padded.
+ * The device table `set_order` is [2^A][A] uint8 with row m = meda_set_order(m, A, ...). */
+int meda_set_order(uint32_t mask_bits, int n_max, uint8_t* out);
 
 /* ------------------------------------------------------------- utilities -- */
 

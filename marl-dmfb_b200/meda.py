@@ -1,0 +1,301 @@
+"""Host-side mirror of the reference MEDA env interface (env/MEDA/meda.py) over GPU-resident state.
+
+* ``BatchedMEDA``  — N independent MEDA chips in HBM, stepped by the sm_100a kernels through the C ABI.
+* ``MEDAEnv`` / ``MEDAEnv_v0_2`` — N = 1 adapters with the reference's Python types.  ``MEDAEnv`` returns the
+  base observation (float64, length 4*fov^2+2, meda.py:613-674), ``MEDAEnv_v0_2`` the int8 one (3*fov^2+2,
+  meda.py:850-897).
+
+Deliberate deviation (SURVEY.md note A): ``get_env_info()['obs_shape']`` is the DMFB-style tuple
+``(C, fov, fov, 2, C*fov*fov+2)`` — the reference's base class returns an int there, which crashes every consumer
+(vdn.py:12, replay_buffer.py:10).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def build_set_order_table(n_agents):
+    """[2^A, A] uint8: row m = iteration order of the python set {i: bit i of m} built by ascending insertion
+    (what `for idx in observed` sees, meda.py:862-872), 0xFF padded.  Built with REAL python sets and cross-checked
+    against the library's own CPython-set emulation (meda_set_order)."""
+    lib = nat.load()
+    tab = np.full((1 << n_agents, n_agents), 0xFF, np.uint8)
+    row = (C.c_uint8 * n_agents)()
+    for m in range(1 << n_agents):
+        s = set()
+        for i in range(n_agents):
+            if (m >> i) & 1:
+                s.add(i)
+        order = list(s)
+        tab[m, :len(order)] = order
+        nat.check(lib.meda_set_order(m, n_agents, row), "meda_set_order")
+        if list(row) != list(tab[m]):
+            raise RuntimeError(f"CPython set order differs from the library's emulation for mask {m:#x}: "
+                               f"{order} vs {list(row)}")
+    return tab
+
+
+class BatchedMEDA:
+    """N chips x A droplets (5x5 micro-electrode squares).  reset/step/get_obs/get_avail_actions/get_env_info."""
+
+    n_actions = 9
+
+    def __init__(self, n_envs, width, length, n_agents, fov=19, b_degrade=False, per_degrade=0.1, obs_version=2,
+                 device="cuda", seed=0, env_base=0, reward_f64=False, degrade=None, layouts=None):
+        self.lib = nat.load()
+        self.cfg = nat.MedaCfg()
+        rc = self.lib.meda_cfg_init(C.byref(self.cfg), width, length, n_agents, fov, int(bool(b_degrade)),
+                                    float(per_degrade), int(obs_version))
+        if rc == 2:  # meda.py:151-154
+            raise RuntimeError("Too many droplets in the " + str(width) + "x" + str(length) + " MEDA array")
+        nat.check(rc, "meda_cfg_init")
+        self.cfg.env_base = int(env_base)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedMEDA needs a CUDA device: there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.N, self.W, self.L, self.A, self.fov = int(n_envs), width, length, n_agents, fov
+        self.obs_version = int(obs_version)
+        self.D = self.cfg.obs_dim
+        self.max_step = self.cfg.max_step
+        self.b_degrade = bool(b_degrade)
+        self.seed = int(seed)
+        self.agents = ["player_{}".format(i) for i in range(n_agents)]
+        N, A, dev = self.N, self.A, self.device
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+        self.drop = z(N, A, 4, dtype=torch.uint8)          # x_center, y_center, goal x_center, goal y_center
+        self.start = z(N, A, 2, dtype=torch.uint8)
+        self.status = z(N, A, dtype=torch.uint8)
+        self.step_count = z(N, dtype=torch.int32)
+        self.fails = z(N, dtype=torch.int32)               # punish count; the reference's `fails` is -0.6 * this
+        self.terminated = z(N, dtype=torch.uint8)
+        self.episode = z(N, dtype=torch.int32)
+        self.usage = z(N, width, length, dtype=torch.int16)
+        self.health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
+        self.degrade = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
+        self.state = nat.MedaState(
+            n_envs=N, drop=self.drop.data_ptr(), start=self.start.data_ptr(), status=self.status.data_ptr(),
+            step_count=self.step_count.data_ptr(), fails=self.fails.data_ptr(), done=None,
+            terminated=self.terminated.data_ptr(), episode=self.episode.data_ptr(), usage=self.usage.data_ptr(),
+            health=self.health.data_ptr() if self.b_degrade else None,
+            degrade=self.degrade.data_ptr() if self.b_degrade else None)
+        self.set_order = None
+        if self.obs_version == nat.MEDA_OBS_V02 and A > 8:
+            self.set_order = torch.as_tensor(build_set_order_table(A)).to(dev)
+        self.obs = z(N, A, self.D, dtype=torch.int8)
+        self.reward = z(N, A, dtype=torch.float32)
+        self.reward_f64 = z(N, A, dtype=torch.float64) if reward_f64 else None
+        self.team_reward = z(N, dtype=torch.float32)
+        self.done = z(N, A, dtype=torch.uint8)
+        self.avail = torch.ones(N, A, self.n_actions, dtype=torch.uint8, device=dev)
+        self.constraints = z(N, dtype=torch.int32)
+        self.success = z(N, dtype=torch.uint8)
+        self.term_out = z(N, dtype=torch.uint8)
+        self.padded = z(N, dtype=torch.uint8)
+        self._out = self._make_out(self.obs)
+        self.reset(new_chip=True, layouts=layouts, degrade=degrade)
+
+    def _make_out(self, obs):
+        return nat.MedaOut(
+            obs=obs.data_ptr(), reward=self.reward.data_ptr(),
+            reward_f64=self.reward_f64.data_ptr() if self.reward_f64 is not None else None,
+            team_reward=self.team_reward.data_ptr(), done=self.done.data_ptr(), avail=self.avail.data_ptr(),
+            constraints=self.constraints.data_ptr(), success=self.success.data_ptr(),
+            terminated=self.term_out.data_ptr(), padded=self.padded.data_ptr(), status=None)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _as(self, t, dtype, shape, name):
+        if t is None:
+            return None
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(np.ascontiguousarray(t))
+        t = t.to(device=self.device, dtype=dtype).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def reset(self, mask=None, layouts=None, new_chip=False, degrade=None, out=None):
+        """MEDAEnv.reset (meda.py:541-550): new tasks, observation, then updateHealth.
+        layouts: optional [N,A,4] (x_c, y_c, goal x_c, goal y_c) with centres in [2, dim-3]."""
+        mask_t = self._as(mask, torch.uint8, (self.N,), "mask")
+        lay_t = self._as(layouts, torch.uint8, (self.N, self.A, 4), "layouts")
+        deg_t = self._as(degrade, torch.float64, (self.N, self.W, self.L), "degrade")
+        obs = self.obs if out is None else out
+        with torch.cuda.device(self.device):
+            rc = self.lib.meda_reset(C.byref(self.cfg), C.byref(self.state), _ptr(mask_t), int(bool(new_chip)),
+                                     _ptr(lay_t), _ptr(deg_t), self.seed, _ptr(self.set_order), _ptr(obs),
+                                     self._stream())
+        nat.check(rc, "meda_reset")
+        return obs
+
+    def step(self, actions, draws=None, freeze_terminated=False, auto_reset=False, out=None):
+        """MEDAEnv.step (meda.py:513-539) on every env; actions [N,A] in 0..8."""
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.ascontiguousarray(actions))
+        if actions.device != self.device:
+            actions = actions.to(self.device)
+        if actions.dtype not in (torch.int8, torch.uint8, torch.int32, torch.int64):
+            actions = actions.to(torch.int64)
+        actions = actions.contiguous()
+        if tuple(actions.shape) != (self.N, self.A):
+            raise RuntimeError("The number of actions is not the same as n_droplets")  # meda.py:242-244
+        draws_t = self._as(draws, torch.float64, (self.N, self.A), "draws")
+        flags = (nat.STEP_FREEZE_TERM if freeze_terminated else 0) | (nat.STEP_AUTO_RESET if auto_reset else 0)
+        obs, o = (self.obs, self._out) if out is None else (out, self._make_out(out))
+        with torch.cuda.device(self.device):
+            rc = self.lib.meda_step(C.byref(self.cfg), C.byref(self.state), _ptr(actions), actions.element_size(),
+                                    _ptr(draws_t), self.seed, flags, _ptr(self.set_order), C.byref(o), self._stream())
+        nat.check(rc, "meda_step")
+        info = {"constraints": self.constraints, "success": self.success, "terminated": self.term_out.view(torch.bool),
+                "team_reward": self.team_reward, "padded": self.padded.view(torch.bool)}
+        return obs, self.reward, self.done.view(torch.bool), info
+
+    def get_obs(self, out=None):
+        obs = self.obs if out is None else out
+        with torch.cuda.device(self.device):
+            rc = self.lib.meda_observe(C.byref(self.cfg), C.byref(self.state), _ptr(self.set_order), _ptr(obs),
+                                       self._stream())
+        nat.check(rc, "meda_observe")
+        return obs
+
+    def get_avail_actions(self):
+        return self.avail
+
+    def get_env_info(self):
+        c = 3 if self.obs_version == nat.MEDA_OBS_V02 else 4
+        return {"n_actions": self.n_actions, "n_agents": self.A, "obs_shape": (c, self.fov, self.fov, 2, self.D),
+                "episode_limit": self.max_step}
+
+    def usage_counts(self):
+        return self.usage.to(torch.int32) & 0xFFFF
+
+
+class _MedaRoutingView:
+    def __init__(self, env):
+        self._e = env
+
+    @property
+    def status(self):
+        return [bool(x) for x in self._e._b.status[0].cpu().numpy()]
+
+    @property
+    def centers(self):
+        return self._e._b.drop[0, :, 0:2].cpu().numpy().astype(int)
+
+    @property
+    def goal_centers(self):
+        return self._e._b.drop[0, :, 2:4].cpu().numpy().astype(int)
+
+
+class MEDAEnv:
+    """Drop-in for env.MEDA.meda.MEDAEnv (meda.py:457-681) on top of a 1-env GPU batch."""
+
+    metadata = {"render.modes": ["human", "rgb_array"]}
+    _obs_version = nat.MEDA_OBS_BASE
+
+    def __init__(self, w, l, n_agents, n_blocks=0, fov=19, stall=True, b_degrade=False, per_degrade=0.1, show=False,
+                 savemp4=False, device="cuda", seed=None, layouts=None, degrade=None):
+        assert w > 0 and l > 0
+        assert n_agents > 0
+        if seed is None:
+            seed = int(np.random.randint(0, 2**31 - 1))
+        self._b = BatchedMEDA(1, w, l, n_agents, fov=fov, b_degrade=b_degrade, per_degrade=per_degrade,
+                              obs_version=self._obs_version, device=device, seed=seed, reward_f64=True,
+                              layouts=None if layouts is None else np.asarray(layouts)[None],
+                              degrade=None if degrade is None else np.asarray(degrade)[None])
+        self.agents = list(self._b.agents)
+        self.possible_agents = self.agents[:]
+        self.width, self.length, self.fov = w, l, fov
+        self.b_degrade = b_degrade
+        self.max_step = self._b.max_step
+        self.mode = None
+        self.rewards = {a: 0.0 for a in self.agents}
+        self.dones = {a: False for a in self.agents}
+        self.routing_manager = _MedaRoutingView(self)
+
+    # reference attributes
+    @property
+    def step_count(self):
+        return int(self._b.step_count[0].item())
+
+    @property
+    def fails(self):
+        return -0.6 * int(self._b.fails[0].item())
+
+    @property
+    def m_health(self):
+        b = self._b
+        return np.ones((b.W, b.L)) if b.health is None else b.health[0].cpu().numpy()
+
+    @property
+    def m_usage(self):
+        return self._b.usage_counts()[0].cpu().numpy().astype(np.float64)
+
+    @property
+    def m_degrade(self):
+        b = self._b
+        return np.ones((b.W, b.L)) if b.degrade is None else b.degrade[0].cpu().numpy()
+
+    def _obs_list(self, obs):
+        o = obs[0].cpu().numpy()
+        if self._obs_version == nat.MEDA_OBS_BASE:
+            o = o.astype(np.float64)   # the base class returns float64 (meda.py:621,673)
+        return [o[i].copy() for i in range(len(self.agents))]
+
+    def step(self, actions):
+        if isinstance(actions, dict):
+            acts = [actions[a] for a in self.agents]
+        elif isinstance(actions, list):
+            acts = actions
+        else:
+            raise UnboundLocalError("acts")                      # meda.py:516-520 leaves `acts` unbound
+        if len(acts) != len(self.agents):
+            raise RuntimeError("The number of actions is not the same as n_droplets")
+        a = torch.as_tensor(np.asarray([int(x) for x in acts], dtype=np.int64)[None])
+        obs, _, done, info = self._b.step(a)
+        r = self._b.reward_f64[0].cpu().numpy()
+        d = done[0].cpu().numpy()
+        for k, name in enumerate(self.agents):
+            self.rewards[name] = float(r[k])
+            self.dones[name] = bool(d[k])
+        cnt = int(info["constraints"][0].item())
+        out_info = {"constraints": -0.6 * cnt if cnt else 0, "success": int(info["success"][0].item())}
+        return self._obs_list(obs), self.rewards, self.dones, out_info
+
+    def reset(self, layouts=None):
+        self.rewards = {a: 0.0 for a in self.agents}
+        self.dones = {a: False for a in self.agents}
+        return self._obs_list(self._b.reset(layouts=None if layouts is None else np.asarray(layouts)[None]))
+
+    def getObs(self):
+        return self._obs_list(self._b.get_obs())
+
+    def getOneObs(self, agent_index):
+        return self.getObs()[agent_index]
+
+    def render(self, close=False):
+        return None
+
+    def seed(self, seed=None):
+        pass
+
+    def close(self):
+        pass
+
+    def get_env_info(self):
+        return self._b.get_env_info()
+
+
+class MEDAEnv_v0_2(MEDAEnv):
+    """env.MEDA.meda.MEDAEnv_v0_2 (meda.py:846-897): int8 observation of length 3*fov^2+2."""
+    _obs_version = nat.MEDA_OBS_V02

@@ -1,0 +1,155 @@
+"""GPU parity for the MEDA hot path: CUDA kernels (through the C ABI) vs golden traces recorded from the
+unmodified reference env and vs the CPU oracle on seeded random inputs.  Bit-exact for positions, status,
+dones, observations (both MEDAEnv and MEDAEnv_v0_2 variants), usage, health and the float64 rewards."""
+import importlib
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def pkg():
+    return importlib.import_module("marl-dmfb_b200")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", golden_names("meda"))
+def test_meda_cuda_matches_reference_trace(name):
+    g = load_golden(name)
+    K, A, W, L = g["K"], g["A"], g["W"], g["L"]
+    env = pkg().BatchedMEDA(K, W, L, A, fov=g["fov"], b_degrade=bool(g["b_degrade"]), per_degrade=g["per_degrade"],
+                            obs_version=2, device="cuda:0", reward_f64=True,
+                            degrade=g["degrade"] if g["b_degrade"] else None, layouts=g["layouts"][0])
+    base = pkg().BatchedMEDA(K, W, L, A, fov=g["fov"], obs_version=0, device="cuda:0", layouts=g["layouts"][0])
+    obs_t = list(g["obs_t"])
+    for ep in range(g["n_ep"]):
+        obs = env.reset(layouts=g["layouts"][ep])
+        np.testing.assert_array_equal(_np(obs), g["obs2_reset"][ep], err_msg=f"{name} v0_2 reset obs ep{ep}")
+        base.drop.copy_(env.drop)
+        np.testing.assert_array_equal(_np(base.get_obs()), g["obs0_reset"][ep], err_msg=f"{name} base reset obs ep{ep}")
+        if g["b_degrade"]:
+            np.testing.assert_array_equal(_np(env.health), g["health_reset"][ep], err_msg=f"health ep{ep}")
+        np.testing.assert_array_equal(_np(env.usage_counts()), g["usage_reset"][ep], err_msg=f"usage ep{ep}")
+        for t in range(g["T"]):
+            acts = torch.as_tensor(g["actions"][ep, t], device="cuda:0")
+            obs, rew, done, info = env.step(acts, draws=g["draws"][ep, t])
+            msg = f"{name} ep{ep} t{t}"
+            np.testing.assert_array_equal(_np(env.drop[:, :, 0:2]), g["pos"][ep, t], err_msg=msg + " pos")
+            np.testing.assert_array_equal(_np(env.reward_f64), g["reward"][ep, t], err_msg=msg + " reward f64")
+            np.testing.assert_allclose(_np(rew), g["reward"][ep, t], rtol=1e-6, atol=0, err_msg=msg + " reward f32")
+            np.testing.assert_array_equal(_np(done).astype(np.uint8), g["done"][ep, t], err_msg=msg + " done")
+            np.testing.assert_array_equal(_np(env.status), g["status"][ep, t], err_msg=msg + " status")
+            np.testing.assert_allclose(-0.6 * _np(info["constraints"]), g["constraints"][ep, t], rtol=1e-12, atol=1e-12)
+            np.testing.assert_array_equal(_np(info["success"]), g["success"][ep, t], err_msg=msg + " success")
+            if t in obs_t:
+                np.testing.assert_array_equal(_np(obs), g["obs2"][ep, obs_t.index(t)], err_msg=msg + " obs v0_2")
+                base.drop.copy_(env.drop)
+                np.testing.assert_array_equal(_np(base.get_obs()), g["obs0"][ep, obs_t.index(t)], err_msg=msg + " obs base")
+        np.testing.assert_array_equal(_np(env.usage_counts()), g["usage_end"][ep], err_msg=f"usage end ep{ep}")
+    if g["b_degrade"]:
+        np.testing.assert_array_equal(_np(env.health), g["health_final"])
+
+
+CASES = [
+    # N, W, L, A, fov, degrade, obs_version
+    (300, 30, 60, 4, 19, True, 0),
+    (300, 30, 60, 4, 19, True, 2),
+    (65, 30, 60, 8, 19, False, 2),
+    (33, 80, 80, 10, 19, True, 2),     # A > 8: python-set write order matters
+    (33, 80, 80, 10, 19, False, 0),
+    (70, 45, 30, 3, 9, True, 2),
+    (50, 60, 45, 6, 13, True, 0),
+    (1, 30, 60, 4, 19, False, 2),
+]
+
+
+@pytest.mark.parametrize("N,W,L,A,fov,deg,ver", CASES)
+def test_meda_cuda_matches_oracle_random(oracle_lib, N, W, L, A, fov, deg, ver):
+    rng = np.random.default_rng(N + 13 * A + ver)
+    ref = oracle_lib.OracleMEDA(N, W, L, A, fov=fov, b_degrade=deg, obs_version=ver)
+    degrade = rng.random((N, W, L)) * 0.4 + 0.6 if deg else None
+    layouts = ref.gen_layouts(seed=N)
+    env = pkg().BatchedMEDA(N, W, L, A, fov=fov, b_degrade=deg, per_degrade=1.0, obs_version=ver, device="cuda:0",
+                            reward_f64=True, degrade=degrade, layouts=layouts)
+    if deg:
+        ref.degrade[...] = degrade
+        ref.health[...] = rng.random((N, W, L)) * 0.7 + 0.3
+        env.health.copy_(torch.as_tensor(ref.health))
+        ref.usage[...] = 40.0
+        env.usage.fill_(40)
+    T = min(W + L + 3, 60)
+    for ep in range(3):
+        layouts = ref.gen_layouts(seed=77 * ep + N)
+        mask = (np.arange(N) % 3 != 0).astype(np.uint8) if ep == 1 else None
+        o_ref = ref.reset(layouts, mask=mask)
+        buf = env.obs.clone()
+        o_gpu = env.reset(layouts=layouts, mask=mask)
+        sel = slice(None) if mask is None else mask.astype(bool)
+        np.testing.assert_array_equal(_np(o_gpu)[sel], o_ref[sel], err_msg=f"reset obs ep{ep}")
+        if mask is not None:
+            np.testing.assert_array_equal(_np(o_gpu)[~sel], _np(buf)[~sel])
+        np.testing.assert_array_equal(_np(env.drop), ref.drop)
+        if deg:
+            np.testing.assert_array_equal(_np(env.health), ref.health)
+        for t in range(T):
+            d = ref.drop.astype(np.int32)
+            dx, dy = d[..., 2] - d[..., 0], d[..., 3] - d[..., 1]
+            toward = np.where(np.abs(dx) >= np.abs(dy), np.where(dx > 0, 1, 3), np.where(dy > 0, 2, 0))
+            acts = np.where(rng.random((N, A)) < 0.75, toward, rng.integers(0, 9, (N, A))).astype(np.int8)
+            draws = rng.random((N, A))
+            obs, rew, done, cons, succ = ref.step(acts, draws)
+            g_obs, g_rew, g_done, info = env.step(torch.as_tensor(acts.astype(np.int32), device="cuda:0"), draws=draws)
+            msg = f"ep{ep} t{t}"
+            np.testing.assert_array_equal(_np(env.drop), ref.drop, err_msg=msg + " drop")
+            np.testing.assert_array_equal(_np(env.status), ref.status, err_msg=msg + " status")
+            np.testing.assert_array_equal(_np(g_obs), obs, err_msg=msg + " obs")
+            np.testing.assert_array_equal(_np(env.reward_f64), rew, err_msg=msg + " reward")
+            np.testing.assert_array_equal(_np(g_done).astype(np.uint8), done, err_msg=msg + " done")
+            np.testing.assert_array_equal(_np(info["constraints"]), cons, err_msg=msg + " punish count")
+            np.testing.assert_array_equal(_np(info["success"]), succ, err_msg=msg + " success")
+            np.testing.assert_array_equal(_np(env.fails), ref.fails)
+            np.testing.assert_array_equal(_np(env.step_count), ref.step_count)
+        np.testing.assert_array_equal(_np(env.usage_counts()), ref.usage, err_msg=f"usage ep{ep}")
+        np.testing.assert_array_equal(_np(env.get_obs(out=torch.empty_like(env.obs))), ref.observe())
+
+
+def test_meda_adapter_types_and_generator():
+    P = pkg()
+    env = P.MEDAEnv(30, 60, 4, fov=19)
+    obs = env.reset()
+    assert len(obs) == 4 and all(o.dtype == np.float64 and o.shape == (1446,) for o in obs)
+    o, r, d, info = env.step([1, 2, 3, 8])
+    assert set(r) == {"player_0", "player_1", "player_2", "player_3"} and all(isinstance(v, float) for v in r.values())
+    assert info["success"] in (0, 1) and env.get_env_info()["obs_shape"] == (4, 19, 19, 2, 1446)
+    env2 = P.MEDAEnv_v0_2(30, 60, 4, fov=19)
+    obs = env2.reset()
+    assert all(o.dtype == np.int8 and o.shape == (1085,) for o in obs)
+    assert env2.get_env_info() == {"n_actions": 9, "n_agents": 4, "obs_shape": (3, 19, 19, 2, 1085), "episode_limit": 90}
+    with pytest.raises(RuntimeError, match="Too many droplets"):
+        P.MEDAEnv(30, 60, 9)
+    # device task generator: the reference's rejection rules (meda.py:78-81,179-182)
+    N, A = 20000, 8
+    b = P.BatchedMEDA(N, 30, 60, A, device="cuda:0", seed=5)
+    b.reset()
+    d = b.drop.to(torch.int32)
+    assert int(d[..., 0].min()) >= 2 and int(d[..., 0].max()) <= 57 and int(d[..., 1].min()) >= 2 and int(d[..., 1].max()) <= 27
+    for lo in (0, 2):
+        p = d[:, :, lo:lo + 2]
+        diff = p[:, :, None, :] - p[:, None, :, :]
+        d2 = (diff * diff).sum(-1) + torch.eye(A, device="cuda:0", dtype=torch.int32)[None] * 10000
+        assert int(d2.min()) >= 81
+    own = (d[..., 0] - d[..., 2]).abs().le(4) & (d[..., 1] - d[..., 3]).abs().le(4)
+    assert not bool(own.any())
+    # auto-reset keeps stepping and resets finished envs
+    gen = torch.Generator(device="cuda:0").manual_seed(1)
+    for t in range(95):
+        acts = torch.randint(0, 9, (N, A), device="cuda:0", generator=gen, dtype=torch.int8)
+        obs, rew, done, info = b.step(acts, auto_reset=True)
+    assert int(b.step_count.max()) < 90 and int(b.terminated.sum()) == 0
