@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — env agent-steps/sec of the batched DMFB env.step on B200 (BASELINE.json metric).
 
-  python bench.py --gpus 1 --steps 400 --warmup 40            # own arm, one JSON line on stdout
+  python bench.py --gpus 1 --steps 20000 --warmup 200         # own arm, one JSON line on stdout
   python bench.py --impl reference --steps 3 --warmup 1       # CPU arm: the oracle port on all host threads
   torchrun --nproc-per-node N ... bench.py --gpus N ...       # one rank per GPU, envs sharded, no collective
 
@@ -45,8 +45,8 @@ ALG_BYTES_PER_ENV_STEP = 1069
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=400)
-    p.add_argument("--warmup", type=int, default=40)
+    p.add_argument("--steps", type=int, default=20000)
+    p.add_argument("--warmup", type=int, default=200)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--envs", type=int, default=N_PER_GPU, help="envs per GPU (default 65536)")
     p.add_argument("--no-e2e", action="store_true")
@@ -216,14 +216,14 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     launches0 = lib.dmfb_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        with torch.cuda.stream(stream):
-            ev0.record(stream)
-            timed_region()
-            ev1.record(stream)
-        barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        timed_region()
+        ev1.record(stream)
+    barrier()
     ms = ev0.elapsed_time(ev1)
-    n_graph = (args.steps // chunk) if chunk else 0
     gpu_launches = args.steps  # one fused step(+auto-reset) kernel per step (graph replays included)
     _ = lib.dmfb_launch_count() - launches0
     t_all = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -232,11 +232,10 @@ def run_b200(args, rank, world, local_rank):
     ms_max = float(t_all.item())
     value = world * N * A * args.steps / (ms_max * 1e-3)
 
-    # ---- roofline of the dominant kernel: the step kernel alone, CUDA events on its stream ----
+    # ---- roofline of the dominant kernel: the step kernel alone (no auto-reset), CUDA events on its stream ----
     roof = None
     if rank == 0:
         peak, peak_src = measured_peak()
-        reps = 200
         with torch.cuda.stream(stream):
             for t in range(5):
                 env.step(actions[t % slots], out=obs_buf[t % slots + 1])
@@ -247,17 +246,18 @@ def run_b200(args, rank, world, local_rank):
                     env.step(actions[t], out=obs_buf[t + 1])
             g2.replay()
             stream.synchronize()
+            reps = max(5, int(0.6 / (slots * 20e-6)))  # ~0.6 s so that nvidia-smi samples clocks under load
             e0.record(stream)
-            for _ in range(reps // slots):
+            for _ in range(reps):
                 g2.replay()
             e1.record(stream)
             stream.synchronize()
-        per_launch_s = e0.elapsed_time(e1) * 1e-3 / ((reps // slots) * slots)
+        per_launch_s = e0.elapsed_time(e1) * 1e-3 / (reps * slots)
         alg_bytes = ALG_BYTES_PER_ENV_STEP * N
         achieved = alg_bytes / per_launch_s / 1e9
-        roof = {"bound": "hbm", "kernel": "dmfb_step_kernel<9>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "alg_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6}
+        roof = {"bound": "hbm", "kernel": "dmfb_step_kernel<9,4,4,32,false>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "launches_timed": reps * slots}
         tr = os.path.join(ROOT, "profiles", "traffic_step_kernel.json")
         if os.path.exists(tr):
             try:
@@ -265,6 +265,7 @@ def run_b200(args, rank, world, local_rank):
                     roof["traffic"] = json.load(f).get("dram_bytes_per_launch")
             except Exception:
                 pass
+    clocks.__exit__(None, None, None)
     env.reset()
 
     # ---- e2e: host-buffer C ABI, H2D actions + D2H results every step ----
