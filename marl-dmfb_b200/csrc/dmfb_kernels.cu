@@ -145,40 +145,60 @@ struct Group {
 };
 
 // _Generate_Start_End (dmfb.py:207-226): 2A uniform cells, the whole set is redrawn until every pairwise
-// squared distance is > 2.  Lane i draws (start_i, goal_i) from a counter-based generator keyed by
-// (seed, env, episode, attempt, i); the group rejects the attempt if any two of its 2A points are within
-// one cell of each other — the same accept/reject rule on the same proposal distribution, so the accepted
-// tasks are distributed exactly like the reference's.  Every lane of the warp must call; `want` is uniform
-// per group.
+// squared distance is > 2.  Attempt number k for (seed, env, episode) is a pure function of those four values:
+// lane i draws (start_i, goal_i) of the attempt from a counter-based generator and the group rejects the
+// attempt if any two of its 2A points are within one cell of each other; the task is the first accepted
+// attempt — the same accept/reject rule on the same proposal distribution as the reference, so tasks are
+// distributed exactly like the reference's.
+// The WHOLE WARP works on one requesting env at a time: its 32/G lane groups evaluate 32/G consecutive
+// attempts in parallel, the lowest accepted attempt wins and is handed to the requesting group.  (One group
+// looping alone would leave the other lanes of the warp idle for ~1/p_accept rounds.)
+// Every lane of the warp must call; `want` and `episode` are uniform per group; env0 = global env index of
+// the warp's group 0.
 template <int G>
 __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const Group<G>& g, int A, uint64_t seed,
-                                                    int64_t env, uint32_t episode, bool lane_on, bool want,
-                                                    uint32_t keep)
+                                                    int64_t env0, uint32_t episode, bool want, uint32_t keep)
 {
+    constexpr int NG = 32 / G;
     uint32_t word = keep;
-    bool pending = want;
-    // per-lane stream: one splitmix64 sequence per (seed, env, episode, droplet); 128 bits per attempt
-    uint64_t state = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
-    state += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)episode << 32 | (uint32_t)g.i) * 0xDA942042E4DD58B5ull;
-    state = mix64(state);
+    unsigned todo = __ballot_sync(kFull, want && g.i == 0);      // leader lanes of the requesting groups
+    if (todo == 0u) return word;
+    const int my_group = g.lane / G;
     const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
-    while (__any_sync(kFull, pending)) {
-        int sx = 0, sy = 0, tx = 0, ty = 0;
-        if (pending && lane_on) {
-            const uint64_t z0 = mix64(state += 0x9E3779B97F4A7C15ull);
-            const uint64_t z1 = mix64(state += 0x9E3779B97F4A7C15ull);
-            sx = (int)__umulhi((uint32_t)z0, W); sy = (int)__umulhi((uint32_t)(z0 >> 32), Lc);
-            tx = (int)__umulhi((uint32_t)z1, W); ty = (int)__umulhi((uint32_t)(z1 >> 32), Lc);
+    const bool lane_in = g.i < A;
+    while (todo) {
+        const int src = __ffs(todo) - 1;                          // leader lane of the group served now
+        todo &= todo - 1;
+        const int64_t env = env0 + src / G;
+        const uint32_t epi = __shfl_sync(kFull, episode, src);
+        // per-(env, episode, droplet) stream; attempt k uses counters 2k+1, 2k+2
+        uint64_t base = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
+        base += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)epi << 32 | (uint32_t)g.i) * 0xDA942042E4DD58B5ull;
+        base = mix64(base);
+        for (uint32_t round = 0;; ++round) {
+            const uint64_t k = (uint64_t)round * NG + (uint64_t)my_group;
+            uint32_t w = 0;
+            if (lane_in) {
+                const uint64_t z0 = mix64(base + (2 * k + 1) * 0x9E3779B97F4A7C15ull);
+                const uint64_t z1 = mix64(base + (2 * k + 2) * 0x9E3779B97F4A7C15ull);
+                w = __umulhi((uint32_t)z0, W) | (__umulhi((uint32_t)(z0 >> 32), Lc) << 8) |
+                    (__umulhi((uint32_t)z1, W) << 16) | (__umulhi((uint32_t)(z1 >> 32), Lc) << 24);
+            }
+            uint32_t bad = near_pair(w, w >> 16) & 1u;            // own start vs own goal
+            for (int j = 0; j < A; ++j) {
+                const uint32_t o = g.get(w, j);
+                const uint32_t hit = near_pair(w, dup_lo(o)) | near_pair(w, dup_hi(o));  // my 2 points vs theirs
+                if (j != g.i) bad |= hit;
+            }
+            const unsigned gb = g.ballot(bad != 0u && lane_in);
+            const unsigned okm = __ballot_sync(kFull, gb == 0u && g.i == 0);   // leaders of accepting groups
+            if (okm) {
+                const int win = __ffs(okm) - 1;                   // lowest attempt number of this round
+                const uint32_t wsel = __shfl_sync(kFull, w, win + g.i);
+                if (my_group == src / G) word = wsel;
+                break;
+            }
         }
-        const uint32_t w = (uint32_t)sx | ((uint32_t)sy << 8) | ((uint32_t)tx << 16) | ((uint32_t)ty << 24);
-        uint32_t bad = near_pair(w, w >> 16) & 1u;           // own start vs own goal
-        for (int j = 0; j < A; ++j) {
-            const uint32_t o = g.get(w, j);
-            const uint32_t hit = near_pair(w, dup_lo(o)) | near_pair(w, dup_hi(o));  // my 2 points vs their 2 points
-            if (j != g.i) bad |= hit;
-        }
-        const unsigned gb = g.ballot(bad != 0u && lane_on && pending);
-        if (pending && gb == 0u) { word = w; pending = false; }
     }
     return word;
 }
@@ -433,7 +453,7 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     uint32_t word = (d & 0xFFFF0000u) | cur;
     const bool do_reset = (flags & DMFB_STEP_AUTO_RESET) && term && !frozen && env_on;
     if (flags & DMFB_STEP_AUTO_RESET) {
-        word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n, episode + 1u, lane_on, do_reset, word);
+        word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.lane / G, episode + 1u, do_reset, word);
         if (do_reset) {
             sc_out = 0;
             cum = 0;
@@ -523,7 +543,7 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
         if (layouts) {
             if (lane_on && selected) word = reinterpret_cast<const uint32_t*>(layouts)[ja];
         } else {
-            word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n, episode, lane_on, selected && env_on, word);
+            word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.lane / G, episode, selected && env_on, word);
         }
         if (leader && selected && st.episode) st.episode[n] = episode;
         if (lane_on && selected && st.start) reinterpret_cast<uint16_t*>(st.start)[ja] = (uint16_t)(word & 0xFFFFu);

@@ -64,6 +64,10 @@ print(f"{name} N={N}: step (no reset, graph)       {us:8.2f} us  {alg * N / us /
 env.reset()
 us = graph_time(lambda i: env.step(actions[i % slots], auto_reset=True, out=obs_buf[i % slots + 1]), T)
 print(f"{name} N={N}: step (auto-reset, graph of T) {us:8.2f} us  {N * c['A'] / us / 1e3:8.2f} G agent-steps/s")
+env.reset()
+env.step_count.copy_(torch.arange(N, device="cuda:0", dtype=torch.int32) % T)   # stagger the episode phases
+us = graph_time(lambda i: env.step(actions[i % slots], auto_reset=True, out=obs_buf[i % slots + 1]), T)
+print(f"{name} N={N}: step (auto-reset, staggered)  {us:8.2f} us  {N * c['A'] / us / 1e3:8.2f} G agent-steps/s")
 us = timeit(lambda i: env.reset(out=obs_buf[i % slots]), 20)
 print(f"{name} N={N}: reset all (device generator)  {us:8.2f} us")
 lay = env.drop.clone()
