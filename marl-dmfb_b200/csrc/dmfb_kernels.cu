@@ -309,83 +309,89 @@ __device__ __forceinline__ void update_health_flagged(const dmfb_cfg_t& cfg, con
 }
 
 // ------------------------------------------------------------------------ step --
-// A_T / E_T: compile-time droplet count and tile size for the shipped configs (0 = run-time values).
-// DEG_T = false strips the degradation path (health / usage / draws) when the state has none.
-template <int FOV_T, int G, int A_T, int E_T, bool DEG_T>
-__global__ void __launch_bounds__(E_T ? E_T * G : kMaxThreads)
-dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, const void* __restrict__ actions,
-                 int aes, const double* __restrict__ u, uint64_t seed, uint32_t flags, const dmfb_out_t out, int E_rt)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int E = E_T ? E_T : E_rt;
-    const int A = A_T ? A_T : cfg.n_agents, W = cfg.width, Lc = cfg.length;
-    const TileLayout L(E, A, FOV_T ? FOV_T : cfg.fov, W, Lc);
-    const TileSmem S(smem_raw, L);
-    const int tid = (int)threadIdx.x;
-    const Group<G> g(tid);
-    const int64_t n0 = (int64_t)blockIdx.x * E;
-    const int e_valid = (int)min((int64_t)E, (int64_t)st.n_envs - n0);
-    const int e = tid / G;                          // env of this lane group inside the tile
-    const int64_t n = n0 + e;
-    const bool env_on = e < e_valid;
-    const bool lane_on = env_on && g.i < A;         // this lane holds droplet g.i of env n
-    const bool leader = env_on && g.i == 0;
-    const int agent = e * A + g.i;                  // agent index inside the tile
-    const size_t ja = (size_t)n * A + g.i;          // index into [N,A] tensors
-    const uint32_t all_mask = (A >= 32) ? 0xFFFFFFFFu : ((1u << A) - 1u);
+// Per-lane view of DMFBenv.step: what one lane (droplet g.i of env n) loads, computes and writes.
+struct LaneIn {
+    uint32_t d;         // packed droplet word
+    int a;              // action
+    double draw;        // injected move-success draw (DEG only)
+    int sc_in, cum_in;  // leader lane only: step_count, cumulative constraints
+    uint32_t episode;   // leader lane only
+    int frozen_i;       // leader lane only
+};
 
-    // ---- global inputs: one coalesced round trip, issued before the shared-memory work ------------
-    uint32_t d = 0;
-    int a = 0;
-    double prob = 1.0, draw = 0.0;
-    const bool have_prob = DEG_T && st.health != nullptr;
+struct LaneOut {
+    uint32_t word;      // droplet word after the step (after the reset when the env was auto-reset)
+    double r;           // float64 reward
+    uint32_t done_mask;
+    int sc_out, cum, constraints, success, term;
+    bool frozen, do_reset;
+    double team;
+    uint32_t episode;
+};
+
+// One coalesced round trip for everything a tile needs from global memory.
+template <bool DEG_T>
+__device__ __forceinline__ LaneIn load_lane_inputs(const dmfb_state_t& st, const void* __restrict__ actions, int aes,
+                                                   const double* __restrict__ u, uint32_t flags, int64_t n, size_t ja,
+                                                   bool lane_on, bool leader)
+{
+    LaneIn in;
+    in.d = 0; in.a = 0; in.draw = 0.0; in.sc_in = 0; in.cum_in = 0; in.episode = 0; in.frozen_i = 0;
     if (lane_on) {
-        d = reinterpret_cast<const uint32_t*>(st.drop)[ja];
-        a = load_action(actions, aes, ja);
-        if (have_prob && u) draw = u[ja];
+        in.d = reinterpret_cast<const uint32_t*>(st.drop)[ja];
+        in.a = load_action(actions, aes, ja);
+        if (DEG_T && st.health && u) in.draw = u[ja];
     }
-    int sc_in = 0, cum_in = 0, frozen_i = 0;
-    uint32_t episode = 0;
     if (leader) {
-        sc_in = st.step_count[n];
-        cum_in = st.constraints[n];
-        if (st.episode) episode = st.episode[n];
-        if (flags & DMFB_STEP_FREEZE_TERM) frozen_i = st.terminated[n];
+        in.sc_in = st.step_count[n];
+        in.cum_in = st.constraints[n];
+        if (st.episode) in.episode = st.episode[n];
+        if (flags & DMFB_STEP_FREEZE_TERM) in.frozen_i = st.terminated[n];
     }
+    return in;
+}
+
+// moveDroplets + step bookkeeping (+ fused auto-reset) for the droplet held by this lane.  Registers and
+// warp shuffles only; every lane of the warp must call.
+template <int G, int A_T, bool DEG_T>
+__device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const Group<G>& g, int A,
+                                                 int64_t n, size_t ja, bool env_on, bool lane_on, LaneIn in,
+                                                 const double* __restrict__ u, uint64_t seed, uint32_t flags,
+                                                 int32_t* status_flag)
+{
+    const int W = cfg.width, Lc = cfg.length;
+    const uint32_t all_mask = (A >= 32) ? 0xFFFFFFFFu : ((1u << A) - 1u);
+    const uint32_t d = in.d;
+    const int a = in.a;
+    double prob = 1.0, draw = in.draw;
+    const bool have_prob = DEG_T && st.health != nullptr;
     if (have_prob && lane_on)  // getMoveProb (:361-363): the cell occupied at the start of the step
         prob = st.health[((size_t)n * W + (d & 255u)) * Lc + ((d >> 8) & 255u)];
-
-    load_tables(cfg, L, S, tid, (int)blockDim.x);
-    if constexpr (FOV_T != 0 && A_T != 0 && E_T != 0)
-        zero_tile_static<((E_T * A_T * (3 * FOV_T * FOV_T + 2) + 15) / 16) * 16, E_T * G>(S.tile, tid);
-    else
-        zero_tile(L, S, tid, (int)blockDim.x);
-
-    sc_in = g.get(sc_in, 0);
-    cum_in = g.get(cum_in, 0);
-    episode = g.get(episode, 0);
-    const bool frozen = g.get(frozen_i, 0) != 0;    // lock-step padding (rollout.py:131-141)
-    const int sc = sc_in + 1;                       // dmfb.py:561
+    const int sc_in = g.get(in.sc_in, 0);
+    const int cum_in = g.get(in.cum_in, 0);
+    const uint32_t episode = g.get(in.episode, 0);
+    const bool frozen = g.get(in.frozen_i, 0) != 0;  // lock-step padding (rollout.py:131-141)
+    const int sc = sc_in + 1;                         // dmfb.py:561
 
     // ---- moveOneDroplet for all droplets (:325-359) ------------------------------------------------
     const uint32_t goal = d >> 16;
-    const uint32_t start_cell = d & 0xFFFFu;        // "past" position
+    const uint32_t start_cell = d & 0xFFFFu;          // "past" position
     const int x = d & 255u, y = (d >> 8) & 255u, gx = goal & 255u, gy = goal >> 8;
-    const int od = abs(x - gx) + abs(y - gy);       // Droplet.distance (:93-95)
-    const bool pre_done = (od == 0);                // getTaskStatus before the moves (:278)
-    const bool stalled = cfg.stall && pre_done;     // reward 0, no move, no draw (:331-332)
+    const int od = abs(x - gx) + abs(y - gy);         // Droplet.distance (:93-95)
+    const bool pre_done = (od == 0);                  // getTaskStatus before the moves (:278)
+    const bool stalled = cfg.stall && pre_done;       // reward 0, no move, no draw (:331-332)
     if (have_prob && !u && lane_on && !stalled) {
         const uint4 r = env_random(seed, kStreamMove, cfg.env_base + n, episode, (uint32_t)sc, (uint32_t)g.i);
         draw = u53(r.x, r.y);
     }
     const bool tries = lane_on && !stalled && !frozen && (draw <= prob);   // random.random() <= prob (:335)
     uint32_t cand = start_cell;
-    if (tries) {                                    // Droplet.move (:103-124)
+    if (tries) {                                      // Droplet.move (:103-124)
         int nx = x + (a == 1) - (a == 2), ny = y + (a == 4) - (a == 3);
         nx = min(max(nx, 0), W - 1);
         ny = min(max(ny, 0), Lc - 1);
         cand = (uint32_t)nx | ((uint32_t)ny << 8);
-        if ((unsigned)a > 4u && out.status) atomicOr(out.status, 1);       // TypeError('action is illegal') (:115-116)
+        if ((unsigned)a > 4u && status_flag) atomicOr(status_flag, 1);     // TypeError('action is illegal') (:115-116)
     }
     // Sequential resolution (:279-283): droplet i moves only if its candidate cell is not occupied by any
     // other droplet at that moment (j < i already moved, j > i still at their old cell) (:341-343).
@@ -398,7 +404,7 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     }
     const int nx = cur & 255u, ny = cur >> 8;
     const int nd = abs(nx - gx) + abs(ny - gy);
-    double r;                                       // base reward (:345-354)
+    double r;                                         // base reward (:345-354)
     if (stalled) r = 0.0;
     else if (nd == od && od == 0) r = -0.1;
     else if (nd == od && a == 0) r = -0.25;
@@ -406,7 +412,7 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     else r = -0.4;
 
     // ---- comflic_static / comflic_dynamic (:254-271): final vs final, saved vs final ---------------
-    const uint32_t both = cur | (start_cell << 16); // my (current, past) cells
+    const uint32_t both = cur | (start_cell << 16);   // my (current, past) cells
     int sta = 0, dyn = 0;
 #pragma unroll
     for (int j = 0; j < A; ++j) {
@@ -431,17 +437,22 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
         if (constraints == 0) r = r + 10.0;
     }
     if (frozen || !lane_on) r = 0.0;
-    const double team = g.sum(r) / (double)A;                              // rollout.py:33
 
+    LaneOut o;
+    o.team = g.sum(r) / (double)A;                                         // rollout.py:33
+    o.r = r;
+    o.frozen = frozen;
+    o.episode = episode;
     // ---- DMFBenv.step bookkeeping (:572-586) --------------------------------------------------------
-    int cum = cum_in + (frozen ? 0 : constraints);
-    int sc_out = frozen ? sc_in : sc;
-    uint32_t done_mask = post_mask;
-    int success = 0;
-    if (sc < cfg.max_step) success = (all_done && cum == 0) ? 1 : 0;
-    else done_mask = all_mask;
-    if (frozen) { done_mask = all_mask; success = 0; }
-    const int term = (done_mask == all_mask) ? 1 : 0;
+    o.cum = cum_in + (frozen ? 0 : constraints);
+    o.sc_out = frozen ? sc_in : sc;
+    o.constraints = frozen ? 0 : constraints;
+    o.done_mask = post_mask;
+    o.success = 0;
+    if (sc < cfg.max_step) o.success = (all_done && o.cum == 0) ? 1 : 0;
+    else o.done_mask = all_mask;
+    if (frozen) { o.done_mask = all_mask; o.success = 0; }
+    o.term = (o.done_mask == all_mask) ? 1 : 0;
 
     if (DEG_T && lane_on && !frozen && (flags & DMFB_STEP_RECORD_USAGE) && st.usage && !post_done) {  // addUsage (:459-463)
         uint16_t* cell = st.usage + ((size_t)n * W + nx) * Lc + ny;
@@ -450,55 +461,228 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     }
 
     // ---- fused auto-reset: DMFBenv.reset(new=False) (:589-597) for envs that just terminated -------
-    uint32_t word = (d & 0xFFFF0000u) | cur;
-    const bool do_reset = (flags & DMFB_STEP_AUTO_RESET) && term && !frozen && env_on;
+    o.word = (d & 0xFFFF0000u) | cur;
+    o.do_reset = (flags & DMFB_STEP_AUTO_RESET) && o.term && !frozen && env_on;
     if (flags & DMFB_STEP_AUTO_RESET) {
-        word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.lane / G, episode + 1u, do_reset, word);
-        if (do_reset) {
-            sc_out = 0;
-            cum = 0;
-            if (lane_on && st.start) reinterpret_cast<uint16_t*>(st.start)[ja] = (uint16_t)(word & 0xFFFFu);
+        o.word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.lane / G, episode + 1u, o.do_reset, o.word);
+        if (o.do_reset) {
+            o.sc_out = 0;
+            o.cum = 0;
+            if (lane_on && st.start) reinterpret_cast<uint16_t*>(st.start)[ja] = (uint16_t)(o.word & 0xFFFFu);
         }
     }
+    return o;
+}
 
-    // ---- write-back (coalesced: consecutive lanes -> consecutive agents / envs) ---------------------
+// Coalesced write-back of the state and of the small per-step outputs (consecutive lanes -> consecutive
+// agents / envs).
+__device__ __forceinline__ void write_back_lane(const dmfb_state_t& st, const dmfb_out_t& out, const LaneOut& o, int64_t n,
+                                                size_t ja, int i, bool lane_on, bool leader)
+{
     if (lane_on) {
-        if (!frozen) reinterpret_cast<uint32_t*>(st.drop)[ja] = word;
-        if (out.reward) out.reward[ja] = (float)r;
-        if (out.reward_f64) out.reward_f64[ja] = r;
-        if (out.done) out.done[ja] = (uint8_t)((done_mask >> g.i) & 1u);
+        if (!o.frozen) reinterpret_cast<uint32_t*>(st.drop)[ja] = o.word;
+        if (out.reward) out.reward[ja] = (float)o.r;
+        if (out.reward_f64) out.reward_f64[ja] = o.r;
+        if (out.done) out.done[ja] = (uint8_t)((o.done_mask >> i) & 1u);
     }
     if (leader) {
-        st.step_count[n] = sc_out;
-        st.constraints[n] = cum;
-        st.terminated[n] = (uint8_t)(term && !do_reset);
-        if (do_reset && st.episode) st.episode[n] = episode + 1u;
-        if (out.team_reward) out.team_reward[n] = (float)team;
-        if (out.constraints) out.constraints[n] = frozen ? 0 : constraints;
-        if (out.success) out.success[n] = (uint8_t)success;
-        if (out.terminated) out.terminated[n] = (uint8_t)term;
-        if (out.padded) out.padded[n] = (uint8_t)frozen;
-        S.flag[e] = (uint8_t)(do_reset ? kFlagNewTask : 0);
+        st.step_count[n] = o.sc_out;
+        st.constraints[n] = o.cum;
+        st.terminated[n] = (uint8_t)(o.term && !o.do_reset);
+        if (o.do_reset && st.episode) st.episode[n] = o.episode + 1u;
+        if (out.team_reward) out.team_reward[n] = (float)o.team;
+        if (out.constraints) out.constraints[n] = o.constraints;
+        if (out.success) out.success[n] = (uint8_t)o.success;
+        if (out.terminated) out.terminated[n] = (uint8_t)o.term;
+        if (out.padded) out.padded[n] = (uint8_t)o.frozen;
     }
-    const int any_frozen = __syncthreads_or(frozen && env_on);   // also the zero-fill / table barrier
+}
 
-    if (out.avail) {  // all ones; zeros for padded envs (rollout.py:22,138-139)
-        const int per_env = A * cfg.n_actions;
-        uint8_t* gav = out.avail + (size_t)n0 * per_env;
-        const int nbytes = e_valid * per_env;
-        if (!any_frozen && (nbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(gav) & 15) == 0) {
-            const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
-            for (int k = tid; k < (nbytes >> 4); k += (int)blockDim.x) reinterpret_cast<uint4*>(gav)[k] = ones;
-        } else if (lane_on) {
-            for (int k = 0; k < cfg.n_actions; ++k) gav[agent * cfg.n_actions + k] = frozen ? 0 : 1;
-        }
+// avail mask of a tile: all ones; zeros for padded envs (rollout.py:22,138-139)
+__device__ __forceinline__ void write_avail(const dmfb_cfg_t& cfg, const dmfb_out_t& out, int A, int64_t n0, int e_valid,
+                                            int any_frozen, int tid, int nthreads, int agent, bool lane_on, bool frozen)
+{
+    if (!out.avail) return;
+    const int per_env = A * cfg.n_actions;
+    uint8_t* gav = out.avail + (size_t)n0 * per_env;
+    const int nbytes = e_valid * per_env;
+    if (!any_frozen && (nbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(gav) & 15) == 0) {
+        const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+        for (int k = tid; k < (nbytes >> 4); k += nthreads) reinterpret_cast<uint4*>(gav)[k] = ones;
+    } else if (lane_on) {
+        for (int k = 0; k < cfg.n_actions; ++k) gav[agent * cfg.n_actions + k] = frozen ? 0 : 1;
     }
+}
+
+// A_T / E_T: compile-time droplet count and tile size for the shipped configs (0 = run-time values).
+// DEG_T = false strips the degradation path (health / usage / draws) when the state has none.
+template <int FOV_T, int G, int A_T, int E_T, bool DEG_T>
+__global__ void __launch_bounds__(E_T ? E_T * G : kMaxThreads)
+dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, const void* __restrict__ actions,
+                 int aes, const double* __restrict__ u, uint64_t seed, uint32_t flags, const dmfb_out_t out, int E_rt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int E = E_T ? E_T : E_rt;
+    const int A = A_T ? A_T : cfg.n_agents, W = cfg.width, Lc = cfg.length;
+    const TileLayout L(E, A, FOV_T ? FOV_T : cfg.fov, W, Lc);
+    const TileSmem S(smem_raw, L);
+    const int tid = (int)threadIdx.x;
+    const Group<G> g(tid);
+    const int64_t n0 = (int64_t)blockIdx.x * E;
+    const int e_valid = (int)min((int64_t)E, (int64_t)st.n_envs - n0);
+    const int e = tid / G;                          // env of this lane group inside the tile
+    const int64_t n = n0 + e;
+    const bool env_on = e < e_valid;
+    const bool lane_on = env_on && g.i < A;         // this lane holds droplet g.i of env n
+    const bool leader = env_on && g.i == 0;
+    const int agent = e * A + g.i;                  // agent index inside the tile
+    const size_t ja = (size_t)n * A + g.i;          // index into [N,A] tensors
+
+    const LaneIn in = load_lane_inputs<DEG_T>(st, actions, aes, u, flags, n, ja, lane_on, leader);
+    load_tables(cfg, L, S, tid, (int)blockDim.x);
+    if constexpr (FOV_T != 0 && A_T != 0 && E_T != 0)
+        zero_tile_static<((E_T * A_T * (3 * FOV_T * FOV_T + 2) + 15) / 16) * 16, E_T * G>(S.tile, tid);
+    else
+        zero_tile(L, S, tid, (int)blockDim.x);
+
+    const LaneOut o = dmfb_dynamics<G, A_T, DEG_T>(cfg, st, g, A, n, ja, env_on, lane_on, in, u, seed, flags, out.status);
+    write_back_lane(st, out, o, n, ja, g.i, lane_on, leader);
+    if (leader) S.flag[e] = (uint8_t)(o.do_reset ? kFlagNewTask : 0);
+    const int any_frozen = __syncthreads_or(o.frozen && env_on);   // also the zero-fill / table barrier
+
+    write_avail(cfg, out, A, n0, e_valid, any_frozen, tid, (int)blockDim.x, agent, lane_on, o.frozen);
     if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) update_health_flagged(cfg, st, S, n0, e_valid);
 
-    const bool on = lane_on && !frozen;
-    auto get = [&](int j) { return g.get(word, j); };
-    paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, on, get);
+    const uint32_t word = o.word;
+    paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); });
     store_tile(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
+}
+
+// ---------------------------------------------------------------- step, persistent warp tiles --
+// When the observation span of the 32/G envs one warp holds is itself a multiple of 16 bytes (C1: 8 envs x
+// 980 B = 7,840 B) a WARP can own a private shared-memory tile: no CTA-wide barrier is needed, the warp walks
+// over tiles (persistent grid), the global inputs of its next tile are already in flight while it computes,
+// and the TMA engine drains tile k while the warp runs the register-only dynamics of tile k+1.
+template <int FOV_T, int G, int A_T, bool DEG_T, int WPC>
+__global__ void __launch_bounds__(WPC * 32)
+dmfb_step_warp_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, const void* __restrict__ actions,
+                      int aes, const double* __restrict__ u, uint64_t seed, uint32_t flags, const dmfb_out_t out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int EW = 32 / G;                      // envs per warp tile
+    const int A = A_T ? A_T : cfg.n_agents, W = cfg.width, Lc = cfg.length;
+    const int fov = FOV_T ? FOV_T : cfg.fov;
+    const int D = 3 * fov * fov + 2;
+    const uint32_t tile_bytes = (uint32_t)(EW * A * D);          // host guarantees % 16 == 0
+    // CTA smem: WPC warp tiles, then the tables (TileLayout with E = WPC * EW gives exactly that carve-up)
+    const TileLayout L(WPC * EW, A, fov, W, Lc);
+    TileSmem S(smem_raw, L);
+    load_tables(cfg, L, S, (int)threadIdx.x, (int)blockDim.x);
+    __syncthreads();                                // the only CTA-wide barrier: tables are read-only afterwards
+
+    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+    S.tile += (size_t)warp * tile_bytes;            // this warp's private tile
+    const Group<G> g(lane);
+    const int e = lane / G;
+    const int64_t n_tiles = ((int64_t)st.n_envs + EW - 1) / EW;
+    const int64_t stride = (int64_t)gridDim.x * WPC;
+    int64_t t = (int64_t)blockIdx.x * WPC + warp;
+    if (t >= n_tiles) return;
+
+    auto lane_ids = [&](int64_t tile, int64_t& n, size_t& ja, bool& env_on, bool& lane_on, bool& leader) {
+        n = tile * EW + e;
+        env_on = n < (int64_t)st.n_envs;
+        lane_on = env_on && g.i < A;
+        leader = env_on && g.i == 0;
+        ja = (size_t)n * A + g.i;
+    };
+    int64_t n; size_t ja; bool env_on, lane_on, leader;
+    lane_ids(t, n, ja, env_on, lane_on, leader);
+    LaneIn in = load_lane_inputs<DEG_T>(st, actions, aes, u, flags, n, ja, lane_on, leader);
+    bool store_pending = false;
+
+    for (;;) {
+        // inputs of the next tile: in flight during this tile's compute
+        const int64_t t_next = t + stride;
+        const bool has_next = t_next < n_tiles;
+        int64_t n2 = 0; size_t ja2 = 0; bool env_on2 = false, lane_on2 = false, leader2 = false;
+        LaneIn in_next = in;
+        if (has_next) {
+            lane_ids(t_next, n2, ja2, env_on2, lane_on2, leader2);
+            in_next = load_lane_inputs<DEG_T>(st, actions, aes, u, flags, n2, ja2, lane_on2, leader2);
+        }
+        const int64_t n0 = t * EW;
+        const int e_valid = (int)min((int64_t)EW, (int64_t)st.n_envs - n0);
+        const int agent = e * A + g.i;
+
+        const LaneOut o = dmfb_dynamics<G, A_T, DEG_T>(cfg, st, g, A, n, ja, env_on, lane_on, in, u, seed, flags, out.status);
+        write_back_lane(st, out, o, n, ja, g.i, lane_on, leader);
+        const int any_frozen = __any_sync(kFull, o.frozen && env_on);
+        write_avail(cfg, out, A, n0, e_valid, any_frozen, lane, 32, agent, lane_on, o.frozen);
+        if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) {
+            // updateHealth (dmfb.py:465-471) of the envs of this warp that just got a new task
+            unsigned todo = __ballot_sync(kFull, o.do_reset && g.i == 0);
+            const int cells = W * Lc;
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t ne = n0 + src / G;
+                uint16_t* usage = st.usage + (size_t)ne * cells;
+                double* health = st.health ? st.health + (size_t)ne * cells : nullptr;
+                const double* degrade = st.degrade ? st.degrade + (size_t)ne * cells : nullptr;
+                __syncwarp();   // addUsage of this step (other lanes) before the scan
+                for (int k = lane; k < cells; k += 32)
+                    if (usage[k] > 50) {
+                        if (health) health[k] = health[k] * (degrade ? degrade[k] : 1.0);
+                        usage[k] = 0;
+                    }
+            }
+        }
+        // the previous tile must have left shared memory before it is overwritten
+        if (store_pending) {
+            if (lane == 0) tma_store_wait_read_all();
+            __syncwarp();
+        }
+        {
+            uint4* t4 = reinterpret_cast<uint4*>(S.tile) + lane;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            const int n16 = (int)(tile_bytes >> 4);
+            if constexpr (FOV_T != 0 && A_T != 0) {
+                constexpr int N16 = (EW * A_T * (3 * FOV_T * FOV_T + 2)) / 16;
+#pragma unroll
+                for (int k = 0; k < (N16 + 31) / 32; ++k)
+                    if (k * 32 + 32 <= N16 || lane + k * 32 < N16) t4[k * 32] = z;
+            } else {
+                for (int k = lane; k < n16; k += 32) t4[k - lane] = z;
+            }
+        }
+        __syncwarp();
+        const uint32_t word = o.word;
+        paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); });
+        // hand the tile to the TMA engine
+        int8_t* gdst = out.obs + (size_t)n0 * A * D;
+        const uint32_t nbytes = (uint32_t)(e_valid * A * D);
+        const bool aligned = ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
+        if (aligned) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            const uint32_t bulk = nbytes & ~15u;
+            if (lane == 0 && bulk) {
+                tma_store_1d(gdst, S.tile, bulk);
+                tma_store_commit();
+            }
+            for (uint32_t b = bulk + lane; b < nbytes; b += 32) gdst[b] = S.tile[b];
+            store_pending = true;
+        } else {
+            __syncwarp();
+            for (uint32_t b = lane; b < nbytes; b += 32) gdst[b] = S.tile[b];
+            __syncwarp();
+            store_pending = false;
+        }
+        if (!has_next) break;
+        t = t_next; n = n2; ja = ja2; env_on = env_on2; lane_on = lane_on2; leader = leader2; in = in_next;
+    }
+    if (store_pending && lane == 0) tma_store_wait_read_all();
 }
 
 // --------------------------------------------------------------------- reset --
@@ -700,8 +884,39 @@ struct StepLaunch {
         dmfb_step_kernel<FOVT, G, AT, ET, DEG><<<grid, E * G, smem, s>>>(*cfg, *st, actions, aes, u, seed, flags, *out, E);
         return DMFB_OK;
     }
+    template <int FOVT, int G, int AT, bool DEG>
+    int go_warp() const {
+        constexpr int WPC = 4, EW = 32 / G;
+        const TileLayout Lw(WPC * EW, cfg->n_agents, cfg->fov, cfg->width, cfg->length);
+        int rc = set_smem(dmfb_step_warp_kernel<FOVT, G, AT, DEG, WPC>, Lw.total);
+        if (rc) return rc;
+        int dev = 0, sms = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmfb_step_warp_kernel<FOVT, G, AT, DEG, WPC>, WPC * 32,
+                                                      Lw.total);
+        if (per_sm < 1) per_sm = 1;
+        const long long n_tiles = ((long long)st->n_envs + EW - 1) / EW;
+        long long blocks = (n_tiles + WPC - 1) / WPC;
+        if (blocks > (long long)sms * per_sm) blocks = (long long)sms * per_sm;   // persistent: one resident wave
+        dmfb_step_warp_kernel<FOVT, G, AT, DEG, WPC><<<(int)blocks, WPC * 32, Lw.total, s>>>(*cfg, *st, actions, aes, u,
+                                                                                             seed, flags, *out);
+        return DMFB_OK;
+    }
     template <int FOVT, int G>
     int operator()() const {
+        // persistent warp-tile kernel when the 32/G envs of one warp span a multiple of 16 bytes
+        if constexpr (G <= 8) {
+            const int warp_span = (32 / G) * cfg->n_agents * cfg->obs_dim;
+            static const bool no_warp = getenv("DMFB_NO_WARP_KERNEL") != nullptr;
+            if (warp_span % 16 == 0 && !no_warp) {
+                const bool deg = st->health != nullptr || st->usage != nullptr;
+                if constexpr (FOVT == 9 && G == 4) {
+                    if (cfg->n_agents == 4) return deg ? go_warp<9, 4, 4, true>() : go_warp<9, 4, 4, false>();
+                }
+                return go_warp<FOVT, G, 0, true>();
+            }
+        }
         // fully specialised instances for the shipped benchmark configs (BASELINE.json C1, C2, C3)
         const bool deg = st->health != nullptr || st->usage != nullptr;
         if constexpr (FOVT == 9 && G == 4) {
