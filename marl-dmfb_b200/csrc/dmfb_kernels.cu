@@ -32,7 +32,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 // Shared-memory carve-up of one tile, computed identically on host and device.
 struct TileLayout {
     int E, A, D, nw, ncodes;
-    uint32_t tile_bytes, off_l2row, off_l2col, off_flag, off_dirx, off_diry, total;
+    uint32_t tile_bytes, off_l2row, off_l2col, off_flag, off_dirx, off_diry, off_sink, total;
     __host__ __device__ TileLayout(int E_, int A_, int fov, int W, int Lc) {
         E = E_; A = A_; D = 3 * fov * fov + 2; nw = (fov * fov + 31) / 32; ncodes = 2 * (fov / 2) + 1;
         tile_bytes = ((uint32_t)(E * A * D) + 15u) & ~15u;
@@ -42,6 +42,7 @@ struct TileLayout {
         off_flag = o; o += ((uint32_t)E + 3u) & ~3u;
         off_dirx = o; o += ((uint32_t)(2 * W) + 3u) & ~3u;
         off_diry = o; o += ((uint32_t)(2 * Lc) + 3u) & ~3u;
+        off_sink = o; o += 16u;
         total = (o + 15u) & ~15u;
     }
     __host__ __device__ TileLayout(const dmfb_cfg_t& c, int E_) : TileLayout(E_, c.n_agents, c.fov, c.width, c.length) {}
@@ -58,6 +59,7 @@ struct TileSmem {
     uint8_t* flag;    // [E]
     int8_t* dirx;
     int8_t* diry;
+    int8_t* sink;     // predicated-off byte stores go here (keeps the paint code branch-free)
     __device__ TileSmem(unsigned char* base, const TileLayout& L) {
         tile = reinterpret_cast<int8_t*>(base);
         l2row = reinterpret_cast<uint32_t*>(base + L.off_l2row);
@@ -65,6 +67,7 @@ struct TileSmem {
         flag = reinterpret_cast<uint8_t*>(base + L.off_flag);
         dirx = reinterpret_cast<int8_t*>(base + L.off_dirx);
         diry = reinterpret_cast<int8_t*>(base + L.off_diry);
+        sink = reinterpret_cast<int8_t*>(base + L.off_sink);
     }
 };
 
@@ -73,12 +76,15 @@ __device__ __forceinline__ void load_tables(const dmfb_cfg_t& cfg, const TileLay
                                             int nthreads)
 {
     const int nt = L.ncodes * L.nw;
+#pragma unroll 1
     for (int k = tid; k < nt; k += nthreads) {
         const int c = k / L.nw, j = k - c * L.nw;
         S.l2row[k] = cfg.l2_row[c][j];
         S.l2col[k] = cfg.l2_col[c][j];
     }
+#pragma unroll 1
     for (int k = tid; k < 2 * cfg.width; k += nthreads) S.dirx[k] = cfg.dir_x[k];
+#pragma unroll 1
     for (int k = tid; k < 2 * cfg.length; k += nthreads) S.diry[k] = cfg.dir_y[k];
 }
 
@@ -129,7 +135,7 @@ struct Group {
     }
     // value of lane j of my group (all 32 lanes must call)
     template <typename T>
-    __device__ __forceinline__ T get(T v, int j) const { return __shfl_sync(kFull, v, base + j); }
+    __device__ __forceinline__ T get(T v, int j) const { return __shfl_sync(kFull, v, j, G); }
     // bits of my group from a warp ballot
     __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(kFull, p) >> base) & kBits; }
     __device__ __forceinline__ int sum(int v) const {
@@ -137,7 +143,7 @@ struct Group {
         for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
         return v;
     }
-    __device__ __forceinline__ double sum(double v) const {
+    __device__ __forceinline__ float sum(float v) const {
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
         return v;
@@ -259,9 +265,9 @@ __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLay
                 wptr[nfull_min] = ((rem & 0xFu) * 0x00204081u) & 0x01010101u;
                 rem >>= 4; nrem -= 4; bp += 4;
             }
-            if (nrem > 0) bp[0] = (int8_t)(rem & 1u);
-            if (nrem > 1) bp[1] = (int8_t)((rem >> 1) & 1u);
-            if (nrem > 2) bp[2] = (int8_t)((rem >> 2) & 1u);
+            *(nrem > 0 ? bp : S.sink) = (int8_t)(rem & 1u);
+            *(nrem > 1 ? bp + 1 : S.sink) = (int8_t)((rem >> 1) & 1u);
+            *(nrem > 2 ? bp + 2 : S.sink) = (int8_t)((rem >> 2) & 1u);
         }
     }
     // ---- layer 0: droplets inside the window (:408-413); layer 1: clipped goals of the other droplets
@@ -275,19 +281,17 @@ __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLay
         const bool vis = ((ad + vis_bias) & 0x8080u) == 0u;           // 2|dx| < fov && 2|dy| < fov
         const int rx = (int)(d & 255u) - ox, ry = (int)((d >> 8) & 255u) - oy;
         const bool in0 = (fov & 1) ? vis : ((unsigned)rx < (unsigned)fov && (unsigned)ry < (unsigned)fov);
-        if (on && in0) rec[rx * fov + ry] = (int8_t)(j + 1);
-        if (on && vis && j != i) {
-            int cx = (int)((d >> 16) & 255u) - ox, cy = (int)(d >> 24) - oy;
-            cx = min(max(cx, 0), fov - 1);
-            cy = min(max(cy, 0), fov - 1);
-            rec[f2 + cx * fov + cy] = (int8_t)(j + 1);  // ascending j in one thread: later index overwrites
-        }
+        // predicated-off stores are redirected to a sink byte instead of branching around them
+        *((on && in0) ? rec + rx * fov + ry : S.sink) = (int8_t)(j + 1);
+        int cx = (int)((d >> 16) & 255u) - ox, cy = (int)(d >> 24) - oy;
+        cx = min(max(cx, 0), fov - 1);
+        cy = min(max(cy, 0), fov - 1);
+        *((on && vis && j != i) ? rec + f2 + cx * fov + cy : S.sink) = (int8_t)(j + 1);  // ascending j: later index overwrites
     }
     // ---- direction bytes (:442-454) from the host-built table -------------------------------------------
-    if (on) {
-        rec[3 * f2] = S.dirx[gx - x + W - 1];
-        rec[3 * f2 + 1] = S.diry[gy - y + Lc - 1];
-    }
+    const int dxi = on ? gx - x + W - 1 : 0, dyi = on ? gy - y + Lc - 1 : 0;
+    *(on ? rec + 3 * f2 : S.sink) = S.dirx[dxi];
+    *(on ? rec + 3 * f2 + 1 : S.sink) = S.diry[dyi];
 }
 
 // updateHealth (dmfb.py:465-471) for the envs of the tile flagged kFlagNewTask; whole CTA cooperates.
@@ -325,7 +329,7 @@ struct LaneOut {
     uint32_t done_mask;
     int sc_out, cum, constraints, success, term;
     bool frozen, do_reset;
-    double team;
+    float team;
     uint32_t episode;
 };
 
@@ -419,10 +423,9 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
         const uint32_t bj = g.get(both, j);                 // (current_j, past_j)
         const uint32_t h1 = near_pair(both, dup_lo(bj));    // bit0: cur_me~cur_j, bit1: past_me~cur_j
         const uint32_t h2 = near_pair(both, dup_hi(bj));    // bit0: cur_me~past_j
-        if (j != g.i) {
-            sta += (int)(h1 & 1u);
-            dyn += (int)(h1 >> 1) + (int)(h2 & 1u);
-        }
+        const uint32_t other = (j != g.i) ? 1u : 0u;
+        sta += (int)(h1 & other);
+        dyn += (int)((h1 >> 1) & other) + (int)(h2 & other);
     }
     if (!lane_on) { sta = 0; dyn = 0; }
     const int constraints = g.sum(sta + dyn);                              // (:287)
@@ -439,7 +442,7 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
     if (frozen || !lane_on) r = 0.0;
 
     LaneOut o;
-    o.team = g.sum(r) / (double)A;                                         // rollout.py:33
+    o.team = g.sum((float)r) / (float)A;                                   // rollout.py:33 (f32 output, 1e-6 contract)
     o.r = r;
     o.frozen = frozen;
     o.episode = episode;
@@ -490,7 +493,7 @@ __device__ __forceinline__ void write_back_lane(const dmfb_state_t& st, const dm
         st.constraints[n] = o.cum;
         st.terminated[n] = (uint8_t)(o.term && !o.do_reset);
         if (o.do_reset && st.episode) st.episode[n] = o.episode + 1u;
-        if (out.team_reward) out.team_reward[n] = (float)o.team;
+        if (out.team_reward) out.team_reward[n] = o.team;
         if (out.constraints) out.constraints[n] = o.constraints;
         if (out.success) out.success[n] = (uint8_t)o.success;
         if (out.terminated) out.terminated[n] = (uint8_t)o.term;
@@ -508,8 +511,10 @@ __device__ __forceinline__ void write_avail(const dmfb_cfg_t& cfg, const dmfb_ou
     const int nbytes = e_valid * per_env;
     if (!any_frozen && (nbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(gav) & 15) == 0) {
         const uint4 ones = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+#pragma unroll 1
         for (int k = tid; k < (nbytes >> 4); k += nthreads) reinterpret_cast<uint4*>(gav)[k] = ones;
     } else if (lane_on) {
+#pragma unroll 1
         for (int k = 0; k < cfg.n_actions; ++k) gav[agent * cfg.n_actions + k] = frozen ? 0 : 1;
     }
 }
