@@ -563,133 +563,6 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     store_tile(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
 }
 
-// ---------------------------------------------------------------- step, persistent warp tiles --
-// When the observation span of the 32/G envs one warp holds is itself a multiple of 16 bytes (C1: 8 envs x
-// 980 B = 7,840 B) a WARP can own a private shared-memory tile: no CTA-wide barrier is needed, the warp walks
-// over tiles (persistent grid), the global inputs of its next tile are already in flight while it computes,
-// and the TMA engine drains tile k while the warp runs the register-only dynamics of tile k+1.
-template <int FOV_T, int G, int A_T, bool DEG_T, int WPC>
-__global__ void __launch_bounds__(WPC * 32)
-dmfb_step_warp_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, const void* __restrict__ actions,
-                      int aes, const double* __restrict__ u, uint64_t seed, uint32_t flags, const dmfb_out_t out)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int EW = 32 / G;                      // envs per warp tile
-    const int A = A_T ? A_T : cfg.n_agents, W = cfg.width, Lc = cfg.length;
-    const int fov = FOV_T ? FOV_T : cfg.fov;
-    const int D = 3 * fov * fov + 2;
-    const uint32_t tile_bytes = (uint32_t)(EW * A * D);          // host guarantees % 16 == 0
-    // CTA smem: WPC warp tiles, then the tables (TileLayout with E = WPC * EW gives exactly that carve-up)
-    const TileLayout L(WPC * EW, A, fov, W, Lc);
-    TileSmem S(smem_raw, L);
-    load_tables(cfg, L, S, (int)threadIdx.x, (int)blockDim.x);
-    __syncthreads();                                // the only CTA-wide barrier: tables are read-only afterwards
-
-    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
-    S.tile += (size_t)warp * tile_bytes;            // this warp's private tile
-    const Group<G> g(lane);
-    const int e = lane / G;
-    const int64_t n_tiles = ((int64_t)st.n_envs + EW - 1) / EW;
-    const int64_t stride = (int64_t)gridDim.x * WPC;
-    int64_t t = (int64_t)blockIdx.x * WPC + warp;
-    if (t >= n_tiles) return;
-
-    auto lane_ids = [&](int64_t tile, int64_t& n, size_t& ja, bool& env_on, bool& lane_on, bool& leader) {
-        n = tile * EW + e;
-        env_on = n < (int64_t)st.n_envs;
-        lane_on = env_on && g.i < A;
-        leader = env_on && g.i == 0;
-        ja = (size_t)n * A + g.i;
-    };
-    int64_t n; size_t ja; bool env_on, lane_on, leader;
-    lane_ids(t, n, ja, env_on, lane_on, leader);
-    LaneIn in = load_lane_inputs<DEG_T>(st, actions, aes, u, flags, n, ja, lane_on, leader);
-    bool store_pending = false;
-
-    for (;;) {
-        // inputs of the next tile: in flight during this tile's compute
-        const int64_t t_next = t + stride;
-        const bool has_next = t_next < n_tiles;
-        int64_t n2 = 0; size_t ja2 = 0; bool env_on2 = false, lane_on2 = false, leader2 = false;
-        LaneIn in_next = in;
-        if (has_next) {
-            lane_ids(t_next, n2, ja2, env_on2, lane_on2, leader2);
-            in_next = load_lane_inputs<DEG_T>(st, actions, aes, u, flags, n2, ja2, lane_on2, leader2);
-        }
-        const int64_t n0 = t * EW;
-        const int e_valid = (int)min((int64_t)EW, (int64_t)st.n_envs - n0);
-        const int agent = e * A + g.i;
-
-        const LaneOut o = dmfb_dynamics<G, A_T, DEG_T>(cfg, st, g, A, n, ja, env_on, lane_on, in, u, seed, flags, out.status);
-        write_back_lane(st, out, o, n, ja, g.i, lane_on, leader);
-        const int any_frozen = __any_sync(kFull, o.frozen && env_on);
-        write_avail(cfg, out, A, n0, e_valid, any_frozen, lane, 32, agent, lane_on, o.frozen);
-        if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) {
-            // updateHealth (dmfb.py:465-471) of the envs of this warp that just got a new task
-            unsigned todo = __ballot_sync(kFull, o.do_reset && g.i == 0);
-            const int cells = W * Lc;
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int64_t ne = n0 + src / G;
-                uint16_t* usage = st.usage + (size_t)ne * cells;
-                double* health = st.health ? st.health + (size_t)ne * cells : nullptr;
-                const double* degrade = st.degrade ? st.degrade + (size_t)ne * cells : nullptr;
-                __syncwarp();   // addUsage of this step (other lanes) before the scan
-                for (int k = lane; k < cells; k += 32)
-                    if (usage[k] > 50) {
-                        if (health) health[k] = health[k] * (degrade ? degrade[k] : 1.0);
-                        usage[k] = 0;
-                    }
-            }
-        }
-        // the previous tile must have left shared memory before it is overwritten
-        if (store_pending) {
-            if (lane == 0) tma_store_wait_read_all();
-            __syncwarp();
-        }
-        {
-            uint4* t4 = reinterpret_cast<uint4*>(S.tile) + lane;
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            const int n16 = (int)(tile_bytes >> 4);
-            if constexpr (FOV_T != 0 && A_T != 0) {
-                constexpr int N16 = (EW * A_T * (3 * FOV_T * FOV_T + 2)) / 16;
-#pragma unroll
-                for (int k = 0; k < (N16 + 31) / 32; ++k)
-                    if (k * 32 + 32 <= N16 || lane + k * 32 < N16) t4[k * 32] = z;
-            } else {
-                for (int k = lane; k < n16; k += 32) t4[k - lane] = z;
-            }
-        }
-        __syncwarp();
-        const uint32_t word = o.word;
-        paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); });
-        // hand the tile to the TMA engine
-        int8_t* gdst = out.obs + (size_t)n0 * A * D;
-        const uint32_t nbytes = (uint32_t)(e_valid * A * D);
-        const bool aligned = ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
-        if (aligned) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            const uint32_t bulk = nbytes & ~15u;
-            if (lane == 0 && bulk) {
-                tma_store_1d(gdst, S.tile, bulk);
-                tma_store_commit();
-            }
-            for (uint32_t b = bulk + lane; b < nbytes; b += 32) gdst[b] = S.tile[b];
-            store_pending = true;
-        } else {
-            __syncwarp();
-            for (uint32_t b = lane; b < nbytes; b += 32) gdst[b] = S.tile[b];
-            __syncwarp();
-            store_pending = false;
-        }
-        if (!has_next) break;
-        t = t_next; n = n2; ja = ja2; env_on = env_on2; lane_on = lane_on2; leader = leader2; in = in_next;
-    }
-    if (store_pending && lane == 0) tma_store_wait_read_all();
-}
-
 // --------------------------------------------------------------------- reset --
 
 // mode 0: reset (new task), mode 1: restart (back to start cells), mode 2: observe only
@@ -889,39 +762,8 @@ struct StepLaunch {
         dmfb_step_kernel<FOVT, G, AT, ET, DEG><<<grid, E * G, smem, s>>>(*cfg, *st, actions, aes, u, seed, flags, *out, E);
         return DMFB_OK;
     }
-    template <int FOVT, int G, int AT, bool DEG>
-    int go_warp() const {
-        constexpr int WPC = 4, EW = 32 / G;
-        const TileLayout Lw(WPC * EW, cfg->n_agents, cfg->fov, cfg->width, cfg->length);
-        int rc = set_smem(dmfb_step_warp_kernel<FOVT, G, AT, DEG, WPC>, Lw.total);
-        if (rc) return rc;
-        int dev = 0, sms = 148, per_sm = 1;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dmfb_step_warp_kernel<FOVT, G, AT, DEG, WPC>, WPC * 32,
-                                                      Lw.total);
-        if (per_sm < 1) per_sm = 1;
-        const long long n_tiles = ((long long)st->n_envs + EW - 1) / EW;
-        long long blocks = (n_tiles + WPC - 1) / WPC;
-        if (blocks > (long long)sms * per_sm) blocks = (long long)sms * per_sm;   // persistent: one resident wave
-        dmfb_step_warp_kernel<FOVT, G, AT, DEG, WPC><<<(int)blocks, WPC * 32, Lw.total, s>>>(*cfg, *st, actions, aes, u,
-                                                                                             seed, flags, *out);
-        return DMFB_OK;
-    }
     template <int FOVT, int G>
     int operator()() const {
-        // persistent warp-tile kernel when the 32/G envs of one warp span a multiple of 16 bytes
-        if constexpr (G <= 8) {
-            const int warp_span = (32 / G) * cfg->n_agents * cfg->obs_dim;
-            static const bool no_warp = getenv("DMFB_NO_WARP_KERNEL") != nullptr;
-            if (warp_span % 16 == 0 && !no_warp) {
-                const bool deg = st->health != nullptr || st->usage != nullptr;
-                if constexpr (FOVT == 9 && G == 4) {
-                    if (cfg->n_agents == 4) return deg ? go_warp<9, 4, 4, true>() : go_warp<9, 4, 4, false>();
-                }
-                return go_warp<FOVT, G, 0, true>();
-            }
-        }
         // fully specialised instances for the shipped benchmark configs (BASELINE.json C1, C2, C3)
         const bool deg = st->health != nullptr || st->usage != nullptr;
         if constexpr (FOVT == 9 && G == 4) {
