@@ -98,7 +98,8 @@ typedef struct dmfb_state {
     int32_t* constraints;   /* [N] episode-cumulative constraint count      (dmfb.py:511,572) */
     uint8_t* terminated;    /* [N] 1 once all(dones) was returned by a step (rollout.py:34-35) */
     uint32_t* episode;      /* [N] episode counter (RNG stream selector) */
-    uint16_t* usage;        /* [N,W,L] actuation counts m_usage, may be NULL when !b_degrade (dmfb.py:148,459-463) */
+    uint32_t* usage;        /* [N,W,L] actuation counts m_usage (updated with fire-and-forget RED.ADD), may be NULL
+                               when !b_degrade (dmfb.py:148,459-463) */
     double* health;         /* [N,W,L] m_health, NULL == all 1.0            (dmfb.py:147,361-363) */
     double* degrade;        /* [N,W,L] m_degrade, NULL == all 1.0           (dmfb.py:151,157-166) */
     uint8_t* blocks;        /* [N,n_blocks,2] (x_min,y_min) of 2x2 blocks, NULL when n_blocks==0 */
@@ -191,7 +192,7 @@ typedef struct meda_state {
     uint8_t* done;          /* reserved (NULL) */
     uint8_t* terminated;    /* [N] */
     uint32_t* episode;      /* [N] */
-    uint16_t* usage;        /* [N,W,L] */
+    uint32_t* usage;        /* [N,W,L] */
     double* health;         /* [N,W,L], NULL == all 1.0 */
     double* degrade;        /* [N,W,L], NULL == all 1.0 */
 } meda_state_t;

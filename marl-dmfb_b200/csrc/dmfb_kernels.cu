@@ -246,11 +246,14 @@ __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLay
                 const uint32_t m = (j < nw) ? (rowm[j] | colm[j]) : 0u;
                 const uint32_t sh = __funnelshift_l(prev, m, s);  // mask bits shifted up by s
                 prev = m;
+                const uint32_t even = sh & 0x0F0F0F0Fu, odd = (sh >> 4) & 0x0F0F0F0Fu;  // nibbles 0,2,4,6 / 1,3,5,7
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const int k = 8 * j + t;
-                    // spread 4 bits to 4 bytes: bit b -> byte b (16 distinct partial products, no carries)
-                    if (k < nfull_min) wptr[k] = (((sh >> (4 * t)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                    // nibble t isolated with one PRMT, then 4 bits -> 4 bytes: bit b -> byte b
+                    // (multiply by 1 + 2^7 + 2^14 + 2^21: 16 distinct partial products, no carries)
+                    const uint32_t nib = __byte_perm((t & 1) ? odd : even, 0u, 0x4440u + (uint32_t)(t >> 1));
+                    if (k < nfull_min) wptr[k] = (nib * 0x00204081u) & 0x01010101u;
                 }
             }
             // the last (f2 & 3) + s <= 6 bytes: one more whole word if they reach 4, then single bytes
@@ -301,7 +304,7 @@ __device__ __forceinline__ void update_health_flagged(const dmfb_cfg_t& cfg, con
     const int cells = cfg.width * cfg.length;
     for (int e = 0; e < e_valid; ++e) {
         if (!(S.flag[e] & kFlagNewTask)) continue;
-        uint16_t* usage = st.usage + (size_t)(n0 + e) * cells;
+        uint32_t* usage = st.usage + (size_t)(n0 + e) * cells;
         double* health = st.health ? st.health + (size_t)(n0 + e) * cells : nullptr;
         const double* degrade = st.degrade ? st.degrade + (size_t)(n0 + e) * cells : nullptr;
         for (int k = threadIdx.x; k < cells; k += blockDim.x)
@@ -458,9 +461,7 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
     o.term = (o.done_mask == all_mask) ? 1 : 0;
 
     if (DEG_T && lane_on && !frozen && (flags & DMFB_STEP_RECORD_USAGE) && st.usage && !post_done) {  // addUsage (:459-463)
-        uint16_t* cell = st.usage + ((size_t)n * W + nx) * Lc + ny;
-        const uint16_t v = *cell;
-        *cell = (uint16_t)(v + (v != 0xFFFFu));
+        atomicAdd(st.usage + ((size_t)n * W + nx) * Lc + ny, 1u);   // result unused -> RED.ADD, no round trip
     }
 
     // ---- fused auto-reset: DMFBenv.reset(new=False) (:589-597) for envs that just terminated -------
@@ -629,7 +630,7 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
             for (int ee = 0; ee < e_valid; ++ee) {
                 if (!S.flag[ee]) continue;
                 const int64_t nn = n0 + ee;
-                uint16_t* usage = st.usage ? st.usage + (size_t)nn * cells : nullptr;
+                uint32_t* usage = st.usage ? st.usage + (size_t)nn * cells : nullptr;
                 double* health = st.health ? st.health + (size_t)nn * cells : nullptr;
                 double* degrade = st.degrade ? st.degrade + (size_t)nn * cells : nullptr;
                 const uint32_t episode = st.episode ? st.episode[nn] : 0u;

@@ -19,7 +19,7 @@ struct dmfb_host_env {
     uint8_t *drop = nullptr, *start = nullptr, *terminated = nullptr;
     int32_t *step_count = nullptr, *constraints = nullptr;
     uint32_t* episode = nullptr;
-    uint16_t* usage = nullptr;
+    uint32_t* usage = nullptr;
     double *health = nullptr, *degrade = nullptr;
     // device staging of per-step inputs / outputs
     int8_t* d_actions = nullptr;

@@ -184,7 +184,7 @@ __device__ __forceinline__ void meda_update_health(const meda_cfg_t& cfg, const 
     const int cells = cfg.width * cfg.length;
     for (int e = 0; e < e_valid; ++e) {
         if (!(S.flag[e] & kEnvSelected)) continue;
-        uint16_t* usage = st.usage + (size_t)(n0 + e) * cells;
+        uint32_t* usage = st.usage + (size_t)(n0 + e) * cells;
         double* health = st.health + (size_t)(n0 + e) * cells;
         const double* degrade = st.degrade ? st.degrade + (size_t)(n0 + e) * cells : nullptr;
         for (int k = threadIdx.x; k < cells; k += blockDim.x)
@@ -335,21 +335,16 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
     }
     __syncthreads();
 
-    // ---- addUsage (:591-598): footprints of one env may overlap -> droplets in turn, lanes = cells ------
+    // ---- addUsage (:591-598): footprints of one env may overlap -> RED.ADD per cell, one warp per droplet ----
     if (st.usage) {
         const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
-        for (int e = warp; e < e_valid; e += nwarps) {
+        for (int g = warp; g < e_valid * A; g += nwarps) {
+            const int e = g / A;
             if (!(S.flag[e] & kEnvUsage) || (S.flag[e] & kEnvFrozen)) continue;
-            uint16_t* usage = st.usage + (size_t)(n0 + e) * cells;
-            for (int i = 0; i < A; ++i) {
-                const uint32_t m = S.misc[e * A + i], w = S.word[e * A + i];
-                if (!((m >> 16) & 1u) && lane < kFootCells) {
-                    const int x = (int)(w & 255u) - kRad + lane % 5, y = (int)((w >> 8) & 255u) - kRad + lane / 5;
-                    uint16_t* cell = usage + y * Lc + x;
-                    const uint16_t v = *cell;
-                    *cell = (uint16_t)(v + (v != 0xFFFFu));
-                }
-                __syncwarp();
+            const uint32_t m = S.misc[g], w = S.word[g];
+            if (!((m >> 16) & 1u) && lane < kFootCells) {
+                const int x = (int)(w & 255u) - kRad + lane % 5, y = (int)((w >> 8) & 255u) - kRad + lane / 5;
+                atomicAdd(st.usage + (size_t)(n0 + e) * cells + y * Lc + x, 1u);
             }
         }
     }

@@ -62,7 +62,7 @@ class BatchedDMFB:
         self.constraints_cum = z(N, dtype=torch.int32)
         self.terminated = z(N, dtype=torch.uint8)
         self.episode = z(N, dtype=torch.int32)
-        self.usage = z(N, width, length, dtype=torch.int16) if track_usage else None  # uint16 bit pattern
+        self.usage = z(N, width, length, dtype=torch.int32) if track_usage else None
         self.health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         self.degrade = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         self.state = nat.DmfbState(
@@ -212,8 +212,8 @@ class BatchedDMFB:
         return self.drop[:, :, 2:4]
 
     def usage_counts(self):
-        """m_usage as an integer tensor (stored as uint16)."""
-        return None if self.usage is None else (self.usage.to(torch.int32) & 0xFFFF)
+        """m_usage as an integer tensor."""
+        return self.usage
 
 
 class _RoutingManagerView:

@@ -78,7 +78,7 @@ class BatchedMEDA:
         self.fails = z(N, dtype=torch.int32)               # punish count; the reference's `fails` is -0.6 * this
         self.terminated = z(N, dtype=torch.uint8)
         self.episode = z(N, dtype=torch.int32)
-        self.usage = z(N, width, length, dtype=torch.int16)
+        self.usage = z(N, width, length, dtype=torch.int32)
         self.health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         self.degrade = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         self.state = nat.MedaState(
@@ -177,7 +177,7 @@ class BatchedMEDA:
                 "episode_limit": self.max_step}
 
     def usage_counts(self):
-        return self.usage.to(torch.int32) & 0xFFFF
+        return self.usage
 
 
 class _MedaRoutingView:
