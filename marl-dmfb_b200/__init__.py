@@ -13,6 +13,8 @@ from .build import build  # noqa: F401
 from .dmfb import BatchedDMFB, DMFBenv  # noqa: F401
 from .host import HostDMFB  # noqa: F401
 from .sharding import shard_range  # noqa: F401
+from .marl import (CRNN, BatchedAgents, BatchedRolloutWorker, EpisodeBatch, ReplayBufferGPU, VDNLearner,  # noqa: F401
+                   allreduce_gradients)
 
 try:  # MEDA kernels are part of the same library
     from .meda import BatchedMEDA, MEDAEnv, MEDAEnv_v0_2  # noqa: F401

@@ -1,0 +1,322 @@
+"""Callers of the hot path, batched: lock-step rollout over N GPU-resident envs with
+one batched CRNN forward per step, a device-resident episode / replay buffer in the reference's wire format, and the
+VDN learner with a single-bucket gradient all-reduce for data-parallel training.
+
+These are the batched counterparts of
+  common/rollout.py:19-39,101-150  (Evaluator.one_step / RolloutWorker.generate_episode)
+  agent/agent.py:22-48             (Agents.choose_action: batch-1 CRNN forward per agent, eps-greedy)
+  common/replay_buffer.py:5-75     (episode ring buffer, uniform sampling with replacement)
+  policy/vdn.py:79-196             (double-network TD learning with the GRU unrolled over the episode)
+  network/base_net.py:23-71        (CRNN), network/vdn_net.py (sum mixer)
+Plain PyTorch: the networks are tiny dense models (about 0.9 MFLOP per agent-step); the env kernels are the product.
+Parameter names follow the reference so that state_dicts interoperate (vdn.py:205-218 file naming kept by
+`VDNLearner.save_model`).
+"""
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------ networks --
+def _conv_stack(fov, in_ch, od):
+    """network/base_net.py:23-33: conv stack chosen by fov (fov 19 applies the same conv3 module twice)."""
+    conv1 = nn.Conv2d(in_ch, od, kernel_size=3, stride=1)
+    conv2 = nn.Conv2d(in_ch, od, kernel_size=3, stride=2)
+    conv3 = nn.Conv2d(od, od, kernel_size=3, stride=1)
+    table = {5: [conv1], 7: [conv1, conv3], 9: [conv1, conv3], 11: [conv1, conv3], 13: [conv1, conv3],
+             19: [conv2, conv3, conv3]}
+    if fov not in table:
+        raise KeyError(fov)  # the reference raises KeyError for any other fov too
+    return table[fov]
+
+
+class CRNN(nn.Module):
+    """network/base_net.py:35-71.  obs_shape = (C, fov, fov, 2, C*fov*fov+2); input = obs ++ last action one-hot."""
+
+    def __init__(self, obs_shape, n_actions, rnn_hidden_dim=128, hyper_hidden_dim=24):
+        super().__init__()
+        self.input_dim = tuple(obs_shape)
+        self.rnn_hidden_dim = rnn_hidden_dim
+        self.n_actions = n_actions
+        fov = obs_shape[1]
+        self.convs = _conv_stack(fov, obs_shape[0], hyper_hidden_dim)
+        size = fov
+        for i, conv in enumerate(self.convs, start=1):
+            self.add_module("conv{}".format(i), conv)          # same (shared) registration as base_net.py:47-50
+            size = (size + 2 * conv.padding[0] - conv.dilation[0] * (conv.kernel_size[0] - 1) - 1) // conv.stride[0] + 1
+        self.out = size * size * hyper_hidden_dim
+        self.mlp1 = nn.Linear(obs_shape[-2] + n_actions, 10)
+        self.rnn = nn.GRUCell(self.out + 10, rnn_hidden_dim)
+        self.fc1 = nn.Linear(rnn_hidden_dim, n_actions)
+
+    def forward(self, inputs, hidden_state):
+        npix = self.input_dim[-1] - self.input_dim[-2]
+        pixel, vec = inputs[:, :npix], inputs[:, npix:]
+        pixel = pixel.reshape((-1,) + self.input_dim[:3])
+        for conv in self.convs:
+            pixel = F.relu(conv(pixel))
+        pixel = pixel.reshape(-1, self.out)
+        vec = F.relu(self.mlp1(vec))
+        h = self.rnn(torch.cat([pixel, vec], dim=1), hidden_state.reshape(-1, self.rnn_hidden_dim))
+        return self.fc1(h), h
+
+
+# ------------------------------------------------------------ action selection --
+class BatchedAgents:
+    """Agents.choose_action (agent/agent.py:22-48) for all N*A agents in one forward pass, on the device."""
+
+    def __init__(self, net, n_agents, n_actions, device, seed=0):
+        self.net, self.n_agents, self.n_actions = net, n_agents, n_actions
+        self.device = torch.device(device)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(int(seed))
+
+    def init_hidden(self, n_envs):
+        return torch.zeros(n_envs * self.n_agents, self.net.rnn_hidden_dim, device=self.device)
+
+    @torch.no_grad()
+    def choose_actions(self, obs, last_onehot, hidden, avail, epsilon):
+        """obs int8 [N,A,D], last_onehot [N,A,n_actions], hidden [N*A,H], avail [N,A,n_actions] (0/1).
+        Returns actions int64 [N,A] and the new hidden state.  Padded rows (avail all zero) get action 0."""
+        N, A = obs.shape[0], obs.shape[1]
+        inputs = torch.cat([obs.to(torch.float32), last_onehot.to(torch.float32)], dim=2).reshape(N * A, -1)
+        q, hidden = self.net(inputs, hidden)
+        q = q.reshape(N, A, self.n_actions).masked_fill(avail == 0, float("-inf"))     # agent.py:43
+        greedy = torch.argmax(torch.nan_to_num(q, neginf=-3.0e38), dim=2)
+        # np.random.choice(avail_actions_ind) (agent.py:44-45): uniform over the available actions
+        w = avail.to(torch.float32) + (avail.sum(dim=2, keepdim=True) == 0).to(torch.float32)
+        rand = torch.multinomial(w.reshape(N * A, -1), 1, generator=self.gen).reshape(N, A)
+        explore = torch.rand(N, A, device=self.device, generator=self.gen) < epsilon
+        return torch.where(explore, rand, greedy), hidden
+
+
+# --------------------------------------------------------------- episode batch --
+class EpisodeBatch:
+    """N lock-step episodes of T = episode_limit transitions in the reference's wire format
+    (common/replay_buffer.py:17-26), on the device.  `o` and `avail_u` are stored for T+1 steps; o_next[t] = o[t+1],
+    avail_u_next[t] = avail_u[t+1].  (One deliberate difference: at the terminating transition the reference stores
+    avail_u_next = ones, here it is zeros like the padding that follows; the learner multiplies that target by
+    (1 - terminated) = 0, so the loss is identical.)"""
+
+    KEYS = ("o", "u", "r", "avail_u", "avail_u_next", "u_onehot", "padded", "terminated")
+
+    def __init__(self, n, T, A, D, n_actions, device):
+        z = lambda *s, dtype: torch.zeros(*s, dtype=dtype, device=device)  # noqa: E731
+        self.n, self.T, self.A, self.D, self.n_actions = n, T, A, D, n_actions
+        self.o_all = z(n, T + 1, A, D, dtype=torch.int8)
+        self.u = z(n, T, A, 1, dtype=torch.int8)
+        self.r = z(n, T, 1, dtype=torch.float32)
+        self.avail_all = z(n, T + 1, A, n_actions, dtype=torch.int8)
+        self.u_onehot = z(n, T, A, n_actions, dtype=torch.int8)
+        self.padded = torch.ones(n, T, 1, dtype=torch.bool, device=device)
+        self.terminated = torch.ones(n, T, 1, dtype=torch.bool, device=device)
+
+    def as_dict(self, idx=None, T=None):
+        """The dict ReplayBuffer.sample returns (replay_buffer.py:51-56), as views (optionally rows idx, first T steps)."""
+        T = self.T if T is None else T
+        s = (lambda x: x) if idx is None else (lambda x: x[idx])
+        return {"o": s(self.o_all)[:, :T], "o_next": s(self.o_all)[:, 1:T + 1], "u": s(self.u)[:, :T],
+                "r": s(self.r)[:, :T], "avail_u": s(self.avail_all)[:, :T], "avail_u_next": s(self.avail_all)[:, 1:T + 1],
+                "u_onehot": s(self.u_onehot)[:, :T], "padded": s(self.padded)[:, :T],
+                "terminated": s(self.terminated)[:, :T]}
+
+
+class ReplayBufferGPU(EpisodeBatch):
+    """common/replay_buffer.py:5-75 on the device: ring of `size` episodes, uniform sampling with replacement."""
+
+    def __init__(self, size, T, A, D, n_actions, device, seed=0):
+        super().__init__(size, T, A, D, n_actions, device)
+        self.size, self.current_idx, self.current_size = size, 0, 0
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(int(seed))
+
+    def _storage_idx(self, inc):
+        """_get_storage_idx (replay_buffer.py:58-75)."""
+        dev = self.o_all.device
+        if self.current_idx + inc <= self.size:
+            idx = torch.arange(self.current_idx, self.current_idx + inc, device=dev)
+            self.current_idx += inc
+        elif self.current_idx < self.size:
+            overflow = inc - (self.size - self.current_idx)
+            idx = torch.cat([torch.arange(self.current_idx, self.size, device=dev), torch.arange(0, overflow, device=dev)])
+            self.current_idx = overflow
+        else:
+            idx = torch.arange(0, inc, device=dev)
+            self.current_idx = inc
+        self.current_size = min(self.size, self.current_size + inc)
+        return idx
+
+    def store_episodes(self, ep):
+        if ep.n > self.size:
+            raise ValueError("more episodes than the buffer holds")
+        idx = self._storage_idx(ep.n)
+        for name in ("o_all", "u", "r", "avail_all", "u_onehot", "padded", "terminated"):
+            getattr(self, name)[idx] = getattr(ep, name)
+
+    def sample(self, batch_size):
+        idx = torch.randint(0, self.current_size, (batch_size,), device=self.o_all.device, generator=self.gen)
+        return self.as_dict(idx)
+
+
+# -------------------------------------------------------------------- rollout --
+class BatchedRolloutWorker:
+    """RolloutWorker.generate_episode (rollout.py:101-150) for all N envs of a batched env in lock step.
+
+    Finished envs are frozen by the env kernel (`freeze_terminated`), which emits exactly the zero padding the
+    reference appends (rollout.py:131-141); the loop stops as soon as every env is done."""
+
+    def __init__(self, env, agents, epsilon=1.0, min_epsilon=0.05, anneal_steps=150000, epsilon_anneal_scale="step"):
+        self.env, self.agents = env, agents
+        info = env.get_env_info()
+        self.T, self.A, self.n_actions, self.D = info["episode_limit"], info["n_agents"], info["n_actions"], info["obs_shape"][-1]
+        self.epsilon, self.min_epsilon = epsilon, min_epsilon
+        self.anneal_epsilon = (epsilon - min_epsilon) / anneal_steps
+        self.epsilon_anneal_scale = epsilon_anneal_scale
+
+    @torch.no_grad()
+    def generate_episodes(self, evaluate=False, batch=None):
+        """Returns (EpisodeBatch, stats) with stats = per-env episode reward, steps (episode_limit when not successful,
+        rollout.py:148-149), constraints and success, all device tensors."""
+        env, N, A, T = self.env, self.env.N, self.A, self.T
+        dev = env.device
+        ep = batch if batch is not None else EpisodeBatch(N, T, A, self.D, self.n_actions, dev)
+        ep.padded.fill_(True); ep.terminated.fill_(True)
+        ep.u.zero_(); ep.u_onehot.zero_(); ep.r.zero_(); ep.avail_all.zero_(); ep.o_all[:, 1:].zero_()
+        ep.o_all[:, 0].copy_(env.reset())
+        ep.avail_all[:, 0] = 1
+        hidden = self.agents.init_hidden(N)
+        last = torch.zeros(N, A, self.n_actions, device=dev)
+        reward = torch.zeros(N, device=dev)
+        constraints = torch.zeros(N, device=dev, dtype=torch.int64)
+        success = torch.zeros(N, device=dev, dtype=torch.int64)
+        steps = torch.zeros(N, device=dev, dtype=torch.int64)
+        alive = torch.ones(N, dtype=torch.bool, device=dev)
+        eps = 0.0 if evaluate else self.epsilon
+        if not evaluate and self.epsilon_anneal_scale == "episode":
+            eps = eps - self.anneal_epsilon if eps > self.min_epsilon else eps
+        obs_t = torch.empty(N, A, self.D, dtype=torch.int8, device=dev)
+        for t in range(T):
+            actions, hidden = self.agents.choose_actions(ep.o_all[:, t], last, hidden, ep.avail_all[:, t], eps)
+            obs, _, _, info = env.step(actions, freeze_terminated=True, out=obs_t)
+            live = alive & ~info["padded"]
+            onehot = F.one_hot(actions, self.n_actions).to(torch.int8) * live[:, None, None]
+            ep.o_all[:, t + 1] = obs
+            ep.u[:, t, :, 0] = (actions * live[:, None]).to(torch.int8)
+            ep.u_onehot[:, t] = onehot
+            ep.r[:, t, 0] = info["team_reward"]
+            ep.avail_all[:, t + 1] = env.get_avail_actions() * (live & ~info["terminated"])[:, None, None]
+            ep.padded[:, t, 0] = ~live
+            ep.terminated[:, t, 0] = info["terminated"] | ~live
+            reward += info["team_reward"] * live
+            constraints += info["constraints"].to(torch.int64) * live
+            success += info["success"].to(torch.int64) * live
+            steps += live.to(torch.int64)
+            last = onehot.to(torch.float32)
+            alive = live & ~info["terminated"]
+            if not evaluate and self.epsilon_anneal_scale == "step":
+                eps = eps - self.anneal_epsilon if eps > self.min_epsilon else eps
+            if t % 8 == 7 and not bool(alive.any()):        # one host sync every 8 steps
+                break
+        if not evaluate:
+            self.epsilon = eps
+        steps = torch.where(success > 0, steps, torch.full_like(steps, T))
+        return ep, {"reward": reward, "steps": steps, "constraints": constraints, "success": (success > 0).to(torch.int64)}
+
+
+# -------------------------------------------------------------------- learner --
+def allreduce_gradients(params, world_size):
+    """One flat fp32 bucket, summed over ranks and divided by the world size (290,765 parameters =
+    1.16 MB per learn step; latency-bound on NVLink, so a single bucket)."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or world_size <= 1:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat)
+    flat.div_(world_size)
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
+
+
+class VDNLearner:
+    """policy/vdn.py: eval/target CRNN, sum mixer, Adam(0.9, 0.99), grad-norm clip, periodic target sync."""
+
+    def __init__(self, obs_shape, n_agents, n_actions, device, lr=5e-4, gamma=0.99, grad_norm_clip=9.0,
+                 target_update_cycle=200, rnn_hidden_dim=128, hyper_hidden_dim=24, world_size=1, seed=0):
+        torch.manual_seed(seed)
+        self.device = torch.device(device)
+        self.n_agents, self.n_actions = n_agents, n_actions
+        self.eval_rnn = CRNN(obs_shape, n_actions, rnn_hidden_dim, hyper_hidden_dim).to(self.device)
+        self.target_rnn = CRNN(obs_shape, n_actions, rnn_hidden_dim, hyper_hidden_dim).to(self.device)
+        self.target_rnn.load_state_dict(self.eval_rnn.state_dict())
+        self.eval_parameters = list(self.eval_rnn.parameters())             # VDNNet has no parameters (vdn_net.py:5-10)
+        self.optimizer = torch.optim.Adam(self.eval_parameters, lr=lr, betas=(0.9, 0.99))   # vdn.py:66-68
+        self.gamma, self.grad_norm_clip, self.target_update_cycle = gamma, grad_norm_clip, target_update_cycle
+        self.world_size = world_size
+
+    @staticmethod
+    def max_episode_len(batch):
+        """Agents._get_max_episode_len (agent.py:51-61): 1 + the latest first-terminated index over the batch."""
+        term = batch["terminated"][:, :, 0]
+        T = term.shape[1]
+        first = torch.where(term.any(dim=1), term.to(torch.int64).argmax(dim=1) + 1, torch.zeros_like(term[:, 0], dtype=torch.int64))
+        return int(min(T, first.max().item()))
+
+    def _inputs(self, batch, t):
+        """VDN._get_inputs (vdn.py:134-165): obs of step t (o for t = 0, o_next[t-1] afterwards) ++ previous action."""
+        B = batch["o"].shape[0]
+        obs = batch["o"][:, 0] if t == 0 else batch["o_next"][:, t - 1]
+        prev = torch.zeros_like(batch["u_onehot"][:, 0]) if t == 0 else batch["u_onehot"][:, t - 1]
+        return torch.cat([obs.to(torch.float32), prev.to(torch.float32)], dim=2).reshape(B * self.n_agents, -1)
+
+    def q_values(self, batch, T):
+        """VDN.get_q_values (vdn.py:167-196): GRU unrolled over the T transitions for both networks."""
+        B = batch["o"].shape[0]
+        h_e = torch.zeros(B * self.n_agents, self.eval_rnn.rnn_hidden_dim, device=self.device)
+        h_t = torch.zeros_like(h_e)
+        q_evals, q_targets = [], []
+        inputs = self._inputs(batch, 0)
+        for t in range(T):
+            inputs_next = self._inputs(batch, t + 1) if t + 1 <= batch["o_next"].shape[1] else inputs
+            q_e, h_e = self.eval_rnn(inputs, h_e)
+            with torch.no_grad():
+                q_t, h_t = self.target_rnn(inputs_next, h_t)
+            q_evals.append(q_e.view(B, self.n_agents, -1))
+            q_targets.append(q_t.view(B, self.n_agents, -1))
+            inputs = inputs_next
+        return torch.stack(q_evals, dim=1), torch.stack(q_targets, dim=1)
+
+    def learn(self, batch, train_step, max_episode_len=None):
+        """VDN.learn (vdn.py:79-132).  batch: dict of device tensors [B, T, ...] (EpisodeBatch.as_dict / sample)."""
+        T = self.max_episode_len(batch) if max_episode_len is None else max_episode_len
+        T = max(T, 1)
+        batch = {k: v[:, :T] for k, v in batch.items()}                      # agent.py:66-68
+        u = batch["u"].to(torch.int64)
+        r = batch["r"].to(torch.float32)
+        terminated = batch["terminated"].to(torch.float32)
+        mask = 1.0 - batch["padded"].to(torch.float32)
+        q_evals, q_targets = self.q_values(batch, T)
+        q_evals = torch.gather(q_evals, dim=3, index=u).squeeze(3)
+        q_targets = q_targets.masked_fill(batch["avail_u_next"] == 0, -9999999.0).max(dim=3)[0]
+        q_total_eval = q_evals.sum(dim=2, keepdim=True)                      # VDNNet
+        q_total_target = q_targets.sum(dim=2, keepdim=True)
+        targets = r + self.gamma * q_total_target * (1.0 - terminated)
+        masked_td = mask * (targets.detach() - q_total_eval)
+        loss = (masked_td ** 2).sum() / mask.sum().clamp_min(1.0)
+        self.optimizer.zero_grad(set_to_none=False)
+        loss.backward()
+        allreduce_gradients(self.eval_parameters, self.world_size)
+        torch.nn.utils.clip_grad_norm_(self.eval_parameters, self.grad_norm_clip)
+        self.optimizer.step()
+        if train_step > 0 and train_step % self.target_update_cycle == 0:
+            self.target_rnn.load_state_dict(self.eval_rnn.state_dict())
+        return loss.detach()
+
+    def save_model(self, model_dir, ith_run=0, train_step=None):
+        """File naming of VDN.save_model (vdn.py:205-218) so that the reference's evaluate.py can load the weights."""
+        os.makedirs(model_dir, exist_ok=True)
+        mid = "" if train_step is None else str(train_step) + "_"
+        torch.save({}, os.path.join(model_dir, "{}_{}vdn_net_params.pkl".format(ith_run, mid)))
+        torch.save(self.eval_rnn.state_dict(), os.path.join(model_dir, "{}_{}rnn_net_params.pkl".format(ith_run, mid)))

@@ -1,0 +1,53 @@
+"""GPU checks of the batched callers on top of the CUDA env: lock-step rollout bookkeeping
+follows rollout.py:101-150, the episode batch has the reference wire format and padding, and a few VDN updates run."""
+import importlib
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def test_lockstep_rollout_and_vdn_updates():
+    P = importlib.import_module("marl-dmfb_b200")
+    dev = torch.device("cuda:0")
+    N = 512
+    env = P.BatchedDMFB(N, 10, 10, 4, fov=9, device=dev, seed=7)
+    info = env.get_env_info()
+    T, A, D, n_act = info["episode_limit"], 4, 245, 5
+    learner = P.VDNLearner(info["obs_shape"], A, n_act, dev, seed=0)
+    agents = P.BatchedAgents(learner.eval_rnn, A, n_act, dev, seed=1)
+    worker = P.BatchedRolloutWorker(env, agents, epsilon=1.0, anneal_steps=1000)
+    ep, stats = worker.generate_episodes()
+    b = ep.as_dict()
+    assert b["o"].shape == (N, T, A, D) and b["o"].dtype == torch.int8 and b["u"].shape == (N, T, A, 1)
+    assert b["r"].shape == (N, T, 1) and b["avail_u"].shape == (N, T, A, n_act) and b["padded"].dtype == torch.bool
+    pad = b["padded"][:, :, 0]
+    # padding is a suffix, and padded transitions are all zero / terminated = 1 (rollout.py:131-141)
+    assert bool((pad[:, 1:] >= pad[:, :-1]).all()) and not bool(pad[:, 0].any())
+    assert not bool(b["o_next"][pad].any()) and not bool(b["u_onehot"][pad].any()) and not bool(b["r"][pad].any())
+    assert bool(b["terminated"][:, :, 0][pad].all()) and not bool(b["avail_u"][pad].any())
+    # exactly one non-padded terminated transition per episode, at its last live step
+    live_term = b["terminated"][:, :, 0] & ~pad
+    assert bool((live_term.sum(1) == 1).all())
+    n_live = (~pad).sum(1)
+    assert bool((live_term.to(torch.int64).argmax(1) + 1 == n_live).all())
+    # one-hot matches u on live transitions; avail all ones there
+    live = ~pad
+    assert bool((b["u_onehot"].argmax(-1)[live] == b["u"][..., 0][live]).all()) and bool((b["avail_u"][live] == 1).all())
+    # stats: failures are charged episode_limit steps (rollout.py:148-149)
+    ok = stats["success"] > 0
+    assert bool((stats["steps"][~ok] == T).all()) and bool((stats["steps"][ok] == n_live[ok]).all())
+    np.testing.assert_allclose(stats["reward"].cpu().numpy(), b["r"][:, :, 0].sum(1).cpu().numpy(), rtol=1e-5, atol=1e-5)
+    assert worker.epsilon < 1.0                                    # annealed per step (rollout.py:126-127)
+    # replay + learning
+    buf = P.ReplayBufferGPU(1024, T, A, D, n_act, dev, seed=3)
+    buf.store_episodes(ep)
+    w0 = learner.eval_rnn.fc1.weight.detach().clone()
+    losses = [float(learner.learn(buf.sample(64), s)) for s in range(5)]
+    assert np.isfinite(losses).all() and not torch.equal(w0, learner.eval_rnn.fc1.weight)
+    # greedy evaluation run (epsilon 0) leaves epsilon untouched
+    e0 = worker.epsilon
+    _, st = worker.generate_episodes(evaluate=True)
+    assert worker.epsilon == e0 and st["steps"].shape == (N,)
