@@ -544,12 +544,17 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     const int agent = e * A + g.i;                  // agent index inside the tile
     const size_t ja = (size_t)n * A + g.i;          // index into [N,A] tensors
 
-    const LaneIn in = load_lane_inputs<DEG_T>(st, actions, aes, u, flags, n, ja, lane_on, leader);
+    // Programmatic dependent launch: let the next kernel of the stream (normally the next env step) start its
+    // own prologue while this grid drains; everything that touches global memory comes after the wait, which
+    // returns only once the preceding grid has completed and its writes are visible.
+    asm volatile("griddepcontrol.launch_dependents;");
     load_tables(cfg, L, S, tid, (int)blockDim.x);
     if constexpr (FOV_T != 0 && A_T != 0 && E_T != 0)
         zero_tile_static<((E_T * A_T * (3 * FOV_T * FOV_T + 2) + 15) / 16) * 16, E_T * G>(S.tile, tid);
     else
         zero_tile(L, S, tid, (int)blockDim.x);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const LaneIn in = load_lane_inputs<DEG_T>(st, actions, aes, u, flags, n, ja, lane_on, leader);
 
     const LaneOut o = dmfb_dynamics<G, A_T, DEG_T>(cfg, st, g, A, n, ja, env_on, lane_on, in, u, seed, flags, out.status);
     write_back_lane(st, out, o, n, ja, g.i, lane_on, leader);
@@ -760,7 +765,19 @@ struct StepLaunch {
     int go() const {
         int rc = set_smem(dmfb_step_kernel<FOVT, G, AT, ET, DEG>, smem);
         if (rc) return rc;
-        dmfb_step_kernel<FOVT, G, AT, ET, DEG><<<grid, E * G, smem, s>>>(*cfg, *st, actions, aes, u, seed, flags, *out, E);
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3((unsigned)grid);
+        lc.blockDim = dim3((unsigned)(E * G));
+        lc.dynamicSmemBytes = smem;
+        lc.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        static const bool no_pdl = getenv("DMFB_NO_PDL") != nullptr;
+        lc.attrs = attr;
+        lc.numAttrs = no_pdl ? 0 : 1;
+        DMFB_CUDA_TRY(cudaLaunchKernelEx(&lc, dmfb_step_kernel<FOVT, G, AT, ET, DEG>, *cfg, *st, actions, aes, u, seed,
+                                         flags, *out, E));
         return DMFB_OK;
     }
     template <int FOVT, int G>
