@@ -39,6 +39,7 @@ extern "C" {
 #define DMFB_MAX_DIM 128    /* max chip width / length (cells) */
 #define DMFB_MAX_AGENTS 32  /* max droplets per chip */
 #define DMFB_MAX_FOV 19     /* max field of view (cells) */
+#define DMFB_MAX_BLOCKS 32  /* max 2x2 obstacles per chip */
 #define DMFB_L2_WORDS 12    /* ceil(19*19/32) bit-mask words per boundary pattern */
 
 enum dmfb_status {
@@ -67,7 +68,8 @@ enum dmfb_status {
 typedef struct dmfb_cfg {
     int32_t width, length;  /* chip cells: x in [0,width), y in [0,length) */
     int32_t n_agents;       /* droplets per chip (A) */
-    int32_t n_blocks;       /* 2x2 obstacles per chip (0 in every shipped config) */
+    int32_t n_blocks;       /* 2x2 obstacles per chip (0 in every shipped config).  Like GenRandomBlocks (dmfb.py:232-234)
+                               dmfb_cfg_init stores 0 here when 4*n_blocks/(W*L) > 0.2. */
     int32_t fov;            /* side of the square partial observation */
     int32_t stall;          /* reference ctor arg `stall` (dmfb.py:331) */
     int32_t b_degrade;      /* electrode degradation on/off */
@@ -102,7 +104,7 @@ typedef struct dmfb_state {
                                when !b_degrade (dmfb.py:148,459-463) */
     double* health;         /* [N,W,L] m_health, NULL == all 1.0            (dmfb.py:147,361-363) */
     double* degrade;        /* [N,W,L] m_degrade, NULL == all 1.0           (dmfb.py:151,157-166) */
-    uint8_t* blocks;        /* [N,n_blocks,2] (x_min,y_min) of 2x2 blocks, NULL when n_blocks==0 */
+    uint8_t* blocks;        /* [N,n_blocks,2] (x_min,y_min) of the 2x2 blocks (Block, dmfb.py:34-41,246); NULL when n_blocks==0 */
 } dmfb_state_t;
 
 /* Per-step outputs, device pointers; any pointer except `obs` may be NULL. */
@@ -140,11 +142,14 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
  *  layouts   [N,A,4] uint8 (x,y,gx,gy) injected task, or NULL: on-device generator equivalent to
  *            _Generate_Start_End (dmfb.py:207-226; uniform cells, whole set rejected until every
  *            pairwise squared distance among the 2A points is > 2)
+ *  block_layouts [N,n_blocks,2] uint8 (x_min,y_min) injected obstacles, or NULL: on-device generator equivalent to
+ *            GenRandomBlocks (dmfb.py:228-251; redrawn while a block covers a start/goal cell or overlaps a block)
  *  degrade   [N,W,L] float64 injected degradation factors (only read when new_task && b_degrade), or NULL:
  *            on-device equivalent of _random_health_statue (dmfb.py:157-164)
  *  obs       [N,A,obs_dim] receives getObs() of the reset envs (rows of other envs untouched), may be NULL */
 int dmfb_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t* mask, int new_task,
-               const uint8_t* layouts, const double* degrade, uint64_t seed, int8_t* obs, void* stream);
+               const uint8_t* layouts, const uint8_t* block_layouts, const double* degrade, uint64_t seed,
+               int8_t* obs, void* stream);
 
 /* DMFBenv.getObs() of the current state for all envs (dmfb.py:614-626). */
 int dmfb_observe(const dmfb_cfg_t* cfg, const dmfb_state_t* state, int8_t* obs, void* stream);

@@ -100,7 +100,7 @@ def load():
     lib.dmfb_cfg_init.argtypes = [C.POINTER(DmfbCfg)] + [C.c_int] * 7 + [C.c_double]
     lib.dmfb_step.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p, C.c_int, C.c_void_p,
                               C.c_uint64, C.c_uint32, C.POINTER(DmfbOut), C.c_void_p]
-    lib.dmfb_reset.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p, C.c_int, C.c_void_p,
+    lib.dmfb_reset.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.dmfb_restart.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dmfb_observe.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p, C.c_void_p]

@@ -93,7 +93,7 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b)
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
-enum : uint32_t { kStreamMove = 1, kStreamLayout = 2, kStreamDegrade = 3 };
+enum : uint32_t { kStreamMove = 1, kStreamLayout = 2, kStreamDegrade = 3, kStreamBlocks = 4 };
 
 // splitmix64 finaliser (Steele/Lea/Flood 2014): cheap counter-based generator for the task sampler
 __device__ __forceinline__ uint64_t mix64(uint64_t z)

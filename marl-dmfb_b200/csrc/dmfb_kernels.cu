@@ -209,6 +209,52 @@ __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const
     return word;
 }
 
+// GenRandomBlocks (dmfb.py:228-251) for the envs whose group has `want` set: every 2x2 block is drawn with x_min
+// uniform in [0, W-4] and y_min uniform in [0, L-4] and redrawn while it covers a start / goal cell of the task
+// `word` (each lane checks its own droplet) or overlaps an earlier block (checked by the leader lane, which also
+// stores the result).  Every lane of the warp must call; `want` / `episode` are uniform per group.
+template <int G>
+__device__ __forceinline__ void generate_blocks(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const Group<G>& g,
+                                                uint64_t seed, int64_t n, uint32_t episode, bool want, bool lane_on,
+                                                uint32_t word)
+{
+    const int nb = cfg.n_blocks;
+    if (nb == 0 || !__any_sync(kFull, want)) return;
+    uint8_t* blocks = st.blocks + (size_t)n * nb * 2;     // only dereferenced by leaders of groups with want
+    uint64_t state = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamBlocks + 1));
+    state += (uint64_t)(cfg.env_base + n) * 0xD1342543DE82EF95ull + ((uint64_t)episode << 32) * 0xDA942042E4DD58B5ull;
+    state = mix64(state);
+    uint8_t bx[DMFB_MAX_BLOCKS], by[DMFB_MAX_BLOCKS];
+    const int sx = word & 255u, sy = (word >> 8) & 255u, tx = (word >> 16) & 255u, ty = word >> 24;
+    for (int b = 0; b < nb; ++b) {
+        bool pending = want;
+        while (__any_sync(kFull, pending)) {
+            uint32_t cand = 0;
+            if (pending && g.i == 0) {
+                const uint64_t z = mix64(state += 0x9E3779B97F4A7C15ull);
+                cand = __umulhi((uint32_t)z, (uint32_t)(cfg.width - 3)) |
+                       (__umulhi((uint32_t)(z >> 32), (uint32_t)(cfg.length - 3)) << 8);
+            }
+            cand = g.get(cand, 0);
+            const int x = cand & 255u, y = cand >> 8;
+            const bool covers = lane_on && (((unsigned)(sx - x) <= 1u && (unsigned)(sy - y) <= 1u) ||
+                                            ((unsigned)(tx - x) <= 1u && (unsigned)(ty - y) <= 1u));
+            const unsigned any_cover = g.ballot(covers);
+            int ok = 0;
+            if (pending && g.i == 0 && any_cover == 0u) {
+                ok = 1;
+                for (int k = 0; k < b; ++k)   // isBlockOverlap (:56-69): inclusive ranges intersect on both axes
+                    if (!(x > bx[k] + 1 || bx[k] > x + 1) && !(y > by[k] + 1 || by[k] > y + 1)) ok = 0;
+                if (ok) {
+                    bx[b] = (uint8_t)x; by[b] = (uint8_t)y;
+                    blocks[2 * b] = (uint8_t)x; blocks[2 * b + 1] = (uint8_t)y;
+                }
+            }
+            if (g.get(ok, 0)) pending = false;
+        }
+    }
+}
+
 // ---- observation painting: getOneObs (dmfb.py:395-457) of one agent into the zero filled tile --------
 // get(j) returns the packed word of droplet j of the same env; every lane must call it (it shuffles).
 // Only lanes with `on` store.  Byte ranges of different agents never overlap: layer 2 is written as whole
@@ -216,7 +262,8 @@ __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const
 // <= 3 bytes of the agent's own layer 1, which is painted afterwards), the rest byte by byte.
 template <int FOV_T, int A_T, typename GetWord>
 __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLayout& L, const TileSmem& S,
-                                            int agent_in_tile, int i, uint32_t me, bool on, GetWord get)
+                                            int agent_in_tile, int i, uint32_t me, bool on, GetWord get,
+                                            const uint8_t* __restrict__ env_blocks = nullptr)
 {
     const int fov = FOV_T ? FOV_T : cfg.fov;
     const int hf = fov >> 1, f2 = fov * fov;
@@ -271,6 +318,17 @@ __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLay
             *(nrem > 0 ? bp : S.sink) = (int8_t)(rem & 1u);
             *(nrem > 1 ? bp + 1 : S.sink) = (int8_t)((rem >> 1) & 1u);
             *(nrem > 2 ? bp + 2 : S.sink) = (int8_t)((rem >> 2) & 1u);
+        }
+    }
+    // ---- layer 2, obstacles: the reference writes block cells at their ABSOLUTE chip coordinates (:422-426) ---
+    if (A_T == 0 && env_blocks != nullptr && on) {
+        for (int b = 0; b < cfg.n_blocks; ++b) {
+            const int bx = env_blocks[2 * b], by = env_blocks[2 * b + 1];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ci = bx + (q >> 1), cj = by + (q & 1);
+                if (ci < fov && cj < fov) rec[2 * f2 + ci * fov + cj] = 1;
+            }
         }
     }
     // ---- layer 0: droplets inside the window (:408-413); layer 1: clipped goals of the other droplets
@@ -399,6 +457,11 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
         ny = min(max(ny, 0), Lc - 1);
         cand = (uint32_t)nx | ((uint32_t)ny << 8);
         if ((unsigned)a > 4u && status_flag) atomicOr(status_flag, 1);     // TypeError('action is illegal') (:115-116)
+        if (A_T == 0 && cfg.n_blocks) {                                    // _isTouchingBlocks -> revert (:338-340)
+            const uint8_t* bl = st.blocks + (size_t)n * cfg.n_blocks * 2;
+            for (int b = 0; b < cfg.n_blocks; ++b)
+                if ((unsigned)(nx - (int)bl[2 * b]) <= 1u && (unsigned)(ny - (int)bl[2 * b + 1]) <= 1u) cand = start_cell;
+        }
     }
     // Sequential resolution (:279-283): droplet i moves only if its candidate cell is not occupied by any
     // other droplet at that moment (j < i already moved, j > i still at their old cell) (:341-343).
@@ -469,6 +532,7 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
     o.do_reset = (flags & DMFB_STEP_AUTO_RESET) && o.term && !frozen && env_on;
     if (flags & DMFB_STEP_AUTO_RESET) {
         o.word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.lane / G, episode + 1u, o.do_reset, o.word);
+        if (A_T == 0) generate_blocks<G>(cfg, st, g, seed, n, episode + 1u, o.do_reset, lane_on, o.word);
         if (o.do_reset) {
             o.sc_out = 0;
             o.cum = 0;
@@ -565,7 +629,9 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) update_health_flagged(cfg, st, S, n0, e_valid);
 
     const uint32_t word = o.word;
-    paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); });
+    const uint8_t* env_blocks = (A_T == 0 && cfg.n_blocks && env_on) ? st.blocks + (size_t)n * cfg.n_blocks * 2 : nullptr;
+    paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); },
+                            env_blocks);
     store_tile(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
 }
 
@@ -575,8 +641,8 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
 template <int FOV_T, int G>
 __global__ void __launch_bounds__(kMaxThreads)
 dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, const uint8_t* __restrict__ mask,
-                  int mode, int new_task, const uint8_t* __restrict__ layouts, const double* __restrict__ degrade_in,
-                  uint64_t seed, int8_t* __restrict__ obs, int E)
+                  int mode, int new_task, const uint8_t* __restrict__ layouts, const uint8_t* __restrict__ block_layouts,
+                  const double* __restrict__ degrade_in, uint64_t seed, int8_t* __restrict__ obs, int E)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TileLayout L(cfg, E);
@@ -612,6 +678,15 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
             if (lane_on && selected) word = reinterpret_cast<const uint32_t*>(layouts)[ja];
         } else {
             word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.lane / G, episode, selected && env_on, word);
+        }
+        if (cfg.n_blocks) {   // refresh() regenerates the obstacles with every task (dmfb.py:174-177)
+            if (block_layouts) {
+                if (leader && selected)
+                    for (int b = 0; b < 2 * cfg.n_blocks; ++b)
+                        st.blocks[(size_t)n * cfg.n_blocks * 2 + b] = block_layouts[(size_t)n * cfg.n_blocks * 2 + b];
+            } else {
+                generate_blocks<G>(cfg, st, g, seed, n, episode, selected && env_on, lane_on, word);
+            }
         }
         if (leader && selected && st.episode) st.episode[n] = episode;
         if (lane_on && selected && st.start) reinterpret_cast<uint16_t*>(st.start)[ja] = (uint16_t)(word & 0xFFFFu);
@@ -662,7 +737,8 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
     if (obs == nullptr) return;
     const bool on = lane_on && selected;
     auto get = [&](int j) { return g.get(word, j); };
-    paint_agent<FOV_T, 0>(cfg, L, S, e * A + g.i, g.i, word, on, get);
+    const uint8_t* env_blocks = (cfg.n_blocks && env_on) ? st.blocks + (size_t)n * cfg.n_blocks * 2 : nullptr;
+    paint_agent<FOV_T, 0>(cfg, L, S, e * A + g.i, g.i, word, on, get, env_blocks);
     int8_t* gobs = obs + (size_t)n0 * A * L.D;
     if (n_selected == e_valid) store_tile(gobs, S.tile, (uint32_t)(e_valid * A * L.D));
     else store_rows_masked(gobs, S.tile, e_valid, A * L.D, S.flag);
@@ -691,6 +767,10 @@ dmfb_global_state_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_stat
             const uint32_t d = gdrop[i];
             g[(d & 255u) * Lc + ((d >> 8) & 255u)] = (int8_t)(i + 1);
             g[W * Lc + ((d >> 16) & 255u) * Lc + (d >> 24)] = (int8_t)(i + 1);
+        }
+        for (int b = 0; b < cfg.n_blocks; ++b) {   // add_blocks_In_gloabal_Obs (:376-381)
+            const uint8_t* bl = st.blocks + ((size_t)(n0 + e) * cfg.n_blocks + b) * 2;
+            for (int q = 0; q < 4; ++q) g[2 * W * Lc + (bl[0] + (q >> 1)) * Lc + bl[1] + (q & 1)] = 1;
         }
     }
     store_tile(out + (size_t)n0 * per_env, tile, (uint32_t)(e_valid * per_env));
@@ -731,8 +811,8 @@ int check_common(const dmfb_cfg_t* cfg, const dmfb_state_t* st)
         snprintf(g_last_error, sizeof(g_last_error), "null cfg/state pointer");
         return DMFB_ERR_BAD_ARG;
     }
-    if (cfg->n_blocks != 0) {
-        snprintf(g_last_error, sizeof(g_last_error), "n_blocks > 0 is not supported yet");
+    if (cfg->n_blocks != 0 && !st->blocks) {
+        snprintf(g_last_error, sizeof(g_last_error), "n_blocks > 0 needs state->blocks");
         return DMFB_ERR_BAD_ARG;
     }
     return DMFB_OK;
@@ -784,6 +864,7 @@ struct StepLaunch {
     int operator()() const {
         // fully specialised instances for the shipped benchmark configs (BASELINE.json C1, C2, C3)
         const bool deg = st->health != nullptr || st->usage != nullptr;
+        if (cfg->n_blocks != 0) return go<FOVT, G, 0, 0, true>();
         if constexpr (FOVT == 9 && G == 4) {
             if (cfg->n_agents == 4 && E == 32) return deg ? go<9, 4, 4, 32, true>() : go<9, 4, 4, 32, false>();
         }
@@ -796,19 +877,21 @@ struct StepLaunch {
 
 struct ResetLaunch {
     const dmfb_cfg_t* cfg; const dmfb_state_t* st; const uint8_t* mask; int mode, new_task; const uint8_t* layouts;
-    const double* degrade; uint64_t seed; int8_t* obs; cudaStream_t s; int E, grid; uint32_t smem;
+    const uint8_t* block_layouts; const double* degrade; uint64_t seed; int8_t* obs; cudaStream_t s; int E, grid;
+    uint32_t smem;
     template <int FOVT, int G>
     int operator()() const {
         int rc = set_smem(dmfb_reset_kernel<FOVT, G>, smem);
         if (rc) return rc;
-        dmfb_reset_kernel<FOVT, G><<<grid, E * G, smem, s>>>(*cfg, *st, mask, mode, new_task, layouts, degrade, seed,
-                                                               obs, E);
+        dmfb_reset_kernel<FOVT, G><<<grid, E * G, smem, s>>>(*cfg, *st, mask, mode, new_task, layouts, block_layouts,
+                                                               degrade, seed, obs, E);
         return DMFB_OK;
     }
 };
 
 int launch_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t* mask, int mode, int new_task,
-                 const uint8_t* layouts, const double* degrade, uint64_t seed, int8_t* obs, void* stream)
+                 const uint8_t* layouts, const uint8_t* block_layouts, const double* degrade, uint64_t seed, int8_t* obs,
+                 void* stream)
 {
     int rc = check_common(cfg, state);
     if (rc) return rc;
@@ -816,8 +899,8 @@ int launch_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t
     const int G = group_size_for(cfg->n_agents);
     const int E = tile_envs_for(*cfg, G);
     const TileLayout L(*cfg, E);
-    ResetLaunch job{cfg, state, mask, mode, new_task, layouts, degrade, seed, obs, static_cast<cudaStream_t>(stream),
-                    E, (state->n_envs + E - 1) / E, L.total};
+    ResetLaunch job{cfg, state, mask, mode, new_task, layouts, block_layouts, degrade, seed, obs,
+                    static_cast<cudaStream_t>(stream), E, (state->n_envs + E - 1) / E, L.total};
     rc = dispatch(cfg->fov, G, job);
     if (rc) return rc;
     g_launches.fetch_add(1);
@@ -849,6 +932,8 @@ int dmfb_cfg_init(dmfb_cfg_t* cfg, int width, int length, int n_agents, int n_bl
         return DMFB_ERR_BAD_ARG;
     const int hf = fov / 2;
     if (hf == 10) return DMFB_ERR_DIV_ZERO;
+    if (n_blocks < 0 || n_blocks > DMFB_MAX_BLOCKS) return DMFB_ERR_BAD_ARG;
+    if ((double)n_blocks * 4.0 / (double)(width * length) > 0.2) n_blocks = 0;   // 'Too many required modules' (dmfb.py:232-234)
     cfg->width = width; cfg->length = length; cfg->n_agents = n_agents; cfg->n_blocks = n_blocks; cfg->fov = fov;
     cfg->stall = stall ? 1 : 0; cfg->b_degrade = b_degrade ? 1 : 0; cfg->per_degrade = per_degrade;
     cfg->max_step = 2 * (width + length);
@@ -905,9 +990,10 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
 }
 
 int dmfb_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t* mask, int new_task,
-               const uint8_t* layouts, const double* degrade, uint64_t seed, int8_t* obs, void* stream)
+               const uint8_t* layouts, const uint8_t* block_layouts, const double* degrade, uint64_t seed, int8_t* obs,
+               void* stream)
 {
-    return launch_reset(cfg, state, mask, 0, new_task, layouts, degrade, seed, obs, stream);
+    return launch_reset(cfg, state, mask, 0, new_task, layouts, block_layouts, degrade, seed, obs, stream);
 }
 
 int dmfb_restart(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t* mask, int8_t* obs, void* stream)
@@ -916,13 +1002,13 @@ int dmfb_restart(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t
         snprintf(g_last_error, sizeof(g_last_error), "dmfb_restart needs state->start");
         return DMFB_ERR_BAD_ARG;
     }
-    return launch_reset(cfg, state, mask, 1, 0, nullptr, nullptr, 0, obs, stream);
+    return launch_reset(cfg, state, mask, 1, 0, nullptr, nullptr, nullptr, 0, obs, stream);
 }
 
 int dmfb_observe(const dmfb_cfg_t* cfg, const dmfb_state_t* state, int8_t* obs, void* stream)
 {
     if (!obs) return DMFB_ERR_BAD_ARG;
-    return launch_reset(cfg, state, nullptr, 2, 0, nullptr, nullptr, 0, obs, stream);
+    return launch_reset(cfg, state, nullptr, 2, 0, nullptr, nullptr, nullptr, 0, obs, stream);
 }
 
 int dmfb_global_state(const dmfb_cfg_t* cfg, const dmfb_state_t* state, int8_t* out, void* stream)

@@ -20,6 +20,7 @@ struct dmfb_host_env {
     int32_t *step_count = nullptr, *constraints = nullptr;
     uint32_t* episode = nullptr;
     uint32_t* usage = nullptr;
+    uint8_t* blocks = nullptr;
     double *health = nullptr, *degrade = nullptr;
     // device staging of per-step inputs / outputs
     int8_t* d_actions = nullptr;
@@ -58,7 +59,7 @@ dmfb_state_t sub_state(const dmfb_host_env* h, int lo, int hi)
     s.usage = h->usage ? h->usage + (size_t)lo * cells : nullptr;
     s.health = h->health ? h->health + (size_t)lo * cells : nullptr;
     s.degrade = h->degrade ? h->degrade + (size_t)lo * cells : nullptr;
-    s.blocks = nullptr;
+    s.blocks = h->blocks ? h->blocks + (size_t)lo * h->cfg.n_blocks * 2 : nullptr;
     return s;
 }
 
@@ -106,6 +107,7 @@ int dmfb_host_create(const dmfb_cfg_t* cfg, int n_envs, int device, int n_chunks
     TRY_ALLOC(step_count, N)
     TRY_ALLOC(constraints, N)
     TRY_ALLOC(episode, N)
+    if (cfg->n_blocks) TRY_ALLOC(blocks, N * (size_t)cfg->n_blocks * 2)
     if (cfg->b_degrade) {
         TRY_ALLOC(usage, N * cells)
         TRY_ALLOC(health, N * cells)
@@ -136,7 +138,7 @@ void dmfb_host_destroy(dmfb_host_env_t* h)
     cudaSetDevice(h->device);
     for (cudaStream_t s : h->streams) cudaStreamDestroy(s);
     void* ptrs[] = {h->drop, h->start, h->terminated, h->step_count, h->constraints, h->episode, h->usage, h->health,
-                    h->degrade, h->d_actions, h->d_u, h->d_obs, h->d_reward, h->d_done, h->d_cons, h->d_succ,
+                    h->degrade, h->blocks, h->d_actions, h->d_u, h->d_obs, h->d_reward, h->d_done, h->d_cons, h->d_succ,
                     h->d_layouts};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -169,7 +171,7 @@ int dmfb_host_reset(dmfb_host_env_t* h, int new_task, const uint8_t* layouts, co
                                           (size_t)(hi - lo) * cells * sizeof(double), cudaMemcpyHostToDevice, s));
             d_deg = h->degrade + (size_t)lo * cells;
         }
-        int rc = dmfb_reset(&cfg, &st, nullptr, new_task, d_lay, d_deg, seed, h->d_obs + (size_t)lo * A * D, s);
+        int rc = dmfb_reset(&cfg, &st, nullptr, new_task, d_lay, nullptr, d_deg, seed, h->d_obs + (size_t)lo * A * D, s);
         if (rc) return rc;
         if (obs)
             DMFB_CUDA_TRY(cudaMemcpyAsync(obs + (size_t)lo * A * D, h->d_obs + (size_t)lo * A * D,

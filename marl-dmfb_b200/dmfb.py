@@ -32,13 +32,14 @@ class BatchedDMFB:
 
     def __init__(self, n_envs, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False,
                  per_degrade=0.1, device="cuda", seed=0, env_base=0, track_usage=None, reward_f64=False,
-                 degrade=None, layouts=None):
+                 degrade=None, layouts=None, block_layouts=None):
         self.lib = nat.load()
         self.cfg = nat.DmfbCfg()
         nat.check(self.lib.dmfb_cfg_init(C.byref(self.cfg), width, length, n_agents, n_blocks, fov, int(bool(stall)),
                                          int(bool(b_degrade)), float(per_degrade)), "dmfb_cfg_init")
-        if n_blocks != 0:
-            raise NotImplementedError("n_blocks > 0 is not supported (every shipped config uses 0 blocks)")
+        if n_blocks and self.cfg.n_blocks == 0:
+            print('Too many required modules in the environment.')    # dmfb.py:232-234: continues without blocks
+        self.n_blocks = int(self.cfg.n_blocks)
         self.cfg.env_base = int(env_base)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -63,6 +64,7 @@ class BatchedDMFB:
         self.terminated = z(N, dtype=torch.uint8)
         self.episode = z(N, dtype=torch.int32)
         self.usage = z(N, width, length, dtype=torch.int32) if track_usage else None
+        self.blocks = z(N, self.n_blocks, 2, dtype=torch.uint8) if self.n_blocks else None   # (x_min, y_min) of 2x2 blocks
         self.health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         self.degrade = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         self.state = nat.DmfbState(
@@ -70,7 +72,8 @@ class BatchedDMFB:
             constraints=self.constraints_cum.data_ptr(), terminated=self.terminated.data_ptr(),
             episode=self.episode.data_ptr(), usage=self.usage.data_ptr() if track_usage else None,
             health=self.health.data_ptr() if self.b_degrade else None,
-            degrade=self.degrade.data_ptr() if self.b_degrade else None, blocks=None)
+            degrade=self.degrade.data_ptr() if self.b_degrade else None,
+            blocks=self.blocks.data_ptr() if self.n_blocks else None)
         # ---- per-step outputs ----
         self.obs = z(N, A, self.D, dtype=torch.int8)
         self.reward = z(N, A, dtype=torch.float32)
@@ -85,7 +88,7 @@ class BatchedDMFB:
         self.status = z(1, dtype=torch.int32)
         self._out = self._make_out(self.obs)
         # the reference constructor draws the degradation matrix and a first task (dmfb.py:151-155)
-        self.reset(new=True, layouts=layouts, degrade=degrade)
+        self.reset(new=True, layouts=layouts, degrade=degrade, block_layouts=block_layouts)
 
     # ------------------------------------------------------------------ helpers --
     def _make_out(self, obs):
@@ -110,7 +113,7 @@ class BatchedDMFB:
         return t
 
     # ---------------------------------------------------------------------- API --
-    def reset(self, mask=None, new=False, layouts=None, degrade=None, out=None):
+    def reset(self, mask=None, new=False, layouts=None, degrade=None, out=None, block_layouts=None):
         """DMFBenv.reset(new) (dmfb.py:589-597) for the envs selected by ``mask`` (None = all).
 
         layouts: optional [N,A,4] (x, y, goal_x, goal_y) injected tasks; default: on-device generator
@@ -119,10 +122,11 @@ class BatchedDMFB:
         mask_t = self._as(mask, torch.uint8, (self.N,), "mask")
         lay_t = self._as(layouts, torch.uint8, (self.N, self.A, 4), "layouts")
         deg_t = self._as(degrade, torch.float64, (self.N, self.W, self.L), "degrade")
+        blk_t = self._as(block_layouts, torch.uint8, (self.N, self.n_blocks, 2), "block_layouts") if self.n_blocks else None
         obs = self.obs if out is None else out
         with torch.cuda.device(self.device):
             rc = self.lib.dmfb_reset(C.byref(self.cfg), C.byref(self.state), _ptr(mask_t), int(bool(new)), _ptr(lay_t),
-                                     _ptr(deg_t), self.seed, _ptr(obs), self._stream())
+                                     _ptr(blk_t), _ptr(deg_t), self.seed, _ptr(obs), self._stream())
         nat.check(rc, "dmfb_reset")
         return obs
 
@@ -263,7 +267,7 @@ class DMFBenv:
     metadata = {"render.modes": ["human", "rgb_array"]}
 
     def __init__(self, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False, per_degrade=0.1,
-                 show=False, savemp4=False, device="cuda", seed=None, layouts=None, degrade=None):
+                 show=False, savemp4=False, device="cuda", seed=None, layouts=None, degrade=None, block_layouts=None):
         assert width >= 5 and length >= 5
         assert n_agents > 0
         if seed is None:
@@ -271,7 +275,8 @@ class DMFBenv:
         self._b = BatchedDMFB(1, width, length, n_agents, n_blocks, fov=fov, stall=stall, b_degrade=b_degrade,
                               per_degrade=per_degrade, device=device, seed=seed, track_usage=True, reward_f64=True,
                               layouts=None if layouts is None else np.asarray(layouts)[None],
-                              degrade=None if degrade is None else np.asarray(degrade)[None])
+                              degrade=None if degrade is None else np.asarray(degrade)[None],
+                              block_layouts=None if block_layouts is None else np.asarray(block_layouts)[None])
         self.mode = None  # rendering is out of scope (dmfb.py:642-720)
         self.agents = list(self._b.agents)
         self.possible_agents = self.agents[:]

@@ -24,7 +24,7 @@
 #include <string.h>
 
 typedef struct orc_dmfb_cfg {
-    int32_t width, length, n_agents, fov, stall, b_degrade;
+    int32_t width, length, n_agents, fov, stall, b_degrade, n_blocks;
 } orc_dmfb_cfg;
 
 #define MAXA 64
@@ -45,6 +45,16 @@ static int orc_move(int *x, int *y, int action, int width, int length)
     return 0;
 }
 
+/* RoutingTaskManager._isTouchingBlocks (dmfb.py:301-308); blocks = [n_blocks][2] (x_min, y_min), 2x2 each (:246) */
+static int orc_touching_blocks(const uint8_t *blocks, int n_blocks, int x, int y)
+{
+    for (int b = 0; b < n_blocks; b++) {
+        int x_min = blocks[2 * b], y_min = blocks[2 * b + 1];
+        if (x >= x_min && x <= x_min + 1 && y >= y_min && y <= y_min + 1) return 1;
+    }
+    return 0;
+}
+
 /* RoutingTaskManager._isinvalidaction (dmfb.py:310-323): any pair of droplets
  * at squared distance 0 (the Gram-matrix EDM of :200-205 is exact on small ints). */
 static int orc_any_pair_equal(const int *x, const int *y, int n)
@@ -61,7 +71,7 @@ static int orc_any_pair_equal(const int *x, const int *y, int n)
 /* RoutingTaskManager.getOneObs (dmfb.py:395-457) + DMFBenv.getOneObs (:614-620):
  * int8 (3,fov,fov) flattened, then the 2-byte direction vector. */
 static void orc_one_obs(const orc_dmfb_cfg *c, const int *x, const int *y, const int *gx, const int *gy,
-                        int agent, int8_t *obs)
+                        const uint8_t *blocks, int agent, int8_t *obs)
 {
     const int fov = c->fov, hf = fov / 2, n = c->n_agents;
     const int f2 = fov * fov;
@@ -83,7 +93,12 @@ static void orc_one_obs(const orc_dmfb_cfg *c, const int *x, const int *y, const
             obs[1 * f2 + rx * fov + ry] = (int8_t)(idx + 1);
         }
     }
-    /* layer 2: blocks (none: n_blocks == 0 in every supported config) + off-chip boundary (:428-439) */
+    /* layer 2: blocks at ABSOLUTE chip coordinates, as the reference writes them (:422-426) ... */
+    for (int b = 0; blocks && b < c->n_blocks; b++)
+        for (int i = blocks[2 * b]; i <= blocks[2 * b] + 1; i++)
+            for (int j = blocks[2 * b + 1]; j <= blocks[2 * b + 1] + 1; j++)
+                if (0 <= i && i < fov && 0 <= j && j < fov) obs[2 * f2 + i * fov + j] = 1;
+    /* ... + off-chip boundary (:428-439) */
     int leftbound = hf - cx, rightbound = hf - (c->width - 1 - cx);
     if (leftbound > 0) {
         for (int r = 0; r < leftbound && r < fov; r++)
@@ -125,19 +140,19 @@ static void orc_load(const orc_dmfb_cfg *c, const uint8_t *drop, int *x, int *y,
 }
 
 /* DMFBenv.getObs (dmfb.py:622-626) for chip state `drop` */
-static void orc_all_obs(const orc_dmfb_cfg *c, const uint8_t *drop, int8_t *obs)
+static void orc_all_obs(const orc_dmfb_cfg *c, const uint8_t *drop, const uint8_t *blocks, int8_t *obs)
 {
     int x[MAXA], y[MAXA], gx[MAXA], gy[MAXA];
     orc_load(c, drop, x, y, gx, gy);
     const int D = 3 * c->fov * c->fov + 2;
-    for (int i = 0; i < c->n_agents; i++) orc_one_obs(c, x, y, gx, gy, i, obs + (size_t)i * D);
+    for (int i = 0; i < c->n_agents; i++) orc_one_obs(c, x, y, gx, gy, blocks, i, obs + (size_t)i * D);
 }
 
 /* DMFBenv.step (dmfb.py:560-587) -> RoutingTaskManager.moveDroplets (:253-299) ->
  * moveOneDroplet (:325-359) -> addUsage (:459-463), for ONE chip.
  * Returns -1 on an illegal action. */
-static int orc_step_one(const orc_dmfb_cfg *c, uint8_t *drop, int32_t *step_count, int32_t *cum_constraints,
-                        double *usage, const double *health, const int8_t *actions, const double *u,
+static int orc_step_one(const orc_dmfb_cfg *c, uint8_t *drop, const uint8_t *blocks, int32_t *step_count,
+                        int32_t *cum_constraints, double *usage, const double *health, const int8_t *actions, const double *u,
                         int record, int8_t *obs, double *reward, uint8_t *done, int32_t *constraints_out,
                         uint8_t *success_out)
 {
@@ -161,7 +176,7 @@ static int orc_step_one(const orc_dmfb_cfg *c, uint8_t *drop, int32_t *step_coun
             double draw = u ? u[i] : 0.0;
             if (draw <= prob) {                            /* random.random() <= prob :335 */
                 if (orc_move(&x[i], &y[i], actions[i], W, L)) return -1;
-                /* _isTouchingBlocks: no blocks */
+                if (blocks && orc_touching_blocks(blocks, c->n_blocks, x[i], y[i])) { x[i] = ox; y[i] = oy; } /* :338-340 */
                 if (orc_any_pair_equal(x, y, n)) { x[i] = ox; y[i] = oy; } /* :341-343 */
             }
             int nd = abs(x[i] - gx[i]) + abs(y[i] - gy[i]);
@@ -202,7 +217,7 @@ static int orc_step_one(const orc_dmfb_cfg *c, uint8_t *drop, int32_t *step_coun
         for (int i = 0; i < n; i++) if (dist[i] != 0) usage[(size_t)x[i] * L + y[i]] += 1.0;
     *cum_constraints += constraints;                                       /* :572 */
     for (int i = 0; i < n; i++) { drop[4 * i + 0] = (uint8_t)x[i]; drop[4 * i + 1] = (uint8_t)y[i]; }
-    if (obs) orc_all_obs(c, drop, obs);                                    /* :576 */
+    if (obs) orc_all_obs(c, drop, blocks, obs);                            /* :576 */
     if (*step_count < 2 * (W + L)) {                                       /* :577-585, max_step :508 */
         if (all_done && *cum_constraints == 0) success = 1;
         for (int i = 0; i < n; i++) done[i] = (uint8_t)(dist[i] == 0);
@@ -228,14 +243,15 @@ static void orc_update_health(const orc_dmfb_cfg *c, double *usage, double *heal
 
 /* ------------------------------------------------------------ batch API -- */
 
-int orc_dmfb_step(const orc_dmfb_cfg *c, int n_envs, uint8_t *drop, int32_t *step_count, int32_t *cum_constraints,
+int orc_dmfb_step(const orc_dmfb_cfg *c, int n_envs, uint8_t *drop, const uint8_t *blocks, int32_t *step_count, int32_t *cum_constraints,
                   double *usage, const double *health, const int8_t *actions, const double *u, int record,
                   int8_t *obs, double *reward, uint8_t *done, int32_t *constraints, uint8_t *success)
 {
     const int A = c->n_agents, cells = c->width * c->length, D = 3 * c->fov * c->fov + 2;
     int err = 0;
     for (int e = 0; e < n_envs; e++) {
-        int rc = orc_step_one(c, drop + (size_t)e * A * 4, step_count + e, cum_constraints + e,
+        int rc = orc_step_one(c, drop + (size_t)e * A * 4, blocks ? blocks + (size_t)e * c->n_blocks * 2 : NULL,
+                              step_count + e, cum_constraints + e,
                               usage ? usage + (size_t)e * cells : NULL, health ? health + (size_t)e * cells : NULL,
                               actions + (size_t)e * A, u ? u + (size_t)e * A : NULL, record,
                               obs ? obs + (size_t)e * A * D : NULL, reward + (size_t)e * A, done + (size_t)e * A,
@@ -249,8 +265,9 @@ int orc_dmfb_step(const orc_dmfb_cfg *c, int n_envs, uint8_t *drop, int32_t *ste
  * refresh (:174-183): new task; new -> health=1, usage=0, degrade redrawn (injected);
  * else updateHealth.  Then getObs. */
 int orc_dmfb_reset(const orc_dmfb_cfg *c, int n_envs, const uint8_t *mask, int new_task, const uint8_t *layouts,
-                   const double *degrade_in, uint8_t *drop, int32_t *step_count, int32_t *cum_constraints,
-                   double *usage, double *health, double *degrade, int8_t *obs)
+                   const uint8_t *block_layouts, const double *degrade_in, uint8_t *drop, uint8_t *blocks,
+                   int32_t *step_count, int32_t *cum_constraints, double *usage, double *health, double *degrade,
+                   int8_t *obs)
 {
     const int A = c->n_agents, cells = c->width * c->length, D = 3 * c->fov * c->fov + 2;
     for (int e = 0; e < n_envs; e++) {
@@ -258,6 +275,8 @@ int orc_dmfb_reset(const orc_dmfb_cfg *c, int n_envs, const uint8_t *mask, int n
         step_count[e] = 0;
         cum_constraints[e] = 0;
         memcpy(drop + (size_t)e * A * 4, layouts + (size_t)e * A * 4, (size_t)A * 4);
+        if (blocks && block_layouts)
+            memcpy(blocks + (size_t)e * c->n_blocks * 2, block_layouts + (size_t)e * c->n_blocks * 2, (size_t)c->n_blocks * 2);
         if (new_task) {
             for (int k = 0; k < cells; k++) {
                 if (health) health[(size_t)e * cells + k] = 1.0;
@@ -268,26 +287,33 @@ int orc_dmfb_reset(const orc_dmfb_cfg *c, int n_envs, const uint8_t *mask, int n
             orc_update_health(c, usage + (size_t)e * cells, health ? health + (size_t)e * cells : NULL,
                               degrade ? degrade + (size_t)e * cells : NULL);
         }
-        if (obs) orc_all_obs(c, drop + (size_t)e * A * 4, obs + (size_t)e * A * D);
+        if (obs) orc_all_obs(c, drop + (size_t)e * A * 4, blocks ? blocks + (size_t)e * c->n_blocks * 2 : NULL,
+                             obs + (size_t)e * A * D);
     }
     return 0;
 }
 
-int orc_dmfb_observe(const orc_dmfb_cfg *c, int n_envs, const uint8_t *drop, int8_t *obs)
+int orc_dmfb_observe(const orc_dmfb_cfg *c, int n_envs, const uint8_t *drop, const uint8_t *blocks, int8_t *obs)
 {
     const int A = c->n_agents, D = 3 * c->fov * c->fov + 2;
-    for (int e = 0; e < n_envs; e++) orc_all_obs(c, drop + (size_t)e * A * 4, obs + (size_t)e * A * D);
+    for (int e = 0; e < n_envs; e++)
+        orc_all_obs(c, drop + (size_t)e * A * 4, blocks ? blocks + (size_t)e * c->n_blocks * 2 : NULL, obs + (size_t)e * A * D);
     return 0;
 }
 
 /* RoutingTaskManager.getglobalobs (dmfb.py:368-392) as int8 [3,W,L] per chip */
-int orc_dmfb_global_state(const orc_dmfb_cfg *c, int n_envs, const uint8_t *drop, int8_t *out)
+int orc_dmfb_global_state(const orc_dmfb_cfg *c, int n_envs, const uint8_t *drop, const uint8_t *blocks, int8_t *out)
 {
     const int A = c->n_agents, W = c->width, L = c->length;
     for (int e = 0; e < n_envs; e++) {
         int8_t *g = out + (size_t)e * 3 * W * L;
         memset(g, 0, (size_t)3 * W * L);
         const uint8_t *d = drop + (size_t)e * A * 4;
+        for (int b = 0; blocks && b < c->n_blocks; b++) {      /* add_blocks_In_gloabal_Obs (:376-381) */
+            const uint8_t *bl = blocks + ((size_t)e * c->n_blocks + b) * 2;
+            for (int i = bl[0]; i <= bl[0] + 1; i++)
+                for (int j = bl[1]; j <= bl[1] + 1; j++) g[2 * W * L + i * L + j] = 1;
+        }
         for (int i = 0; i < A; i++) {
             g[0 * W * L + d[4 * i + 0] * L + d[4 * i + 1]] = (int8_t)(i + 1);
             g[1 * W * L + d[4 * i + 2] * L + d[4 * i + 3]] = (int8_t)(i + 1);
@@ -327,6 +353,30 @@ void orc_dmfb_gen_layout(const orc_dmfb_cfg *c, uint64_t *rng, uint8_t *layout)
     for (int i = 0; i < A; i++) {
         layout[4 * i + 0] = (uint8_t)px[i]; layout[4 * i + 1] = (uint8_t)py[i];
         layout[4 * i + 2] = (uint8_t)px[A + i]; layout[4 * i + 3] = (uint8_t)py[A + i];
+    }
+}
+
+/* GenRandomBlocks (dmfb.py:228-251): each 2x2 block uniform with x_min in [0,W-4], y_min in [0,L-4], redrawn while
+ * it contains a start/goal cell or overlaps an earlier block. */
+void orc_dmfb_gen_blocks(const orc_dmfb_cfg *c, uint64_t *rng, const uint8_t *layout, uint8_t *blocks)
+{
+    const int A = c->n_agents;
+    if (c->width < 5 || c->length < 5 || c->n_blocks * 4.0 / (c->width * c->length) > 0.2) return;
+    for (int b = 0; b < c->n_blocks; b++) {
+        for (;;) {
+            int y = (int)(orc_splitmix(rng) % (uint64_t)(c->length - 3));
+            int x = (int)(orc_splitmix(rng) % (uint64_t)(c->width - 3));
+            int bad = 0;
+            for (int i = 0; i < 2 * A && !bad; i++) {
+                int px = layout[4 * (i % A) + (i < A ? 0 : 2)], py = layout[4 * (i % A) + (i < A ? 1 : 3)];
+                if (px >= x && px <= x + 1 && py >= y && py <= y + 1) bad = 1;
+            }
+            for (int k = 0; k < b && !bad; k++) {
+                int ox = blocks[2 * k], oy = blocks[2 * k + 1];
+                if (!(x > ox + 1 || ox > x + 1) && !(y > oy + 1 || oy > y + 1)) bad = 1;
+            }
+            if (!bad) { blocks[2 * b] = (uint8_t)x; blocks[2 * b + 1] = (uint8_t)y; break; }
+        }
     }
 }
 
@@ -372,7 +422,7 @@ static void *orc_dmfb_roll_thread(void *arg)
                 acts[i] = (int8_t)(orc_splitmix(&rng) % 5u);
                 u[i] = (double)(orc_splitmix(&rng) >> 11) * (1.0 / 9007199254740992.0);
             }
-            orc_step_one(c, drop, &sc, &cc, usage, c->b_degrade ? health : NULL, acts, u, 1, obs, rew, done,
+            orc_step_one(c, drop, NULL, &sc, &cc, usage, c->b_degrade ? health : NULL, acts, u, 1, obs, rew, done,
                          &cons, &succ);
             int all = 1;
             for (int i = 0; i < A; i++) { all &= done[i]; total += (uint64_t)(rew[i] < 0.0); }
@@ -380,7 +430,7 @@ static void *orc_dmfb_roll_thread(void *arg)
                 sc = 0; cc = 0;
                 orc_dmfb_gen_layout(c, &rng, drop);
                 orc_update_health(c, usage, health, degrade);
-                orc_all_obs(c, drop, obs);
+                orc_all_obs(c, drop, NULL, obs);
             }
         }
     }

@@ -37,7 +37,7 @@ def lib():
 
 
 class _DmfbCfg(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("width", "length", "n_agents", "fov", "stall", "b_degrade")]
+    _fields_ = [(n, C.c_int32) for n in ("width", "length", "n_agents", "fov", "stall", "b_degrade", "n_blocks")]
 
 
 def _p(a, ct=None):
@@ -50,10 +50,12 @@ def _p(a, ct=None):
 class OracleDMFB:
     """N independent DMFB chips stepped by the C restatement of env/DMFB/dmfb.py."""
 
-    def __init__(self, n_envs, width, length, n_agents, fov=9, stall=True, b_degrade=False):
+    def __init__(self, n_envs, width, length, n_agents, fov=9, stall=True, b_degrade=False, n_blocks=0):
         self.N, self.W, self.L, self.A, self.fov = n_envs, width, length, n_agents, fov
         self.D = 3 * fov * fov + 2
-        self.cfg = _DmfbCfg(width, length, n_agents, fov, int(stall), int(b_degrade))
+        self.n_blocks = n_blocks
+        self.cfg = _DmfbCfg(width, length, n_agents, fov, int(stall), int(b_degrade), n_blocks)
+        self.blocks = np.zeros((n_envs, n_blocks, 2), np.uint8) if n_blocks else None
         self.b_degrade = bool(b_degrade)
         N, A = n_envs, n_agents
         self.drop = np.zeros((N, A, 4), np.uint8)
@@ -63,15 +65,17 @@ class OracleDMFB:
         self.health = np.ones((N, width, length), np.float64)
         self.degrade = np.ones((N, width, length), np.float64)
 
-    def reset(self, layouts, new=False, degrade=None, mask=None):
+    def reset(self, layouts, new=False, degrade=None, mask=None, blocks=None):
         obs = np.zeros((self.N, self.A, self.D), np.int8)
         layouts = np.ascontiguousarray(layouts, np.uint8)
+        if blocks is not None:
+            blocks = np.ascontiguousarray(blocks, np.uint8)
         if degrade is not None:
             degrade = np.ascontiguousarray(degrade, np.float64)
         if mask is not None:
             mask = np.ascontiguousarray(mask, np.uint8)
-        lib().orc_dmfb_reset(C.byref(self.cfg), self.N, _p(mask), int(new), _p(layouts), _p(degrade),
-                             _p(self.drop), _p(self.step_count), _p(self.constraints), _p(self.usage),
+        lib().orc_dmfb_reset(C.byref(self.cfg), self.N, _p(mask), int(new), _p(layouts), _p(blocks), _p(degrade),
+                             _p(self.drop), _p(self.blocks), _p(self.step_count), _p(self.constraints), _p(self.usage),
                              _p(self.health), _p(self.degrade), _p(obs))
         return obs
 
@@ -85,7 +89,7 @@ class OracleDMFB:
         done = np.zeros((N, A), np.uint8)
         cons = np.zeros(N, np.int32)
         succ = np.zeros(N, np.uint8)
-        rc = lib().orc_dmfb_step(C.byref(self.cfg), N, _p(self.drop), _p(self.step_count), _p(self.constraints),
+        rc = lib().orc_dmfb_step(C.byref(self.cfg), N, _p(self.drop), _p(self.blocks), _p(self.step_count), _p(self.constraints),
                                  _p(self.usage), _p(self.health) if self.b_degrade else None, _p(actions),
                                  _p(draws), int(record), _p(obs), _p(reward), _p(done), _p(cons), _p(succ))
         if rc:
@@ -94,12 +98,12 @@ class OracleDMFB:
 
     def observe(self):
         obs = np.zeros((self.N, self.A, self.D), np.int8)
-        lib().orc_dmfb_observe(C.byref(self.cfg), self.N, _p(self.drop), _p(obs))
+        lib().orc_dmfb_observe(C.byref(self.cfg), self.N, _p(self.drop), _p(self.blocks), _p(obs))
         return obs
 
     def global_state(self):
         out = np.zeros((self.N, 3, self.W, self.L), np.int8)
-        lib().orc_dmfb_global_state(C.byref(self.cfg), self.N, _p(self.drop), _p(out))
+        lib().orc_dmfb_global_state(C.byref(self.cfg), self.N, _p(self.drop), _p(self.blocks), _p(out))
         return out
 
     def gen_layouts(self, seed):
@@ -110,10 +114,19 @@ class OracleDMFB:
             lib().orc_dmfb_gen_layout(C.byref(self.cfg), C.byref(s), _p(out[e]))
         return out
 
+    def gen_blocks(self, seed, layouts):
+        """Reference-distributed random 2x2 blocks (dmfb.py:228-251) for the given tasks."""
+        layouts = np.ascontiguousarray(layouts, np.uint8)
+        out = np.zeros((self.N, self.n_blocks, 2), np.uint8)
+        for e in range(self.N):
+            s = C.c_uint64((seed << 21) + e)
+            lib().orc_dmfb_gen_blocks(C.byref(self.cfg), C.byref(s), _p(layouts[e]), _p(out[e]))
+        return out
+
 
 def dmfb_rollout(width, length, n_agents, fov, stall, b_degrade, n_envs, steps, seed=1, threads=1):
     """Timed CPU leg: returns agent-steps executed (see orc_dmfb_rollout)."""
-    cfg = _DmfbCfg(width, length, n_agents, fov, int(stall), int(b_degrade))
+    cfg = _DmfbCfg(width, length, n_agents, fov, int(stall), int(b_degrade), 0)
     obs = np.zeros((n_envs, n_agents, 3 * fov * fov + 2), np.int8)
     chk = C.c_uint64(0)
     n = lib().orc_dmfb_rollout(C.byref(cfg), n_envs, steps, C.c_uint64(seed), _p(obs), int(threads), C.byref(chk))

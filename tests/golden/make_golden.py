@@ -61,6 +61,12 @@ DMFB_SCENARIOS = {
                            K=4, n_ep=4, T=38, seed=109, p_goal=0.6, state_every=4),
     "dmfb_30x30_f11": dict(W=30, L=30, A=7, fov=11, stall=True, b_degrade=True, per_degrade=1.0,
                            K=2, n_ep=2, T=122, seed=110, p_goal=0.8, state_every=20, obs_every=2),
+    # 2x2 obstacles (dmfb.py:228-251,301-308,422-426): moves into a block are reverted, blocks appear in obs layer 2
+    # at ABSOLUTE coordinates and in the global state
+    "dmfb_blocks_12x12": dict(W=12, L=12, A=3, fov=9, stall=True, b_degrade=False, per_degrade=0.1, n_blocks=5,
+                              K=6, n_ep=6, T=50, seed=111, p_goal=0.6, state_every=5),
+    "dmfb_blocks_20x16_f5": dict(W=20, L=16, A=5, fov=5, stall=True, b_degrade=True, per_degrade=1.0, n_blocks=8,
+                                 K=4, n_ep=4, T=74, seed=112, p_goal=0.7, state_every=9, obs_every=2),
 }
 
 MEDA_SCENARIOS = {
@@ -96,12 +102,12 @@ def _dmfb_policy(rng, env, p_goal):
 
 
 def gen_dmfb(name, W, L, A, fov, stall, b_degrade, per_degrade, K, n_ep, T, seed, p_goal,
-             state_every=1, obs_every=1):
+             state_every=1, obs_every=1, n_blocks=0):
     rng = np.random.default_rng(seed)
     np.random.seed(seed)  # the reference draws layouts/degrade from the global numpy RNG
     envs, injs = [], []
     for _ in range(K):
-        e = ref_dmfb.DMFBenv(W, L, A, 0, fov=fov, stall=stall, b_degrade=b_degrade,
+        e = ref_dmfb.DMFBenv(W, L, A, n_blocks, fov=fov, stall=stall, b_degrade=b_degrade,
                              per_degrade=per_degrade)
         envs.append(e)
         injs.append(ref_shim.DrawInjector(ref_dmfb, e.routing_manager))
@@ -114,10 +120,11 @@ def gen_dmfb(name, W, L, A, fov, stall, b_degrade, per_degrade, K, n_ep, T, seed
     t_state = list(range(0, T, state_every)) if state_every else []
     out = dict(
         kind="dmfb", W=W, L=L, A=A, fov=fov, stall=int(stall), b_degrade=int(b_degrade),
-        per_degrade=per_degrade, K=K, n_ep=n_ep, T=T,
+        per_degrade=per_degrade, K=K, n_ep=n_ep, T=T, n_blocks=n_blocks,
         episode_limit=info0["episode_limit"], n_actions=info0["n_actions"],
         degrade=np.stack([e.routing_manager.m_degrade for e in envs]),
         layouts=np.zeros((n_ep, K, A, 4), np.int16),
+        blocks=np.zeros((n_ep, K, n_blocks, 2), np.int16),   # (x_min, y_min) of every 2x2 block
         actions=np.zeros((n_ep, T, K, A), np.int8),
         draws=rng.random((n_ep, T, K, A)),
         draws_used=np.zeros((n_ep, T, K, A), np.uint8),
@@ -141,6 +148,10 @@ def gen_dmfb(name, W, L, A, fov, stall, b_degrade, per_degrade, K, n_ep, T, seed
             rm = e.routing_manager
             out["layouts"][ep, k, :, 0:2] = rm.starts
             out["layouts"][ep, k, :, 2:4] = rm.ends
+            assert len(rm.blocks) == n_blocks
+            for b, blk in enumerate(rm.blocks):
+                assert (blk.x_max, blk.y_max) == (blk.x_min + 1, blk.y_min + 1)
+                out["blocks"][ep, k, b] = (blk.x_min, blk.y_min)
             out["obs_reset"][ep, k] = np.stack(obs)
             assert all(o.dtype == np.int8 for o in obs)
             out["health_reset"][ep, k] = rm.m_health

@@ -26,12 +26,14 @@ def _np(t):
 def test_dmfb_cuda_matches_reference_trace(name):
     g = load_golden(name)
     K, A, W, L = g["K"], g["A"], g["W"], g["L"]
-    env = pkg().BatchedDMFB(K, W, L, A, fov=g["fov"], stall=bool(g["stall"]), b_degrade=bool(g["b_degrade"]),
+    nb = int(g.get("n_blocks", 0))
+    env = pkg().BatchedDMFB(K, W, L, A, nb, fov=g["fov"], stall=bool(g["stall"]), b_degrade=bool(g["b_degrade"]),
                             per_degrade=g["per_degrade"], device="cuda:0", track_usage=True, reward_f64=True,
-                            degrade=g["degrade"] if g["b_degrade"] else None, layouts=g["layouts"][0])
+                            degrade=g["degrade"] if g["b_degrade"] else None, layouts=g["layouts"][0],
+                            block_layouts=g["blocks"][0] if nb else None)
     obs_t, state_t = list(g["obs_t"]), list(g["state_t"])
     for ep in range(g["n_ep"]):
-        obs = env.reset(new=False, layouts=g["layouts"][ep])
+        obs = env.reset(new=False, layouts=g["layouts"][ep], block_layouts=g["blocks"][ep] if nb else None)
         np.testing.assert_array_equal(_np(obs), g["obs_reset"][ep], err_msg=f"{name} reset obs ep{ep}")
         if g["b_degrade"]:
             np.testing.assert_array_equal(_np(env.health), g["health_reset"][ep], err_msg=f"health ep{ep}")
@@ -61,8 +63,11 @@ def test_dmfb_cuda_matches_reference_trace(name):
 
 
 CASES = [
-    # N, W, L, A, fov, stall, degrade
+    # N, W, L, A, fov, stall, degrade[, n_blocks]
     (1000, 10, 10, 4, 9, True, True),
+    (400, 14, 14, 4, 9, True, False, 6),
+    (300, 20, 24, 7, 7, True, True, 12),
+    (200, 12, 12, 2, 5, False, False, 4),
     (333, 20, 20, 10, 9, True, False),
     (130, 50, 50, 10, 9, True, True),
     (257, 12, 15, 6, 7, False, True),
@@ -75,14 +80,17 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("N,W,L,A,fov,stall,deg", CASES)
-def test_dmfb_cuda_matches_oracle_random(oracle_lib, N, W, L, A, fov, stall, deg):
+@pytest.mark.parametrize("case", CASES)
+def test_dmfb_cuda_matches_oracle_random(oracle_lib, case):
+    N, W, L, A, fov, stall, deg = case[:7]
+    nb = case[7] if len(case) > 7 else 0
     rng = np.random.default_rng(N * 7 + W)
-    ref = oracle_lib.OracleDMFB(N, W, L, A, fov=fov, stall=stall, b_degrade=deg)
+    ref = oracle_lib.OracleDMFB(N, W, L, A, fov=fov, stall=stall, b_degrade=deg, n_blocks=nb)
     degrade = rng.random((N, W, L)) * 0.4 + 0.6 if deg else None
     layouts = ref.gen_layouts(seed=N)
-    env = pkg().BatchedDMFB(N, W, L, A, fov=fov, stall=stall, b_degrade=deg, per_degrade=1.0, device="cuda:0",
-                            track_usage=True, reward_f64=True, degrade=degrade, layouts=layouts)
+    blocks = ref.gen_blocks(N, layouts) if nb else None
+    env = pkg().BatchedDMFB(N, W, L, A, nb, fov=fov, stall=stall, b_degrade=deg, per_degrade=1.0, device="cuda:0",
+                            track_usage=True, reward_f64=True, degrade=degrade, layouts=layouts, block_layouts=blocks)
     if deg:
         ref.degrade[...] = degrade
         # pre-age the chips so that health < 1 matters from the first step
@@ -91,18 +99,21 @@ def test_dmfb_cuda_matches_oracle_random(oracle_lib, N, W, L, A, fov, stall, deg
     T = min(2 * (W + L) + 3, 70)
     for ep in range(3):
         layouts = ref.gen_layouts(seed=1000 * ep + N)
+        blocks = ref.gen_blocks(1000 * ep + N, layouts) if nb else None
         if ep == 1:  # masked reset: only even envs get a new task
             mask = (np.arange(N) % 2 == 0).astype(np.uint8)
         else:
             mask = None
-        o_ref = ref.reset(layouts, mask=mask)
+        o_ref = ref.reset(layouts, mask=mask, blocks=blocks)
         buf = env.obs.clone()
-        o_gpu = env.reset(layouts=layouts, mask=mask)
+        o_gpu = env.reset(layouts=layouts, mask=mask, block_layouts=blocks)
         sel = slice(None) if mask is None else mask.astype(bool)
         np.testing.assert_array_equal(_np(o_gpu)[sel], o_ref[sel], err_msg=f"reset obs ep{ep}")
         if mask is not None:  # rows of unselected envs must be untouched
             np.testing.assert_array_equal(_np(o_gpu)[~sel], _np(buf)[~sel])
         np.testing.assert_array_equal(_np(env.drop), ref.drop)
+        if nb:
+            np.testing.assert_array_equal(_np(env.blocks), ref.blocks)
         for t in range(T):
             # goal-biased actions so that arrivals, collisions and the +10/+10 bonus all occur
             d = ref.drop.astype(np.int32)
@@ -269,3 +280,38 @@ def test_dmfb_fused_auto_reset_equals_step_plus_masked_reset(W, L, A, fov, deg):
     assert n_resets > N  # every env finished at least one episode
     if deg:
         assert float(e1.health.min()) < 1.0
+
+
+def test_dmfb_device_block_generator_obeys_reference_rules():
+    """GenRandomBlocks (dmfb.py:228-251) on the device: blocks inside the chip, never on a start / goal cell, never
+    overlapping; auto-reset regenerates them with the task; too many blocks -> none, like the reference."""
+    P = pkg()
+    N, W, L, A, nb = 20000, 16, 14, 4, 8
+    env = P.BatchedDMFB(N, W, L, A, nb, fov=7, device="cuda:0", seed=3)
+
+    def check():
+        b = env.blocks.to(torch.int32)                      # [N, nb, 2]
+        assert int(b[..., 0].min()) >= 0 and int(b[..., 0].max()) <= W - 4 and int(b[..., 1].max()) <= L - 4
+        d = env.drop.to(torch.int32)
+        pts = torch.cat([d[:, :, 0:2], d[:, :, 2:4]], dim=1)            # [N, 2A, 2]
+        rel = pts[:, :, None, :] - b[:, None, :, :]                      # [N, 2A, nb, 2]
+        inside = ((rel >= 0) & (rel <= 1)).all(-1)
+        assert not bool(inside.any())
+        db = (b[:, :, None, :] - b[:, None, :, :]).abs()
+        overlap = (db <= 1).all(-1) & ~torch.eye(nb, dtype=torch.bool, device="cuda:0")[None]
+        assert not bool(overlap.any())
+    check()
+    first = env.blocks.clone()
+    env.reset()
+    check()
+    assert not torch.equal(first, env.blocks)
+    gen = torch.Generator(device="cuda:0").manual_seed(2)
+    for t in range(2 * (W + L) + 2):
+        acts = torch.randint(0, 5, (N, A), device="cuda:0", generator=gen, dtype=torch.int8)
+        obs, rew, done, info = env.step(acts, auto_reset=True)
+        # no droplet ever stands on a block
+        d = env.drop.to(torch.int32)
+        rel = d[:, :, None, 0:2] - env.blocks.to(torch.int32)[:, None, :, :]
+        assert not bool(((rel >= 0) & (rel <= 1)).all(-1).any())
+    check()
+    assert P.BatchedDMFB(4, 10, 10, 2, 6, fov=5, device="cuda:0").n_blocks == 0   # 24/100 > 0.2 -> no blocks

@@ -11,12 +11,14 @@ from conftest import golden_names, load_golden
 def test_dmfb_oracle_matches_reference_trace(oracle_lib, name):
     g = load_golden(name)
     K, A, W, L = g["K"], g["A"], g["W"], g["L"]
-    env = oracle_lib.OracleDMFB(K, W, L, A, fov=g["fov"], stall=bool(g["stall"]), b_degrade=bool(g["b_degrade"]))
+    nb = int(g.get("n_blocks", 0))
+    env = oracle_lib.OracleDMFB(K, W, L, A, fov=g["fov"], stall=bool(g["stall"]), b_degrade=bool(g["b_degrade"]),
+                                n_blocks=nb)
     env.degrade[...] = g["degrade"]
     obs_t = list(g["obs_t"])
     state_t = list(g["state_t"])
     for ep in range(g["n_ep"]):
-        obs = env.reset(g["layouts"][ep], new=False)
+        obs = env.reset(g["layouts"][ep], new=False, blocks=g["blocks"][ep] if nb else None)
         np.testing.assert_array_equal(obs, g["obs_reset"][ep], err_msg=f"reset obs ep{ep}")
         np.testing.assert_array_equal(env.health, g["health_reset"][ep], err_msg=f"health at reset ep{ep}")
         np.testing.assert_array_equal(env.usage, g["usage_reset"][ep], err_msg=f"usage at reset ep{ep}")
