@@ -8,10 +8,9 @@
 evaluate: `evaluate_task` greedy episodes on `evaluate_task` independent chips in ONE lock-step rollout; prints the
 averages rollout.py:69-85 returns (reward, steps with failures charged episode_limit, constraints, success rate).
 
-degrade sweep: `chips` independent degrading chips (b_degrade=True, per_degrade=1.0, evaDegre.py:37-38); every chip is
-replicated `evaluate_task` times?  No - the reference runs the tasks of an epoch SEQUENTIALLY on one chip so that wear
-accumulates; here each chip is one env and an epoch is `evaluate_task` consecutive episodes on it, all chips in lock
-step.  Health is snapshotted at the start of every epoch (evaDegre.py:21) and the four arrays are written like
+degrade sweep: `chips` independent degrading chips (b_degrade=True, per_degrade=1.0, evaDegre.py:37-38).  The reference
+runs the tasks of an epoch sequentially on one chip so that wear accumulates; here each chip is one env, an epoch is
+`evaluate_task` consecutive episodes on it, and all chips advance in lock step.  Health is snapshotted at the start of every epoch (evaDegre.py:21) and the four arrays are written like
 evaDegre.py:52-56: rewards/steps/success (chips, epochs) and health (chips, epochs, W, L).
 """
 import argparse
