@@ -23,13 +23,16 @@ constexpr int kFootCells = 25;   // (2r+1)^2
 
 struct MedaLayout {
     int E, A, D;
-    uint32_t tile_bytes, off_word, off_misc, off_flag, off_dirx, off_diry, total;
+    uint32_t tile_bytes, off_word, off_misc, off_rew, off_envi, off_done, off_flag, off_dirx, off_diry, total;
     __host__ __device__ MedaLayout(const meda_cfg_t& c, int E_) {
         E = E_; A = c.n_agents; D = c.obs_dim;
         tile_bytes = ((uint32_t)(E * A * D) + 15u) & ~15u;
         uint32_t o = tile_bytes;
         off_word = o; o += (uint32_t)(E * A) * 4u;     // packed droplet words after the moves
-        off_misc = o; o += (uint32_t)(E * A) * 4u;     // status | code<<8 | done<<16 per droplet
+        off_misc = o; o += (uint32_t)(E * A) * 4u;     // status | code<<8 per droplet
+        off_rew = o; o += (uint32_t)(E * A) * 4u;      // float rewards (for the team mean)
+        off_envi = o; o += (uint32_t)E * 8u;           // fails, step_count per env
+        off_done = o; o += ((uint32_t)(E * A) + 3u) & ~3u;
         off_flag = o; o += ((uint32_t)E + 3u) & ~3u;   // per env flags
         off_dirx = o; o += ((uint32_t)(2 * c.length) + 3u) & ~3u;
         off_diry = o; o += ((uint32_t)(2 * c.width) + 3u) & ~3u;
@@ -45,6 +48,9 @@ struct MedaSmem {
     int8_t* tile;
     uint32_t* word;
     uint32_t* misc;
+    float* rew;
+    int32_t* envi;
+    uint8_t* done;
     uint8_t* flag;
     int8_t* dirx;   // indexed d + length-1
     int8_t* diry;   // indexed d + width-1
@@ -52,6 +58,9 @@ struct MedaSmem {
         tile = reinterpret_cast<int8_t*>(base);
         word = reinterpret_cast<uint32_t*>(base + L.off_word);
         misc = reinterpret_cast<uint32_t*>(base + L.off_misc);
+        rew = reinterpret_cast<float*>(base + L.off_rew);
+        envi = reinterpret_cast<int32_t*>(base + L.off_envi);
+        done = reinterpret_cast<uint8_t*>(base + L.off_done);
         flag = reinterpret_cast<uint8_t*>(base + L.off_flag);
         dirx = reinterpret_cast<int8_t*>(base + L.off_dirx);
         diry = reinterpret_cast<int8_t*>(base + L.off_diry);
@@ -152,11 +161,12 @@ __device__ void meda_paint_agent(const meda_cfg_t& cfg, const MedaSmem& S, const
         int r_lo = 0, r_hi = 0, q_lo = 0, q_hi = 0;   // [lo, hi) of rows / cols set to 1
         if (lb > 0) { r_lo = 0; r_hi = min(lb, fov); } else if (rb > 0) { r_lo = max(fov - rb, 0); r_hi = fov; }
         if (ub > 0) { q_lo = 0; q_hi = min(ub, fov); } else if (db > 0) { q_lo = max(fov - db, 0); q_hi = fov; }
-        if (r_hi > r_lo || q_hi > q_lo) {
-            for (int k = lane; k < f2; k += 32) {
-                const int r = k / fov, q = k - r * fov;
-                if ((r >= r_lo && r < r_hi) || (q >= q_lo && q < q_hi)) rec[2 * f2 + k] = 1;
-            }
+        // whole rows are one contiguous byte range; the column band is written row by row, one lane per column
+        for (int k = r_lo * fov + lane; k < r_hi * fov; k += 32) rec[2 * f2 + k] = 1;
+        if (q_hi > q_lo) {
+            const int nq = q_hi - q_lo;
+            for (int q = lane; q < nq; q += 32)
+                for (int r = 0; r < fov; ++r) rec[2 * f2 + r * fov + q_lo + q] = 1;
         }
         if (lane == 0) {                                                          // direction vector (:895)
             rec[3 * f2] = S.diry[gy - cy + cfg.width - 1];
@@ -257,83 +267,84 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
     }
     __syncthreads();
 
-    // ---- calPunish (:321-330) + MEDAEnv.step bookkeeping (:521-538): one thread per env -----------------
-    for (int e = threadIdx.x; e < e_valid; e += blockDim.x) {
+    // ---- calPunish (:321-330) + MEDAEnv.step bookkeeping (:521-538): one thread per droplet; every thread
+    //      recomputes the (cheap, A^2) pairwise counts of its env, the env scalars are written by droplet 0 ------
+    for (int t = threadIdx.x; t < e_valid * A; t += blockDim.x) {
+        const int e = t / A, i = t - e * A;
         const int64_t n = n0 + e;
+        const size_t ja = (size_t)n * A + i;
         const uint32_t* words = S.word + e * A;
-        uint32_t* misc = S.misc + e * A;
+        const uint32_t* misc = S.misc + e * A;
         const bool frozen = S.flag[e] & kEnvFrozen;
-        int total = 0, all = 1;
-        for (int i = 0; i < A; ++i) {
-            const int xi = words[i] & 255u, yi = (words[i] >> 8) & 255u;
+        int total = 0, all = 1, my_pun = 0;
+        for (int a = 0; a < A; ++a) {
+            const int xa = words[a] & 255u, ya = (words[a] >> 8) & 255u;
             int pun = 0;
             for (int j = 0; j < A; ++j) {
-                const int dx = xi - (int)(words[j] & 255u), dy = yi - (int)((words[j] >> 8) & 255u);
-                pun += (j != i) & (dx * dx + dy * dy < 36);   // centre distance < 1.5 * (r_i + r_j) = 6
+                const int dx = xa - (int)(words[j] & 255u), dy = ya - (int)((words[j] >> 8) & 255u);
+                pun += (j != a) & (dx * dx + dy * dy < 36);   // centre distance < 1.5 * (r_i + r_j) = 6
             }
-            misc[i] |= (uint32_t)pun << 24;
             total += pun;
-            all &= (int)(misc[i] & 1u);
+            all &= (int)(misc[a] & 1u);
+            if (a == i) my_pun = pun;
         }
         if (frozen) total = 0;
         const int fails = st.fails[n] + total;                // the reference keeps -0.6 * this count (:521)
         const int sc = st.step_count[n] + (frozen ? 0 : 1);
-        double sum = 0.0;
-        for (int i = 0; i < A; ++i) {
-            const uint32_t m = misc[i];
-            const uint32_t code = (m >> 8) & 3u;
-            double r = code == 0 ? 0.0 : code == 1 ? -0.2 : code == 2 ? -0.08 : -0.4;
-            const int pun = (int)(m >> 24);
-            if (pun) {                                        // punish[i] -= 0.6, pun times; rewards[i] += punish[i]
-                double p = 0.0;
-                for (int k = 0; k < pun; ++k) p -= 0.6;
-                r = r + p;
-            }
-            if (all) {                                        // (:522-525)
-                r = r + 3.0;
-                if (fails == 0) r = r + 3.0;
-            }
-            if (frozen) r = 0.0;
-            const size_t ja = (size_t)n * A + i;
-            if (out.reward) out.reward[ja] = (float)r;
-            if (out.reward_f64) out.reward_f64[ja] = r;
-            sum += r;
+        const uint32_t m = misc[i];
+        const uint32_t code = (m >> 8) & 3u;
+        double r = code == 0 ? 0.0 : code == 1 ? -0.2 : code == 2 ? -0.08 : -0.4;
+        if (my_pun) {                                         // punish[i] -= 0.6, pun times; rewards[i] += punish[i]
+            double p = 0.0;
+            for (int k = 0; k < my_pun; ++k) p -= 0.6;
+            r = r + p;
         }
-        int success = 0, term = 1;
-        uint8_t eflag = S.flag[e];
-        if (!frozen && sc < cfg.max_step) {                   // (:529-534)
-            success = (all && fails == 0) ? 1 : 0;
-            term = all;
-            eflag |= kEnvUsage;
-            for (int i = 0; i < A; ++i) misc[i] |= (misc[i] & 1u) << 16;   // done = status
-        } else {
-            for (int i = 0; i < A; ++i) misc[i] |= 1u << 16;               // done = True (:535-537)
+        if (all) {                                            // (:522-525)
+            r = r + 3.0;
+            if (fails == 0) r = r + 3.0;
         }
-        S.flag[e] = eflag;
-        for (int i = 0; i < A; ++i) {
-            const size_t ja = (size_t)n * A + i;
-            if (out.done) out.done[ja] = (uint8_t)((misc[i] >> 16) & 1u);
-            if (!frozen) {
-                reinterpret_cast<uint32_t*>(st.drop)[ja] = words[i];
-                st.status[ja] = (uint8_t)(misc[i] & 1u);
-            }
-        }
+        if (frozen) r = 0.0;
+        const bool in_time = !frozen && sc < cfg.max_step;    // (:529-537)
+        const uint32_t done = in_time ? (m & 1u) : 1u;
+        if (out.reward) out.reward[ja] = (float)r;
+        if (out.reward_f64) out.reward_f64[ja] = r;
+        if (out.done) out.done[ja] = (uint8_t)done;
         if (!frozen) {
-            st.fails[n] = fails;
-            st.step_count[n] = sc;
-            st.terminated[n] = (uint8_t)term;
+            reinterpret_cast<uint32_t*>(st.drop)[ja] = words[i];
+            st.status[ja] = (uint8_t)(m & 1u);
         }
-        if (out.team_reward) out.team_reward[n] = (float)(sum / (double)A);
-        if (out.constraints) out.constraints[n] = total;
-        if (out.success) out.success[n] = (uint8_t)success;
-        if (out.terminated) out.terminated[n] = (uint8_t)term;
-        if (out.padded) out.padded[n] = (uint8_t)frozen;
+        S.rew[t] = (float)r;
+        S.done[t] = (uint8_t)done;
+        if (i == 0) {
+            const int term = in_time ? all : 1;
+            S.flag[e] = (uint8_t)(S.flag[e] | (in_time ? kEnvUsage : 0));
+            S.envi[2 * e] = fails;
+            S.envi[2 * e + 1] = sc;
+            if (out.constraints) out.constraints[n] = total;
+            if (out.success) out.success[n] = (uint8_t)((in_time && all && fails == 0) ? 1 : 0);
+            if (out.terminated) out.terminated[n] = (uint8_t)term;
+            if (out.padded) out.padded[n] = (uint8_t)frozen;
+            if (!frozen) st.terminated[n] = (uint8_t)term;
+        }
         if (out.avail) {
-            uint8_t* av = out.avail + (size_t)n * A * cfg.n_actions;
-            for (int k = 0; k < A * cfg.n_actions; ++k) av[k] = frozen ? 0 : 1;
+            uint8_t* av = out.avail + ja * cfg.n_actions;
+            for (int k = 0; k < cfg.n_actions; ++k) av[k] = frozen ? 0 : 1;
         }
     }
     __syncthreads();
+    // env counters are read by every droplet thread above, so they are written only after the barrier
+    for (int e = threadIdx.x; e < e_valid; e += blockDim.x) {
+        const int64_t n = n0 + e;
+        if (!(S.flag[e] & kEnvFrozen)) {
+            st.fails[n] = S.envi[2 * e];
+            st.step_count[n] = S.envi[2 * e + 1];
+        }
+        if (out.team_reward) {
+            float sum = 0.f;
+            for (int i = 0; i < A; ++i) sum += S.rew[e * A + i];
+            out.team_reward[n] = sum / (float)A;
+        }
+    }
 
     // ---- addUsage (:591-598): footprints of one env may overlap -> RED.ADD per cell, one warp per droplet ----
     if (st.usage) {
@@ -341,8 +352,8 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
         for (int g = warp; g < e_valid * A; g += nwarps) {
             const int e = g / A;
             if (!(S.flag[e] & kEnvUsage) || (S.flag[e] & kEnvFrozen)) continue;
-            const uint32_t m = S.misc[g], w = S.word[g];
-            if (!((m >> 16) & 1u) && lane < kFootCells) {
+            const uint32_t w = S.word[g];
+            if (!S.done[g] && lane < kFootCells) {
                 const int x = (int)(w & 255u) - kRad + lane % 5, y = (int)((w >> 8) & 255u) - kRad + lane / 5;
                 atomicAdd(st.usage + (size_t)(n0 + e) * cells + y * Lc + x, 1u);
             }
