@@ -194,7 +194,6 @@ typedef struct meda_state {
     uint8_t* status;        /* [N,A] sticky arrival flags (meda.py:159,277) */
     int32_t* step_count;    /* [N] */
     int32_t* fails;         /* [N] episode-cumulative punish count; reference `fails` == -0.6*count (meda.py:521) */
-    uint8_t* done;          /* reserved (NULL) */
     uint8_t* terminated;    /* [N] */
     uint32_t* episode;      /* [N] */
     uint32_t* usage;        /* [N,W,L] */

@@ -61,7 +61,7 @@ class MedaState(C.Structure):
     _fields_ = [
         ("n_envs", C.c_int32), ("reserved0", C.c_int32),
         ("drop", C.c_void_p), ("start", C.c_void_p), ("status", C.c_void_p), ("step_count", C.c_void_p),
-        ("fails", C.c_void_p), ("done", C.c_void_p), ("terminated", C.c_void_p), ("episode", C.c_void_p),
+        ("fails", C.c_void_p), ("terminated", C.c_void_p), ("episode", C.c_void_p),
         ("usage", C.c_void_p), ("health", C.c_void_p), ("degrade", C.c_void_p),
     ]
 

@@ -626,7 +626,10 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     const int any_frozen = __syncthreads_or(o.frozen && env_on);   // also the zero-fill / table barrier
 
     write_avail(cfg, out, A, n0, e_valid, any_frozen, tid, (int)blockDim.x, agent, lane_on, o.frozen);
-    if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) update_health_flagged(cfg, st, S, n0, e_valid);
+    if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) {
+        // rare: only tiles in which an env was just reset scan its electrodes (updateHealth, dmfb.py:465-471)
+        if (__syncthreads_or(o.do_reset)) update_health_flagged(cfg, st, S, n0, e_valid);
+    }
 
     const uint32_t word = o.word;
     const uint8_t* env_blocks = (A_T == 0 && cfg.n_blocks && env_on) ? st.blocks + (size_t)n * cfg.n_blocks * 2 : nullptr;

@@ -83,7 +83,7 @@ class BatchedMEDA:
         self.degrade = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         self.state = nat.MedaState(
             n_envs=N, drop=self.drop.data_ptr(), start=self.start.data_ptr(), status=self.status.data_ptr(),
-            step_count=self.step_count.data_ptr(), fails=self.fails.data_ptr(), done=None,
+            step_count=self.step_count.data_ptr(), fails=self.fails.data_ptr(),
             terminated=self.terminated.data_ptr(), episode=self.episode.data_ptr(), usage=self.usage.data_ptr(),
             health=self.health.data_ptr() if self.b_degrade else None,
             degrade=self.degrade.data_ptr() if self.b_degrade else None)
