@@ -53,6 +53,7 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-clocks", action="store_true")
+    p.add_argument("--no-others", action="store_true", help="skip the context timings of the other BASELINE configs")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     return p.parse_args()
 
@@ -261,7 +262,7 @@ def run_b200(args, rank, world, local_rank):
         per_launch_s = e0.elapsed_time(e1) * 1e-3 / (reps * slots)
         alg_bytes = ALG_BYTES_PER_ENV_STEP * N
         achieved = alg_bytes / per_launch_s / 1e9
-        roof = {"bound": "hbm", "kernel": "dmfb_step_kernel<9,4,4,32,false>", "achieved": achieved, "peak": peak,
+        roof = {"bound": "hbm", "kernel": "dmfb_step_kernel<fov=9,G=4,A=4,E=16,deg=false>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "launches_timed": reps * slots}
         tr = os.path.join(ROOT, "profiles", "traffic_step_kernel.json")
@@ -275,11 +276,52 @@ def run_b200(args, rank, world, local_rank):
         clocks.__exit__(None, None, None)
     env.reset()
 
+    # ---- the other BASELINE configs, step kernel only (reported for context, not part of `value`) ----
+    others = None
+    if rank == 0 and not args.no_others:
+        others = {}
+        del obs_buf
+        torch.cuda.empty_cache()
+
+        def quick(make, n_act, alg_bytes, slots2=8):
+            e2 = make()
+            buf = torch.empty(slots2 + 1, e2.N, e2.A, e2.D, dtype=torch.int8, device=dev)
+            acts = torch.randint(0, n_act, (slots2, e2.N, e2.A), device=dev, generator=gen, dtype=torch.int8)
+            with torch.cuda.stream(stream):
+                for t in range(3):
+                    e2.step(acts[t], out=buf[t + 1])
+                stream.synchronize()
+                gq = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gq, stream=stream):
+                    for t in range(slots2):
+                        e2.step(acts[t], out=buf[t + 1])
+                gq.replay()
+                stream.synchronize()
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q0.record(stream)
+                for _ in range(10):
+                    gq.replay()
+                q1.record(stream)
+                stream.synchronize()
+            us = q0.elapsed_time(q1) * 1e3 / (10 * slots2)
+            return {"us_per_step": us, "agent_steps_per_s": e2.N * e2.A / (us * 1e-6),
+                    "alg_GBps": alg_bytes * e2.N / (us * 1e-6) / 1e9, "frac_of_peak": alg_bytes * e2.N / (us * 1e-6) / 1e9 / peak}
+
+        others["C2 DMFB 20x20 10d fov9"] = quick(lambda: pkg.BatchedDMFB(N, 20, 20, 10, fov=9, device=dev, seed=1), 5, 2641)
+        torch.cuda.empty_cache()
+        others["C3 DMFB 50x50 10d fov9 degrade"] = quick(lambda: pkg.BatchedDMFB(N, 50, 50, 10, fov=9, b_degrade=True,
+                                                                                  per_degrade=1.0, device=dev, seed=1), 5, 2761)
+        torch.cuda.empty_cache()
+        others["C4 MEDA 30x60 4d fov19 (v0_2 obs)"] = quick(lambda: pkg.BatchedMEDA(N, 30, 60, 4, fov=19, obs_version=2,
+                                                                                     device=dev, seed=1), 9, 4453)
+        torch.cuda.empty_cache()
+        obs_buf = None
+
     # ---- e2e: host-buffer C ABI, H2D actions + D2H results every step ----
     e2e = None
     if not args.no_e2e:
         import numpy as np
-        del obs_buf
+        obs_buf = None
         torch.cuda.empty_cache()
         henv = pkg.HostDMFB(N, W, L, A, fov=FOV, device=local_rank, seed=1234, env_base=rank * N, n_chunks=8)
         henv.reset()
@@ -314,7 +356,7 @@ def run_b200(args, rank, world, local_rank):
                            "l2": f"outputs rotate over {(slots + 1) * N * A * D / 1e9:.2f} GB > L2 (no explicit flush)",
                            "cuda_graph_steps": chunk},
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": gpu_launches,
-                "roofline": roof, "cpu_baseline": cpu}
+                "roofline": roof, "cpu_baseline": cpu, "other_configs": others}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

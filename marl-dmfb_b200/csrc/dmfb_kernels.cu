@@ -124,31 +124,49 @@ __device__ __forceinline__ uint32_t near_pair(uint32_t a, uint32_t b)
 __device__ __forceinline__ uint32_t dup_lo(uint32_t w) { return __byte_perm(w, 0, 0x1010); }  // cell0 | cell0<<16
 __device__ __forceinline__ uint32_t dup_hi(uint32_t w) { return __byte_perm(w, 0, 0x3232); }  // cell1 | cell1<<16
 
+// A lane group = the G consecutive lanes of a warp that hold the droplets of one env.  G is a power of two
+// (4, 8, 16, 32) or, to avoid idle lanes, exactly the droplet count (G = 10: three envs per warp, lanes 30-31 idle).
 template <int G>
 struct Group {
+    static constexpr bool kPow2 = (G & (G - 1)) == 0;
+    static constexpr int kPerWarp = 32 / G;                      // envs per warp
     static constexpr unsigned kBits = (G == 32) ? 0xFFFFFFFFu : ((1u << G) - 1u);
-    int lane, base, i;
+    int lane, base, i, idx;
+    bool valid;                                                  // false for the spare lanes of a non-power-of-two G
     __device__ explicit Group(int tid) {
         lane = tid & 31;
-        i = lane & (G - 1);
-        base = lane & ~(G - 1);
+        idx = lane / G;                                          // group index inside the warp
+        valid = idx < kPerWarp;
+        i = lane - idx * G;
+        base = valid ? idx * G : 0;
     }
+    // env (inside the tile) held by this lane's group
+    __device__ __forceinline__ int env_in_tile(int tid) const { return (tid >> 5) * kPerWarp + idx; }
     // value of lane j of my group (all 32 lanes must call)
     template <typename T>
-    __device__ __forceinline__ T get(T v, int j) const { return __shfl_sync(kFull, v, j, G); }
+    __device__ __forceinline__ T get(T v, int j) const {
+        if constexpr (kPow2) return __shfl_sync(kFull, v, j, G);
+        else return __shfl_sync(kFull, v, base + j);
+    }
     // bits of my group from a warp ballot
     __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(kFull, p) >> base) & kBits; }
-    __device__ __forceinline__ int sum(int v) const {
+    template <typename T>
+    __device__ __forceinline__ T sum(T v) const {
+        if constexpr (kPow2) {
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        return v;
-    }
-    __device__ __forceinline__ float sum(float v) const {
+            for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            return v;
+        } else {
+            T s = 0;
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        return v;
+            for (int j = 0; j < G; ++j) s += __shfl_sync(kFull, v, base + j);
+            return s;
+        }
     }
 };
+
+// threads per CTA for E envs with G lanes per env
+__host__ __device__ constexpr int cta_threads(int E, int G) { return ((E + 32 / G - 1) / (32 / G)) * 32; }
 
 // _Generate_Start_End (dmfb.py:207-226): 2A uniform cells, the whole set is redrawn until every pairwise
 // squared distance is > 2.  Attempt number k for (seed, env, episode) is a pure function of those four values:
@@ -165,13 +183,13 @@ template <int G>
 __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const Group<G>& g, int A, uint64_t seed,
                                                     int64_t env0, uint32_t episode, bool want, uint32_t keep)
 {
-    constexpr int NG = 32 / G;
+    constexpr int NG = Group<G>::kPerWarp;
     uint32_t word = keep;
     unsigned todo = __ballot_sync(kFull, want && g.i == 0);      // leader lanes of the requesting groups
     if (todo == 0u) return word;
-    const int my_group = g.lane / G;
+    const int my_group = g.idx;
     const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
-    const bool lane_in = g.i < A;
+    const bool lane_in = g.valid && g.i < A;
     while (todo) {
         const int src = __ffs(todo) - 1;                          // leader lane of the group served now
         todo &= todo - 1;
@@ -197,7 +215,7 @@ __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const
                 if (j != g.i) bad |= hit;
             }
             const unsigned gb = g.ballot(bad != 0u && lane_in);
-            const unsigned okm = __ballot_sync(kFull, gb == 0u && g.i == 0);   // leaders of accepting groups
+            const unsigned okm = __ballot_sync(kFull, g.valid && gb == 0u && g.i == 0);   // leaders of accepting groups
             if (okm) {
                 const int win = __ffs(okm) - 1;                   // lowest attempt number of this round
                 const uint32_t wsel = __shfl_sync(kFull, w, win + g.i);
@@ -531,7 +549,7 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
     o.word = (d & 0xFFFF0000u) | cur;
     o.do_reset = (flags & DMFB_STEP_AUTO_RESET) && o.term && !frozen && env_on;
     if (flags & DMFB_STEP_AUTO_RESET) {
-        o.word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.lane / G, episode + 1u, o.do_reset, o.word);
+        o.word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.idx, episode + 1u, o.do_reset, o.word);
         if (A_T == 0) generate_blocks<G>(cfg, st, g, seed, n, episode + 1u, o.do_reset, lane_on, o.word);
         if (o.do_reset) {
             o.sc_out = 0;
@@ -587,7 +605,7 @@ __device__ __forceinline__ void write_avail(const dmfb_cfg_t& cfg, const dmfb_ou
 // A_T / E_T: compile-time droplet count and tile size for the shipped configs (0 = run-time values).
 // DEG_T = false strips the degradation path (health / usage / draws) when the state has none.
 template <int FOV_T, int G, int A_T, int E_T, bool DEG_T>
-__global__ void __launch_bounds__(E_T ? E_T * G : kMaxThreads)
+__global__ void __launch_bounds__(E_T ? cta_threads(E_T, G) : kMaxThreads)
 dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, const void* __restrict__ actions,
                  int aes, const double* __restrict__ u, uint64_t seed, uint32_t flags, const dmfb_out_t out, int E_rt)
 {
@@ -600,9 +618,9 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     const Group<G> g(tid);
     const int64_t n0 = (int64_t)blockIdx.x * E;
     const int e_valid = (int)min((int64_t)E, (int64_t)st.n_envs - n0);
-    const int e = tid / G;                          // env of this lane group inside the tile
+    const int e = g.env_in_tile(tid);               // env of this lane group inside the tile
     const int64_t n = n0 + e;
-    const bool env_on = e < e_valid;
+    const bool env_on = g.valid && e < e_valid;
     const bool lane_on = env_on && g.i < A;         // this lane holds droplet g.i of env n
     const bool leader = env_on && g.i == 0;
     const int agent = e * A + g.i;                  // agent index inside the tile
@@ -614,7 +632,7 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     asm volatile("griddepcontrol.launch_dependents;");
     load_tables(cfg, L, S, tid, (int)blockDim.x);
     if constexpr (FOV_T != 0 && A_T != 0 && E_T != 0)
-        zero_tile_static<((E_T * A_T * (3 * FOV_T * FOV_T + 2) + 15) / 16) * 16, E_T * G>(S.tile, tid);
+        zero_tile_static<((E_T * A_T * (3 * FOV_T * FOV_T + 2) + 15) / 16) * 16, cta_threads(E_T, G)>(S.tile, tid);
     else
         zero_tile(L, S, tid, (int)blockDim.x);
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -655,9 +673,9 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
     const int A = L.A;
     const int64_t n0 = (int64_t)blockIdx.x * E;
     const int e_valid = (int)min((int64_t)E, (int64_t)st.n_envs - n0);
-    const int e = tid / G;
+    const int e = g.env_in_tile(tid);
     const int64_t n = n0 + e;
-    const bool env_on = e < e_valid;
+    const bool env_on = g.valid && e < e_valid;
     const bool lane_on = env_on && g.i < A;
     const bool leader = env_on && g.i == 0;
     const size_t ja = (size_t)n * A + g.i;
@@ -680,7 +698,7 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
         if (layouts) {
             if (lane_on && selected) word = reinterpret_cast<const uint32_t*>(layouts)[ja];
         } else {
-            word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.lane / G, episode, selected && env_on, word);
+            word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.idx, episode, selected && env_on, word);
         }
         if (cfg.n_blocks) {   // refresh() regenerates the obstacles with every task (dmfb.py:174-177)
             if (block_layouts) {
@@ -781,21 +799,23 @@ dmfb_global_state_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_stat
 
 int group_size_for(int n_agents)
 {
+    if (n_agents == 10) return 10;   // three envs per warp instead of two with 16-lane groups (C2 / C3)
     int g = 4;
     while (g < n_agents) g <<= 1;
     return g;
 }
 
-// Envs per tile: a multiple of the 16-byte alignment unit, at most kMaxThreads/G lane groups, ~40 KB of smem.
+// Envs per tile: a multiple of the 16-byte alignment unit, at most kMaxThreads worth of lane groups, ~40 KB of smem.
 int tile_envs_for(const dmfb_cfg_t& cfg, int G)
 {
     const int row = cfg.n_agents * cfg.obs_dim;
-    int max_envs = kMaxThreads / G;
-    const int cap = G <= 4 ? 32 : 256 / G;  // 128-256 threads per CTA keeps several CTAs resident per SM
+    const int per_warp = 32 / G;
+    int max_envs = (kMaxThreads / 32) * per_warp;
+    const int cap = G <= 4 ? 16 : (G == 10 ? 8 : 8 * per_warp);   // measured: C1 best with 16 envs, C2/C3 with 8 envs per CTA
     if (cap >= 16 / gcd_int(16, row) && cap < max_envs) max_envs = cap;
     if (const char* ev = getenv("DMFB_TILE_ENVS")) {
         const int v = atoi(ev);
-        if (v > 0 && v * G <= kMaxThreads) return v;
+        if (v > 0 && cta_threads(v, G) <= kMaxThreads) return v;
     }
     return pick_tile_envs(row, 40 * 1024, max_envs);
 }
@@ -829,6 +849,7 @@ int dispatch(int fov, int G, F&& f)
     switch (G) {                                       \
     case 4: return f.template operator()<FOVT, 4>();   \
     case 8: return f.template operator()<FOVT, 8>();   \
+    case 10: return f.template operator()<FOVT, 10>(); \
     case 16: return f.template operator()<FOVT, 16>(); \
     default: return f.template operator()<FOVT, 32>(); \
     }
@@ -850,7 +871,7 @@ struct StepLaunch {
         if (rc) return rc;
         cudaLaunchConfig_t lc{};
         lc.gridDim = dim3((unsigned)grid);
-        lc.blockDim = dim3((unsigned)(E * G));
+        lc.blockDim = dim3((unsigned)cta_threads(E, G));
         lc.dynamicSmemBytes = smem;
         lc.stream = s;
         cudaLaunchAttribute attr[1];
@@ -870,9 +891,12 @@ struct StepLaunch {
         if (cfg->n_blocks != 0) return go<FOVT, G, 0, 0, true>();
         if constexpr (FOVT == 9 && G == 4) {
             if (cfg->n_agents == 4 && E == 32) return deg ? go<9, 4, 4, 32, true>() : go<9, 4, 4, 32, false>();
+            if (cfg->n_agents == 4 && E == 16) return deg ? go<9, 4, 4, 16, true>() : go<9, 4, 4, 16, false>();
         }
-        if constexpr (FOVT == 9 && G == 16) {
-            if (cfg->n_agents == 10 && E == 16) return deg ? go<9, 16, 10, 16, true>() : go<9, 16, 10, 16, false>();
+        if constexpr (FOVT == 9 && G == 10) {
+            if (E == 24) return deg ? go<9, 10, 10, 24, true>() : go<9, 10, 10, 24, false>();
+            if (E == 16) return deg ? go<9, 10, 10, 16, true>() : go<9, 10, 10, 16, false>();
+            if (E == 8) return deg ? go<9, 10, 10, 8, true>() : go<9, 10, 10, 8, false>();
         }
         return go<FOVT, G, 0, 0, true>();
     }
@@ -886,7 +910,7 @@ struct ResetLaunch {
     int operator()() const {
         int rc = set_smem(dmfb_reset_kernel<FOVT, G>, smem);
         if (rc) return rc;
-        dmfb_reset_kernel<FOVT, G><<<grid, E * G, smem, s>>>(*cfg, *st, mask, mode, new_task, layouts, block_layouts,
+        dmfb_reset_kernel<FOVT, G><<<grid, cta_threads(E, G), smem, s>>>(*cfg, *st, mask, mode, new_task, layouts, block_layouts,
                                                                degrade, seed, obs, E);
         return DMFB_OK;
     }
