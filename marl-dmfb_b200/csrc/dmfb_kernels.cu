@@ -830,6 +830,7 @@ int set_smem(K kernel, uint32_t bytes)
 
 int check_common(const dmfb_cfg_t* cfg, const dmfb_state_t* st)
 {
+    if (cfg && st && st->n_envs == 0) return DMFB_OK;   // empty batch: nothing to check, the callers return early
     if (!cfg || !st || st->n_envs < 0 || !st->drop || !st->step_count || !st->constraints || !st->terminated) {
         snprintf(g_last_error, sizeof(g_last_error), "null cfg/state pointer");
         return DMFB_ERR_BAD_ARG;
@@ -999,11 +1000,11 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
 {
     int rc = check_common(cfg, state);
     if (rc) return rc;
+    if (state->n_envs == 0) return DMFB_OK;
     if (!actions || !out || !out->obs || (action_elem_size != 1 && action_elem_size != 4 && action_elem_size != 8)) {
         snprintf(g_last_error, sizeof(g_last_error), "dmfb_step: bad actions/out");
         return DMFB_ERR_BAD_ARG;
     }
-    if (state->n_envs == 0) return DMFB_OK;
     const int G = group_size_for(cfg->n_agents);
     const int E = tile_envs_for(*cfg, G);
     const TileLayout L(*cfg, E);
@@ -1034,6 +1035,7 @@ int dmfb_restart(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t
 
 int dmfb_observe(const dmfb_cfg_t* cfg, const dmfb_state_t* state, int8_t* obs, void* stream)
 {
+    if (state && state->n_envs == 0) return DMFB_OK;
     if (!obs) return DMFB_ERR_BAD_ARG;
     return launch_reset(cfg, state, nullptr, 2, 0, nullptr, nullptr, nullptr, 0, obs, stream);
 }
@@ -1042,8 +1044,8 @@ int dmfb_global_state(const dmfb_cfg_t* cfg, const dmfb_state_t* state, int8_t* 
 {
     int rc = check_common(cfg, state);
     if (rc) return rc;
-    if (!out) return DMFB_ERR_BAD_ARG;
     if (state->n_envs == 0) return DMFB_OK;
+    if (!out) return DMFB_ERR_BAD_ARG;
     const int per_env = 3 * cfg->width * cfg->length;
     const int E2 = pick_tile_envs(per_env, 32 * 1024, 64);
     const uint32_t tile_bytes = ((uint32_t)(E2 * per_env) + 15u) & ~15u;

@@ -488,6 +488,7 @@ int meda_tile_envs(const meda_cfg_t& cfg)
 
 int meda_check(const meda_cfg_t* cfg, const meda_state_t* st)
 {
+    if (cfg && st && st->n_envs == 0) return DMFB_OK;   // empty batch
     if (!cfg || !st || st->n_envs < 0 || !st->drop || !st->status || !st->step_count || !st->fails || !st->terminated) {
         snprintf(g_last_error, sizeof(g_last_error), "meda: null cfg/state pointer");
         return DMFB_ERR_BAD_ARG;
@@ -552,6 +553,7 @@ int meda_step(const meda_cfg_t* cfg, const meda_state_t* state, const void* acti
 {
     int rc = meda_check(cfg, state);
     if (rc) return rc;
+    if (state->n_envs == 0) return DMFB_OK;
     if (!actions || !out || !out->obs || (action_elem_size != 1 && action_elem_size != 4 && action_elem_size != 8)) {
         snprintf(g_last_error, sizeof(g_last_error), "meda_step: bad actions/out");
         return DMFB_ERR_BAD_ARG;
@@ -583,6 +585,7 @@ int meda_reset(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t* 
 
 int meda_observe(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t* set_order, int8_t* obs, void* stream)
 {
+    if (state && state->n_envs == 0) return DMFB_OK;
     if (!obs) return DMFB_ERR_BAD_ARG;
     return meda_launch_reset(cfg, state, nullptr, 2, 0, nullptr, nullptr, 0, set_order, obs, stream);
 }

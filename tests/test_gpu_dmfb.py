@@ -315,3 +315,22 @@ def test_dmfb_device_block_generator_obeys_reference_rules():
         assert not bool(((rel >= 0) & (rel <= 1)).all(-1).any())
     check()
     assert P.BatchedDMFB(4, 10, 10, 2, 6, fov=5, device="cuda:0").n_blocks == 0   # 24/100 > 0.2 -> no blocks
+
+
+def test_empty_and_tiny_batches():
+    """N = 0 (empty batch) is a no-op through every entry point; N = 1..3 (ragged: far below one tile) work."""
+    P = pkg()
+    env = P.BatchedDMFB(0, 10, 10, 4, fov=9, device="cuda:0")
+    assert env.reset().shape == (0, 4, 245)
+    obs, rew, done, info = env.step(torch.zeros(0, 4, dtype=torch.int8, device="cuda:0"), auto_reset=True)
+    assert obs.shape == (0, 4, 245) and rew.shape == (0, 4) and env.get_state().shape == (0, 3, 10, 10)
+    assert env.get_obs().shape == (0, 4, 245)
+    m = P.BatchedMEDA(0, 30, 60, 4, device="cuda:0")
+    assert m.step(torch.zeros(0, 4, dtype=torch.int8, device="cuda:0"))[0].shape == (0, 4, 1085)
+    for n in (1, 2, 3):
+        e = P.BatchedDMFB(n, 10, 10, 4, fov=9, device="cuda:0", seed=n)
+        o = e.reset()
+        assert o.shape == (n, 4, 245) and bool((o[:, :, 40] == torch.arange(1, 5, device="cuda:0", dtype=torch.int8)).all())
+        for t in range(45):
+            o, r, d, info = e.step(torch.randint(0, 5, (n, 4), device="cuda:0"), auto_reset=True)
+        assert int(e.step_count.max()) < 40
