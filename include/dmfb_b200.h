@@ -18,7 +18,10 @@
  *    API) and never frees caller memory.
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *    Calls on one env batch are ordered by that stream; the library is
- *    re-entrant across batches / devices.
+ *    re-entrant across batches / devices.  dmfb_step is launched with
+ *    programmatic stream serialization: back-to-back steps overlap the
+ *    prologue of step t+1 with the tail of step t, every global access of
+ *    step t+1 still waits for step t to complete.
  *  - Return value: DMFB_OK (0) or a DMFB_ERR_* code.  The Python host layer
  *    maps the codes onto the exception types the reference raises.
  *  - Coordinates: DMFB x in [0,width), y in [0,length) (dmfb.py:103-124).
@@ -226,6 +229,10 @@ int meda_reset(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t* 
                const uint8_t* layouts, const double* degrade, uint64_t seed, const uint8_t* set_order,
                int8_t* obs, void* stream);
 int meda_observe(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t* set_order,
+                 int8_t* obs, void* stream);
+/* MEDAEnv.restart (meda.py:552-561 -> RoutingTaskManager.restart :170-173): droplets back to their start squares,
+ * status and step_count cleared, `fails` kept (as in the reference).  Needs state->start. */
+int meda_restart(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t* mask, const uint8_t* set_order,
                  int8_t* obs, void* stream);
 /* Host helper: iteration order of the CPython set {i : bit i of mask_bits} built by ascending insertion
  * (MEDAEnv_v0_2 iterates such a set, meda.py:862-872).  out[0..n_max) = elements in iteration order, 0xFF padded.

@@ -71,7 +71,7 @@ MedaOut = DmfbOut  # same field list (include/dmfb_b200.h: meda_out_t)
 # every symbol include/dmfb_b200.h declares
 EXPORTS = [
     "dmfb_cfg_init", "dmfb_step", "dmfb_reset", "dmfb_observe", "dmfb_global_state", "dmfb_restart",
-    "meda_cfg_init", "meda_step", "meda_reset", "meda_observe", "meda_set_order",
+    "meda_cfg_init", "meda_step", "meda_reset", "meda_observe", "meda_restart", "meda_set_order",
     "dmfb_abi_version", "dmfb_last_cuda_error", "dmfb_launch_count",
     "dmfb_host_create", "dmfb_host_destroy", "dmfb_host_reset", "dmfb_host_step",
     "dmfb_host_alloc_pinned", "dmfb_host_free_pinned",
@@ -113,6 +113,8 @@ def load():
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.meda_observe.argtypes = [C.POINTER(MedaCfg), C.POINTER(MedaState), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.meda_set_order.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+        lib.meda_restart.argtypes = [C.POINTER(MedaCfg), C.POINTER(MedaState), C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]
     if hasattr(lib, "dmfb_host_create"):
         lib.dmfb_host_create.argtypes = [C.POINTER(DmfbCfg), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         lib.dmfb_host_destroy.argtypes = [C.c_void_p]

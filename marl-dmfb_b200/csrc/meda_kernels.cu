@@ -402,7 +402,7 @@ __device__ void meda_generate_tasks(const meda_cfg_t& cfg, uint64_t seed, int64_
     }
 }
 
-// mode 0: reset, mode 2: observe only
+// mode 0: reset, mode 1: restart (droplets back to their start cells, meda.py:170-173,552-561), mode 2: observe only
 __global__ void __launch_bounds__(kThreads)
 meda_reset_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, const uint8_t* __restrict__ mask, int mode,
                   int new_chip, const uint8_t* __restrict__ layouts, const double* __restrict__ degrade_in, uint64_t seed,
@@ -442,6 +442,14 @@ meda_reset_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st,
             }
             st.step_count[n] = 0;
             st.fails[n] = 0;
+            st.terminated[n] = 0;
+        } else if (sel && mode == 1) {
+            for (int i = 0; i < A; ++i) {
+                words[i] = (gdrop[i] & 0xFFFF0000u) | reinterpret_cast<const uint16_t*>(st.start)[(size_t)n * A + i];
+                gdrop[i] = words[i];
+                st.status[(size_t)n * A + i] = 0;
+            }
+            st.step_count[n] = 0;      // `fails` is NOT cleared by the reference's restart (meda.py:552-561)
             st.terminated[n] = 0;
         } else {
             for (int i = 0; i < A; ++i) words[i] = gdrop[i];
@@ -581,6 +589,16 @@ int meda_reset(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t* 
                const double* degrade, uint64_t seed, const uint8_t* set_order, int8_t* obs, void* stream)
 {
     return meda_launch_reset(cfg, state, mask, 0, new_chip, layouts, degrade, seed, set_order, obs, stream);
+}
+
+int meda_restart(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t* mask, const uint8_t* set_order,
+                 int8_t* obs, void* stream)
+{
+    if (state && state->n_envs != 0 && !state->start) {
+        snprintf(g_last_error, sizeof(g_last_error), "meda_restart needs state->start");
+        return DMFB_ERR_BAD_ARG;
+    }
+    return meda_launch_reset(cfg, state, mask, 1, 0, nullptr, nullptr, 0, set_order, obs, stream);
 }
 
 int meda_observe(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t* set_order, int8_t* obs, void* stream)

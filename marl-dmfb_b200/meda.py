@@ -138,6 +138,15 @@ class BatchedMEDA:
         nat.check(rc, "meda_reset")
         return obs
 
+    def restart(self, mask=None):
+        """MEDAEnv.restart (meda.py:552-561): droplets back to their start squares; `fails` is kept."""
+        mask_t = self._as(mask, torch.uint8, (self.N,), "mask")
+        with torch.cuda.device(self.device):
+            rc = self.lib.meda_restart(C.byref(self.cfg), C.byref(self.state), _ptr(mask_t), _ptr(self.set_order),
+                                       _ptr(self.obs), self._stream())
+        nat.check(rc, "meda_restart")
+        return self.obs
+
     def step(self, actions, draws=None, freeze_terminated=False, auto_reset=False, out=None):
         """MEDAEnv.step (meda.py:513-539) on every env; actions [N,A] in 0..8."""
         if not torch.is_tensor(actions):
@@ -276,6 +285,12 @@ class MEDAEnv:
         self.rewards = {a: 0.0 for a in self.agents}
         self.dones = {a: False for a in self.agents}
         return self._obs_list(self._b.reset(layouts=None if layouts is None else np.asarray(layouts)[None]))
+
+    def restart(self, index=None):
+        self.rewards = {a: 0.0 for a in self.agents}
+        self.dones = {a: False for a in self.agents}
+        obs = self._obs_list(self._b.restart())
+        return obs[index] if index else obs                       # meda.py:558-561 (index 0 returns everything)
 
     def getObs(self):
         return self._obs_list(self._b.get_obs())

@@ -334,3 +334,17 @@ def test_empty_and_tiny_batches():
         for t in range(45):
             o, r, d, info = e.step(torch.randint(0, 5, (n, 4), device="cuda:0"), auto_reset=True)
         assert int(e.step_count.max()) < 40
+
+
+def test_dmfb_restart_returns_to_the_start_cells():
+    P = pkg()
+    env = P.BatchedDMFB(700, 10, 10, 4, fov=9, device="cuda:0", seed=2)
+    first = env.reset().clone()
+    start = env.drop.clone()
+    gen = torch.Generator(device="cuda:0").manual_seed(4)
+    for t in range(9):
+        env.step(torch.randint(0, 5, (700, 4), device="cuda:0", generator=gen, dtype=torch.int8))
+    assert not torch.equal(env.drop, start)
+    obs = env.restart()
+    assert torch.equal(env.drop, start) and torch.equal(obs, first)
+    assert int(env.step_count.max()) == 0 and int(env.constraints_cum.max()) == 0

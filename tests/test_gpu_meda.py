@@ -153,3 +153,18 @@ def test_meda_adapter_types_and_generator():
         acts = torch.randint(0, 9, (N, A), device="cuda:0", generator=gen, dtype=torch.int8)
         obs, rew, done, info = b.step(acts, auto_reset=True)
     assert int(b.step_count.max()) < 90 and int(b.terminated.sum()) == 0
+
+
+def test_meda_restart_returns_to_the_start_squares():
+    P = pkg()
+    env = P.BatchedMEDA(500, 30, 60, 4, fov=19, obs_version=2, device="cuda:0", seed=9)
+    first = env.reset().clone()
+    start = env.drop.clone()
+    gen = torch.Generator(device="cuda:0").manual_seed(4)
+    for t in range(12):
+        env.step(torch.randint(0, 8, (500, 4), device="cuda:0", generator=gen, dtype=torch.int8))
+    assert not torch.equal(env.drop, start)
+    fails = env.fails.clone()
+    obs = env.restart()
+    assert torch.equal(env.drop, start) and torch.equal(obs, first)
+    assert int(env.step_count.max()) == 0 and int(env.status.max()) == 0 and torch.equal(env.fails, fails)
