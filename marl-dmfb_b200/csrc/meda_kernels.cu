@@ -162,7 +162,21 @@ __device__ void meda_paint_agent(const meda_cfg_t& cfg, const MedaSmem& S, const
         if (lb > 0) { r_lo = 0; r_hi = min(lb, fov); } else if (rb > 0) { r_lo = max(fov - rb, 0); r_hi = fov; }
         if (ub > 0) { q_lo = 0; q_hi = min(ub, fov); } else if (db > 0) { q_lo = max(fov - db, 0); q_hi = fov; }
         // whole rows are one contiguous byte range; the column band is written row by row, one lane per column
-        for (int k = r_lo * fov + lane; k < r_hi * fov; k += 32) rec[2 * f2 + k] = 1;
+        {
+            // bytes [b0, b1) of the record; unaligned head / tail by bytes, the middle as 4-byte words
+            int8_t* const lay = rec + 2 * f2;
+            const int b0 = r_lo * fov, b1 = r_hi * fov;
+            if (b1 > b0) {
+                const int mis = (int)(reinterpret_cast<uintptr_t>(lay + b0) & 3u);
+                const int head = min((4 - mis) & 3, b1 - b0);
+                const int nwords = (b1 - b0 - head) >> 2;
+                const int tail0 = b0 + head + 4 * nwords;
+                if (lane < head) lay[b0 + lane] = 1;
+                uint32_t* w4 = reinterpret_cast<uint32_t*>(lay + b0 + head);
+                for (int k = lane; k < nwords; k += 32) w4[k] = 0x01010101u;
+                if (lane < b1 - tail0) lay[tail0 + lane] = 1;
+            }
+        }
         if (q_hi > q_lo) {
             const int nq = q_hi - q_lo;
             for (int q = lane; q < nq; q += 32)
@@ -179,8 +193,9 @@ __device__ __forceinline__ void meda_paint_tile(const meda_cfg_t& cfg, const Med
                                                 int e_valid, uint8_t need_flag, const uint8_t* __restrict__ set_order)
 {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t inv_a = 0xFFFFFFFFu / (uint32_t)L.A + 1u;                  // g / A == umulhi(g, inv_a) for g < 2^16
     for (int g = warp; g < e_valid * L.A; g += nwarps) {
-        const int e = g / L.A, i = g - e * L.A;
+        const int e = (int)__umulhi((uint32_t)g, inv_a), i = g - e * L.A;
         if (!(S.flag[e] & need_flag) || (S.flag[e] & kEnvFrozen)) continue;   // warp-uniform
         meda_paint_agent(cfg, S, S.word + e * L.A, i, S.tile + (size_t)g * L.D, set_order);
     }
@@ -349,8 +364,9 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
     // ---- addUsage (:591-598): footprints of one env may overlap -> RED.ADD per cell, one warp per droplet ----
     if (st.usage) {
         const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+        const uint32_t inv_a = 0xFFFFFFFFu / (uint32_t)A + 1u;
         for (int g = warp; g < e_valid * A; g += nwarps) {
-            const int e = g / A;
+            const int e = (int)__umulhi((uint32_t)g, inv_a);
             if (!(S.flag[e] & kEnvUsage) || (S.flag[e] & kEnvFrozen)) continue;
             const uint32_t w = S.word[g];
             if (!S.done[g] && lane < kFootCells) {
