@@ -169,7 +169,19 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout when the communicator is created; stdout must carry exactly one
+        # JSON line, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     lib = pkg._native.load()
