@@ -31,7 +31,7 @@ class _Pinned:
 
 class HostDMFB:
     def __init__(self, n_envs, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False,
-                 per_degrade=0.1, device=0, seed=0, env_base=0, n_chunks=8):
+                 per_degrade=0.1, device=0, seed=0, env_base=0, n_chunks=1):
         self.lib = nat.load()
         self.cfg = nat.DmfbCfg()
         nat.check(self.lib.dmfb_cfg_init(C.byref(self.cfg), width, length, n_agents, n_blocks, fov, int(bool(stall)),
