@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """CUDA-event timing of the MEDA step at benchmark size (C4: 30x60 chip, 4 droplets, fov 19).
-usage: python tools/time_meda.py [obs_version 0|2] [n_envs] [degrade 0|1]"""
+usage: python tools/time_meda.py [obs_version 0|2] [n_envs] [degrade 0|1] [usage 1|0]
+(usage 0 drops the addUsage counters from the step: an experiment knob, not a supported mode)"""
 import importlib
 import os
 import sys
@@ -15,6 +16,8 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 deg = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
 W, L, A, fov = 30, 60, 4, 19
 env = pkg.BatchedMEDA(N, W, L, A, fov=fov, obs_version=ver, b_degrade=deg, per_degrade=1.0, device="cuda:0", seed=1)
+if len(sys.argv) > 4 and not int(sys.argv[4]):
+    env.state.usage = None
 slots = 8
 obs_buf = torch.empty(slots + 1, N, A, env.D, dtype=torch.int8, device="cuda:0")
 gen = torch.Generator(device="cuda:0").manual_seed(1)
