@@ -168,6 +168,8 @@ int dmfb_restart(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t
 /* ------------------------------------------------------------------ MEDA -- */
 
 #define MEDA_OBS_BASE 0 /* MEDAEnv.getOneObs      (4,fov,fov)+2, meda.py:613-674 (emitted as int8; all values integral) */
+#define MEDA_OBS_V01 1  /* MEDAEnv_v0_1.getOneObs (4,fov,fov)+2, meda.py:788-844; the two direction entries are emitted as the
+                         * integer numerators (dy, dx) of the reference's (dy / width, dx / length) */
 #define MEDA_OBS_V02 2  /* MEDAEnv_v0_2.getOneObs (3,fov,fov)+2 int8, meda.py:850-897 */
 
 typedef struct meda_cfg {
@@ -175,7 +177,7 @@ typedef struct meda_cfg {
     int32_t n_agents;
     int32_t fov;
     int32_t b_degrade;
-    int32_t obs_version;    /* MEDA_OBS_BASE or MEDA_OBS_V02 */
+    int32_t obs_version;    /* MEDA_OBS_BASE, MEDA_OBS_V01 or MEDA_OBS_V02 */
     int32_t max_step;       /* width+length, meda.py:492 */
     int32_t n_actions;      /* 9, meda.py:23-32 */
     int32_t obs_dim;        /* 4*fov^2+2 (base) or 3*fov^2+2 (v0_2) */
@@ -220,7 +222,7 @@ typedef struct meda_out {
 
 int meda_cfg_init(meda_cfg_t* cfg, int width, int length, int n_agents, int fov, int b_degrade,
                   double per_degrade, int obs_version);
-/* MEDAEnv.step (meda.py:513-539). `set_order` is NULL or a device table [2^A][A] uint8 (v0_2, A>8). */
+/* MEDAEnv.step (meda.py:513-539). `set_order` is NULL or a device table [2^A][A] uint8 (v0_1 / v0_2, A>8). */
 int meda_step(const meda_cfg_t* cfg, const meda_state_t* state, const void* actions,
               int action_elem_size, const double* u_inject, uint64_t seed, uint32_t flags,
               const uint8_t* set_order, const meda_out_t* out, void* stream);

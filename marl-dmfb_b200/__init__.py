@@ -17,8 +17,8 @@ from .marl import (CRNN, BatchedAgents, BatchedRolloutWorker, EpisodeBatch, Repl
                    allreduce_gradients)
 
 try:  # MEDA kernels are part of the same library
-    from .meda import BatchedMEDA, MEDAEnv, MEDAEnv_v0_2  # noqa: F401
+    from .meda import BatchedMEDA, MEDAEnv, MEDAEnv_v0_1, MEDAEnv_v0_2  # noqa: F401
 except ImportError:  # pragma: no cover - only while the package is being bootstrapped
     pass
 
-__all__ = ["BatchedDMFB", "DMFBenv", "HostDMFB", "BatchedMEDA", "MEDAEnv", "MEDAEnv_v0_2", "shard_range", "build"]
+__all__ = ["BatchedDMFB", "DMFBenv", "HostDMFB", "BatchedMEDA", "MEDAEnv", "MEDAEnv_v0_1", "MEDAEnv_v0_2", "shard_range", "build"]

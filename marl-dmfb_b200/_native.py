@@ -15,6 +15,7 @@ STEP_FREEZE_TERM = 2
 STEP_AUTO_RESET = 4
 
 MEDA_OBS_BASE = 0
+MEDA_OBS_V01 = 1
 MEDA_OBS_V02 = 2
 
 

@@ -112,7 +112,7 @@ __device__ __forceinline__ void fill_rect(uint32_t layer, int fov, const FootRec
 //   v0_2  (MEDAEnv_v0_2.getOneObs, meda.py:850-897): lane = (env, agent, layer 0..1): all droplets ascending /
 //         goals of the OBSERVED others (droplets with a cell in the window) in python-set order, clipped; a second
 //         pass, lane = (env, agent, rows | columns), writes the border layer and the direction bytes.
-template <bool V02, int A_T, int FOV_T>
+template <int VER, int A_T, int FOV_T>
 __device__ __forceinline__ void meda_paint_warp(const meda_cfg_t& cfg, const uint32_t* words, const uint8_t* flags,
                                                 int8_t* tile_ptr, int n_env, const uint8_t* __restrict__ set_order)
 {
@@ -120,7 +120,7 @@ __device__ __forceinline__ void meda_paint_warp(const meda_cfg_t& cfg, const uin
     const int A = A_T ? A_T : cfg.n_agents, fov = FOV_T ? FOV_T : cfg.fov, f2 = fov * fov, hf = fov >> 1;
     const int D = cfg.obs_dim;
     const int lane = threadIdx.x & 31;
-    constexpr int PL = V02 ? 2 : 4;
+    constexpr int PL = VER == MEDA_OBS_V02 ? 2 : 4;
     const int n_items = n_env * A * PL;
     for (int p0 = 0; p0 < n_items; p0 += 32) {
         const int p = p0 + lane;
@@ -135,7 +135,7 @@ __device__ __forceinline__ void meda_paint_warp(const meda_cfg_t& cfg, const uin
         const int ox = cx - hf, oy = cy - hf;
         const uint32_t rec = tile + (uint32_t)(g * D);
         const uint32_t layer = rec + (uint32_t)(l * f2);
-        if (!V02) {
+        if (VER == MEDA_OBS_BASE) {
             const bool own = l < 2, goal = l & 1, clip = l == 3;
             const int n_iter = A > 1 ? A - 1 : 1;
             for (int k = 0; k < n_iter; ++k) {
@@ -150,23 +150,30 @@ __device__ __forceinline__ void meda_paint_warp(const meda_cfg_t& cfg, const uin
                 sts_u8(rec + 4 * f2 + 1, (uint32_t)(gy - cy));
             }
         } else {
+            // role 0: all droplets ascending; 1: own goal (v0_1 only, meda.py:808-816); 2: goals of the observed
+            // others in python-set order, clipped; 3: idle lane.  v0_1 layers = roles; v0_2 has no own-goal layer.
+            const int role = (VER == MEDA_OBS_V02) ? 2 * l : l;
             uint32_t observed = 0;                                     // droplets with a cell inside the window (:858-866)
             for (int j = 0; j < A; ++j) {
                 const int dx = (int)(w[j] & 255u) - cx, dy = (int)((w[j] >> 8) & 255u) - cy;
                 observed |= (uint32_t)(abs(dx) <= hf + kRad && abs(dy) <= hf + kRad) << j;
             }
-            const uint8_t* order = (set_order && l == 1) ? set_order + (size_t)observed * A : nullptr;
+            const uint8_t* order = (set_order && role == 2) ? set_order + (size_t)observed * A : nullptr;
             for (int k = 0; k < A; ++k) {
-                const int j = order ? (int)order[k] : k;               // 0xFF terminates the set
-                const bool act = live && (l == 0 || (j < A && ((observed >> j) & 1u) && j != i));
+                int j = order ? (int)order[k] : k;                     // 0xFF terminates the set
+                if (role == 1) j = i;
+                const bool act = live && (role == 0 || (role == 1 && k == 0) ||
+                                          (role == 2 && j < A && ((observed >> j) & 1u) && j != i));
                 const uint32_t d = w[min(j, A - 1)];
-                const int X = l ? (d >> 16) & 255u : d & 255u, Y = l ? d >> 24 : (d >> 8) & 255u;
-                fill_rect(layer, fov, foot_rect(fov, ox, oy, X, Y, l == 1), j + 1, act);
+                const int X = role ? (d >> 16) & 255u : d & 255u, Y = role ? d >> 24 : (d >> 8) & 255u;
+                fill_rect(layer, fov, foot_rect(fov, ox, oy, X, Y, role == 2), j + 1, act);
             }
         }
     }
-    if (V02) {
-        // layer 2 (:880-891): x-derived bounds on the ROW axis with `width`, y-derived on the column axis with `length`
+    if (VER != MEDA_OBS_BASE) {
+        // border layer (v0_2 layer 2, :880-891; v0_1 layer 3, :826-839): x-derived bounds on the ROW axis with `width`,
+        // y-derived on the column axis with `length`
+        constexpr int kBorder = VER == MEDA_OBS_V02 ? 2 : 3;
         const int n_b = n_env * A * 2;
         for (int p0 = 0; p0 < n_b; p0 += 32) {
             const int p = p0 + lane;
@@ -178,7 +185,7 @@ __device__ __forceinline__ void meda_paint_warp(const meda_cfg_t& cfg, const uin
             const uint32_t me = words[e * A + i];
             const int cx = me & 255u, cy = (me >> 8) & 255u, gx = (me >> 16) & 255u, gy = me >> 24;
             const uint32_t rec = tile + (uint32_t)(g * D);
-            const uint32_t lay = rec + 2 * f2;
+            const uint32_t lay = rec + kBorder * f2;
             if (kind == 0) {
                 const int lb = hf - cx, rb = hf - (cfg.width - 1 - cx);
                 int r_lo = 0, r_hi = 0;                                // rows [lo, hi) set to 1
@@ -202,9 +209,13 @@ __device__ __forceinline__ void meda_paint_warp(const meda_cfg_t& cfg, const uin
                         for (int k = 8; k < nq; ++k) sts_u8(q + k, 1u);
                     }
                 }
-                if (live) {                                            // direction vector (:895)
+                if (live && VER == MEDA_OBS_V02) {                     // direction vector (:895)
                     sts_u8(rec + 3 * f2, (uint32_t)cfg.dir_y[gy - cy + cfg.width - 1]);
                     sts_u8(rec + 3 * f2 + 1, (uint32_t)cfg.dir_x[gx - cx + cfg.length - 1]);
+                }
+                if (live && VER == MEDA_OBS_V01) {                     // (:840) numerators of (dy / width, dx / length)
+                    sts_u8(rec + 4 * f2, (uint32_t)(gy - cy));
+                    sts_u8(rec + 4 * f2 + 1, (uint32_t)(gx - cx));
                 }
             }
         }
@@ -298,7 +309,7 @@ __device__ __forceinline__ DropIn meda_load_inputs(const meda_state_t& st, const
 // MEDAEnv.step (meda.py:513-539).  Warp w of the grid takes the groups w, w + n_warps, ... of EW consecutive envs
 // (EW * A <= 32); with the default grid that is one group per warp.  When it loops (capped grid) it keeps the
 // inputs of its next group in flight and lets the TMA store of a tile drain while the next dynamics run.
-template <bool V02, int A_T, int FOV_T>
+template <int VER, int A_T, int FOV_T>
 __global__ void __launch_bounds__(kThreads)
 meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, const void* __restrict__ actions, int aes,
                  const double* __restrict__ u, uint64_t seed, uint32_t flags, const uint8_t* __restrict__ set_order,
@@ -451,7 +462,7 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
             }
         }
         __syncwarp();
-        meda_paint_warp<V02, A_T, FOV_T>(cfg, s_word, s_flag, tile, ev, set_order);
+        meda_paint_warp<VER, A_T, FOV_T>(cfg, s_word, s_flag, tile, ev, set_order);
         store_pending = store_tile_warp(out.obs + (size_t)n0 * A * D, tile, (uint32_t)(ev * A * D));
     }
     if (store_pending && lane == 0) tma_store_wait_read_all();
@@ -586,10 +597,13 @@ meda_reset_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st,
         const int share = (e_valid + nwarps - 1) / nwarps, e0 = warp * share;
         const int ne = min(share, e_valid - e0);
         if (ne > 0) {
+            int8_t* t = S.tile + (size_t)e0 * A * L.D;
             if (cfg.obs_version == MEDA_OBS_V02)
-                meda_paint_warp<true, 0, 0>(cfg, S.word + e0 * A, S.flag + e0, S.tile + (size_t)e0 * A * L.D, ne, set_order);
+                meda_paint_warp<MEDA_OBS_V02, 0, 0>(cfg, S.word + e0 * A, S.flag + e0, t, ne, set_order);
+            else if (cfg.obs_version == MEDA_OBS_V01)
+                meda_paint_warp<MEDA_OBS_V01, 0, 0>(cfg, S.word + e0 * A, S.flag + e0, t, ne, set_order);
             else
-                meda_paint_warp<false, 0, 0>(cfg, S.word + e0 * A, S.flag + e0, S.tile + (size_t)e0 * A * L.D, ne, set_order);
+                meda_paint_warp<MEDA_OBS_BASE, 0, 0>(cfg, S.word + e0 * A, S.flag + e0, t, ne, set_order);
         }
     }
     int8_t* gobs = obs + (size_t)n0 * A * L.D;
@@ -647,7 +661,7 @@ int meda_warp_envs(const meda_cfg_t& cfg)
     return 32 / A;
 }
 
-template <bool V02, int A_T, int FOV_T>
+template <int VER, int A_T, int FOV_T>
 int meda_launch_step_t(const meda_cfg_t* cfg, const meda_state_t* st, const void* actions, int aes, const double* u,
                        uint64_t seed, uint32_t flags, const uint8_t* set_order, const meda_out_t* out, void* stream)
 {
@@ -659,7 +673,7 @@ int meda_launch_step_t(const meda_cfg_t* cfg, const meda_state_t* st, const void
     }
     while (wpc > 1 && StepLayout(*cfg, EW, wpc).total > 200u * 1024u) wpc >>= 1;
     const StepLayout L(*cfg, EW, wpc);
-    auto kern = meda_step_kernel<V02, A_T, FOV_T>;
+    auto kern = meda_step_kernel<VER, A_T, FOV_T>;
     static thread_local uint32_t smem_set = 0;
     if (L.total > 48 * 1024 && L.total > smem_set) {
         DMFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
@@ -687,12 +701,17 @@ int meda_launch_step_t(const meda_cfg_t* cfg, const meda_state_t* st, const void
 int meda_launch_step(const meda_cfg_t* cfg, const meda_state_t* st, const void* actions, int aes, const double* u,
                      uint64_t seed, uint32_t flags, const uint8_t* set_order, const meda_out_t* out, void* stream)
 {
-    const bool v02 = cfg->obs_version == MEDA_OBS_V02;
-    if (cfg->n_agents == 4 && cfg->fov == 19)
-        return v02 ? meda_launch_step_t<true, 4, 19>(cfg, st, actions, aes, u, seed, flags, set_order, out, stream)
-                   : meda_launch_step_t<false, 4, 19>(cfg, st, actions, aes, u, seed, flags, set_order, out, stream);
-    return v02 ? meda_launch_step_t<true, 0, 0>(cfg, st, actions, aes, u, seed, flags, set_order, out, stream)
-               : meda_launch_step_t<false, 0, 0>(cfg, st, actions, aes, u, seed, flags, set_order, out, stream);
+#define MEDA_STEP_ARGS cfg, st, actions, aes, u, seed, flags, set_order, out, stream
+    const bool c4 = cfg->n_agents == 4 && cfg->fov == 19;
+    switch (cfg->obs_version) {
+    case MEDA_OBS_V02:
+        return c4 ? meda_launch_step_t<MEDA_OBS_V02, 4, 19>(MEDA_STEP_ARGS) : meda_launch_step_t<MEDA_OBS_V02, 0, 0>(MEDA_STEP_ARGS);
+    case MEDA_OBS_V01:
+        return c4 ? meda_launch_step_t<MEDA_OBS_V01, 4, 19>(MEDA_STEP_ARGS) : meda_launch_step_t<MEDA_OBS_V01, 0, 0>(MEDA_STEP_ARGS);
+    default:
+        return c4 ? meda_launch_step_t<MEDA_OBS_BASE, 4, 19>(MEDA_STEP_ARGS) : meda_launch_step_t<MEDA_OBS_BASE, 0, 0>(MEDA_STEP_ARGS);
+    }
+#undef MEDA_STEP_ARGS
 }
 
 }  // namespace
@@ -711,7 +730,7 @@ int meda_cfg_init(meda_cfg_t* cfg, int width, int length, int n_agents, int fov,
     if (n_agents > (width / 15) * (length / 15)) return DMFB_ERR_TOO_MANY_DROPLETS;        // n_limit, meda.py:151-154
     if (width > DMFB_MAX_DIM || length > DMFB_MAX_DIM || n_agents > DMFB_MAX_AGENTS || fov < 5 || fov > 2 * DMFB_MAX_FOV)
         return DMFB_ERR_BAD_ARG;
-    if (obs_version != MEDA_OBS_BASE && obs_version != MEDA_OBS_V02) return DMFB_ERR_BAD_ARG;
+    if (obs_version != MEDA_OBS_BASE && obs_version != MEDA_OBS_V01 && obs_version != MEDA_OBS_V02) return DMFB_ERR_BAD_ARG;
     cfg->width = width; cfg->length = length; cfg->n_agents = n_agents; cfg->fov = fov;
     cfg->b_degrade = b_degrade ? 1 : 0; cfg->per_degrade = per_degrade; cfg->obs_version = obs_version;
     cfg->max_step = width + length;                                                        // meda.py:492
@@ -737,8 +756,8 @@ int meda_step(const meda_cfg_t* cfg, const meda_state_t* state, const void* acti
         snprintf(g_last_error, sizeof(g_last_error), "meda_step: bad actions/out");
         return DMFB_ERR_BAD_ARG;
     }
-    if (cfg->obs_version == MEDA_OBS_V02 && cfg->n_agents > 8 && !set_order) {
-        snprintf(g_last_error, sizeof(g_last_error), "meda_step: v0_2 obs with more than 8 agents needs set_order");
+    if (cfg->obs_version != MEDA_OBS_BASE && cfg->n_agents > 8 && !set_order) {
+        snprintf(g_last_error, sizeof(g_last_error), "meda_step: v0_1 / v0_2 obs with more than 8 agents needs set_order");
         return DMFB_ERR_BAD_ARG;
     }
     if (state->n_envs == 0) return DMFB_OK;

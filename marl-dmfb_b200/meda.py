@@ -88,7 +88,7 @@ class BatchedMEDA:
             health=self.health.data_ptr() if self.b_degrade else None,
             degrade=self.degrade.data_ptr() if self.b_degrade else None)
         self.set_order = None
-        if self.obs_version == nat.MEDA_OBS_V02 and A > 8:
+        if self.obs_version != nat.MEDA_OBS_BASE and A > 8:
             self.set_order = torch.as_tensor(build_set_order_table(A)).to(dev)
         self.obs = z(N, A, self.D, dtype=torch.int8)
         self.reward = z(N, A, dtype=torch.float32)
@@ -257,8 +257,12 @@ class MEDAEnv:
 
     def _obs_list(self, obs):
         o = obs[0].cpu().numpy()
-        if self._obs_version == nat.MEDA_OBS_BASE:
-            o = o.astype(np.float64)   # the base class returns float64 (meda.py:621,673)
+        if self._obs_version != nat.MEDA_OBS_V02:
+            o = o.astype(np.float64)   # the base class and v0_1 return float64 (meda.py:621,673 / :795,841)
+        if self._obs_version == nat.MEDA_OBS_V01:
+            # the kernel emits the numerators; dir_VEC = (dy / width, dx / length) (meda.py:840)
+            o[:, -2] = o[:, -2] / self.width
+            o[:, -1] = o[:, -1] / self.length
         return [o[i].copy() for i in range(len(self.agents))]
 
     def step(self, actions):
@@ -309,6 +313,14 @@ class MEDAEnv:
 
     def get_env_info(self):
         return self._b.get_env_info()
+
+
+class MEDAEnv_v0_1(MEDAEnv):
+    """env.MEDA.meda.MEDAEnv_v0_1 (meda.py:784-844; `--version 0.1`, common/config.py:14-16): float64 observation
+    of length 4*fov^2+2 = all droplets / own goal / goals of the observed others / border, and the direction
+    (dy / width, dx / length).  The batched kernel emits int8 with the direction NUMERATORS (dy, dx); this
+    adapter divides."""
+    _obs_version = nat.MEDA_OBS_V01
 
 
 class MEDAEnv_v0_2(MEDAEnv):

@@ -19,7 +19,7 @@
 #include <string.h>
 
 typedef struct orc_meda_cfg {
-    int32_t width, length, n_agents, fov, b_degrade, obs_version; /* 0 = MEDAEnv, 2 = MEDAEnv_v0_2 */
+    int32_t width, length, n_agents, fov, b_degrade, obs_version; /* 0 = MEDAEnv, 1 = MEDAEnv_v0_1, 2 = MEDAEnv_v0_2 */
 } orc_meda_cfg;
 
 #define MAXA 64
@@ -163,12 +163,16 @@ static void meda_obs_base(const orc_meda_cfg *c, const int *xc, const int *yc, c
     obs[4 * f2 + 1] = (int8_t)(gy[agent] - cy);
 }
 
-/* MEDAEnv_v0_2.getOneObs (meda.py:850-897) */
-static void meda_obs_v02(const orc_meda_cfg *c, const int *xc, const int *yc, const int *gx, const int *gy,
+/* MEDAEnv_v0_2.getOneObs (meda.py:850-897) and MEDAEnv_v0_1.getOneObs (meda.py:788-844).  v0_1 is v0_2 with one
+ * more layer (own goal, index 1, :808-816) in front of the others' goals and with the direction entries
+ * (dy / width, dx / length) as float64 (:840); their integer numerators (dy, dx) are emitted here. */
+static void meda_obs_v0x(const orc_meda_cfg *c, const int *xc, const int *yc, const int *gx, const int *gy,
                          int agent, int8_t *obs)
 {
     const int fov = c->fov, f2 = fov * fov, n = c->n_agents, W = c->width, L = c->length, hf = fov / 2;
-    memset(obs, 0, (size_t)(3 * f2 + 2));
+    const int v1 = c->obs_version == 1;
+    const int l_goals = v1 ? 2 : 1, l_border = v1 ? 3 : 2, n_layers = v1 ? 4 : 3;
+    memset(obs, 0, (size_t)(n_layers * f2 + 2));
     const int cx = xc[agent], cy = yc[agent];
     const int ox = cx - hf, oy = cy - hf;
     uint32_t observed = 0;
@@ -181,6 +185,8 @@ static void meda_obs_v02(const orc_meda_cfg *c, const int *xc, const int *yc, co
                     observed |= 1u << idx;
                 }
             }
+    if (v1)                                                 /* own goal, clipped to the chip, where inside the window */
+        meda_foot(obs + 1 * f2, fov, ox, oy, gx[agent], gy[agent], W, L, agent + 1, 0);
     int order[MAXA];
     const int no = cpython_set_order(observed, n, order);   /* `for idx in observed` (:871-872) */
     for (int k = 0; k < no; k++) {
@@ -189,28 +195,34 @@ static void meda_obs_v02(const orc_meda_cfg *c, const int *xc, const int *yc, co
         for (int y = gy[idx] - RAD; y <= gy[idx] + RAD; y++)
             for (int x = gx[idx] - RAD; x <= gx[idx] + RAD; x++) {
                 int nx = clipi(x - ox, 0, fov - 1), ny = clipi(y - oy, 0, fov - 1);
-                obs[1 * f2 + ny * fov + nx] = (int8_t)(idx + 1);
+                obs[l_goals * f2 + ny * fov + nx] = (int8_t)(idx + 1);
             }
     }
-    /* layer 2 (:880-891): the reference indexes the ROW axis with the x-derived bounds and uses `width`
-     * for the x extent and `length` for the y extent; python slicing clamps oversize bounds */
+    /* border layer (:880-891 / :826-839): the reference indexes the ROW axis with the x-derived bounds and uses
+     * `width` for the x extent and `length` for the y extent; python slicing clamps oversize bounds */
+    int8_t *bl = obs + l_border * f2;
     int leftbound = hf - cx, rightbound = hf - (W - 1 - cx);
     if (leftbound > 0) {
-        for (int r = 0; r < leftbound && r < fov; r++) for (int q = 0; q < fov; q++) obs[2 * f2 + r * fov + q] = 1;
+        for (int r = 0; r < leftbound && r < fov; r++) for (int q = 0; q < fov; q++) bl[r * fov + q] = 1;
     } else if (rightbound > 0) {
         for (int r = (fov - rightbound < 0 ? 0 : fov - rightbound); r < fov; r++)
-            for (int q = 0; q < fov; q++) obs[2 * f2 + r * fov + q] = 1;
+            for (int q = 0; q < fov; q++) bl[r * fov + q] = 1;
     }
     int upbound = hf - cy, downbound = hf - (L - 1 - cy);
     if (upbound > 0) {
-        for (int r = 0; r < fov; r++) for (int q = 0; q < upbound && q < fov; q++) obs[2 * f2 + r * fov + q] = 1;
+        for (int r = 0; r < fov; r++) for (int q = 0; q < upbound && q < fov; q++) bl[r * fov + q] = 1;
     } else if (downbound > 0) {
         for (int r = 0; r < fov; r++)
-            for (int q = (fov - downbound < 0 ? 0 : fov - downbound); q < fov; q++) obs[2 * f2 + r * fov + q] = 1;
+            for (int q = (fov - downbound < 0 ? 0 : fov - downbound); q < fov; q++) bl[r * fov + q] = 1;
     }
-    /* direction vector (:895): round((dy)/(width/30)), round((dx)/(length/30)) */
-    obs[3 * f2 + 0] = (int8_t)(int)rint((double)(gy[agent] - cy) / ((double)W / 30.0));
-    obs[3 * f2 + 1] = (int8_t)(int)rint((double)(gx[agent] - cx) / ((double)L / 30.0));
+    if (v1) {
+        obs[4 * f2 + 0] = (int8_t)(gy[agent] - cy);
+        obs[4 * f2 + 1] = (int8_t)(gx[agent] - cx);
+    } else {
+        /* direction vector (:895): round((dy)/(width/30)), round((dx)/(length/30)) */
+        obs[3 * f2 + 0] = (int8_t)(int)rint((double)(gy[agent] - cy) / ((double)W / 30.0));
+        obs[3 * f2 + 1] = (int8_t)(int)rint((double)(gx[agent] - cx) / ((double)L / 30.0));
+    }
 }
 
 static void meda_load(const orc_meda_cfg *c, const uint8_t *drop, int *xc, int *yc, int *gx, int *gy)
@@ -226,7 +238,7 @@ static void meda_all_obs(const orc_meda_cfg *c, const uint8_t *drop, int8_t *obs
     meda_load(c, drop, xc, yc, gx, gy);
     const int D = meda_obs_dim(c);
     for (int i = 0; i < c->n_agents; i++) {
-        if (c->obs_version == 2) meda_obs_v02(c, xc, yc, gx, gy, i, obs + (size_t)i * D);
+        if (c->obs_version != 0) meda_obs_v0x(c, xc, yc, gx, gy, i, obs + (size_t)i * D);
         else meda_obs_base(c, xc, yc, gx, gy, i, obs + (size_t)i * D);
     }
 }

@@ -139,7 +139,8 @@ class _MedaCfg(C.Structure):
 
 class OracleMEDA:
     """N independent MEDA chips stepped by the C restatement of env/MEDA/meda.py.
-    obs_version 0 = MEDAEnv.getOneObs (int8-cast), 2 = MEDAEnv_v0_2.getOneObs."""
+    obs_version 0 = MEDAEnv.getOneObs (int8-cast), 1 = MEDAEnv_v0_1.getOneObs (int8 layers, direction
+    entries = integer numerators of the reference's floats), 2 = MEDAEnv_v0_2.getOneObs."""
 
     def __init__(self, n_envs, width, length, n_agents, fov=19, b_degrade=False, obs_version=0):
         self.N, self.W, self.L, self.A, self.fov = n_envs, width, length, n_agents, fov

@@ -225,6 +225,14 @@ def gen_meda(name, W, L, A, fov, b_degrade, per_degrade, K, n_ep, T, seed, p_goa
         assert o.dtype == np.int8
         return o
 
+    def v1_obs(e):
+        # MEDAEnv_v0_1.getOneObs (meda.py:788-844): float64; the 4 layers are integral, the two direction
+        # entries are (dy / width, dx / length) and are kept as float64
+        o = np.stack([ref_meda.MEDAEnv_v0_1.getOneObs(e, i) for i in range(A)])
+        lay = o[:, :-2]
+        assert o.dtype == np.float64 and np.all(lay == np.round(lay)) and np.abs(lay).max() < 128
+        return lay.astype(np.int8), o[:, -2:].copy()
+
     out = dict(
         kind="meda", W=W, L=L, A=A, fov=fov, b_degrade=int(b_degrade), per_degrade=per_degrade,
         K=K, n_ep=n_ep, T=T, episode_limit=envs[0].max_step, n_actions=9,
@@ -238,6 +246,10 @@ def gen_meda(name, W, L, A, fov, b_degrade, per_degrade, K, n_ep, T, seed, p_goa
         obs2_reset=np.zeros((n_ep, K, A, D2), np.int8),
         obs0=np.zeros((n_ep, len(t_obs), K, A, D0), np.int8),
         obs2=np.zeros((n_ep, len(t_obs), K, A, D2), np.int8),
+        obs1_reset=np.zeros((n_ep, K, A, D0 - 2), np.int8),
+        dir1_reset=np.zeros((n_ep, K, A, 2), np.float64),
+        obs1=np.zeros((n_ep, len(t_obs), K, A, D0 - 2), np.int8),
+        dir1=np.zeros((n_ep, len(t_obs), K, A, 2), np.float64),
         reward=np.zeros((n_ep, T, K, A), np.float64),
         done=np.zeros((n_ep, T, K, A), np.uint8),
         status=np.zeros((n_ep, T, K, A), np.uint8),
@@ -256,6 +268,7 @@ def gen_meda(name, W, L, A, fov, b_degrade, per_degrade, K, n_ep, T, seed, p_goa
                                      for d, g in zip(rm.droplets, rm.destinations)]
             out["obs2_reset"][ep, k] = np.stack(obs)
             out["obs0_reset"][ep, k] = base_obs(e)
+            out["obs1_reset"][ep, k], out["dir1_reset"][ep, k] = v1_obs(e)
             out["health_reset"][ep, k] = e.m_health
             out["usage_reset"][ep, k] = e.m_usage
         for t in range(T):
@@ -267,6 +280,7 @@ def gen_meda(name, W, L, A, fov, b_degrade, per_degrade, K, n_ep, T, seed, p_goa
                 if t in t_obs:
                     out["obs2"][ep, t_obs.index(t), k] = np.stack(obs)
                     out["obs0"][ep, t_obs.index(t), k] = base_obs(e)
+                    out["obs1"][ep, t_obs.index(t), k], out["dir1"][ep, t_obs.index(t), k] = v1_obs(e)
                 out["reward"][ep, t, k] = [rew[a] for a in e.agents]
                 out["done"][ep, t, k] = [done[a] for a in e.agents]
                 out["status"][ep, t, k] = e.routing_manager.status

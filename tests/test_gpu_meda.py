@@ -28,12 +28,22 @@ def test_meda_cuda_matches_reference_trace(name):
                             obs_version=2, device="cuda:0", reward_f64=True,
                             degrade=g["degrade"] if g["b_degrade"] else None, layouts=g["layouts"][0])
     base = pkg().BatchedMEDA(K, W, L, A, fov=g["fov"], obs_version=0, device="cuda:0", layouts=g["layouts"][0])
+    v01 = pkg().BatchedMEDA(K, W, L, A, fov=g["fov"], obs_version=1, device="cuda:0", layouts=g["layouts"][0])
+
+    def check_v01(layers, dirs, msg):
+        v01.drop.copy_(env.drop)
+        o = _np(v01.get_obs())
+        np.testing.assert_array_equal(o[..., :-2], layers, err_msg=msg + " obs v0_1 layers")
+        np.testing.assert_array_equal(o[..., -2] / W, dirs[..., 0], err_msg=msg + " obs v0_1 dir y")
+        np.testing.assert_array_equal(o[..., -1] / L, dirs[..., 1], err_msg=msg + " obs v0_1 dir x")
+
     obs_t = list(g["obs_t"])
     for ep in range(g["n_ep"]):
         obs = env.reset(layouts=g["layouts"][ep])
         np.testing.assert_array_equal(_np(obs), g["obs2_reset"][ep], err_msg=f"{name} v0_2 reset obs ep{ep}")
         base.drop.copy_(env.drop)
         np.testing.assert_array_equal(_np(base.get_obs()), g["obs0_reset"][ep], err_msg=f"{name} base reset obs ep{ep}")
+        check_v01(g["obs1_reset"][ep], g["dir1_reset"][ep], f"{name} reset ep{ep}")
         if g["b_degrade"]:
             np.testing.assert_array_equal(_np(env.health), g["health_reset"][ep], err_msg=f"health ep{ep}")
         np.testing.assert_array_equal(_np(env.usage_counts()), g["usage_reset"][ep], err_msg=f"usage ep{ep}")
@@ -52,6 +62,7 @@ def test_meda_cuda_matches_reference_trace(name):
                 np.testing.assert_array_equal(_np(obs), g["obs2"][ep, obs_t.index(t)], err_msg=msg + " obs v0_2")
                 base.drop.copy_(env.drop)
                 np.testing.assert_array_equal(_np(base.get_obs()), g["obs0"][ep, obs_t.index(t)], err_msg=msg + " obs base")
+                check_v01(g["obs1"][ep, obs_t.index(t)], g["dir1"][ep, obs_t.index(t)], msg)
         np.testing.assert_array_equal(_np(env.usage_counts()), g["usage_end"][ep], err_msg=f"usage end ep{ep}")
     if g["b_degrade"]:
         np.testing.assert_array_equal(_np(env.health), g["health_final"])
@@ -67,6 +78,9 @@ CASES = [
     (70, 45, 30, 3, 9, True, 2),
     (50, 60, 45, 6, 13, True, 0),
     (1, 30, 60, 4, 19, False, 2),
+    (300, 30, 60, 4, 19, False, 1),    # MEDAEnv_v0_1 through the step kernel (specialised instance)
+    (33, 80, 80, 10, 19, True, 1),     # ... and the generic instance with the python-set order table
+    (70, 45, 30, 3, 9, False, 1),
 ]
 
 
@@ -132,6 +146,14 @@ def test_meda_adapter_types_and_generator():
     obs = env2.reset()
     assert all(o.dtype == np.int8 and o.shape == (1085,) for o in obs)
     assert env2.get_env_info() == {"n_actions": 9, "n_agents": 4, "obs_shape": (3, 19, 19, 2, 1085), "episode_limit": 90}
+    # MEDAEnv_v0_1 (`--version 0.1`, common/config.py:14-16): float64 obs, direction = (dy / width, dx / length)
+    g = load_golden("meda_c4")
+    env1 = P.MEDAEnv_v0_1(g["W"], g["L"], g["A"], fov=g["fov"], layouts=g["layouts"][0][0])
+    obs = env1.reset(layouts=g["layouts"][0][0])
+    assert all(o.dtype == np.float64 and o.shape == (1446,) for o in obs)
+    want = np.concatenate([g["obs1_reset"][0, 0].astype(np.float64), g["dir1_reset"][0, 0]], axis=-1)
+    np.testing.assert_array_equal(np.stack(obs), want)
+    assert env1.get_env_info()["obs_shape"] == (4, 19, 19, 2, 1446)
     with pytest.raises(RuntimeError, match="Too many droplets"):
         P.MEDAEnv(30, 60, 9)
     # device task generator: the reference's rejection rules (meda.py:78-81,179-182)

@@ -45,6 +45,15 @@ def test_meda_oracle_matches_reference_trace(oracle_lib, name):
     K, A, W, L = g["K"], g["A"], g["W"], g["L"]
     env = oracle_lib.OracleMEDA(K, W, L, A, fov=g["fov"], b_degrade=bool(g["b_degrade"]), obs_version=2)
     env0 = env.with_version(0)
+    env1 = env.with_version(1)
+
+    def check_v01(o, layers, dirs, msg):
+        # MEDAEnv_v0_1 (meda.py:788-844): int8 layers bit-exact; the reference's float64 direction entries are the
+        # emitted numerators divided by width / length (same float64 division)
+        np.testing.assert_array_equal(o[..., :-2], layers, err_msg=msg + " obs v0_1 layers")
+        np.testing.assert_array_equal(o[..., -2] / W, dirs[..., 0], err_msg=msg + " obs v0_1 dir y")
+        np.testing.assert_array_equal(o[..., -1] / L, dirs[..., 1], err_msg=msg + " obs v0_1 dir x")
+
     env.degrade[...] = g["degrade"]
     obs_t = list(g["obs_t"])
     for ep in range(g["n_ep"]):
@@ -53,6 +62,7 @@ def test_meda_oracle_matches_reference_trace(oracle_lib, name):
         obs2 = env.reset(g["layouts"][ep])
         np.testing.assert_array_equal(obs2, g["obs2_reset"][ep], err_msg=f"v0_2 reset obs ep{ep}")
         np.testing.assert_array_equal(env0.observe(), g["obs0_reset"][ep], err_msg=f"base reset obs ep{ep}")
+        check_v01(env1.observe(), g["obs1_reset"][ep], g["dir1_reset"][ep], f"reset ep{ep}")
         np.testing.assert_array_equal(env.health, g["health_reset"][ep], err_msg=f"health at reset ep{ep}")
         np.testing.assert_array_equal(env.usage, g["usage_reset"][ep], err_msg=f"usage at reset ep{ep}")
         for t in range(g["T"]):
@@ -67,6 +77,7 @@ def test_meda_oracle_matches_reference_trace(oracle_lib, name):
             if t in obs_t:
                 np.testing.assert_array_equal(obs, g["obs2"][ep, obs_t.index(t)], err_msg=msg + " obs v0_2")
                 np.testing.assert_array_equal(env0.observe(), g["obs0"][ep, obs_t.index(t)], err_msg=msg + " obs base")
+                check_v01(env1.observe(), g["obs1"][ep, obs_t.index(t)], g["dir1"][ep, obs_t.index(t)], msg)
         np.testing.assert_array_equal(env.usage, g["usage_end"][ep], err_msg=f"usage end ep{ep}")
     np.testing.assert_array_equal(env.health, g["health_final"])
 
