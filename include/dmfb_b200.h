@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DMFB_ABI_VERSION 1
+#define DMFB_ABI_VERSION 2
 #define DMFB_MAX_DIM 128    /* max chip width / length (cells) */
 #define DMFB_MAX_AGENTS 32  /* max droplets per chip */
 #define DMFB_MAX_FOV 19     /* max field of view (cells) */
@@ -78,9 +78,9 @@ typedef struct dmfb_cfg {
     int32_t b_degrade;      /* electrode degradation on/off */
     int32_t max_step;       /* 2*(width+length), dmfb.py:508 */
     int32_t n_actions;      /* 5, dmfb.py:26-31 */
-    int32_t obs_dim;        /* 3*fov*fov+2, dmfb.py:633-640 */
+    int32_t obs_dim;        /* 3*fov*fov+2, dmfb.py:633-640 (4*fov*fov+2 for DMFB_OBS_V01) */
     int32_t l2_words;       /* ceil(fov*fov/32) */
-    int32_t reserved0;
+    int32_t obs_version;    /* DMFB_OBS_BASE (dmfb_cfg_init) or DMFB_OBS_V01 (dmfb_cfg_set_obs_version) */
     double per_degrade;     /* fraction of degrading electrodes, dmfb.py:157-164 */
     int64_t env_base;       /* global index of env 0 of this batch (multi-GPU sharding; RNG stream id) */
     /* dirct table: dir_x[d + width-1] for d = goal_x - x (dmfb.py:442-454), same for y */
@@ -129,6 +129,16 @@ typedef struct dmfb_out {
  * 487-508) and fill the derived fields and tables. */
 int dmfb_cfg_init(dmfb_cfg_t* cfg, int width, int length, int n_agents, int n_blocks, int fov,
                   int stall, int b_degrade, double per_degrade);
+
+/* Observation variant.  DMFB_OBS_BASE: DMFBenv.getOneObs -> RoutingTaskManager.getOneObs (dmfb.py:395-457,614-620).
+ * DMFB_OBS_V01: DMFBenv_v0_1.getOneObs (dmfb.py:723-835, selected by `--version 0.1`, common/config.py:6-8):
+ * (4,fov,fov) = droplets / own goal / goals of the visible others drawn where the ray to the goal leaves the
+ * window / obstacles + border, then 2 direction entries.  The reference returns float64 with the direction
+ * ((tar_y-y)/length, (tar_x-x)/width); the layers are integral and are emitted as int8, the direction entries as
+ * their integer numerators (tar_y-y, tar_x-x).  Sets obs_version and obs_dim; returns DMFB_ERR_BAD_ARG otherwise. */
+#define DMFB_OBS_BASE 0
+#define DMFB_OBS_V01 1
+int dmfb_cfg_set_obs_version(dmfb_cfg_t* cfg, int obs_version);
 
 /* DMFBenv.step (dmfb.py:560-587) for every env of the batch.
  *  actions   [N,A] device, element size `action_elem_size` in {1,4,8} bytes (int8/int32/int64), values 0..4

@@ -14,6 +14,8 @@ STEP_RECORD_USAGE = 1
 STEP_FREEZE_TERM = 2
 STEP_AUTO_RESET = 4
 
+DMFB_OBS_BASE = 0
+DMFB_OBS_V01 = 1
 MEDA_OBS_BASE = 0
 MEDA_OBS_V01 = 1
 MEDA_OBS_V02 = 2
@@ -23,7 +25,7 @@ class DmfbCfg(C.Structure):
     _fields_ = [
         ("width", C.c_int32), ("length", C.c_int32), ("n_agents", C.c_int32), ("n_blocks", C.c_int32),
         ("fov", C.c_int32), ("stall", C.c_int32), ("b_degrade", C.c_int32), ("max_step", C.c_int32),
-        ("n_actions", C.c_int32), ("obs_dim", C.c_int32), ("l2_words", C.c_int32), ("reserved0", C.c_int32),
+        ("n_actions", C.c_int32), ("obs_dim", C.c_int32), ("l2_words", C.c_int32), ("obs_version", C.c_int32),
         ("per_degrade", C.c_double), ("env_base", C.c_int64),
         ("dir_x", C.c_int8 * (2 * DMFB_MAX_DIM)), ("dir_y", C.c_int8 * (2 * DMFB_MAX_DIM)),
         ("l2_row", (C.c_uint32 * DMFB_L2_WORDS) * DMFB_MAX_FOV),
@@ -71,7 +73,7 @@ MedaOut = DmfbOut  # same field list (include/dmfb_b200.h: meda_out_t)
 
 # every symbol include/dmfb_b200.h declares
 EXPORTS = [
-    "dmfb_cfg_init", "dmfb_step", "dmfb_reset", "dmfb_observe", "dmfb_global_state", "dmfb_restart",
+    "dmfb_cfg_init", "dmfb_cfg_set_obs_version", "dmfb_step", "dmfb_reset", "dmfb_observe", "dmfb_global_state", "dmfb_restart",
     "meda_cfg_init", "meda_step", "meda_reset", "meda_observe", "meda_restart", "meda_set_order",
     "dmfb_abi_version", "dmfb_last_cuda_error", "dmfb_launch_count",
     "dmfb_host_create", "dmfb_host_destroy", "dmfb_host_reset", "dmfb_host_step",
@@ -99,6 +101,7 @@ def load():
     lib.dmfb_last_cuda_error.restype = C.c_char_p
     lib.dmfb_launch_count.restype = C.c_uint64
     lib.dmfb_cfg_init.argtypes = [C.POINTER(DmfbCfg)] + [C.c_int] * 7 + [C.c_double]
+    lib.dmfb_cfg_set_obs_version.argtypes = [C.POINTER(DmfbCfg), C.c_int]
     lib.dmfb_step.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p, C.c_int, C.c_void_p,
                               C.c_uint64, C.c_uint32, C.POINTER(DmfbOut), C.c_void_p]
     lib.dmfb_reset.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

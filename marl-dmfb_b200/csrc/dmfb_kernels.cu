@@ -33,8 +33,8 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 struct TileLayout {
     int E, A, D, nw, ncodes;
     uint32_t tile_bytes, off_l2row, off_l2col, off_flag, off_dirx, off_diry, off_sink, total;
-    __host__ __device__ TileLayout(int E_, int A_, int fov, int W, int Lc) {
-        E = E_; A = A_; D = 3 * fov * fov + 2; nw = (fov * fov + 31) / 32; ncodes = 2 * (fov / 2) + 1;
+    __host__ __device__ TileLayout(int E_, int A_, int fov, int W, int Lc, int D_) {
+        E = E_; A = A_; D = D_; nw = (fov * fov + 31) / 32; ncodes = 2 * (fov / 2) + 1;
         tile_bytes = ((uint32_t)(E * A * D) + 15u) & ~15u;
         uint32_t o = tile_bytes;
         off_l2row = o; o += (uint32_t)(ncodes * nw) * 4u;
@@ -45,7 +45,8 @@ struct TileLayout {
         off_sink = o; o += 16u;
         total = (o + 15u) & ~15u;
     }
-    __host__ __device__ TileLayout(const dmfb_cfg_t& c, int E_) : TileLayout(E_, c.n_agents, c.fov, c.width, c.length) {}
+    __host__ __device__ TileLayout(const dmfb_cfg_t& c, int E_)
+        : TileLayout(E_, c.n_agents, c.fov, c.width, c.length, c.obs_dim) {}
 };
 
 // S.flag values
@@ -373,6 +374,99 @@ __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLay
     *(on ? rec + 3 * f2 + 1 : S.sink) = S.diry[dyi];
 }
 
+// ---- DMFBenv_v0_1.getOneObs (dmfb.py:727-835) of one agent: generic path only, one thread per agent ----------
+// Layers: 0 droplets in the window; 1 own goal (projected onto the window for fewer than 10 droplets, :751-761);
+// 2 goals of the visible others, nearest-to-goal first, each drawn where the ray droplet -> goal leaves the
+// window and pushed to a free 4-neighbour when the cell is taken (:764-808); 3 obstacles at absolute
+// coordinates + border (:811-831); then the NUMERATORS of the direction ((tar_y-y)/length, (tar_x-x)/width) (:833).
+template <typename GetWord>
+__device__ __noinline__ void paint_agent_v01(const dmfb_cfg_t& cfg, const TileLayout& L, const TileSmem& S, int agent_in_tile,
+                                             int i, uint32_t me, bool on, GetWord get,
+                                             const uint8_t* __restrict__ env_blocks)
+{
+    const int fov = cfg.fov, hf = fov >> 1, f2 = fov * fov, A = L.A, W = cfg.width, Lc = cfg.length;
+    uint32_t w[DMFB_MAX_AGENTS];
+    for (int j = 0; j < A; ++j) w[j] = get(j);              // every lane takes part in the shuffles
+    if (!on) return;
+    const int x = me & 255u, y = (me >> 8) & 255u, gx = (me >> 16) & 255u, gy = me >> 24;
+    const int ox = x - hf, oy = y - hf;
+    int8_t* rec = S.tile + agent_in_tile * L.D;
+    uint32_t seen = 0;                                      // other droplets inside the window
+    for (int j = 0; j < A; ++j) {
+        const int rx = (int)(w[j] & 255u) - ox, ry = (int)((w[j] >> 8) & 255u) - oy;
+        if ((unsigned)rx < (unsigned)fov && (unsigned)ry < (unsigned)fov) {
+            rec[rx * fov + ry] = (int8_t)(j + 1);
+            if (j != i) seen |= 1u << j;
+        }
+    }
+    {
+        int rx = gx - ox, ry = gy - oy;
+        const bool inside = (unsigned)rx < (unsigned)fov && (unsigned)ry < (unsigned)fov;
+        if (A < 10) {
+            rx = min(max(rx, 0), fov - 1);
+            ry = min(max(ry, 0), fov - 1);
+        }
+        if (A < 10 || inside) rec[f2 + rx * fov + ry] = (int8_t)(i + 1);
+    }
+    int8_t* l2 = rec + 2 * f2;
+    while (seen) {
+        // list.sort(key=distance) is stable: smallest Manhattan distance to the goal first, ties by index
+        int best = 0, bd = 0x7FFFFFFF;
+        for (uint32_t m = seen; m; m &= m - 1u) {
+            const int j = __ffs(m) - 1;
+            const uint32_t d = w[j];
+            const int dist = abs((int)(d & 255u) - (int)((d >> 16) & 255u)) + abs((int)((d >> 8) & 255u) - (int)(d >> 24));
+            if (dist < bd) { bd = dist; best = j; }
+        }
+        seen &= ~(1u << best);
+        const uint32_t d = w[best];
+        const int sx = (int)(d & 255u) - ox, sy = (int)((d >> 8) & 255u) - oy;
+        const int dx = (int)((d >> 16) & 255u) - (int)(d & 255u), dy = (int)(d >> 24) - (int)((d >> 8) & 255u);
+        const int boundx = dx >= 0 ? fov - 1 - sx : -sx;
+        const int boundy = dy >= 0 ? fov - 1 - sy : -sy;
+        int cdx, cdy;
+        if (abs(dx) <= abs(boundx) && abs(dy) <= abs(boundy)) { cdx = dx; cdy = dy; }
+        else if (dx == 0) { cdx = 0; cdy = boundy; }
+        else if (dy == 0) { cdx = boundx; cdy = 0; }
+        else {
+            // python: dx / dy * boundy == (dx / dy) * boundy in float64; dy * boundx / dx == (dy * boundx) / dx
+            const double qx = __dmul_rn(__ddiv_rn((double)dx, (double)dy), (double)boundy);
+            const double qy = __ddiv_rn((double)(dy * boundx), (double)dx);
+            cdx = dx >= 0 ? min(boundx, (int)ceil(qx)) : max(boundx, (int)floor(qx));
+            cdy = dy >= 0 ? min(boundy, (int)ceil(qy)) : max(boundy, (int)floor(qy));
+        }
+        const int ci = sx + cdx, cj = sy + cdy;
+        const int8_t v = (int8_t)(best + 1);
+        if (l2[ci * fov + cj] == 0) l2[ci * fov + cj] = v;
+        else if (ci == sx && cj == sy) {}
+        else if (ci + 1 < fov && l2[(ci + 1) * fov + cj] == 0) l2[(ci + 1) * fov + cj] = v;
+        else if (ci - 1 >= 0 && l2[(ci - 1) * fov + cj] == 0) l2[(ci - 1) * fov + cj] = v;
+        else if (cj + 1 < fov && l2[ci * fov + cj + 1] == 0) l2[ci * fov + cj + 1] = v;
+        else if (cj - 1 >= 0 && l2[ci * fov + cj - 1] == 0) l2[ci * fov + cj - 1] = v;
+    }
+    int8_t* l3 = rec + 3 * f2;
+    if (env_blocks != nullptr) {
+        for (int b = 0; b < cfg.n_blocks; ++b) {
+            const int bx = env_blocks[2 * b], by = env_blocks[2 * b + 1];
+            for (int q = 0; q < 4; ++q) {
+                const int ci = bx + (q >> 1), cj = by + (q & 1);
+                if (ci < fov && cj < fov) l3[ci * fov + cj] = 1;
+            }
+        }
+    }
+    {
+        const int lb = hf - x, rb = hf - (W - 1 - x), ub = hf - y, db = hf - (Lc - 1 - y);
+        int r_lo = 0, r_hi = 0, q_lo = 0, q_hi = 0;
+        if (lb > 0) { r_hi = min(lb, fov); } else if (rb > 0) { r_lo = max(fov - rb, 0); r_hi = fov; }
+        if (ub > 0) { q_hi = min(ub, fov); } else if (db > 0) { q_lo = max(fov - db, 0); q_hi = fov; }
+        for (int b = r_lo * fov; b < r_hi * fov; ++b) l3[b] = 1;
+        for (int r = 0; r < fov; ++r)
+            for (int q = q_lo; q < q_hi; ++q) l3[r * fov + q] = 1;
+    }
+    rec[4 * f2] = (int8_t)(gy - y);
+    rec[4 * f2 + 1] = (int8_t)(gx - x);
+}
+
 // updateHealth (dmfb.py:465-471) for the envs of the tile flagged kFlagNewTask; whole CTA cooperates.
 __device__ __forceinline__ void update_health_flagged(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const TileSmem& S,
                                                       int64_t n0, int e_valid)
@@ -612,7 +706,7 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int E = E_T ? E_T : E_rt;
     const int A = A_T ? A_T : cfg.n_agents, W = cfg.width, Lc = cfg.length;
-    const TileLayout L(E, A, FOV_T ? FOV_T : cfg.fov, W, Lc);
+    const TileLayout L(E, A, FOV_T ? FOV_T : cfg.fov, W, Lc, FOV_T ? 3 * FOV_T * FOV_T + 2 : cfg.obs_dim);
     const TileSmem S(smem_raw, L);
     const int tid = (int)threadIdx.x;
     const Group<G> g(tid);
@@ -651,8 +745,13 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
 
     const uint32_t word = o.word;
     const uint8_t* env_blocks = (A_T == 0 && cfg.n_blocks && env_on) ? st.blocks + (size_t)n * cfg.n_blocks * 2 : nullptr;
-    paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); },
-                            env_blocks);
+    bool v01 = false;
+    if constexpr (FOV_T == 0 && A_T == 0) v01 = cfg.obs_version == DMFB_OBS_V01;   // generic instance only
+    if (v01)
+        paint_agent_v01(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); }, env_blocks);
+    else
+        paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); },
+                                env_blocks);
     store_tile(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
 }
 
@@ -759,7 +858,10 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
     const bool on = lane_on && selected;
     auto get = [&](int j) { return g.get(word, j); };
     const uint8_t* env_blocks = (cfg.n_blocks && env_on) ? st.blocks + (size_t)n * cfg.n_blocks * 2 : nullptr;
-    paint_agent<FOV_T, 0>(cfg, L, S, e * A + g.i, g.i, word, on, get, env_blocks);
+    bool v01 = false;
+    if constexpr (FOV_T == 0) v01 = cfg.obs_version == DMFB_OBS_V01;
+    if (v01) paint_agent_v01(cfg, L, S, e * A + g.i, g.i, word, on, get, env_blocks);
+    else paint_agent<FOV_T, 0>(cfg, L, S, e * A + g.i, g.i, word, on, get, env_blocks);
     int8_t* gobs = obs + (size_t)n0 * A * L.D;
     if (n_selected == e_valid) store_tile(gobs, S.tile, (uint32_t)(e_valid * A * L.D));
     else store_rows_masked(gobs, S.tile, e_valid, A * L.D, S.flag);
@@ -929,7 +1031,7 @@ int launch_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t
     const TileLayout L(*cfg, E);
     ResetLaunch job{cfg, state, mask, mode, new_task, layouts, block_layouts, degrade, seed, obs,
                     static_cast<cudaStream_t>(stream), E, (state->n_envs + E - 1) / E, L.total};
-    rc = dispatch(cfg->fov, G, job);
+    rc = dispatch(cfg->obs_version == DMFB_OBS_V01 ? 0 : cfg->fov, G, job);   // v0_1: generic instance only
     if (rc) return rc;
     g_launches.fetch_add(1);
     DMFB_CUDA_TRY(cudaGetLastError());
@@ -967,6 +1069,7 @@ int dmfb_cfg_init(dmfb_cfg_t* cfg, int width, int length, int n_agents, int n_bl
     cfg->max_step = 2 * (width + length);
     cfg->n_actions = 5;
     cfg->obs_dim = 3 * fov * fov + 2;
+    cfg->obs_version = DMFB_OBS_BASE;
     cfg->l2_words = (fov * fov + 31) / 32;
     cfg->env_base = 0;
     // direction table (dmfb.py:442-454): float64 division + round-half-even, as python's round()
@@ -995,6 +1098,14 @@ int dmfb_cfg_init(dmfb_cfg_t* cfg, int width, int length, int n_agents, int n_bl
     return DMFB_OK;
 }
 
+int dmfb_cfg_set_obs_version(dmfb_cfg_t* cfg, int obs_version)
+{
+    if (!cfg || cfg->fov < 1 || (obs_version != DMFB_OBS_BASE && obs_version != DMFB_OBS_V01)) return DMFB_ERR_BAD_ARG;
+    cfg->obs_version = obs_version;
+    cfg->obs_dim = (obs_version == DMFB_OBS_V01 ? 4 : 3) * cfg->fov * cfg->fov + 2;
+    return DMFB_OK;
+}
+
 int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* actions, int action_elem_size,
               const double* u_inject, uint64_t seed, uint32_t flags, const dmfb_out_t* out, void* stream)
 {
@@ -1010,7 +1121,7 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
     const TileLayout L(*cfg, E);
     StepLaunch job{cfg, state, actions, action_elem_size, u_inject, seed, flags, out, static_cast<cudaStream_t>(stream),
                    E, (state->n_envs + E - 1) / E, L.total};
-    rc = dispatch(cfg->fov, G, job);
+    rc = dispatch(cfg->obs_version == DMFB_OBS_V01 ? 0 : cfg->fov, G, job);   // v0_1: generic instance only
     if (rc) return rc;
     g_launches.fetch_add(1);
     DMFB_CUDA_TRY(cudaGetLastError());

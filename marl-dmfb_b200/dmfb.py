@@ -32,11 +32,16 @@ class BatchedDMFB:
 
     def __init__(self, n_envs, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False,
                  per_degrade=0.1, device="cuda", seed=0, env_base=0, track_usage=None, reward_f64=False,
-                 degrade=None, layouts=None, block_layouts=None):
+                 degrade=None, layouts=None, block_layouts=None, obs_version=0):
         self.lib = nat.load()
         self.cfg = nat.DmfbCfg()
         nat.check(self.lib.dmfb_cfg_init(C.byref(self.cfg), width, length, n_agents, n_blocks, fov, int(bool(stall)),
                                          int(bool(b_degrade)), float(per_degrade)), "dmfb_cfg_init")
+        # obs_version 1 = DMFBenv_v0_1.getOneObs (dmfb.py:723-835): 4 layers; the two direction entries hold the
+        # integer numerators (tar_y - y, tar_x - x) of the reference's ((tar_y - y) / length, (tar_x - x) / width)
+        self.obs_version = int(obs_version)
+        if self.obs_version:
+            nat.check(self.lib.dmfb_cfg_set_obs_version(C.byref(self.cfg), self.obs_version), "dmfb_cfg_set_obs_version")
         if n_blocks and self.cfg.n_blocks == 0:
             print('Too many required modules in the environment.')    # dmfb.py:232-234: continues without blocks
         self.n_blocks = int(self.cfg.n_blocks)
@@ -197,7 +202,8 @@ class BatchedDMFB:
     def get_env_info(self):
         """dmfb.py:633-640."""
         return {"n_actions": self.n_actions, "n_agents": self.A,
-                "obs_shape": (3, self.fov, self.fov, 2, self.D), "episode_limit": self.max_step}
+                "obs_shape": (4 if self.obs_version else 3, self.fov, self.fov, 2, self.D),
+                "episode_limit": self.max_step}
 
     def check_actions(self):
         """Raises the reference's TypeError if an illegal action was applied since the last check
@@ -265,6 +271,7 @@ class DMFBenv:
     3*fov*fov+2; step(list|dict) -> (obs list, rewards dict, dones dict, info dict)."""
 
     metadata = {"render.modes": ["human", "rgb_array"]}
+    _obs_version = nat.DMFB_OBS_BASE
 
     def __init__(self, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False, per_degrade=0.1,
                  show=False, savemp4=False, device="cuda", seed=None, layouts=None, degrade=None, block_layouts=None):
@@ -276,7 +283,8 @@ class DMFBenv:
                               per_degrade=per_degrade, device=device, seed=seed, track_usage=True, reward_f64=True,
                               layouts=None if layouts is None else np.asarray(layouts)[None],
                               degrade=None if degrade is None else np.asarray(degrade)[None],
-                              block_layouts=None if block_layouts is None else np.asarray(block_layouts)[None])
+                              block_layouts=None if block_layouts is None else np.asarray(block_layouts)[None],
+                              obs_version=self._obs_version)
         self.mode = None  # rendering is out of scope (dmfb.py:642-720)
         self.agents = list(self._b.agents)
         self.possible_agents = self.agents[:]
@@ -347,3 +355,26 @@ class DMFBenv:
 
     def get_env_info(self):
         return self._b.get_env_info()
+
+
+class DMFBenv_v0_1(DMFBenv):
+    """env.DMFB.dmfb.DMFBenv_v0_1 (dmfb.py:723-835; `--version 0.1`, common/config.py:6-8): float64 observation of
+    length 4*fov^2+2 = droplets / own goal / goals of the visible others drawn where the ray to the goal leaves
+    the window / obstacles + border, then ((tar_y - y) / length, (tar_x - x) / width).  The batched kernel emits
+    int8 with the direction NUMERATORS; this adapter divides."""
+    _obs_version = nat.DMFB_OBS_V01
+
+    def _obs_list(self, obs):
+        o = obs[0].cpu().numpy().astype(np.float64)
+        o[:, -2] = o[:, -2] / self.length                        # dmfb.py:833
+        o[:, -1] = o[:, -1] / self.width
+        return [o[i].copy() for i in range(len(self.agents))]
+
+    def get_env_info(self):
+        # the reference takes obs_shape from RoutingTaskManager.getOneObs, i.e. from the BASE observation
+        # (dmfb.py:633-640), also for this subclass
+        info = self._b.get_env_info()
+        f = self._b.fov
+        info["obs_shape"] = (3, f, f, 2, 3 * f * f + 2)
+        return info
+

@@ -25,7 +25,10 @@
 
 typedef struct orc_dmfb_cfg {
     int32_t width, length, n_agents, fov, stall, b_degrade, n_blocks;
+    int32_t obs_version; /* 0 = DMFBenv.getOneObs, 1 = DMFBenv_v0_1.getOneObs */
 } orc_dmfb_cfg;
+
+static int orc_obs_dim(const orc_dmfb_cfg *c) { return (c->obs_version == 1 ? 4 : 3) * c->fov * c->fov + 2; }
 
 #define MAXA 64
 
@@ -131,6 +134,105 @@ static void orc_one_obs(const orc_dmfb_cfg *c, const int *x, const int *y, const
     obs[3 * f2 + 1] = (int8_t)dry;
 }
 
+/* DMFBenv_v0_1.getOneObs (dmfb.py:727-835; `--version 0.1`, common/config.py:6-8): float64 (4,fov,fov) + 2 in the
+ * reference; the layers are integral and are emitted as int8, the two direction entries
+ * ((tar_y - cy) / length, (tar_x - cx) / width) (:833) are emitted as their integer numerators. */
+static void orc_one_obs_v01(const orc_dmfb_cfg *c, const int *x, const int *y, const int *gx, const int *gy,
+                            const uint8_t *blocks, int agent, int8_t *obs)
+{
+    const int fov = c->fov, hf = fov / 2, n = c->n_agents, f2 = fov * fov;
+    memset(obs, 0, (size_t)(4 * f2 + 2));
+    const int cx = x[agent], cy = y[agent];
+    const int ox = cx - hf, oy = cy - hf;
+    /* layer 0 (:741-747): every droplet inside the window; the OTHER visible ones are remembered */
+    int see_idx[MAXA], see_x[MAXA], see_y[MAXA], see_dist[MAXA], n_see = 0;
+    for (int idx = 0; idx < n; idx++) {
+        int rx = x[idx] - ox, ry = y[idx] - oy;
+        if (0 <= rx && rx < fov && 0 <= ry && ry < fov) {
+            obs[0 * f2 + rx * fov + ry] = (int8_t)(idx + 1);
+            if (idx != agent) {
+                see_idx[n_see] = idx; see_x[n_see] = rx; see_y[n_see] = ry;
+                see_dist[n_see] = abs(x[idx] - gx[idx]) + abs(y[idx] - gy[idx]);
+                n_see++;
+            }
+        }
+    }
+    /* layer 1 (:751-761): own goal, projected onto the window for fewer than 10 droplets, else only if inside */
+    {
+        int rx = gx[agent] - ox, ry = gy[agent] - oy;
+        if (n < 10) {
+            rx = rx < 0 ? 0 : (rx > fov - 1 ? fov - 1 : rx);
+            ry = ry < 0 ? 0 : (ry > fov - 1 ? fov - 1 : ry);
+            obs[1 * f2 + rx * fov + ry] = (int8_t)(agent + 1);
+        } else if (0 <= rx && rx < fov && 0 <= ry && ry < fov) {
+            obs[1 * f2 + rx * fov + ry] = (int8_t)(agent + 1);
+        }
+    }
+    /* layer 2 (:764-808): goals of the visible others, nearest-to-goal first (list.sort is stable), each drawn
+     * where the ray droplet -> goal leaves the window; an occupied cell pushes the mark to a free 4-neighbour */
+    for (int a = 1; a < n_see; a++) {                    /* stable insertion sort by distance */
+        int ti = see_idx[a], tx = see_x[a], ty = see_y[a], td = see_dist[a], b = a - 1;
+        while (b >= 0 && see_dist[b] > td) {
+            see_idx[b + 1] = see_idx[b]; see_x[b + 1] = see_x[b]; see_y[b + 1] = see_y[b]; see_dist[b + 1] = see_dist[b];
+            b--;
+        }
+        see_idx[b + 1] = ti; see_x[b + 1] = tx; see_y[b + 1] = ty; see_dist[b + 1] = td;
+    }
+    int8_t *l2 = obs + 2 * f2;
+    for (int s = 0; s < n_see; s++) {
+        const int idx = see_idx[s], sx = see_x[s], sy = see_y[s];
+        const int dx = gx[idx] - x[idx], dy = gy[idx] - y[idx];
+        const int boundx = dx >= 0 ? fov - 1 - sx : -sx;
+        const int boundy = dy >= 0 ? fov - 1 - sy : -sy;
+        int clipdx, clipdy;
+        if (abs(dx) <= abs(boundx) && abs(dy) <= abs(boundy)) { clipdx = dx; clipdy = dy; }
+        else if (dx == 0) { clipdx = 0; clipdy = boundy; }
+        else if (dy == 0) { clipdx = boundx; clipdy = 0; }
+        else {
+            /* python: dx / dy * boundy == (dx / dy) * boundy in float64; dy * boundx / dx == (dy * boundx) / dx */
+            const double qx = (double)dx / (double)dy * (double)boundy;
+            const double qy = (double)(dy * boundx) / (double)dx;
+            if (dx >= 0) { int v = (int)ceil(qx); clipdx = boundx < v ? boundx : v; }
+            else { int v = (int)floor(qx); clipdx = boundx > v ? boundx : v; }
+            if (dy >= 0) { int v = (int)ceil(qy); clipdy = boundy < v ? boundy : v; }
+            else { int v = (int)floor(qy); clipdy = boundy > v ? boundy : v; }
+        }
+        const int i = sx + clipdx, j = sy + clipdy;
+        /* 0 <= i, j < fov: the clipped offsets keep the sign of (dx, dy) and never pass the window bounds */
+#define L2AT(I, J) l2[(I) * fov + (J)]
+        if (L2AT(i, j) == 0) { L2AT(i, j) = (int8_t)(idx + 1); continue; }
+        if (i == sx && j == sy) continue;
+        if (i + 1 < fov && L2AT(i + 1, j) == 0) { L2AT(i + 1, j) = (int8_t)(idx + 1); continue; }
+        if (i - 1 >= 0 && L2AT(i - 1, j) == 0) { L2AT(i - 1, j) = (int8_t)(idx + 1); continue; }
+        if (j + 1 < fov && L2AT(i, j + 1) == 0) { L2AT(i, j + 1) = (int8_t)(idx + 1); continue; }
+        if (j - 1 >= 0 && L2AT(i, j - 1) == 0) { L2AT(i, j - 1) = (int8_t)(idx + 1); continue; }
+#undef L2AT
+    }
+    /* layer 3: blocks at ABSOLUTE chip coordinates (:813-817) + off-chip boundary (:819-831) */
+    for (int b = 0; blocks && b < c->n_blocks; b++)
+        for (int i = blocks[2 * b]; i <= blocks[2 * b] + 1; i++)
+            for (int j = blocks[2 * b + 1]; j <= blocks[2 * b + 1] + 1; j++)
+                if (0 <= i && i < fov && 0 <= j && j < fov) obs[3 * f2 + i * fov + j] = 1;
+    int leftbound = hf - cx, rightbound = hf - (c->width - 1 - cx);
+    if (leftbound > 0) {
+        for (int r = 0; r < leftbound && r < fov; r++)
+            for (int q = 0; q < fov; q++) obs[3 * f2 + r * fov + q] = 1;
+    } else if (rightbound > 0) {
+        for (int r = (fov - rightbound < 0 ? 0 : fov - rightbound); r < fov; r++)
+            for (int q = 0; q < fov; q++) obs[3 * f2 + r * fov + q] = 1;
+    }
+    int upbound = hf - cy, downbound = hf - (c->length - 1 - cy);
+    if (upbound > 0) {
+        for (int r = 0; r < fov; r++)
+            for (int q = 0; q < upbound && q < fov; q++) obs[3 * f2 + r * fov + q] = 1;
+    } else if (downbound > 0) {
+        for (int r = 0; r < fov; r++)
+            for (int q = (fov - downbound < 0 ? 0 : fov - downbound); q < fov; q++) obs[3 * f2 + r * fov + q] = 1;
+    }
+    obs[4 * f2 + 0] = (int8_t)(gy[agent] - cy);          /* numerator of (tar_y - cy) / length */
+    obs[4 * f2 + 1] = (int8_t)(gx[agent] - cx);          /* numerator of (tar_x - cx) / width  */
+}
+
 static void orc_load(const orc_dmfb_cfg *c, const uint8_t *drop, int *x, int *y, int *gx, int *gy)
 {
     for (int i = 0; i < c->n_agents; i++) {
@@ -144,8 +246,11 @@ static void orc_all_obs(const orc_dmfb_cfg *c, const uint8_t *drop, const uint8_
 {
     int x[MAXA], y[MAXA], gx[MAXA], gy[MAXA];
     orc_load(c, drop, x, y, gx, gy);
-    const int D = 3 * c->fov * c->fov + 2;
-    for (int i = 0; i < c->n_agents; i++) orc_one_obs(c, x, y, gx, gy, blocks, i, obs + (size_t)i * D);
+    const int D = orc_obs_dim(c);
+    for (int i = 0; i < c->n_agents; i++) {
+        if (c->obs_version == 1) orc_one_obs_v01(c, x, y, gx, gy, blocks, i, obs + (size_t)i * D);
+        else orc_one_obs(c, x, y, gx, gy, blocks, i, obs + (size_t)i * D);
+    }
 }
 
 /* DMFBenv.step (dmfb.py:560-587) -> RoutingTaskManager.moveDroplets (:253-299) ->
@@ -247,7 +352,7 @@ int orc_dmfb_step(const orc_dmfb_cfg *c, int n_envs, uint8_t *drop, const uint8_
                   double *usage, const double *health, const int8_t *actions, const double *u, int record,
                   int8_t *obs, double *reward, uint8_t *done, int32_t *constraints, uint8_t *success)
 {
-    const int A = c->n_agents, cells = c->width * c->length, D = 3 * c->fov * c->fov + 2;
+    const int A = c->n_agents, cells = c->width * c->length, D = orc_obs_dim(c);
     int err = 0;
     for (int e = 0; e < n_envs; e++) {
         int rc = orc_step_one(c, drop + (size_t)e * A * 4, blocks ? blocks + (size_t)e * c->n_blocks * 2 : NULL,
@@ -269,7 +374,7 @@ int orc_dmfb_reset(const orc_dmfb_cfg *c, int n_envs, const uint8_t *mask, int n
                    int32_t *step_count, int32_t *cum_constraints, double *usage, double *health, double *degrade,
                    int8_t *obs)
 {
-    const int A = c->n_agents, cells = c->width * c->length, D = 3 * c->fov * c->fov + 2;
+    const int A = c->n_agents, cells = c->width * c->length, D = orc_obs_dim(c);
     for (int e = 0; e < n_envs; e++) {
         if (mask && !mask[e]) continue;
         step_count[e] = 0;
@@ -295,7 +400,7 @@ int orc_dmfb_reset(const orc_dmfb_cfg *c, int n_envs, const uint8_t *mask, int n
 
 int orc_dmfb_observe(const orc_dmfb_cfg *c, int n_envs, const uint8_t *drop, const uint8_t *blocks, int8_t *obs)
 {
-    const int A = c->n_agents, D = 3 * c->fov * c->fov + 2;
+    const int A = c->n_agents, D = orc_obs_dim(c);
     for (int e = 0; e < n_envs; e++)
         orc_all_obs(c, drop + (size_t)e * A * 4, blocks ? blocks + (size_t)e * c->n_blocks * 2 : NULL, obs + (size_t)e * A * D);
     return 0;
@@ -399,7 +504,7 @@ static void *orc_dmfb_roll_thread(void *arg)
 {
     orc_roll_job *job = (orc_roll_job *)arg;
     const orc_dmfb_cfg *c = job->c;
-    const int A = c->n_agents, cells = c->width * c->length, D = 3 * c->fov * c->fov + 2;
+    const int A = c->n_agents, cells = c->width * c->length, D = orc_obs_dim(c);
     double *usage = (double *)calloc((size_t)cells, sizeof(double));
     double *health = (double *)malloc((size_t)cells * sizeof(double));
     double *degrade = (double *)malloc((size_t)cells * sizeof(double));

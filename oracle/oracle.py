@@ -37,7 +37,8 @@ def lib():
 
 
 class _DmfbCfg(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("width", "length", "n_agents", "fov", "stall", "b_degrade", "n_blocks")]
+    _fields_ = [(n, C.c_int32) for n in ("width", "length", "n_agents", "fov", "stall", "b_degrade", "n_blocks",
+                                         "obs_version")]
 
 
 def _p(a, ct=None):
@@ -48,13 +49,16 @@ def _p(a, ct=None):
 
 
 class OracleDMFB:
-    """N independent DMFB chips stepped by the C restatement of env/DMFB/dmfb.py."""
+    """N independent DMFB chips stepped by the C restatement of env/DMFB/dmfb.py.
+    obs_version 0 = DMFBenv.getOneObs, 1 = DMFBenv_v0_1.getOneObs (int8 layers, direction entries = integer
+    numerators of the reference's floats)."""
 
-    def __init__(self, n_envs, width, length, n_agents, fov=9, stall=True, b_degrade=False, n_blocks=0):
+    def __init__(self, n_envs, width, length, n_agents, fov=9, stall=True, b_degrade=False, n_blocks=0, obs_version=0):
         self.N, self.W, self.L, self.A, self.fov = n_envs, width, length, n_agents, fov
-        self.D = 3 * fov * fov + 2
+        self.D = (4 if obs_version == 1 else 3) * fov * fov + 2
         self.n_blocks = n_blocks
-        self.cfg = _DmfbCfg(width, length, n_agents, fov, int(stall), int(b_degrade), n_blocks)
+        self.obs_version = obs_version
+        self.cfg = _DmfbCfg(width, length, n_agents, fov, int(stall), int(b_degrade), n_blocks, obs_version)
         self.blocks = np.zeros((n_envs, n_blocks, 2), np.uint8) if n_blocks else None
         self.b_degrade = bool(b_degrade)
         N, A = n_envs, n_agents
@@ -64,6 +68,15 @@ class OracleDMFB:
         self.usage = np.zeros((N, width, length), np.float64)
         self.health = np.ones((N, width, length), np.float64)
         self.degrade = np.ones((N, width, length), np.float64)
+
+    def with_version(self, obs_version):
+        """observation of the current state under the other obs variant (state is shared, not copied)"""
+        o = OracleDMFB.__new__(OracleDMFB)
+        o.__dict__.update(self.__dict__)
+        o.obs_version = obs_version
+        o.D = (4 if obs_version == 1 else 3) * self.fov * self.fov + 2
+        o.cfg = _DmfbCfg(self.W, self.L, self.A, self.fov, self.cfg.stall, self.cfg.b_degrade, self.n_blocks, obs_version)
+        return o
 
     def reset(self, layouts, new=False, degrade=None, mask=None, blocks=None):
         obs = np.zeros((self.N, self.A, self.D), np.int8)
@@ -126,7 +139,7 @@ class OracleDMFB:
 
 def dmfb_rollout(width, length, n_agents, fov, stall, b_degrade, n_envs, steps, seed=1, threads=1):
     """Timed CPU leg: returns agent-steps executed (see orc_dmfb_rollout)."""
-    cfg = _DmfbCfg(width, length, n_agents, fov, int(stall), int(b_degrade), 0)
+    cfg = _DmfbCfg(width, length, n_agents, fov, int(stall), int(b_degrade), 0, 0)
     obs = np.zeros((n_envs, n_agents, 3 * fov * fov + 2), np.int8)
     chk = C.c_uint64(0)
     n = lib().orc_dmfb_rollout(C.byref(cfg), n_envs, steps, C.c_uint64(seed), _p(obs), int(threads), C.byref(chk))

@@ -105,12 +105,16 @@ def gen_dmfb(name, W, L, A, fov, stall, b_degrade, per_degrade, K, n_ep, T, seed
              state_every=1, obs_every=1, n_blocks=0):
     rng = np.random.default_rng(seed)
     np.random.seed(seed)  # the reference draws layouts/degrade from the global numpy RNG
+    import random as pyrandom
     envs, injs = [], []
     for _ in range(K):
         e = ref_dmfb.DMFBenv(W, L, A, n_blocks, fov=fov, stall=stall, b_degrade=b_degrade,
                              per_degrade=per_degrade)
         envs.append(e)
         injs.append(ref_shim.DrawInjector(ref_dmfb, e.routing_manager))
+    # block retries come from python's random (dmfb.py:248-249), which every RoutingTaskManager re-seeds from the
+    # clock (dmfb.py:154): seed it after the chips exist so that the fixtures are reproducible
+    pyrandom.seed(seed)
     D = 3 * fov * fov + 2
     info0 = envs[0].get_env_info()
     assert info0["obs_shape"] == (3, fov, fov, 2, D)
@@ -118,6 +122,15 @@ def gen_dmfb(name, W, L, A, fov, stall, b_degrade, per_degrade, K, n_ep, T, seed
     if (T - 1) not in t_obs:
         t_obs.append(T - 1)
     t_state = list(range(0, T, state_every)) if state_every else []
+
+    def v1_obs(e):
+        # DMFBenv_v0_1.getOneObs (dmfb.py:727-835) of the same chip: float64; the 4 layers are integral, the two
+        # direction entries ((tar_y - cy) / length, (tar_x - cx) / width) are kept as float64
+        o = np.stack([ref_dmfb.DMFBenv_v0_1.getOneObs(e, i) for i in range(A)])
+        lay = o[:, :-2]
+        assert o.dtype == np.float64 and np.all(lay == np.round(lay)) and np.abs(lay).max() < 128
+        return lay.astype(np.int8), o[:, -2:].copy()
+
     out = dict(
         kind="dmfb", W=W, L=L, A=A, fov=fov, stall=int(stall), b_degrade=int(b_degrade),
         per_degrade=per_degrade, K=K, n_ep=n_ep, T=T, n_blocks=n_blocks,
@@ -131,6 +144,10 @@ def gen_dmfb(name, W, L, A, fov, stall, b_degrade, per_degrade, K, n_ep, T, seed
         obs_reset=np.zeros((n_ep, K, A, D), np.int8),
         obs_t=np.array(t_obs, np.int32),
         obs=np.zeros((n_ep, len(t_obs), K, A, D), np.int8),
+        obs1_reset=np.zeros((n_ep, K, A, 4 * fov * fov), np.int8),
+        dir1_reset=np.zeros((n_ep, K, A, 2), np.float64),
+        obs1=np.zeros((n_ep, len(t_obs), K, A, 4 * fov * fov), np.int8),
+        dir1=np.zeros((n_ep, len(t_obs), K, A, 2), np.float64),
         reward=np.zeros((n_ep, T, K, A), np.float64),
         done=np.zeros((n_ep, T, K, A), np.uint8),
         constraints=np.zeros((n_ep, T, K), np.int32),
@@ -154,6 +171,7 @@ def gen_dmfb(name, W, L, A, fov, stall, b_degrade, per_degrade, K, n_ep, T, seed
                 out["blocks"][ep, k, b] = (blk.x_min, blk.y_min)
             out["obs_reset"][ep, k] = np.stack(obs)
             assert all(o.dtype == np.int8 for o in obs)
+            out["obs1_reset"][ep, k], out["dir1_reset"][ep, k] = v1_obs(e)
             out["health_reset"][ep, k] = rm.m_health
             out["usage_reset"][ep, k] = rm.m_usage
         for t in range(T):
@@ -164,6 +182,7 @@ def gen_dmfb(name, W, L, A, fov, stall, b_degrade, per_degrade, K, n_ep, T, seed
                 out["draws_used"][ep, t, k] = injs[k].consumed
                 if t in t_obs:
                     out["obs"][ep, t_obs.index(t), k] = np.stack(obs)
+                    out["obs1"][ep, t_obs.index(t), k], out["dir1"][ep, t_obs.index(t), k] = v1_obs(e)
                 out["reward"][ep, t, k] = [rew[a] for a in e.agents]
                 out["done"][ep, t, k] = [done[a] for a in e.agents]
                 out["constraints"][ep, t, k] = info["constraints"]

@@ -32,9 +32,23 @@ def test_dmfb_cuda_matches_reference_trace(name):
                             degrade=g["degrade"] if g["b_degrade"] else None, layouts=g["layouts"][0],
                             block_layouts=g["blocks"][0] if nb else None)
     obs_t, state_t = list(g["obs_t"]), list(g["state_t"])
+    v01 = pkg().BatchedDMFB(K, W, L, A, nb, fov=g["fov"], device="cuda:0", layouts=g["layouts"][0],
+                            block_layouts=g["blocks"][0] if nb else None, obs_version=1)
+
+    def check_v01(layers, dirs, msg):
+        # DMFBenv_v0_1 (dmfb.py:723-835) of the same chips: int8 layers bit-exact, direction = numerators / (L, W)
+        v01.drop.copy_(env.drop)
+        if nb:
+            v01.blocks.copy_(env.blocks)
+        o = _np(v01.get_obs())
+        np.testing.assert_array_equal(o[..., :-2], layers, err_msg=msg + " obs v0_1 layers")
+        np.testing.assert_array_equal(o[..., -2] / L, dirs[..., 0], err_msg=msg + " obs v0_1 dir y")
+        np.testing.assert_array_equal(o[..., -1] / W, dirs[..., 1], err_msg=msg + " obs v0_1 dir x")
+
     for ep in range(g["n_ep"]):
         obs = env.reset(new=False, layouts=g["layouts"][ep], block_layouts=g["blocks"][ep] if nb else None)
         np.testing.assert_array_equal(_np(obs), g["obs_reset"][ep], err_msg=f"{name} reset obs ep{ep}")
+        check_v01(g["obs1_reset"][ep], g["dir1_reset"][ep], f"{name} reset ep{ep}")
         if g["b_degrade"]:
             np.testing.assert_array_equal(_np(env.health), g["health_reset"][ep], err_msg=f"health ep{ep}")
         np.testing.assert_array_equal(_np(env.usage_counts()), g["usage_reset"][ep], err_msg=f"usage ep{ep}")
@@ -53,6 +67,7 @@ def test_dmfb_cuda_matches_reference_trace(name):
             if t in obs_t:
                 np.testing.assert_array_equal(_np(obs), g["obs"][ep, obs_t.index(t)], err_msg=msg + " obs")
                 np.testing.assert_array_equal(_np(env.get_obs(out=torch.empty_like(obs))), _np(obs))
+                check_v01(g["obs1"][ep, obs_t.index(t)], g["dir1"][ep, obs_t.index(t)], msg)
             if t in state_t:
                 np.testing.assert_array_equal(_np(env.get_state()), g["state"][ep, state_t.index(t)],
                                               err_msg=msg + " state")
@@ -63,7 +78,7 @@ def test_dmfb_cuda_matches_reference_trace(name):
 
 
 CASES = [
-    # N, W, L, A, fov, stall, degrade[, n_blocks]
+    # N, W, L, A, fov, stall, degrade[, n_blocks[, obs_version]]
     (1000, 10, 10, 4, 9, True, True),
     (400, 14, 14, 4, 9, True, False, 6),
     (300, 20, 24, 7, 7, True, True, 12),
@@ -77,6 +92,10 @@ CASES = [
     (33, 9, 9, 2, 9, True, False),
     (31, 40, 40, 12, 19, True, True),
     (1, 10, 10, 4, 9, True, True),
+    (500, 10, 10, 4, 9, True, False, 0, 1),      # DMFBenv_v0_1 through the fused step kernel
+    (200, 20, 20, 10, 9, True, True, 0, 1),      # >= 10 droplets: own goal not projected (dmfb.py:756-761)
+    (150, 14, 14, 5, 7, True, False, 6, 1),
+    (60, 30, 30, 12, 11, False, True, 0, 1),
 ]
 
 
@@ -84,13 +103,15 @@ CASES = [
 def test_dmfb_cuda_matches_oracle_random(oracle_lib, case):
     N, W, L, A, fov, stall, deg = case[:7]
     nb = case[7] if len(case) > 7 else 0
+    ver = case[8] if len(case) > 8 else 0
     rng = np.random.default_rng(N * 7 + W)
-    ref = oracle_lib.OracleDMFB(N, W, L, A, fov=fov, stall=stall, b_degrade=deg, n_blocks=nb)
+    ref = oracle_lib.OracleDMFB(N, W, L, A, fov=fov, stall=stall, b_degrade=deg, n_blocks=nb, obs_version=ver)
     degrade = rng.random((N, W, L)) * 0.4 + 0.6 if deg else None
     layouts = ref.gen_layouts(seed=N)
     blocks = ref.gen_blocks(N, layouts) if nb else None
     env = pkg().BatchedDMFB(N, W, L, A, nb, fov=fov, stall=stall, b_degrade=deg, per_degrade=1.0, device="cuda:0",
-                            track_usage=True, reward_f64=True, degrade=degrade, layouts=layouts, block_layouts=blocks)
+                            track_usage=True, reward_f64=True, degrade=degrade, layouts=layouts, block_layouts=blocks,
+                            obs_version=ver)
     if deg:
         ref.degrade[...] = degrade
         # pre-age the chips so that health < 1 matters from the first step
@@ -348,3 +369,21 @@ def test_dmfb_restart_returns_to_the_start_cells():
     obs = env.restart()
     assert torch.equal(env.drop, start) and torch.equal(obs, first)
     assert int(env.step_count.max()) == 0 and int(env.constraints_cum.max()) == 0
+
+
+def test_dmfb_v0_1_adapter_returns_reference_types():
+    """DMFBenv_v0_1 (`--version 0.1`, common/config.py:6-8): float64 obs of length 4*fov^2+2 with the direction
+    ((tar_y - y) / length, (tar_x - x) / width); env_info keeps the BASE obs_shape like the reference."""
+    P = pkg()
+    g = load_golden("dmfb_c1")
+    env = P.DMFBenv_v0_1(g["W"], g["L"], g["A"], fov=g["fov"], layouts=g["layouts"][0][0])
+    obs = env.reset(layouts=g["layouts"][0][0])
+    assert len(obs) == g["A"] and all(o.dtype == np.float64 and o.shape == (4 * 81 + 2,) for o in obs)
+    want = np.concatenate([g["obs1_reset"][0, 0].astype(np.float64), g["dir1_reset"][0, 0]], axis=-1)
+    np.testing.assert_array_equal(np.stack(obs), want)
+    o, r, d, info = env.step([int(a) for a in g["actions"][0, 0, 0]])
+    want = np.concatenate([g["obs1"][0, 0, 0].astype(np.float64), g["dir1"][0, 0, 0]], axis=-1)
+    np.testing.assert_array_equal(np.stack(o), want)
+    assert env.get_env_info()["obs_shape"] == (3, 9, 9, 2, 245)
+    assert env._b.get_env_info()["obs_shape"] == (4, 9, 9, 2, 326)
+

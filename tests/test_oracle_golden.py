@@ -15,11 +15,23 @@ def test_dmfb_oracle_matches_reference_trace(oracle_lib, name):
     env = oracle_lib.OracleDMFB(K, W, L, A, fov=g["fov"], stall=bool(g["stall"]), b_degrade=bool(g["b_degrade"]),
                                 n_blocks=nb)
     env.degrade[...] = g["degrade"]
+    env1 = env.with_version(1)
     obs_t = list(g["obs_t"])
     state_t = list(g["state_t"])
+
+    def check_v01(layers, dirs, msg):
+        # DMFBenv_v0_1 (dmfb.py:727-835): int8 layers bit-exact; the reference's float64 direction entries are the
+        # emitted numerators divided by length / width (same float64 division)
+        o = env1.observe()
+        np.testing.assert_array_equal(o[..., :-2], layers, err_msg=msg + " obs v0_1 layers")
+        np.testing.assert_array_equal(o[..., -2] / L, dirs[..., 0], err_msg=msg + " obs v0_1 dir y")
+        np.testing.assert_array_equal(o[..., -1] / W, dirs[..., 1], err_msg=msg + " obs v0_1 dir x")
+
     for ep in range(g["n_ep"]):
         obs = env.reset(g["layouts"][ep], new=False, blocks=g["blocks"][ep] if nb else None)
         np.testing.assert_array_equal(obs, g["obs_reset"][ep], err_msg=f"reset obs ep{ep}")
+        env1.blocks = env.blocks
+        check_v01(g["obs1_reset"][ep], g["dir1_reset"][ep], f"{name} reset ep{ep}")
         np.testing.assert_array_equal(env.health, g["health_reset"][ep], err_msg=f"health at reset ep{ep}")
         np.testing.assert_array_equal(env.usage, g["usage_reset"][ep], err_msg=f"usage at reset ep{ep}")
         for t in range(g["T"]):
@@ -32,6 +44,7 @@ def test_dmfb_oracle_matches_reference_trace(oracle_lib, name):
             np.testing.assert_array_equal(succ, g["success"][ep, t], err_msg=msg + " success")
             if t in obs_t:
                 np.testing.assert_array_equal(obs, g["obs"][ep, obs_t.index(t)], err_msg=msg + " obs")
+                check_v01(g["obs1"][ep, obs_t.index(t)], g["dir1"][ep, obs_t.index(t)], msg)
             if t in state_t:
                 np.testing.assert_array_equal(env.global_state(), g["state"][ep, state_t.index(t)],
                                               err_msg=msg + " state")
