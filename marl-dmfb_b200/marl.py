@@ -8,6 +8,9 @@ These are the batched counterparts of
   common/replay_buffer.py:5-75     (episode ring buffer, uniform sampling with replacement)
   policy/vdn.py:79-196             (double-network TD learning with the GRU unrolled over the episode)
   network/base_net.py:23-71        (CRNN), network/vdn_net.py (sum mixer)
+  policy/qmix.py:73-123, network/qmix_net.py:7-63, network/base_net.py:7-21   (QMIX: monotonic mixer over the global
+                                   state; the reference never fills `s`/`s_next` - here they come from the env's
+                                   get_state kernel, getglobalobs dmfb.py:368-392)
 Plain PyTorch: the networks are tiny dense models (about 0.9 MFLOP per agent-step); the env kernels are the product.
 Parameter names follow the reference so that state_dicts interoperate (vdn.py:205-218 file naming kept by
 `VDNLearner.save_model`).
@@ -63,6 +66,53 @@ class CRNN(nn.Module):
         return self.fc1(h), h
 
 
+class RNN(nn.Module):
+    """network/base_net.py:7-21: the MLP-GRU agent network policy/qmix.py builds (fc1 -> GRUCell -> fc2)."""
+
+    def __init__(self, input_shape, n_actions, rnn_hidden_dim=64):
+        super().__init__()
+        self.rnn_hidden_dim = rnn_hidden_dim
+        self.n_actions = n_actions
+        self.fc1 = nn.Linear(input_shape, rnn_hidden_dim)
+        self.rnn = nn.GRUCell(rnn_hidden_dim, rnn_hidden_dim)
+        self.fc2 = nn.Linear(rnn_hidden_dim, n_actions)
+
+    def forward(self, obs, hidden_state):
+        x = F.relu(self.fc1(obs))
+        h = self.rnn(x, hidden_state.reshape(-1, self.rnn_hidden_dim))
+        return self.fc2(h), h
+
+
+class QMixNet(nn.Module):
+    """network/qmix_net.py:7-63: hypernetworks of the global state produce the non-negative mixing weights."""
+
+    def __init__(self, state_shape, n_agents, qmix_hidden_dim=32, hyper_hidden_dim=64, two_hyper_layers=False):
+        super().__init__()
+        self.state_shape, self.n_agents, self.qmix_hidden_dim = state_shape, n_agents, qmix_hidden_dim
+        if two_hyper_layers:
+            self.hyper_w1 = nn.Sequential(nn.Linear(state_shape, hyper_hidden_dim), nn.ReLU(),
+                                          nn.Linear(hyper_hidden_dim, n_agents * qmix_hidden_dim))
+            self.hyper_w2 = nn.Sequential(nn.Linear(state_shape, hyper_hidden_dim), nn.ReLU(),
+                                          nn.Linear(hyper_hidden_dim, qmix_hidden_dim))
+        else:
+            self.hyper_w1 = nn.Linear(state_shape, n_agents * qmix_hidden_dim)
+            self.hyper_w2 = nn.Linear(state_shape, qmix_hidden_dim)
+        self.hyper_b1 = nn.Linear(state_shape, qmix_hidden_dim)
+        self.hyper_b2 = nn.Sequential(nn.Linear(state_shape, qmix_hidden_dim), nn.ReLU(), nn.Linear(qmix_hidden_dim, 1))
+
+    def forward(self, q_values, states):
+        """q_values [B, T, n_agents], states [B, T, state_shape] -> q_total [B, T, 1]."""
+        B = q_values.size(0)
+        q_values = q_values.reshape(-1, 1, self.n_agents)
+        states = states.reshape(-1, self.state_shape)
+        w1 = torch.abs(self.hyper_w1(states)).view(-1, self.n_agents, self.qmix_hidden_dim)
+        b1 = self.hyper_b1(states).view(-1, 1, self.qmix_hidden_dim)
+        hidden = F.elu(torch.bmm(q_values, w1) + b1)
+        w2 = torch.abs(self.hyper_w2(states)).view(-1, self.qmix_hidden_dim, 1)
+        b2 = self.hyper_b2(states).view(-1, 1, 1)
+        return (torch.bmm(hidden, w2) + b2).view(B, -1, 1)
+
+
 # ------------------------------------------------------------ action selection --
 class BatchedAgents:
     """Agents.choose_action (agent/agent.py:22-48) for all N*A agents in one forward pass, on the device."""
@@ -102,9 +152,12 @@ class EpisodeBatch:
 
     KEYS = ("o", "u", "r", "avail_u", "avail_u_next", "u_onehot", "padded", "terminated")
 
-    def __init__(self, n, T, A, D, n_actions, device):
+    def __init__(self, n, T, A, D, n_actions, device, state_dim=0):
         z = lambda *s, dtype: torch.zeros(*s, dtype=dtype, device=device)  # noqa: E731
         self.n, self.T, self.A, self.D, self.n_actions = n, T, A, D, n_actions
+        # QMIX only: global state for T+1 steps (s_next[t] = s[t+1]), the flattened (3,W,L) get_state tensor
+        self.state_dim = state_dim
+        self.s_all = z(n, T + 1, state_dim, dtype=torch.int8) if state_dim else None
         self.o_all = z(n, T + 1, A, D, dtype=torch.int8)
         self.u = z(n, T, A, 1, dtype=torch.int8)
         self.r = z(n, T, 1, dtype=torch.float32)
@@ -117,17 +170,20 @@ class EpisodeBatch:
         """The dict ReplayBuffer.sample returns (replay_buffer.py:51-56), as views (optionally rows idx, first T steps)."""
         T = self.T if T is None else T
         s = (lambda x: x) if idx is None else (lambda x: x[idx])
-        return {"o": s(self.o_all)[:, :T], "o_next": s(self.o_all)[:, 1:T + 1], "u": s(self.u)[:, :T],
-                "r": s(self.r)[:, :T], "avail_u": s(self.avail_all)[:, :T], "avail_u_next": s(self.avail_all)[:, 1:T + 1],
-                "u_onehot": s(self.u_onehot)[:, :T], "padded": s(self.padded)[:, :T],
-                "terminated": s(self.terminated)[:, :T]}
+        d = {"o": s(self.o_all)[:, :T], "o_next": s(self.o_all)[:, 1:T + 1], "u": s(self.u)[:, :T],
+             "r": s(self.r)[:, :T], "avail_u": s(self.avail_all)[:, :T], "avail_u_next": s(self.avail_all)[:, 1:T + 1],
+             "u_onehot": s(self.u_onehot)[:, :T], "padded": s(self.padded)[:, :T],
+             "terminated": s(self.terminated)[:, :T]}
+        if self.s_all is not None:
+            d["s"], d["s_next"] = s(self.s_all)[:, :T], s(self.s_all)[:, 1:T + 1]
+        return d
 
 
 class ReplayBufferGPU(EpisodeBatch):
     """common/replay_buffer.py:5-75 on the device: ring of `size` episodes, uniform sampling with replacement."""
 
-    def __init__(self, size, T, A, D, n_actions, device, seed=0):
-        super().__init__(size, T, A, D, n_actions, device)
+    def __init__(self, size, T, A, D, n_actions, device, seed=0, state_dim=0):
+        super().__init__(size, T, A, D, n_actions, device, state_dim=state_dim)
         self.size, self.current_idx, self.current_size = size, 0, 0
         self.gen = torch.Generator(device=device)
         self.gen.manual_seed(int(seed))
@@ -154,6 +210,8 @@ class ReplayBufferGPU(EpisodeBatch):
         idx = self._storage_idx(ep.n)
         for name in ("o_all", "u", "r", "avail_all", "u_onehot", "padded", "terminated"):
             getattr(self, name)[idx] = getattr(ep, name)
+        if self.s_all is not None:
+            self.s_all[idx] = ep.s_all
 
     def sample(self, batch_size):
         idx = torch.randint(0, self.current_size, (batch_size,), device=self.o_all.device, generator=self.gen)
@@ -167,8 +225,10 @@ class BatchedRolloutWorker:
     Finished envs are frozen by the env kernel (`freeze_terminated`), which emits exactly the zero padding the
     reference appends (rollout.py:131-141); the loop stops as soon as every env is done."""
 
-    def __init__(self, env, agents, epsilon=1.0, min_epsilon=0.05, anneal_steps=150000, epsilon_anneal_scale="step"):
+    def __init__(self, env, agents, epsilon=1.0, min_epsilon=0.05, anneal_steps=150000, epsilon_anneal_scale="step",
+                 record_state=False):
         self.env, self.agents = env, agents
+        self.record_state = record_state      # QMIX: store get_state() of every step as `s` / `s_next`
         info = env.get_env_info()
         self.T, self.A, self.n_actions, self.D = info["episode_limit"], info["n_agents"], info["n_actions"], info["obs_shape"][-1]
         self.epsilon, self.min_epsilon = epsilon, min_epsilon
@@ -181,10 +241,14 @@ class BatchedRolloutWorker:
         rollout.py:148-149), constraints and success, all device tensors."""
         env, N, A, T = self.env, self.env.N, self.A, self.T
         dev = env.device
-        ep = batch if batch is not None else EpisodeBatch(N, T, A, self.D, self.n_actions, dev)
+        state_dim = 3 * env.W * env.L if self.record_state else 0
+        ep = batch if batch is not None else EpisodeBatch(N, T, A, self.D, self.n_actions, dev, state_dim=state_dim)
         ep.padded.fill_(True); ep.terminated.fill_(True)
         ep.u.zero_(); ep.u_onehot.zero_(); ep.r.zero_(); ep.avail_all.zero_(); ep.o_all[:, 1:].zero_()
         ep.o_all[:, 0].copy_(env.reset())
+        if ep.s_all is not None:
+            ep.s_all[:, 1:].zero_()
+            ep.s_all[:, 0].copy_(env.get_state().reshape(N, -1))
         ep.avail_all[:, 0] = 1
         hidden = self.agents.init_hidden(N)
         last = torch.zeros(N, A, self.n_actions, device=dev)
@@ -203,6 +267,8 @@ class BatchedRolloutWorker:
             live = alive & ~info["padded"]
             onehot = F.one_hot(actions, self.n_actions).to(torch.int8) * live[:, None, None]
             ep.o_all[:, t + 1] = obs
+            if ep.s_all is not None:                            # padded steps keep the zero state, like the zero obs
+                ep.s_all[:, t + 1] = env.get_state().reshape(N, -1) * live[:, None]
             ep.u[:, t, :, 0] = (actions * live[:, None]).to(torch.int8)
             ep.u_onehot[:, t] = onehot
             ep.r[:, t, 0] = info["team_reward"]
@@ -320,3 +386,56 @@ class VDNLearner:
         mid = "" if train_step is None else str(train_step) + "_"
         torch.save({}, os.path.join(model_dir, "{}_{}vdn_net_params.pkl".format(ith_run, mid)))
         torch.save(self.eval_rnn.state_dict(), os.path.join(model_dir, "{}_{}rnn_net_params.pkl".format(ith_run, mid)))
+
+
+class QMIXLearner(VDNLearner):
+    """policy/qmix.py:73-123: the VDN learner with the sum replaced by QMixNet(q, s) / QMixNet_target(q', s_next).
+    The reference builds its agents from the MLP-GRU `RNN` and never produces `s`; here the agent network is the same
+    CRNN the batched rollout uses (so `BatchedAgents` / `BatchedRolloutWorker(record_state=True)` feed it unchanged)
+    and `s` is the env's global state (3*W*L int8, get_state)."""
+
+    def __init__(self, obs_shape, n_agents, n_actions, state_shape, device, qmix_hidden_dim=32, hyper_hidden_dim_mix=64,
+                 two_hyper_layers=False, **kw):
+        super().__init__(obs_shape, n_agents, n_actions, device, **kw)
+        self.eval_qmix_net = QMixNet(state_shape, n_agents, qmix_hidden_dim, hyper_hidden_dim_mix, two_hyper_layers).to(self.device)
+        self.target_qmix_net = QMixNet(state_shape, n_agents, qmix_hidden_dim, hyper_hidden_dim_mix, two_hyper_layers).to(self.device)
+        self.target_qmix_net.load_state_dict(self.eval_qmix_net.state_dict())
+        self.eval_parameters = list(self.eval_qmix_net.parameters()) + list(self.eval_rnn.parameters())   # qmix.py:53-54
+        lr = kw.get("lr", 5e-4)
+        self.optimizer = torch.optim.Adam(self.eval_parameters, lr=lr, betas=(0.9, 0.99))                   # qmix.py:61-63
+
+    def learn(self, batch, train_step, max_episode_len=None):
+        T = self.max_episode_len(batch) if max_episode_len is None else max_episode_len
+        T = max(T, 1)
+        batch = {k: v[:, :T] for k, v in batch.items()}
+        u = batch["u"].to(torch.int64)
+        r = batch["r"].to(torch.float32)
+        s, s_next = batch["s"].to(torch.float32), batch["s_next"].to(torch.float32)
+        terminated = batch["terminated"].to(torch.float32)
+        mask = 1.0 - batch["padded"].to(torch.float32)
+        q_evals, q_targets = self.q_values(batch, T)
+        q_evals = torch.gather(q_evals, dim=3, index=u).squeeze(3)
+        q_targets = q_targets.masked_fill(batch["avail_u_next"] == 0, -9999999.0).max(dim=3)[0]
+        q_total_eval = self.eval_qmix_net(q_evals, s)
+        with torch.no_grad():
+            q_total_target = self.target_qmix_net(q_targets, s_next)
+        targets = r + self.gamma * q_total_target * (1.0 - terminated)
+        masked_td = mask * (q_total_eval - targets.detach())
+        loss = (masked_td ** 2).sum() / mask.sum().clamp_min(1.0)
+        self.optimizer.zero_grad(set_to_none=False)
+        loss.backward()
+        allreduce_gradients(self.eval_parameters, self.world_size)
+        torch.nn.utils.clip_grad_norm_(self.eval_parameters, self.grad_norm_clip)
+        self.optimizer.step()
+        if train_step > 0 and train_step % self.target_update_cycle == 0:
+            self.target_rnn.load_state_dict(self.eval_rnn.state_dict())
+            self.target_qmix_net.load_state_dict(self.eval_qmix_net.state_dict())
+        return loss.detach()
+
+    def save_model(self, model_dir, ith_run=0, train_step=None):
+        """File naming of QMIX.save_model / save_final_model (qmix.py:196-212)."""
+        os.makedirs(model_dir, exist_ok=True)
+        mid = "" if train_step is None else str(train_step) + "_"
+        torch.save(self.eval_qmix_net.state_dict(), os.path.join(model_dir, "{}_{}qmix_net_params.pkl".format(ith_run, mid)))
+        torch.save(self.eval_rnn.state_dict(), os.path.join(model_dir, "{}_{}rnn_net_params.pkl".format(ith_run, mid)))
+

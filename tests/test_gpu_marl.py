@@ -51,3 +51,32 @@ def test_lockstep_rollout_and_vdn_updates():
     e0 = worker.epsilon
     _, st = worker.generate_episodes(evaluate=True)
     assert worker.epsilon == e0 and st["steps"].shape == (N,)
+
+
+def test_qmix_rollout_records_the_global_state_and_learns():
+    """QMIX (policy/qmix.py:73-123) on top of the env's get_state kernel: `s` of a live step is getglobalobs() of
+    that step, padded steps carry zeros, and a few updates move both the agent network and the mixer."""
+    P = importlib.import_module("marl-dmfb_b200")
+    dev = torch.device("cuda:0")
+    N, W, L, A, n_act = 256, 10, 10, 4, 5
+    env = P.BatchedDMFB(N, W, L, A, fov=9, device=dev, seed=11)
+    info = env.get_env_info()
+    T = info["episode_limit"]
+    learner = P.QMIXLearner(info["obs_shape"], A, n_act, 3 * W * L, dev, seed=0)
+    agents = P.BatchedAgents(learner.eval_rnn, A, n_act, dev, seed=1)
+    worker = P.BatchedRolloutWorker(env, agents, epsilon=1.0, anneal_steps=1000, record_state=True)
+    ep, stats = worker.generate_episodes()
+    b = ep.as_dict()
+    assert b["s"].shape == (N, T, 3 * W * L) and b["s"].dtype == torch.int8
+    pad = b["padded"][:, :, 0]
+    assert not bool(b["s_next"][pad].any())
+    s0 = b["s"][:, 0].reshape(N, 3, W, L)
+    # layer 0 of getglobalobs marks every droplet with idx+1, layer 1 every goal (dmfb.py:368-392): A cells each
+    assert bool(((s0[:, 0] > 0).sum((1, 2)) == A).all()) and bool(((s0[:, 1] > 0).sum((1, 2)) == A).all())
+    buf = P.ReplayBufferGPU(512, T, A, info["obs_shape"][-1], n_act, dev, seed=3, state_dim=3 * W * L)
+    buf.store_episodes(ep)
+    w0 = learner.eval_qmix_net.hyper_w1.weight.detach().clone()
+    r0 = learner.eval_rnn.fc1.weight.detach().clone()
+    losses = [float(learner.learn(buf.sample(32), s)) for s in range(4)]
+    assert np.isfinite(losses).all()
+    assert not torch.equal(w0, learner.eval_qmix_net.hyper_w1.weight) and not torch.equal(r0, learner.eval_rnn.fc1.weight)

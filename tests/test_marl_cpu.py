@@ -51,6 +51,56 @@ def test_crnn_matches_reference_network(P):
     assert torch.equal(q, q_ref) and torch.equal(h2, h_ref)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/network"), reason="reference checkout not mounted")
+def test_qmix_networks_match_reference(P):
+    sys.path.insert(0, "/root/reference")
+    try:
+        from network.base_net import RNN as RefRNN
+        from network.qmix_net import QMixNet as RefMix
+    finally:
+        sys.path.pop(0)
+
+    class Args:
+        state_shape, n_agents, qmix_hidden_dim, hyper_hidden_dim, rnn_hidden_dim, n_actions = 300, 4, 32, 64, 64, 5
+        two_hyper_layers = False
+    for two in (False, True):
+        Args.two_hyper_layers = two
+        torch.manual_seed(0)
+        ref = RefMix(Args)
+        mine = P.QMixNet(300, 4, 32, 64, two)
+        mine.load_state_dict(ref.state_dict())                        # same parameter names / shapes
+        q, s = torch.randn(3, 7, 4), torch.randn(3, 7, 300)
+        assert torch.equal(ref(q, s), mine(q, s))
+    ref = RefRNN(254, Args)
+    mine = P.RNN(254, 5, 64)
+    mine.load_state_dict(ref.state_dict())
+    x, h = torch.randn(6, 254), torch.randn(6, 64)
+    assert all(torch.equal(a, b) for a, b in zip(ref(x, h), mine(x, h)))
+
+
+def test_qmix_mixer_is_monotonic_and_learner_reduces_td_error(P):
+    mix = P.QMixNet(300, 4)
+    s = torch.randn(5, 3, 300)
+    q = torch.randn(5, 3, 4)
+    bump = torch.zeros_like(q)
+    bump[..., 2] = 0.5
+    assert bool((mix(q + bump, s) >= mix(q, s)).all())                # dQtot/dQa >= 0 (abs of the hyper weights)
+    learner = P.QMIXLearner(OBS_SHAPE, 4, 5, 300, "cpu", seed=1)
+    batch = _synthetic_batch(6, 5, 4, 245, 5, seed=2)
+    g = torch.Generator().manual_seed(5)
+    s_all = torch.randint(0, 5, (6, 6, 300), generator=g, dtype=torch.int8)
+    batch["s"], batch["s_next"] = s_all[:, :5], s_all[:, 1:]
+    losses = [float(learner.learn(dict(batch), step)) for step in range(12)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    ep = P.EpisodeBatch(2, 4, 4, 245, 5, "cpu", state_dim=300)
+    d = ep.as_dict()
+    assert d["s"].shape == (2, 4, 300) and d["s_next"].shape == (2, 4, 300)
+    buf = P.ReplayBufferGPU(3, 4, 4, 245, 5, "cpu", state_dim=300)
+    ep.s_all.fill_(7)
+    buf.store_episodes(ep)
+    assert int(buf.sample(4)["s"].max()) == 7
+
+
 def _synthetic_batch(B, T, A, D, n_act, seed, device="cpu"):
     g = torch.Generator().manual_seed(seed)
     o = torch.randint(0, 5, (B, T + 1, A, D), generator=g, dtype=torch.int8)
