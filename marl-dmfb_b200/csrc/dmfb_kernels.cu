@@ -17,6 +17,8 @@
 //    bit masks (4 output bytes per multiply), sparse byte scatter for droplet ids / clipped goals /
 //    direction bytes, then ONE TMA bulk store (cp.async.bulk.global.shared::cta) per tile;
 //  * HBM-bound integer/byte work: no tensor cores.
+#include <cstddef>
+
 #include "common.cuh"
 
 namespace dmfb {
@@ -72,6 +74,8 @@ struct TileSmem {
     }
 };
 
+static_assert(offsetof(dmfb_cfg_t, dir_x) % 4 == 0 && offsetof(dmfb_cfg_t, dir_y) % 4 == 0, "word-wise table loads");
+
 // tid / nthreads: the (sub)set of CTA threads that cooperates on the fill
 __device__ __forceinline__ void load_tables(const dmfb_cfg_t& cfg, const TileLayout& L, const TileSmem& S, int tid,
                                             int nthreads)
@@ -83,10 +87,13 @@ __device__ __forceinline__ void load_tables(const dmfb_cfg_t& cfg, const TileLay
         S.l2row[k] = cfg.l2_row[c][j];
         S.l2col[k] = cfg.l2_col[c][j];
     }
+    // 4 table bytes per (lane-divergent, hence serialised) constant-bank load; both tables are 4-byte aligned
+    const uint32_t* dx4 = reinterpret_cast<const uint32_t*>(cfg.dir_x);
+    const uint32_t* dy4 = reinterpret_cast<const uint32_t*>(cfg.dir_y);
 #pragma unroll 1
-    for (int k = tid; k < 2 * cfg.width; k += nthreads) S.dirx[k] = cfg.dir_x[k];
+    for (int k = tid; k < (2 * cfg.width + 3) / 4; k += nthreads) reinterpret_cast<uint32_t*>(S.dirx)[k] = dx4[k];
 #pragma unroll 1
-    for (int k = tid; k < 2 * cfg.length; k += nthreads) S.diry[k] = cfg.dir_y[k];
+    for (int k = tid; k < (2 * cfg.length + 3) / 4; k += nthreads) reinterpret_cast<uint32_t*>(S.diry)[k] = dy4[k];
 }
 
 __device__ __forceinline__ void zero_tile(const TileLayout& L, const TileSmem& S, int tid, int nthreads)
@@ -557,11 +564,20 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
     const int od = abs(x - gx) + abs(y - gy);         // Droplet.distance (:93-95)
     const bool pre_done = (od == 0);                  // getTaskStatus before the moves (:278)
     const bool stalled = cfg.stall && pre_done;       // reward 0, no move, no draw (:331-332)
-    if (have_prob && !u && lane_on && !stalled) {
-        const uint4 r = env_random(seed, kStreamMove, cfg.env_base + n, episode, (uint32_t)sc, (uint32_t)g.i);
-        draw = u53(r.x, r.y);
+    bool pass = true;                                 // random.random() <= prob (:335)
+    if (have_prob && lane_on && !stalled) {
+        if (u) {
+            pass = draw <= prob;
+        } else if (prob < 1.0) {
+            // A draw in [0,1) never exceeds prob >= 1, and the stream is counter based: nothing to consume.
+            // Otherwise u53(r.x, r.y) = m / 2^53 with the 53-bit integer m, and m / 2^53 <= prob  <=>
+            // m <= floor(prob * 2^53); the scaling is exact, so the integer compare equals the float64 one.
+            const uint4 r = env_random(seed, kStreamMove, cfg.env_base + n, episode, (uint32_t)sc, (uint32_t)g.i);
+            const uint64_t m = ((uint64_t)(r.x >> 5) << 26) | (uint64_t)(r.y >> 6);
+            pass = prob >= 0.0 && m <= (uint64_t)__double2ll_rd(prob * 9007199254740992.0);
+        }
     }
-    const bool tries = lane_on && !stalled && !frozen && (draw <= prob);   // random.random() <= prob (:335)
+    const bool tries = lane_on && !stalled && !frozen && pass;
     uint32_t cand = start_cell;
     if (tries) {                                      // Droplet.move (:103-124)
         int nx = x + (a == 1) - (a == 2), ny = y + (a == 4) - (a == 3);

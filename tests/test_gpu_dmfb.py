@@ -387,3 +387,36 @@ def test_dmfb_v0_1_adapter_returns_reference_types():
     assert env.get_env_info()["obs_shape"] == (3, 9, 9, 2, 245)
     assert env._b.get_env_info()["obs_shape"] == (4, 9, 9, 2, 326)
 
+
+
+def test_device_move_draws_equal_injected_philox_draws():
+    """Without injected draws the kernel takes random.random() (dmfb.py:335) from Philox4x32-10 keyed by (seed, global
+    env, episode, step, agent) and compares it with the health as a 53-bit integer.  The numpy restatement of the same
+    stream (tests/philox_ref.py), injected as float64 draws into a twin env, must give the same trajectory - on
+    degraded cells, on healthy cells (prob == 1: no draw needed) and on dead cells (prob == 0)."""
+    import philox_ref
+    P = pkg()
+    N, W, L, A, seed, base = 700, 12, 12, 4, 0x12345678_9ABCDEF1, 5_000_000_123   # env index above 2^32
+    rng = np.random.default_rng(3)
+    kw = dict(fov=9, b_degrade=True, per_degrade=1.0, device="cuda:0", seed=seed, env_base=base, track_usage=True,
+              reward_f64=True)
+    a, b = P.BatchedDMFB(N, W, L, A, **kw), P.BatchedDMFB(N, W, L, A, **kw)
+    a.reset(new=True)
+    b.reset(new=True)
+    assert torch.equal(a.drop, b.drop)
+    health = rng.random((N, W, L))
+    health[rng.random((N, W, L)) < 0.2] = 1.0
+    health[rng.random((N, W, L)) < 0.05] = 0.0
+    a.health.copy_(torch.as_tensor(health))
+    b.health.copy_(torch.as_tensor(health))
+    moved = 0
+    for t in range(30):
+        acts = torch.as_tensor(rng.integers(1, 5, (N, A)).astype(np.int8), device="cuda:0")
+        draws = philox_ref.move_draws(seed, base + np.arange(N), _np(b.episode), _np(b.step_count) + 1, A)
+        before = a.drop.clone()
+        a.step(acts)                       # device draws
+        b.step(acts, draws=draws)          # the same draws, computed on the host
+        np.testing.assert_array_equal(_np(a.drop), _np(b.drop), err_msg=f"t{t}")
+        np.testing.assert_array_equal(_np(a.reward_f64), _np(b.reward_f64), err_msg=f"t{t}")
+        moved += int((before != a.drop).any(-1).sum())
+    assert 0.2 < moved / (30 * N * A) < 0.9   # some moves failed on degraded cells, some succeeded

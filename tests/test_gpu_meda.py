@@ -190,3 +190,27 @@ def test_meda_restart_returns_to_the_start_squares():
     obs = env.restart()
     assert torch.equal(env.drop, start) and torch.equal(obs, first)
     assert int(env.step_count.max()) == 0 and int(env.status.max()) == 0 and torch.equal(env.fails, fails)
+
+
+def test_meda_device_move_draws_equal_injected_philox_draws():
+    """Same pin as for DMFB: the MEDA kernel's own draws (Philox4x32-10 keyed by seed, global env, episode, step,
+    agent; meda.py:280) equal the host restatement of that stream injected as float64 draws."""
+    import philox_ref
+    P = pkg()
+    N, W, L, A, seed, base = 400, 30, 60, 4, 0xFEDCBA98_76543210, 7_000_000_001
+    rng = np.random.default_rng(5)
+    kw = dict(fov=19, b_degrade=True, per_degrade=1.0, obs_version=2, device="cuda:0", seed=seed, env_base=base, reward_f64=True)
+    a, b = P.BatchedMEDA(N, W, L, A, **kw), P.BatchedMEDA(N, W, L, A, **kw)
+    a.reset()
+    b.reset()
+    assert torch.equal(a.drop, b.drop)
+    health = rng.random((N, W, L)) * 0.8 + 0.2
+    a.health.copy_(torch.as_tensor(health))
+    b.health.copy_(torch.as_tensor(health))
+    for t in range(25):
+        acts = torch.as_tensor(rng.integers(0, 8, (N, A)).astype(np.int8), device="cuda:0")
+        draws = philox_ref.move_draws(seed, base + np.arange(N), _np(b.episode), _np(b.step_count) + 1, A)
+        a.step(acts)
+        b.step(acts, draws=draws)
+        np.testing.assert_array_equal(_np(a.drop), _np(b.drop), err_msg=f"t{t}")
+        np.testing.assert_array_equal(_np(a.reward_f64), _np(b.reward_f64), err_msg=f"t{t}")
