@@ -274,6 +274,16 @@ int dmfb_host_reset(dmfb_host_env_t* h, int new_task, const uint8_t* layouts, co
 int dmfb_host_step(dmfb_host_env_t* h, const int8_t* actions, const double* u_inject, uint64_t seed,
                    uint32_t flags, int8_t* obs, float* reward, uint8_t* done, int32_t* constraints,
                    uint8_t* success);
+/* Packed observation transfer for dmfb_host_step.  n_threads > 0 turns it on: `dma_percent` % of the envs still
+ * arrive unpacked by DMA, the rest crosses PCIe as 4-bit cells (cell values are 0..n_agents, so n_agents <= 15) and
+ * is expanded into `obs` by a pool of n_threads host threads (the caller's thread included) while that DMA runs.
+ * The result in `obs` is byte-identical.  n_threads <= 0 turns it off again. */
+int dmfb_host_set_transfer(dmfb_host_env_t* h, int n_threads, int dma_percent);
+/* The host half of that transfer on its own (no GPU involved): expands n_records packed records - ceil(cells/2) bytes
+ * of two 4-bit cells each (cell 2j in the low nibble of byte j), then 2 raw bytes, `packed_stride` bytes apart - into
+ * contiguous int8 records of cells+2 bytes with n_threads threads. */
+int dmfb_host_unpack_records(const uint8_t* packed, size_t packed_stride, int8_t* out, int cells, size_t n_records,
+                             int n_threads);
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so that callers outside torch can
  * give the copies a DMA-able buffer */
 void* dmfb_host_alloc_pinned(size_t bytes);

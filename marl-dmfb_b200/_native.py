@@ -76,7 +76,7 @@ EXPORTS = [
     "dmfb_cfg_init", "dmfb_cfg_set_obs_version", "dmfb_step", "dmfb_reset", "dmfb_observe", "dmfb_global_state", "dmfb_restart",
     "meda_cfg_init", "meda_step", "meda_reset", "meda_observe", "meda_restart", "meda_set_order",
     "dmfb_abi_version", "dmfb_last_cuda_error", "dmfb_launch_count",
-    "dmfb_host_create", "dmfb_host_destroy", "dmfb_host_reset", "dmfb_host_step",
+    "dmfb_host_create", "dmfb_host_destroy", "dmfb_host_reset", "dmfb_host_step", "dmfb_host_set_transfer", "dmfb_host_unpack_records",
     "dmfb_host_alloc_pinned", "dmfb_host_free_pinned",
 ]
 
@@ -121,6 +121,8 @@ def load():
                                      C.c_void_p]
     if hasattr(lib, "dmfb_host_create"):
         lib.dmfb_host_create.argtypes = [C.POINTER(DmfbCfg), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        lib.dmfb_host_set_transfer.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.dmfb_host_unpack_records.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_size_t, C.c_int]
         lib.dmfb_host_destroy.argtypes = [C.c_void_p]
         lib.dmfb_host_destroy.restype = None
         lib.dmfb_host_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]

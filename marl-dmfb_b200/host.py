@@ -58,6 +58,19 @@ class HostDMFB:
     def _p(self, a):
         return None if a is None else a.ctypes.data_as(C.c_void_p)
 
+    def set_transfer(self, n_threads, dma_percent=50):
+        """Packed observation transfer (dmfb_host_set_transfer): `dma_percent` % of the envs arrive unpacked by DMA,
+        the rest as 4-bit cells expanded by `n_threads` host threads meanwhile.  n_threads=0: plain DMA."""
+        nat.check(self.lib.dmfb_host_set_transfer(self._h, int(n_threads), int(dma_percent)), "dmfb_host_set_transfer")
+        N, A, D = self.N, self.A, self.D
+        small = N * A * 4 + N * A + N * 4 + N
+        if n_threads <= 0:
+            self.d2h_bytes_per_step = N * A * D + small
+        else:   # mirrors host_step_packed(): DMA share in 64-env units, the rest as packed records
+            n_dma = N if dma_percent == 100 else (N * int(dma_percent) // 100) & ~63
+            stride = (((D - 2) + 1) // 2 + 2 + 3) & ~3
+            self.d2h_bytes_per_step = n_dma * A * D + (N - n_dma) * A * stride + small
+
     def reset(self, new=False, layouts=None, degrade=None):
         lay = None if layouts is None else np.ascontiguousarray(layouts, np.uint8)
         deg = None if degrade is None else np.ascontiguousarray(degrade, np.float64)

@@ -121,3 +121,27 @@ def test_shard_range_partitions(P, n, world):
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     sizes = [b - a for a, b in spans]
     assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("cells,n,threads", [(243, 1000, 4), (324, 257, 3), (75, 33, 1), (7, 5, 8), (1083, 64, 2)])
+def test_host_unpack_expands_packed_records(P, cells, n, threads):
+    """Host half of the packed observation transfer (dmfb_host_set_transfer): 4-bit cells -> int8, direction bytes
+    unchanged.  Runs without a GPU."""
+    import ctypes as C
+    lib = P._native.load()
+    rng = np.random.default_rng(cells + n)
+    obs = rng.integers(0, 16, (n, cells + 2)).astype(np.int8)
+    obs[:, -2:] = rng.integers(-10, 11, (n, 2))
+    nb = (cells + 1) // 2
+    stride = (nb + 2 + 3) & ~3
+    packed = np.zeros((n, stride), np.uint8)
+    padded = np.zeros((n, 2 * nb), np.uint8)
+    padded[:, :cells] = obs[:, :cells]
+    packed[:, :nb] = padded[:, 0::2] | (padded[:, 1::2] << 4)
+    packed[:, nb:nb + 2] = obs[:, -2:].view(np.uint8)
+    out = np.full((n, cells + 2), 99, np.int8)
+    rc = lib.dmfb_host_unpack_records(packed.ctypes.data_as(C.c_void_p), stride, out.ctypes.data_as(C.c_void_p), cells, n,
+                                      threads)
+    assert rc == 0
+    np.testing.assert_array_equal(out, obs)
+

@@ -420,3 +420,42 @@ def test_device_move_draws_equal_injected_philox_draws():
         np.testing.assert_array_equal(_np(a.reward_f64), _np(b.reward_f64), err_msg=f"t{t}")
         moved += int((before != a.drop).any(-1).sum())
     assert 0.2 < moved / (30 * N * A) < 0.9   # some moves failed on degraded cells, some succeeded
+
+
+@pytest.mark.parametrize("n_envs,W,L,A,fov,deg", [(1000, 10, 10, 4, 9, False), (333, 20, 20, 10, 9, True), (64, 12, 15, 6, 7, False)])
+def test_host_buffer_path_equals_device_path_plain_and_packed(n_envs, W, L, A, fov, deg):
+    """dmfb_host_step (host buffers; what bench.py's e2e times) returns exactly what the device-resident API
+    returns, with the plain DMA transfer, with chunk streams, and with the packed transfer (4-bit cells expanded
+    by host threads beside the DMA of the rest) at several splits."""
+    P = pkg()
+    rng = np.random.default_rng(n_envs)
+    dev = P.BatchedDMFB(n_envs, W, L, A, fov=fov, b_degrade=deg, per_degrade=1.0, device="cuda:0", seed=77, track_usage=deg)
+    hosts = [P.HostDMFB(n_envs, W, L, A, fov=fov, b_degrade=deg, per_degrade=1.0, device=0, seed=77, n_chunks=c)
+             for c in (1, 3, 1, 1, 1)]
+    hosts[2].set_transfer(4, 50)
+    hosts[3].set_transfer(3, 0)        # everything packed
+    hosts[4].set_transfer(2, 100)      # pool on, nothing packed
+    o_dev = _np(dev.reset(new=True))
+    n_resets = int(dev.episode[0])         # tasks are keyed by (seed, env, episode): replay the same episode count
+    for h in hosts:
+        for _ in range(n_resets):
+            o_host = h.reset(new=True)
+        np.testing.assert_array_equal(o_host, o_dev)
+    for t in range(2 * (W + L) + 5):
+        acts = rng.integers(0, 5, (n_envs, A)).astype(np.int8)
+        o, r, d, info = dev.step(torch.as_tensor(acts, device="cuda:0"), auto_reset=True)
+        for k, h in enumerate(hosts):
+            ho, hr, hd, hinfo = h.step(acts, auto_reset=True)
+            np.testing.assert_array_equal(ho, _np(o), err_msg=f"host {k} obs t{t}")
+            np.testing.assert_array_equal(hr, _np(r), err_msg=f"host {k} reward t{t}")
+            np.testing.assert_array_equal(hd, _np(d), err_msg=f"host {k} done t{t}")
+            np.testing.assert_array_equal(hinfo["constraints"], _np(info["constraints"]))
+            np.testing.assert_array_equal(hinfo["success"], _np(info["success"]))
+    for h in hosts:
+        h.close()
+    with pytest.raises(ValueError):
+        big = P.HostDMFB(8, 30, 30, 20, fov=9, device=0)
+        try:
+            big.set_transfer(2, 50)    # 20 droplets do not fit 4-bit cells
+        finally:
+            big.close()
