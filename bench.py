@@ -324,6 +324,9 @@ def run_b200(args, rank, world, local_rank):
         others["C3 DMFB 50x50 10d fov9 degrade"] = quick(lambda: pkg.BatchedDMFB(N, 50, 50, 10, fov=9, b_degrade=True,
                                                                                   per_degrade=1.0, device=dev, seed=1), 5, 2761)
         torch.cuda.empty_cache()
+        others["C4 MEDA 30x60 4d fov19 (base obs, int8)"] = quick(lambda: pkg.BatchedMEDA(N, 30, 60, 4, fov=19, obs_version=0,
+                                                                                           device=dev, seed=1), 9, 5897)
+        torch.cuda.empty_cache()
         others["C4 MEDA 30x60 4d fov19 (v0_2 obs)"] = quick(lambda: pkg.BatchedMEDA(N, 30, 60, 4, fov=19, obs_version=2,
                                                                                      device=dev, seed=1), 9, 4453)
         torch.cuda.empty_cache()
