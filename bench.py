@@ -324,11 +324,19 @@ def run_b200(args, rank, world, local_rank):
         others["C3 DMFB 50x50 10d fov9 degrade"] = quick(lambda: pkg.BatchedDMFB(N, 50, 50, 10, fov=9, b_degrade=True,
                                                                                   per_degrade=1.0, device=dev, seed=1), 5, 2761)
         torch.cuda.empty_cache()
-        others["C4 MEDA 30x60 4d fov19 (base obs, int8)"] = quick(lambda: pkg.BatchedMEDA(N, 30, 60, 4, fov=19, obs_version=0,
-                                                                                           device=dev, seed=1), 9, 5897)
+        # MEDA: without degradation nothing reads the usage counters, so they are not kept (BatchedMEDA default); the
+        # "usage" / "degrade" lines add the counters (RED.ADD per footprint cell) and the 25-cell health gather
+        def meda(ver, **kw):
+            return lambda: pkg.BatchedMEDA(N, 30, 60, 4, fov=19, obs_version=ver, device=dev, seed=1, **kw)
+
+        others["C4 MEDA 30x60 4d fov19 (base obs, int8)"] = quick(meda(0), 9, 5897)
         torch.cuda.empty_cache()
-        others["C4 MEDA 30x60 4d fov19 (v0_2 obs)"] = quick(lambda: pkg.BatchedMEDA(N, 30, 60, 4, fov=19, obs_version=2,
-                                                                                     device=dev, seed=1), 9, 4453)
+        others["C4 MEDA 30x60 4d fov19 (v0_2 obs)"] = quick(meda(2), 9, 4453)
+        torch.cuda.empty_cache()
+        others["C4 MEDA 30x60 4d fov19 (base obs, usage counters kept)"] = quick(meda(0, track_usage=True), 9, 5897 + 400)
+        torch.cuda.empty_cache()
+        others["C4 MEDA 30x60 4d fov19 (base obs, degrade)"] = quick(meda(0, b_degrade=True, per_degrade=1.0), 9,
+                                                                     5897 + 400 + 800)
         torch.cuda.empty_cache()
         obs_buf = None
 

@@ -48,7 +48,10 @@ class BatchedMEDA:
     n_actions = 9
 
     def __init__(self, n_envs, width, length, n_agents, fov=19, b_degrade=False, per_degrade=0.1, obs_version=2,
-                 device="cuda", seed=0, env_base=0, reward_f64=False, degrade=None, layouts=None):
+                 device="cuda", seed=0, env_base=0, reward_f64=False, degrade=None, layouts=None, track_usage=None):
+        # track_usage: keep the m_usage actuation counters (addUsage, meda.py:591-598).  Nothing reads them unless the
+        # chip degrades (updateHealth runs only `if self.b_degrade`, meda.py:547-548), so like BatchedDMFB the default
+        # is `b_degrade`; the N=1 adapters always track them because `m_usage` is a visible attribute there.
         self.lib = nat.load()
         self.cfg = nat.MedaCfg()
         rc = self.lib.meda_cfg_init(C.byref(self.cfg), width, length, n_agents, fov, int(bool(b_degrade)),
@@ -78,13 +81,16 @@ class BatchedMEDA:
         self.fails = z(N, dtype=torch.int32)               # punish count; the reference's `fails` is -0.6 * this
         self.terminated = z(N, dtype=torch.uint8)
         self.episode = z(N, dtype=torch.int32)
-        self.usage = z(N, width, length, dtype=torch.int32)
+        if track_usage is None:
+            track_usage = self.b_degrade
+        self.usage = z(N, width, length, dtype=torch.int32) if (track_usage or self.b_degrade) else None
         self.health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         self.degrade = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         self.state = nat.MedaState(
             n_envs=N, drop=self.drop.data_ptr(), start=self.start.data_ptr(), status=self.status.data_ptr(),
             step_count=self.step_count.data_ptr(), fails=self.fails.data_ptr(),
-            terminated=self.terminated.data_ptr(), episode=self.episode.data_ptr(), usage=self.usage.data_ptr(),
+            terminated=self.terminated.data_ptr(), episode=self.episode.data_ptr(),
+            usage=self.usage.data_ptr() if self.usage is not None else None,
             health=self.health.data_ptr() if self.b_degrade else None,
             degrade=self.degrade.data_ptr() if self.b_degrade else None)
         self.set_order = None
@@ -219,7 +225,7 @@ class MEDAEnv:
         if seed is None:
             seed = int(np.random.randint(0, 2**31 - 1))
         self._b = BatchedMEDA(1, w, l, n_agents, fov=fov, b_degrade=b_degrade, per_degrade=per_degrade,
-                              obs_version=self._obs_version, device=device, seed=seed, reward_f64=True,
+                              obs_version=self._obs_version, device=device, seed=seed, reward_f64=True, track_usage=True,
                               layouts=None if layouts is None else np.asarray(layouts)[None],
                               degrade=None if degrade is None else np.asarray(degrade)[None])
         self.agents = list(self._b.agents)

@@ -25,7 +25,7 @@ def test_meda_cuda_matches_reference_trace(name):
     g = load_golden(name)
     K, A, W, L = g["K"], g["A"], g["W"], g["L"]
     env = pkg().BatchedMEDA(K, W, L, A, fov=g["fov"], b_degrade=bool(g["b_degrade"]), per_degrade=g["per_degrade"],
-                            obs_version=2, device="cuda:0", reward_f64=True,
+                            obs_version=2, device="cuda:0", reward_f64=True, track_usage=True,
                             degrade=g["degrade"] if g["b_degrade"] else None, layouts=g["layouts"][0])
     base = pkg().BatchedMEDA(K, W, L, A, fov=g["fov"], obs_version=0, device="cuda:0", layouts=g["layouts"][0])
     v01 = pkg().BatchedMEDA(K, W, L, A, fov=g["fov"], obs_version=1, device="cuda:0", layouts=g["layouts"][0])
@@ -91,7 +91,7 @@ def test_meda_cuda_matches_oracle_random(oracle_lib, N, W, L, A, fov, deg, ver):
     degrade = rng.random((N, W, L)) * 0.4 + 0.6 if deg else None
     layouts = ref.gen_layouts(seed=N)
     env = pkg().BatchedMEDA(N, W, L, A, fov=fov, b_degrade=deg, per_degrade=1.0, obs_version=ver, device="cuda:0",
-                            reward_f64=True, degrade=degrade, layouts=layouts)
+                            reward_f64=True, degrade=degrade, layouts=layouts, track_usage=True)
     if deg:
         ref.degrade[...] = degrade
         ref.health[...] = rng.random((N, W, L)) * 0.7 + 0.3

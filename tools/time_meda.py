@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """CUDA-event timing of the MEDA step at benchmark size (C4: 30x60 chip, 4 droplets, fov 19).
 usage: python tools/time_meda.py [obs_version 0|2] [n_envs] [degrade 0|1] [usage 1|0]
-(usage 0 drops the addUsage counters from the step: an experiment knob, not a supported mode)"""
+(usage 0: BatchedMEDA(track_usage=False), the default of a chip that does not degrade)"""
 import importlib
 import os
 import sys
@@ -15,9 +15,9 @@ ver = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 deg = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
 W, L, A, fov = 30, 60, 4, 19
-env = pkg.BatchedMEDA(N, W, L, A, fov=fov, obs_version=ver, b_degrade=deg, per_degrade=1.0, device="cuda:0", seed=1)
-if len(sys.argv) > 4 and not int(sys.argv[4]):
-    env.state.usage = None
+usage = bool(int(sys.argv[4])) if len(sys.argv) > 4 else True
+env = pkg.BatchedMEDA(N, W, L, A, fov=fov, obs_version=ver, b_degrade=deg, per_degrade=1.0, device="cuda:0", seed=1,
+                      track_usage=usage)
 slots = 8
 obs_buf = torch.empty(slots + 1, N, A, env.D, dtype=torch.int8, device="cuda:0")
 gen = torch.Generator(device="cuda:0").manual_seed(1)
@@ -40,5 +40,5 @@ with torch.cuda.stream(s):
     s.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / (5 * slots)
 bytes_env = A * env.D + 16 + 4 + 4 + 36 + 5 + 4 + 32 + 12
-print(f"MEDA v{ver} deg={int(deg)} N={N}: step {us:8.2f} us  {N * A / us / 1e3:7.2f} G agent-steps/s  "
+print(f"MEDA v{ver} deg={int(deg)} usage={int(usage or deg)} N={N}: step {us:8.2f} us  {N * A / us / 1e3:7.2f} G agent-steps/s  "
       f"{bytes_env * N / us / 1e3:8.1f} GB/s alg ({bytes_env} B/env-step)")
