@@ -94,6 +94,9 @@ class BatchedMEDA:
             health=self.health.data_ptr() if self.b_degrade else None,
             degrade=self.degrade.data_ptr() if self.b_degrade else None)
         self.set_order = None
+        if self.obs_version != nat.MEDA_OBS_BASE and A > 16:
+            # the others' goals are painted in CPython-set iteration order (meda.py:862-878), served from a [2^A][A] table
+            raise ValueError("MEDAEnv_v0_1 / _v0_2 observations are supported for at most 16 droplets")
         if self.obs_version != nat.MEDA_OBS_BASE and A > 8:
             self.set_order = torch.as_tensor(build_set_order_table(A)).to(dev)
         self.obs = z(N, A, self.D, dtype=torch.int8)

@@ -78,6 +78,8 @@ CASES = [
     (70, 45, 30, 3, 9, True, 2),
     (50, 60, 45, 6, 13, True, 0),
     (1, 30, 60, 4, 19, False, 2),
+    (9, 128, 128, 32, 19, True, 0),    # the library's maxima: chip side, droplets (one env per warp)
+    (7, 120, 120, 16, 19, False, 2),   # largest python-set order table (2^16 rows)
     (300, 30, 60, 4, 19, False, 1),    # MEDAEnv_v0_1 through the step kernel (specialised instance)
     (33, 80, 80, 10, 19, True, 1),     # ... and the generic instance with the python-set order table
     (70, 45, 30, 3, 9, False, 1),
