@@ -3,7 +3,7 @@
 // Replaces, for N independent chips at once, the reference call tree
 //   MEDAEnv.step (env/MEDA/meda.py:513-539) -> RoutingTaskManager.moveDroplets (:241-259)
 //   -> moveOneDroplet (:261-292) / getMoveProb (:302-309) / Droplet.move (:106-138) -> calPunish (:321-330)
-//   -> getObs (:607-611) -> getOneObs (:613-674, or MEDAEnv_v0_2 :850-897) -> addUsage (:591-598)
+//   -> getObs (:607-611) -> getOneObs (:613-674, or MEDAEnv_v0_1 :788-844 / MEDAEnv_v0_2 :850-897) -> addUsage (:591-598)
 // plus MEDAEnv.reset (:541-550) with refresh/addTask (:161-185) and updateHealth (:600-605).
 //
 // Design: WARP-AUTONOMOUS.  A warp owns EW consecutive envs (EW chosen so that their observation span is a
@@ -652,10 +652,8 @@ int meda_launch_reset(const meda_cfg_t* cfg, const meda_state_t* st, const uint8
 int meda_warp_envs(const meda_cfg_t& cfg)
 {
     const int A = cfg.n_agents;
-    if (const char* s = getenv("MEDA_WARP_ENVS")) {
-        const int v = atoi(s);
-        if (v >= 1 && v * A <= 32) return v;
-    }
+    static const int forced = getenv("MEDA_WARP_ENVS") ? atoi(getenv("MEDA_WARP_ENVS")) : 0;   // tuning knob
+    if (forced >= 1 && forced * A <= 32) return forced;
     const int unit = 16 / gcd_int(16, A * cfg.obs_dim);
     if (unit * A <= 32) return unit;
     return 32 / A;
@@ -667,10 +665,8 @@ int meda_launch_step_t(const meda_cfg_t* cfg, const meda_state_t* st, const void
 {
     const int EW = meda_warp_envs(*cfg);
     int wpc = 2;   // small CTAs pack the shared memory of an SM best (measured: 2 warps < 4 < 8)
-    if (const char* s = getenv("MEDA_WARPS_PER_CTA")) {
-        const int v = atoi(s);
-        if (v >= 1 && v <= kThreads / 32) wpc = v;
-    }
+    static const int forced_wpc = getenv("MEDA_WARPS_PER_CTA") ? atoi(getenv("MEDA_WARPS_PER_CTA")) : 0;   // tuning knob
+    if (forced_wpc >= 1 && forced_wpc <= kThreads / 32) wpc = forced_wpc;
     while (wpc > 1 && StepLayout(*cfg, EW, wpc).total > 200u * 1024u) wpc >>= 1;
     const StepLayout L(*cfg, EW, wpc);
     auto kern = meda_step_kernel<VER, A_T, FOV_T>;
@@ -683,7 +679,8 @@ int meda_launch_step_t(const meda_cfg_t* cfg, const meda_state_t* st, const void
     // groups with its next inputs prefetched; measured on B200 at 64K envs: base 115 us vs 100 us, v0_2 95 vs 97 us.
     const int n_groups = (st->n_envs + EW - 1) / EW;
     int grid = (n_groups + wpc - 1) / wpc;
-    if (getenv("MEDA_PERSIST")) {
+    static const bool persist = getenv("MEDA_PERSIST") != nullptr;
+    if (persist) {
         int dev = 0, sms = 0, per_sm = 0;
         DMFB_CUDA_TRY(cudaGetDevice(&dev));
         DMFB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
