@@ -461,3 +461,33 @@ def test_host_buffer_path_equals_device_path_plain_and_packed(n_envs, W, L, A, f
             big.set_transfer(2, 50)    # 20 droplets do not fit 4-bit cells
         finally:
             big.close()
+
+
+def test_device_task_generator_is_uniform_over_the_valid_tasks():
+    """_Generate_Start_End (dmfb.py:207-226) redraws the whole point set until no two points are within one cell, i.e.
+    it samples UNIFORMLY from the valid ordered point sets.  On a 5x5 chip with one droplet there are 456 valid
+    (start, goal) pairs; the device generator must hit only those, all
+    equally often (chi-square over ~460K tasks)."""
+    P = pkg()
+    N, W = 65536, 5
+    env = P.BatchedDMFB(N, W, W, 1, fov=5, device="cuda:0", seed=2024)
+    counts = torch.zeros(W ** 4, dtype=torch.int64, device="cuda:0")
+    reps = 7
+    for _ in range(reps):
+        env.reset()
+        d = env.drop[:, 0].to(torch.int64)
+        counts += torch.bincount(((d[:, 0] * W + d[:, 1]) * W + d[:, 2]) * W + d[:, 3], minlength=W ** 4)
+    c = counts.cpu().numpy().reshape(W, W, W, W)
+    xs = np.arange(W)
+    valid = np.maximum(np.abs(xs[:, None, None, None] - xs[None, None, :, None]),
+                       np.abs(xs[None, :, None, None] - xs[None, None, None, :])) >= 2
+    assert int(valid.sum()) == 456 and int(c[~valid].sum()) == 0
+    expected = N * reps / 456
+    chi2 = float(((c[valid] - expected) ** 2 / expected).sum())
+    assert chi2 < 455 + 5 * np.sqrt(2 * 455), chi2          # 5 sigma above the mean of chi-square(455)
+    # two droplets: the four points are pairwise apart, and every cell is used as a start
+    env2 = P.BatchedDMFB(N, 6, 7, 2, fov=5, device="cuda:0", seed=7)
+    pts = env2.drop.to(torch.int32).reshape(N, 4, 2)
+    diff = (pts[:, :, None, :] - pts[:, None, :, :]).abs().amax(-1) + 9 * torch.eye(4, dtype=torch.int32, device="cuda:0")
+    assert int(diff.min()) >= 2
+    assert len(torch.unique(pts[:, 0, 0] * 7 + pts[:, 0, 1])) == 42
