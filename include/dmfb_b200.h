@@ -96,7 +96,7 @@ typedef struct dmfb_cfg {
 /* Per-env state, struct-of-arrays over N envs, device pointers. */
 typedef struct dmfb_state {
     int32_t n_envs;
-    int32_t reserved0;
+    int32_t usage_log_cap;  /* entries per env in usage_log (0 = no log) */
     uint8_t* drop;          /* [N,A,4] = x, y, goal_x, goal_y              (Droplet, dmfb.py:74-79) */
     uint8_t* start;         /* [N,A,2] start cells for restart(), may be NULL (dmfb.py:185-190) */
     int32_t* step_count;    /* [N]                                          (dmfb.py:510,561) */
@@ -108,6 +108,13 @@ typedef struct dmfb_state {
     double* health;         /* [N,W,L] m_health, NULL == all 1.0            (dmfb.py:147,361-363) */
     double* degrade;        /* [N,W,L] m_degrade, NULL == all 1.0           (dmfb.py:151,157-166) */
     uint8_t* blocks;        /* [N,n_blocks,2] (x_min,y_min) of the 2x2 blocks (Block, dmfb.py:34-41,246); NULL when n_blocks==0 */
+    /* Optional (both NULL = off) log of the actuated cells.  Nothing reads m_usage between two resets (updateHealth runs
+     * at reset, dmfb.py:465-471), so a step appends the A cells it would increment (x | y<<8, 0xFFFF = none) - 2A
+     * coalesced bytes instead of A scattered read-modify-writes in an array that does not fit L2 - and the reset that
+     * needs the counters replays the env's log into `usage` first.  usage + log together are always the reference's
+     * m_usage; dmfb_flush_usage() folds the log in for a reader.  A full log falls back to direct increments. */
+    uint16_t* usage_log;    /* [N, usage_log_cap, A] */
+    int32_t* usage_log_len; /* [N] entries in use */
 } dmfb_state_t;
 
 /* Per-step outputs, device pointers; any pointer except `obs` may be NULL. */
@@ -163,6 +170,9 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
 int dmfb_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t* mask, int new_task,
                const uint8_t* layouts, const uint8_t* block_layouts, const double* degrade, uint64_t seed,
                int8_t* obs, void* stream);
+
+/* Folds state->usage_log into state->usage for every env and empties the log (no-op without a log). */
+int dmfb_flush_usage(const dmfb_cfg_t* cfg, const dmfb_state_t* state, void* stream);
 
 /* DMFBenv.getObs() of the current state for all envs (dmfb.py:614-626). */
 int dmfb_observe(const dmfb_cfg_t* cfg, const dmfb_state_t* state, int8_t* obs, void* stream);

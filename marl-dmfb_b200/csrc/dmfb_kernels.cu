@@ -474,11 +474,33 @@ __device__ __noinline__ void paint_agent_v01(const dmfb_cfg_t& cfg, const TileLa
     rec[4 * f2 + 1] = (int8_t)(gx - x);
 }
 
+// Folds the usage log of env n into its counters (threads tid, tid + nthreads, ... of the caller cooperate).  The
+// caller synchronises before anyone reads the counters and clears usage_log_len afterwards.
+__device__ __forceinline__ void replay_usage_log(const dmfb_cfg_t& cfg, const dmfb_state_t& st, int64_t n, int tid,
+                                                 int nthreads)
+{
+    const int A = cfg.n_agents, Lc = cfg.length;
+    const int len = min(st.usage_log_len[n], st.usage_log_cap);
+    const uint16_t* log = st.usage_log + (size_t)n * st.usage_log_cap * A;
+    uint32_t* usage = st.usage + (size_t)n * cfg.width * Lc;
+    for (int k = tid; k < len * A; k += nthreads) {
+        const uint32_t c = log[k];
+        if (c != 0xFFFFu) atomicAdd(usage + (c & 255u) * Lc + (c >> 8), 1u);
+    }
+}
+
 // updateHealth (dmfb.py:465-471) for the envs of the tile flagged kFlagNewTask; whole CTA cooperates.
 __device__ __forceinline__ void update_health_flagged(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const TileSmem& S,
                                                       int64_t n0, int e_valid)
 {
     const int cells = cfg.width * cfg.length;
+    if (st.usage_log != nullptr && st.usage_log_len != nullptr) {   // the counters are read below: fold the log in first
+        for (int e = 0; e < e_valid; ++e)
+            if (S.flag[e] & kFlagNewTask) replay_usage_log(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x);
+        __syncthreads();
+        for (int e = (int)threadIdx.x; e < e_valid; e += (int)blockDim.x)
+            if (S.flag[e] & kFlagNewTask) st.usage_log_len[n0 + e] = 0;
+    }
     for (int e = 0; e < e_valid; ++e) {
         if (!(S.flag[e] & kFlagNewTask)) continue;
         uint32_t* usage = st.usage + (size_t)(n0 + e) * cells;
@@ -651,8 +673,20 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
     if (frozen) { o.done_mask = all_mask; o.success = 0; }
     o.term = (o.done_mask == all_mask) ? 1 : 0;
 
-    if (DEG_T && lane_on && !frozen && (flags & DMFB_STEP_RECORD_USAGE) && st.usage && !post_done) {  // addUsage (:459-463)
-        atomicAdd(st.usage + ((size_t)n * W + nx) * Lc + ny, 1u);   // result unused -> RED.ADD, no round trip
+    if (DEG_T && (flags & DMFB_STEP_RECORD_USAGE) && st.usage) {   // addUsage (:459-463): droplets not done after the move
+        const bool add = lane_on && !frozen && !post_done;
+        bool logged = false;
+        if (st.usage_log != nullptr && st.usage_log_len != nullptr) {
+            int len = 0;
+            if (env_on && g.i == 0 && !frozen) len = st.usage_log_len[n];
+            len = g.get(len, 0);
+            logged = len < st.usage_log_cap;                       // a full log falls back to direct increments
+            if (logged && lane_on && !frozen) {
+                st.usage_log[((size_t)n * st.usage_log_cap + len) * A + g.i] = add ? (uint16_t)(nx | (ny << 8)) : (uint16_t)0xFFFFu;
+                if (g.i == 0) st.usage_log_len[n] = len + 1;
+            }
+        }
+        if (add && !logged) atomicAdd(st.usage + ((size_t)n * W + nx) * Lc + ny, 1u);   // result unused -> RED.ADD
     }
 
     // ---- fused auto-reset: DMFBenv.reset(new=False) (:589-597) for envs that just terminated -------
@@ -850,6 +884,7 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
                 double* health = st.health ? st.health + (size_t)nn * cells : nullptr;
                 double* degrade = st.degrade ? st.degrade + (size_t)nn * cells : nullptr;
                 const uint32_t episode = st.episode ? st.episode[nn] : 0u;
+                if (threadIdx.x == 0 && st.usage_log_len) st.usage_log_len[nn] = 0;   // usage = 0: the log goes with it
                 for (int k = threadIdx.x; k < cells; k += blockDim.x) {
                     if (usage) usage[k] = 0;
                     if (health) health[k] = 1.0;
@@ -881,6 +916,17 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
     int8_t* gobs = obs + (size_t)n0 * A * L.D;
     if (n_selected == e_valid) store_tile(gobs, S.tile, (uint32_t)(e_valid * A * L.D));
     else store_rows_masked(gobs, S.tile, e_valid, A * L.D, S.flag);
+}
+
+// --------------------------------------------------------------- flush usage --
+__global__ void __launch_bounds__(128)
+dmfb_flush_usage_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st)
+{
+    const int64_t n = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);   // one warp per env
+    if (n >= st.n_envs) return;
+    replay_usage_log(cfg, st, n, (int)(threadIdx.x & 31), 32);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) st.usage_log_len[n] = 0;
 }
 
 // ----------------------------------------------------------------- get_state --
@@ -1111,6 +1157,17 @@ int dmfb_cfg_init(dmfb_cfg_t* cfg, int width, int length, int n_agents, int n_bl
                 if (col_on) cfg->l2_col[c][q >> 5] |= 1u << (q & 31);
             }
     }
+    return DMFB_OK;
+}
+
+int dmfb_flush_usage(const dmfb_cfg_t* cfg, const dmfb_state_t* state, void* stream)
+{
+    int rc = check_common(cfg, state);
+    if (rc) return rc;
+    if (state->n_envs == 0 || !state->usage || !state->usage_log || !state->usage_log_len) return DMFB_OK;
+    dmfb_flush_usage_kernel<<<(state->n_envs + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, *state);
+    g_launches.fetch_add(1);
+    DMFB_CUDA_TRY(cudaGetLastError());
     return DMFB_OK;
 }
 

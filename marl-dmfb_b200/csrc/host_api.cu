@@ -27,6 +27,8 @@ struct dmfb_host_env {
     uint32_t* episode = nullptr;
     uint32_t* usage = nullptr;
     uint8_t* blocks = nullptr;
+    uint16_t* usage_log = nullptr;      // [N, max_step, A] actuated cells since the last reset (dmfb_state_t)
+    int32_t* usage_log_len = nullptr;
     double *health = nullptr, *degrade = nullptr;
     // device staging of per-step inputs / outputs
     int8_t* d_actions = nullptr;
@@ -76,6 +78,9 @@ dmfb_state_t sub_state(const dmfb_host_env* h, int lo, int hi)
     s.health = h->health ? h->health + (size_t)lo * cells : nullptr;
     s.degrade = h->degrade ? h->degrade + (size_t)lo * cells : nullptr;
     s.blocks = h->blocks ? h->blocks + (size_t)lo * h->cfg.n_blocks * 2 : nullptr;
+    s.usage_log_cap = h->usage_log ? h->cfg.max_step : 0;
+    s.usage_log = h->usage_log ? h->usage_log + (size_t)lo * h->cfg.max_step * A : nullptr;
+    s.usage_log_len = h->usage_log_len ? h->usage_log_len + lo : nullptr;
     return s;
 }
 
@@ -156,6 +161,8 @@ int dmfb_host_create(const dmfb_cfg_t* cfg, int n_envs, int device, int n_chunks
         TRY_ALLOC(usage, N * cells)
         TRY_ALLOC(health, N * cells)
         TRY_ALLOC(degrade, N * cells)
+        TRY_ALLOC(usage_log, N * (size_t)cfg->max_step * A)
+        TRY_ALLOC(usage_log_len, N)
     }
     TRY_ALLOC(d_actions, N * A)
     TRY_ALLOC(d_u, N * A)
@@ -188,7 +195,7 @@ void dmfb_host_destroy(dmfb_host_env_t* h)
     if (h->d_packed) cudaFree(h->d_packed);
     if (h->h_packed) cudaFreeHost(h->h_packed);
     void* ptrs[] = {h->drop, h->start, h->terminated, h->step_count, h->constraints, h->episode, h->usage, h->health,
-                    h->degrade, h->blocks, h->d_actions, h->d_u, h->d_obs, h->d_reward, h->d_done, h->d_cons, h->d_succ,
+                    h->degrade, h->blocks, h->usage_log, h->usage_log_len, h->d_actions, h->d_u, h->d_obs, h->d_reward, h->d_done, h->d_cons, h->d_succ,
                     h->d_layouts};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -32,7 +32,7 @@ class BatchedDMFB:
 
     def __init__(self, n_envs, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False,
                  per_degrade=0.1, device="cuda", seed=0, env_base=0, track_usage=None, reward_f64=False,
-                 degrade=None, layouts=None, block_layouts=None, obs_version=0):
+                 degrade=None, layouts=None, block_layouts=None, obs_version=0, usage_log=True):
         self.lib = nat.load()
         self.cfg = nat.DmfbCfg()
         nat.check(self.lib.dmfb_cfg_init(C.byref(self.cfg), width, length, n_agents, n_blocks, fov, int(bool(stall)),
@@ -72,8 +72,15 @@ class BatchedDMFB:
         self.blocks = z(N, self.n_blocks, 2, dtype=torch.uint8) if self.n_blocks else None   # (x_min, y_min) of 2x2 blocks
         self.health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         self.degrade = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
+        # Steps append the actuated cells to a per-env log instead of incrementing `usage` in place; resets (and
+        # usage_counts()) fold the log in.  `usage` alone is therefore NOT m_usage between resets: read usage_counts().
+        self._usage_log = bool(usage_log) and track_usage
+        self.usage_log = z(N, self.max_step, A, dtype=torch.int16) if self._usage_log else None
+        self.usage_log_len = z(N, dtype=torch.int32) if self._usage_log else None
         self.state = nat.DmfbState(
-            n_envs=N, drop=self.drop.data_ptr(), start=self.start.data_ptr(), step_count=self.step_count.data_ptr(),
+            n_envs=N, usage_log_cap=self.max_step if self._usage_log else 0,
+            usage_log=self.usage_log.data_ptr() if self._usage_log else None,
+            usage_log_len=self.usage_log_len.data_ptr() if self._usage_log else None, drop=self.drop.data_ptr(), start=self.start.data_ptr(), step_count=self.step_count.data_ptr(),
             constraints=self.constraints_cum.data_ptr(), terminated=self.terminated.data_ptr(),
             episode=self.episode.data_ptr(), usage=self.usage.data_ptr() if track_usage else None,
             health=self.health.data_ptr() if self.b_degrade else None,
@@ -222,7 +229,11 @@ class BatchedDMFB:
         return self.drop[:, :, 2:4]
 
     def usage_counts(self):
-        """m_usage as an integer tensor."""
+        """m_usage as an integer tensor (folds the usage log into the counters first)."""
+        if self._usage_log:
+            with torch.cuda.device(self.device):
+                rc = self.lib.dmfb_flush_usage(C.byref(self.cfg), C.byref(self.state), self._stream())
+            nat.check(rc, "dmfb_flush_usage")
         return self.usage
 
 

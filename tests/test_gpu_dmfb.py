@@ -297,7 +297,7 @@ def test_dmfb_fused_auto_reset_equals_step_plus_masked_reset(W, L, A, fov, deg):
         assert torch.equal(e1.drop, e2.drop) and torch.equal(o1, e2.obs)
         assert torch.equal(e1.step_count, e2.step_count) and torch.equal(e1.constraints_cum, e2.constraints_cum)
         assert torch.equal(e1.terminated, e2.terminated) and int(e1.terminated.sum()) == 0
-        assert torch.equal(e1.usage, e2.usage) and torch.equal(e1.start, e2.start)
+        assert torch.equal(e1.usage_counts(), e2.usage_counts()) and torch.equal(e1.start, e2.start)
         if deg:
             assert torch.equal(e1.health, e2.health)
     assert n_resets > N  # every env finished at least one episode
@@ -491,3 +491,40 @@ def test_device_task_generator_is_uniform_over_the_valid_tasks():
     diff = (pts[:, :, None, :] - pts[:, None, :, :]).abs().amax(-1) + 9 * torch.eye(4, dtype=torch.int32, device="cuda:0")
     assert int(diff.min()) >= 2
     assert len(torch.unique(pts[:, 0, 0] * 7 + pts[:, 0, 1])) == 42
+
+
+def test_usage_log_is_transparent():
+    """Steps append the actuated cells to a per-env log and the resets fold it into m_usage before updateHealth reads
+    the counters (dmfb_state_t.usage_log).  With and without the log: same counters, same health, same trajectories -
+    through fused auto-resets, masked resets, steps past the log capacity (max_step) and record=False steps."""
+    P = pkg()
+    N, W, L, A = 700, 10, 12, 4
+    rng = np.random.default_rng(8)
+    kw = dict(fov=9, b_degrade=True, per_degrade=1.0, device="cuda:0", seed=5, track_usage=True, reward_f64=True)
+    a = P.BatchedDMFB(N, W, L, A, usage_log=True, **kw)
+    b = P.BatchedDMFB(N, W, L, A, usage_log=False, **kw)
+    assert a.usage_log is not None and b.usage_log is None and torch.equal(a.drop, b.drop)
+    for env in (a, b):
+        env.usage.fill_(47)                     # updateHealth fires soon (usage > 50)
+
+    def run(steps, tag, **skw):
+        for t in range(steps):
+            acts = torch.as_tensor(rng.integers(0, 5, (N, A)).astype(np.int8), device="cuda:0")
+            a.step(acts, **skw)
+            b.step(acts, **skw)
+            assert torch.equal(a.drop, b.drop) and torch.equal(a.reward_f64, b.reward_f64), f"{tag} t{t}"
+            assert torch.equal(a.health, b.health), f"{tag} t{t} health"
+        assert torch.equal(a.usage_counts(), b.usage_counts()), tag
+        assert int(a.usage_log_len.max()) == 0          # usage_counts() folded everything in
+
+    run(50, "auto-reset", auto_reset=True)
+    run(2 * (W + L) + 9, "past the log capacity")       # no reset: the log fills up, the rest is added in place
+    mask = (np.arange(N) % 2 == 0).astype(np.uint8)
+    a.reset(mask=mask)
+    b.reset(mask=mask)
+    assert torch.equal(a.health, b.health)
+    run(15, "record off", record=False)
+    run(30, "after masked reset", auto_reset=True)
+    a.reset(new=True)
+    b.reset(new=True)
+    assert int(a.usage_counts().max()) == 0 and torch.equal(a.health, b.health)
