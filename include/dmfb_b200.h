@@ -213,7 +213,7 @@ typedef struct meda_cfg {
 
 typedef struct meda_state {
     int32_t n_envs;
-    int32_t reserved0;
+    int32_t usage_log_cap;  /* entries per env in usage_log (0 = no log) */
     uint8_t* drop;          /* [N,A,4] = x_center, y_center, goal x_center, goal y_center (meda.py:35-47) */
     uint8_t* start;         /* [N,A,2] may be NULL */
     uint8_t* status;        /* [N,A] sticky arrival flags (meda.py:159,277) */
@@ -224,6 +224,10 @@ typedef struct meda_state {
     uint32_t* usage;        /* [N,W,L] */
     double* health;         /* [N,W,L], NULL == all 1.0 */
     double* degrade;        /* [N,W,L], NULL == all 1.0 */
+    /* Optional log of the actuated droplets, same idea as dmfb_state_t.usage_log: a step appends the centre of every
+     * droplet whose 5x5 footprint it would increment (x | y<<8, 0xFFFF = none); meda_reset / meda_flush_usage replay it. */
+    uint16_t* usage_log;    /* [N, usage_log_cap, A] */
+    int32_t* usage_log_len; /* [N] */
 } meda_state_t;
 
 typedef struct meda_out {
@@ -256,6 +260,8 @@ int meda_observe(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t
  * status and step_count cleared, `fails` kept (as in the reference).  Needs state->start. */
 int meda_restart(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t* mask, const uint8_t* set_order,
                  int8_t* obs, void* stream);
+/* Folds state->usage_log into state->usage for every env and empties the log (no-op without a log). */
+int meda_flush_usage(const meda_cfg_t* cfg, const meda_state_t* state, void* stream);
 /* Host helper: iteration order of the CPython set {i : bit i of mask_bits} built by ascending insertion
  * (MEDAEnv_v0_2 iterates such a set, meda.py:862-872).  out[0..n_max) = elements in iteration order, 0xFF padded.
  * The device table `set_order` is [2^A][A] uint8 with row m = meda_set_order(m, A, ...). */

@@ -62,10 +62,11 @@ class MedaCfg(C.Structure):
 
 class MedaState(C.Structure):
     _fields_ = [
-        ("n_envs", C.c_int32), ("reserved0", C.c_int32),
+        ("n_envs", C.c_int32), ("usage_log_cap", C.c_int32),
         ("drop", C.c_void_p), ("start", C.c_void_p), ("status", C.c_void_p), ("step_count", C.c_void_p),
         ("fails", C.c_void_p), ("terminated", C.c_void_p), ("episode", C.c_void_p),
         ("usage", C.c_void_p), ("health", C.c_void_p), ("degrade", C.c_void_p),
+        ("usage_log", C.c_void_p), ("usage_log_len", C.c_void_p),
     ]
 
 
@@ -74,7 +75,7 @@ MedaOut = DmfbOut  # same field list (include/dmfb_b200.h: meda_out_t)
 # every symbol include/dmfb_b200.h declares
 EXPORTS = [
     "dmfb_cfg_init", "dmfb_cfg_set_obs_version", "dmfb_flush_usage", "dmfb_step", "dmfb_reset", "dmfb_observe", "dmfb_global_state", "dmfb_restart",
-    "meda_cfg_init", "meda_step", "meda_reset", "meda_observe", "meda_restart", "meda_set_order",
+    "meda_cfg_init", "meda_step", "meda_reset", "meda_observe", "meda_restart", "meda_set_order", "meda_flush_usage",
     "dmfb_abi_version", "dmfb_last_cuda_error", "dmfb_launch_count",
     "dmfb_host_create", "dmfb_host_destroy", "dmfb_host_reset", "dmfb_host_step", "dmfb_host_set_transfer", "dmfb_host_unpack_records",
     "dmfb_host_alloc_pinned", "dmfb_host_free_pinned",
@@ -118,6 +119,7 @@ def load():
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.meda_observe.argtypes = [C.POINTER(MedaCfg), C.POINTER(MedaState), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.meda_set_order.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+        lib.meda_flush_usage.argtypes = [C.POINTER(MedaCfg), C.POINTER(MedaState), C.c_void_p]
         lib.meda_restart.argtypes = [C.POINTER(MedaCfg), C.POINTER(MedaState), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]
     if hasattr(lib, "dmfb_host_create"):

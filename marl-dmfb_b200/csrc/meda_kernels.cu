@@ -244,6 +244,24 @@ __device__ __forceinline__ bool store_tile_warp(int8_t* __restrict__ gdst, const
     return false;
 }
 
+// Folds the usage log of env n into its counters: every logged droplet centre stands for its 5x5 footprint
+// (addUsage, meda.py:591-598).  Threads tid, tid + nthreads, ... cooperate; the caller synchronises and clears the length.
+__device__ __forceinline__ void meda_replay_usage_log(const meda_cfg_t& cfg, const meda_state_t& st, int64_t n, int tid,
+                                                      int nthreads)
+{
+    const int A = cfg.n_agents, Lc = cfg.length;
+    const int len = min(st.usage_log_len[n], st.usage_log_cap);
+    const uint16_t* log = st.usage_log + (size_t)n * st.usage_log_cap * A;
+    uint32_t* usage = st.usage + (size_t)n * cfg.width * Lc;
+    for (int k = tid; k < len * A; k += nthreads) {
+        const uint32_t c = log[k];
+        if (c == 0xFFFFu) continue;
+        uint32_t* p = usage + ((int)(c >> 8) - kRad) * Lc + ((int)(c & 255u) - kRad);
+        for (int dy = 0; dy <= 2 * kRad; ++dy)
+            for (int dx = 0; dx <= 2 * kRad; ++dx) atomicAdd(p + dy * Lc + dx, 1u);
+    }
+}
+
 // updateHealth (meda.py:600-605) for the flagged envs of the tile
 __device__ __forceinline__ void meda_update_health(const meda_cfg_t& cfg, const meda_state_t& st, const MedaSmem& S,
                                                    int64_t n0, int e_valid)
@@ -281,7 +299,7 @@ struct StepLayout {
 // Per-lane (= per-droplet) inputs of one step, loaded one group ahead of their use.
 struct DropIn {
     uint32_t d, status;
-    int a, fails0, sc0;
+    int a, fails0, sc0, log_len;
     bool frozen;
 };
 
@@ -290,7 +308,7 @@ __device__ __forceinline__ DropIn meda_load_inputs(const meda_state_t& st, const
 {
     const int lane = threadIdx.x & 31;
     DropIn in;
-    in.d = 0; in.status = 1; in.a = 8; in.fails0 = 0; in.sc0 = 0; in.frozen = false;
+    in.d = 0; in.status = 1; in.a = 8; in.fails0 = 0; in.sc0 = 0; in.log_len = 0; in.frozen = false;
     const int ev = (int)min((int64_t)EW, (int64_t)st.n_envs - n0);
     if (lane < ev * A) {
         const int e = lane / A;
@@ -302,13 +320,14 @@ __device__ __forceinline__ DropIn meda_load_inputs(const meda_state_t& st, const
         in.fails0 = st.fails[n];
         in.sc0 = st.step_count[n];
         in.frozen = (flags & DMFB_STEP_FREEZE_TERM) && st.terminated[n];
+        if (st.usage_log_len) in.log_len = st.usage_log_len[n];
     }
     return in;
 }
 
-// MEDAEnv.step (meda.py:513-539).  Warp w of the grid takes the groups w, w + n_warps, ... of EW consecutive envs
-// (EW * A <= 32); with the default grid that is one group per warp.  When it loops (capped grid) it keeps the
-// inputs of its next group in flight and lets the TMA store of a tile drain while the next dynamics run.
+// MEDAEnv.step (meda.py:513-539).  Warp w of the grid takes group w of EW consecutive envs (EW * A <= 32).
+// (A persistent variant - grid capped at the resident CTAs, every warp looping over groups with its next inputs
+// prefetched and the TMA drain overlapped - was measured slower, 115 vs 100 us, and removed.)
 template <int VER, int A_T, int FOV_T>
 __global__ void __launch_bounds__(kThreads)
 meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, const void* __restrict__ actions, int aes,
@@ -323,15 +342,17 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
     uint32_t* const s_word = reinterpret_cast<uint32_t*>(smem_raw + L.off_word) + warp * EW * A;
     uint8_t* const s_flag = smem_raw + L.off_flag + warp * EW;
     const int cells = W * Lc;
-    const int n_warps = gridDim.x * wpc;
 
-    int grp = blockIdx.x * wpc + warp;
+    const int grp = blockIdx.x * wpc + warp;
     if (grp >= n_groups) return;                              // no CTA-wide barrier below
-    DropIn nxt = meda_load_inputs(st, actions, aes, flags, (int64_t)grp * EW, EW, A);
-    bool store_pending = false;
-    for (; grp < n_groups; grp += n_warps) {
-        const DropIn in = nxt;
-        if (grp + n_warps < n_groups) nxt = meda_load_inputs(st, actions, aes, flags, (int64_t)(grp + n_warps) * EW, EW, A);
+    {
+        // loads first (lane = droplet), so that their latency overlaps the zero fill of the tile
+        const DropIn in = meda_load_inputs(st, actions, aes, flags, (int64_t)grp * EW, EW, A);
+        {
+            uint4* t4 = reinterpret_cast<uint4*>(tile);
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            for (int k = lane; k < (int)(L.warp_tile >> 4); k += 32) t4[k] = z;
+        }
         const int64_t n0 = (int64_t)grp * EW;
         const int ev = (int)min((int64_t)EW, (int64_t)st.n_envs - n0);
         const bool mine = lane < ev * A;
@@ -411,14 +432,6 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
         float team = 0.f;
         for (int j = 0; j < A; ++j) team += __shfl_sync(0xFFFFFFFFu, rf, (eb + j) & 31);
 
-        // the tile and the word / flag arrays are free again once the previous bulk store has read them
-        if (store_pending && lane == 0) tma_store_wait_read_all();
-        __syncwarp();
-        {
-            uint4* t4 = reinterpret_cast<uint4*>(tile);
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            for (int k = lane; k < (int)(L.warp_tile >> 4); k += 32) t4[k] = z;
-        }
         if (mine) {
             if (out.reward) out.reward[ja] = rf;
             if (out.reward_f64) out.reward_f64[ja] = r;
@@ -451,7 +464,14 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
         // ---- addUsage (:591-598): footprints of one env may overlap -> RED.ADD per cell; one instruction per
         //      droplet, lane = footprint cell, so that the 25 cells coalesce into the few sectors they share ------
         if (st.usage) {
-            const bool use = mine && in_time && !done;        // only while step_count < max_step, agents not done
+            bool use = mine && in_time && !done;              // only while step_count < max_step, agents not done
+            if (st.usage_log != nullptr && st.usage_log_len != nullptr && mine && !frozen && in.log_len < st.usage_log_cap) {
+                // log the droplet instead (2 bytes); a reset or meda_flush_usage replays the footprint
+                st.usage_log[((size_t)n * st.usage_log_cap + in.log_len) * A + i] =
+                    use ? (uint16_t)(xc | (yc << 8)) : (uint16_t)0xFFFFu;
+                if (i == 0) st.usage_log_len[n] = in.log_len + 1;
+                use = false;
+            }
             const int cell_off = (lane / 5 - kRad) * Lc + (lane % 5 - kRad);
             for (uint32_t m = __ballot_sync(0xFFFFFFFFu, use); m; m &= m - 1u) {
                 const int src = __ffs(m) - 1;
@@ -463,9 +483,9 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
         }
         __syncwarp();
         meda_paint_warp<VER, A_T, FOV_T>(cfg, s_word, s_flag, tile, ev, set_order);
-        store_pending = store_tile_warp(out.obs + (size_t)n0 * A * D, tile, (uint32_t)(ev * A * D));
+        if (store_tile_warp(out.obs + (size_t)n0 * A * D, tile, (uint32_t)(ev * A * D)) && lane == 0)
+            tma_store_wait_read_all();                        // shared memory must outlive the bulk read
     }
-    if (store_pending && lane == 0) tma_store_wait_read_all();
 }
 
 // refresh/addTask/_genLegalDroplet (meda.py:161-185,213-233): centres uniform in [r, dim-r-1]; a droplet
@@ -571,6 +591,7 @@ meda_reset_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st,
                 if (!S.flag[e]) continue;
                 const int64_t n = n0 + e;
                 const uint32_t episode = st.episode ? st.episode[n] : 0u;
+                if (threadIdx.x == 0 && st.usage_log_len) st.usage_log_len[n] = 0;   // usage = 0: the log goes with it
                 for (int k = threadIdx.x; k < cells; k += blockDim.x) {
                     if (st.usage) st.usage[(size_t)n * cells + k] = 0;
                     if (st.health) st.health[(size_t)n * cells + k] = 1.0;
@@ -587,6 +608,13 @@ meda_reset_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st,
                 }
             }
         } else {
+            if (st.usage && st.usage_log != nullptr && st.usage_log_len != nullptr) {   // m_usage is about to be read
+                for (int e = 0; e < e_valid; ++e)
+                    if (S.flag[e]) meda_replay_usage_log(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x);
+                __syncthreads();
+                for (int e = (int)threadIdx.x; e < e_valid; e += (int)blockDim.x)
+                    if (S.flag[e]) st.usage_log_len[n0 + e] = 0;
+            }
             meda_update_health(cfg, st, S, n0, e_valid);  // after the observation in the reference (:547-548); obs does not read health
         }
     }
@@ -609,6 +637,16 @@ meda_reset_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st,
     int8_t* gobs = obs + (size_t)n0 * A * L.D;
     if (n_selected == e_valid) store_tile(gobs, S.tile, (uint32_t)(e_valid * A * L.D));
     else store_rows_masked(gobs, S.tile, e_valid, A * L.D, S.flag);
+}
+
+__global__ void __launch_bounds__(128)
+meda_flush_usage_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st)
+{
+    const int64_t n = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);   // one warp per env
+    if (n >= st.n_envs) return;
+    meda_replay_usage_log(cfg, st, n, (int)(threadIdx.x & 31), 32);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) st.usage_log_len[n] = 0;
 }
 
 int meda_tile_envs(const meda_cfg_t& cfg)
@@ -675,19 +713,8 @@ int meda_launch_step_t(const meda_cfg_t* cfg, const meda_state_t* st, const void
         DMFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
         smem_set = L.total;
     }
-    // One group per warp by default.  MEDA_PERSIST=1 caps the grid at the resident CTAs, every warp then loops over
-    // groups with its next inputs prefetched; measured on B200 at 64K envs: base 115 us vs 100 us, v0_2 95 vs 97 us.
-    const int n_groups = (st->n_envs + EW - 1) / EW;
-    int grid = (n_groups + wpc - 1) / wpc;
-    static const bool persist = getenv("MEDA_PERSIST") != nullptr;
-    if (persist) {
-        int dev = 0, sms = 0, per_sm = 0;
-        DMFB_CUDA_TRY(cudaGetDevice(&dev));
-        DMFB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        DMFB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, L.total));
-        const int resident = sms * (per_sm > 0 ? per_sm : 1);
-        if (grid > resident) grid = resident;
-    }
+    const int n_groups = (st->n_envs + EW - 1) / EW;          // one group of EW envs per warp
+    const int grid = (n_groups + wpc - 1) / wpc;
     kern<<<grid, wpc * 32, L.total, static_cast<cudaStream_t>(stream)>>>(*cfg, *st, actions, aes, u, seed, flags, set_order,
                                                                          *out, EW, n_groups);
     g_launches.fetch_add(1);
@@ -786,6 +813,17 @@ int meda_observe(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t
     if (state && state->n_envs == 0) return DMFB_OK;
     if (!obs) return DMFB_ERR_BAD_ARG;
     return meda_launch_reset(cfg, state, nullptr, 2, 0, nullptr, nullptr, 0, set_order, obs, stream);
+}
+
+int meda_flush_usage(const meda_cfg_t* cfg, const meda_state_t* state, void* stream)
+{
+    int rc = meda_check(cfg, state);
+    if (rc) return rc;
+    if (state->n_envs == 0 || !state->usage || !state->usage_log || !state->usage_log_len) return DMFB_OK;
+    meda_flush_usage_kernel<<<(state->n_envs + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, *state);
+    g_launches.fetch_add(1);
+    DMFB_CUDA_TRY(cudaGetLastError());
+    return DMFB_OK;
 }
 
 // Iteration order of a CPython set holding the small ints of `mask_bits`, inserted in ascending order

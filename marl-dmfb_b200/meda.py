@@ -48,7 +48,8 @@ class BatchedMEDA:
     n_actions = 9
 
     def __init__(self, n_envs, width, length, n_agents, fov=19, b_degrade=False, per_degrade=0.1, obs_version=2,
-                 device="cuda", seed=0, env_base=0, reward_f64=False, degrade=None, layouts=None, track_usage=None):
+                 device="cuda", seed=0, env_base=0, reward_f64=False, degrade=None, layouts=None, track_usage=None,
+                 usage_log=True):
         # track_usage: keep the m_usage actuation counters (addUsage, meda.py:591-598).  Nothing reads them unless the
         # chip degrades (updateHealth runs only `if self.b_degrade`, meda.py:547-548), so like BatchedDMFB the default
         # is `b_degrade`; the N=1 adapters always track them because `m_usage` is a visible attribute there.
@@ -86,8 +87,14 @@ class BatchedMEDA:
         self.usage = z(N, width, length, dtype=torch.int32) if (track_usage or self.b_degrade) else None
         self.health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         self.degrade = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
+        # steps log the actuated droplets; resets and usage_counts() fold the log into `usage` (meda_state_t.usage_log)
+        self._usage_log = bool(usage_log) and self.usage is not None
+        self.usage_log = z(N, self.max_step, A, dtype=torch.int16) if self._usage_log else None
+        self.usage_log_len = z(N, dtype=torch.int32) if self._usage_log else None
         self.state = nat.MedaState(
-            n_envs=N, drop=self.drop.data_ptr(), start=self.start.data_ptr(), status=self.status.data_ptr(),
+            n_envs=N, usage_log_cap=self.max_step if self._usage_log else 0,
+            usage_log=self.usage_log.data_ptr() if self._usage_log else None,
+            usage_log_len=self.usage_log_len.data_ptr() if self._usage_log else None, drop=self.drop.data_ptr(), start=self.start.data_ptr(), status=self.status.data_ptr(),
             step_count=self.step_count.data_ptr(), fails=self.fails.data_ptr(),
             terminated=self.terminated.data_ptr(), episode=self.episode.data_ptr(),
             usage=self.usage.data_ptr() if self.usage is not None else None,
@@ -195,6 +202,11 @@ class BatchedMEDA:
                 "episode_limit": self.max_step}
 
     def usage_counts(self):
+        """m_usage (folds the usage log into the counters first)."""
+        if self._usage_log:
+            with torch.cuda.device(self.device):
+                rc = self.lib.meda_flush_usage(C.byref(self.cfg), C.byref(self.state), self._stream())
+            nat.check(rc, "meda_flush_usage")
         return self.usage
 
 

@@ -216,3 +216,35 @@ def test_meda_device_move_draws_equal_injected_philox_draws():
         b.step(acts, draws=draws)
         np.testing.assert_array_equal(_np(a.drop), _np(b.drop), err_msg=f"t{t}")
         np.testing.assert_array_equal(_np(a.reward_f64), _np(b.reward_f64), err_msg=f"t{t}")
+
+
+def test_meda_usage_log_is_transparent():
+    """meda_state_t.usage_log: steps log the droplet centres whose footprints addUsage would increment, resets replay
+    the log before updateHealth.  Same counters, health and trajectories with and without it - through auto-resets,
+    steps past the log capacity and a new chip."""
+    P = pkg()
+    N, W, L, A = 300, 30, 60, 4
+    rng = np.random.default_rng(12)
+    kw = dict(fov=19, b_degrade=True, per_degrade=1.0, obs_version=2, device="cuda:0", seed=31, reward_f64=True)
+    a = P.BatchedMEDA(N, W, L, A, usage_log=True, **kw)
+    b = P.BatchedMEDA(N, W, L, A, usage_log=False, **kw)
+    assert a.usage_log is not None and b.usage_log is None and torch.equal(a.drop, b.drop)
+    for env in (a, b):
+        env.usage.fill_(45)
+
+    def run(steps, tag, **skw):
+        for t in range(steps):
+            acts = torch.as_tensor(rng.integers(0, 9, (N, A)).astype(np.int8), device="cuda:0")
+            a.step(acts, **skw)
+            b.step(acts, **skw)
+            assert torch.equal(a.drop, b.drop) and torch.equal(a.reward_f64, b.reward_f64), f"{tag} t{t}"
+            assert torch.equal(a.health, b.health), f"{tag} t{t} health"
+        assert torch.equal(a.usage_counts(), b.usage_counts()), tag
+        assert int(a.usage_log_len.max()) == 0
+
+    run(40, "auto-reset", auto_reset=True)
+    run(W + L + 12, "past max_step")            # no resets: the log fills up; usage stops growing at max_step anyway
+    a.reset()
+    b.reset()
+    assert torch.equal(a.health, b.health)
+    run(30, "after reset", auto_reset=True)
