@@ -325,7 +325,8 @@ def run_b200(args, rank, world, local_rank):
                                                                                   per_degrade=1.0, device=dev, seed=1), 5, 2761)
         torch.cuda.empty_cache()
         # MEDA: without degradation nothing reads the usage counters, so they are not kept (BatchedMEDA default); the
-        # "usage" / "degrade" lines add the counters (RED.ADD per footprint cell) and the 25-cell health gather
+        # "usage" / "degrade" lines add the counters (a 2-byte usage-log entry per droplet-step, replayed at reset)
+        # and the 25-cell float64 health gather
         def meda(ver, **kw):
             return lambda: pkg.BatchedMEDA(N, 30, 60, 4, fov=19, obs_version=ver, device=dev, seed=1, **kw)
 
@@ -333,10 +334,10 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.empty_cache()
         others["C4 MEDA 30x60 4d fov19 (v0_2 obs)"] = quick(meda(2), 9, 4453)
         torch.cuda.empty_cache()
-        others["C4 MEDA 30x60 4d fov19 (base obs, usage counters kept)"] = quick(meda(0, track_usage=True), 9, 5897 + 400)
+        others["C4 MEDA 30x60 4d fov19 (base obs, usage counters kept)"] = quick(meda(0, track_usage=True), 9, 5897 + 8)
         torch.cuda.empty_cache()
         others["C4 MEDA 30x60 4d fov19 (base obs, degrade)"] = quick(meda(0, b_degrade=True, per_degrade=1.0), 9,
-                                                                     5897 + 400 + 800)
+                                                                     5897 + 8 + 800)
         torch.cuda.empty_cache()
         obs_buf = None
 
