@@ -222,26 +222,25 @@ __device__ __forceinline__ void meda_paint_warp(const meda_cfg_t& cfg, const uin
     }
 }
 
-// Warp-level counterpart of store_tile(): the calling warp's finished tile -> global memory, one TMA bulk
-// store issued by lane 0.  Returns true when a bulk store is in flight: lane 0 must tma_store_wait_read_all()
-// before the tile is written again or the CTA exits.
+// Warp-level counterpart of store_tile(): the calling warp's finished tile -> global memory.  `tile` has the same
+// 16-byte phase as `gdst` (the kernel places it so), hence everything between the first and the last 16-byte boundary
+// of the destination leaves as ONE TMA bulk store issued by lane 0, whatever the alignment of the destination; the
+// < 16 head and tail bytes are ordinary stores.  Returns true when a bulk store is in flight: lane 0 must
+// tma_store_wait_read_all() before the tile is written again or the CTA exits.
 __device__ __forceinline__ bool store_tile_warp(int8_t* __restrict__ gdst, const int8_t* tile, uint32_t nbytes)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    if ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) {
-        fence_proxy_async_smem();
-        __syncwarp();
-        const uint32_t bulk = nbytes & ~15u;
-        if (lane == 0 && bulk) {
-            tma_store_1d(gdst, tile, bulk);
-            tma_store_commit();
-        }
-        for (uint32_t b = bulk + lane; b < nbytes; b += 32u) gdst[b] = tile[b];
-        return bulk != 0;
-    }
+    const uint32_t head = min((16u - (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u)) & 15u, nbytes);
+    const uint32_t bulk = (nbytes - head) & ~15u;
+    fence_proxy_async_smem();
     __syncwarp();
-    for (uint32_t b = lane; b < nbytes; b += 32u) gdst[b] = tile[b];
-    return false;
+    if (lane == 0 && bulk) {
+        tma_store_1d(gdst + head, tile + head, bulk);
+        tma_store_commit();
+    }
+    if (lane < head) gdst[lane] = tile[lane];
+    for (uint32_t b = head + bulk + lane; b < nbytes; b += 32u) gdst[b] = tile[b];
+    return bulk != 0;
 }
 
 // Folds the usage log of env n into its counters: every logged droplet centre stands for its 5x5 footprint
@@ -288,7 +287,7 @@ struct StepLayout {
     uint32_t warp_tile, off_word, off_flag, total;
     __host__ __device__ StepLayout(const meda_cfg_t& c, int EW_, int WPC_) {
         EW = EW_; WPC = WPC_;
-        warp_tile = ((uint32_t)(EW * c.n_agents * c.obs_dim) + 15u) & ~15u;
+        warp_tile = (((uint32_t)(EW * c.n_agents * c.obs_dim) + 15u) & ~15u) + 16u;   // + room for the store's phase
         uint32_t o = warp_tile * (uint32_t)WPC;
         off_word = o; o += (uint32_t)(WPC * EW * c.n_agents) * 4u;
         off_flag = o; o += ((uint32_t)(WPC * EW) + 3u) & ~3u;
@@ -338,7 +337,7 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
     const int A = A_T ? A_T : cfg.n_agents, W = cfg.width, Lc = cfg.length, D = cfg.obs_dim;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
     const StepLayout L(cfg, EW, wpc);
-    int8_t* const tile = reinterpret_cast<int8_t*>(smem_raw + (size_t)warp * L.warp_tile);
+    int8_t* const region = reinterpret_cast<int8_t*>(smem_raw + (size_t)warp * L.warp_tile);
     uint32_t* const s_word = reinterpret_cast<uint32_t*>(smem_raw + L.off_word) + warp * EW * A;
     uint8_t* const s_flag = smem_raw + L.off_flag + warp * EW;
     const int cells = W * Lc;
@@ -349,11 +348,14 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
         // loads first (lane = droplet), so that their latency overlaps the zero fill of the tile
         const DropIn in = meda_load_inputs(st, actions, aes, flags, (int64_t)grp * EW, EW, A);
         {
-            uint4* t4 = reinterpret_cast<uint4*>(tile);
+            uint4* t4 = reinterpret_cast<uint4*>(region);
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
             for (int k = lane; k < (int)(L.warp_tile >> 4); k += 32) t4[k] = z;
         }
         const int64_t n0 = (int64_t)grp * EW;
+        // the tile starts at the 16-byte phase of its destination, so that the middle of it can leave by TMA
+        int8_t* const gobs = out.obs + (size_t)n0 * A * D;
+        int8_t* const tile = region + (reinterpret_cast<uintptr_t>(gobs) & 15u);
         const int ev = (int)min((int64_t)EW, (int64_t)st.n_envs - n0);
         const bool mine = lane < ev * A;
         const int e = mine ? lane / A : 0, i = lane - e * A;
@@ -483,7 +485,7 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
         }
         __syncwarp();
         meda_paint_warp<VER, A_T, FOV_T>(cfg, s_word, s_flag, tile, ev, set_order);
-        if (store_tile_warp(out.obs + (size_t)n0 * A * D, tile, (uint32_t)(ev * A * D)) && lane == 0)
+        if (store_tile_warp(gobs, tile, (uint32_t)(ev * A * D)) && lane == 0)
             tma_store_wait_read_all();                        // shared memory must outlive the bulk read
     }
 }
@@ -685,8 +687,8 @@ int meda_launch_reset(const meda_cfg_t* cfg, const meda_state_t* st, const uint8
     return DMFB_OK;
 }
 
-// Envs per warp of the step kernel: the smallest count whose observation span is a multiple of 16 bytes (TMA
-// bulk store), as long as their droplets fit the 32 lanes; otherwise as many envs as fit (plain stores).
+// Envs per warp of the step kernel (EW * A <= 32 droplet lanes).  Any count works with the phase-matched store; the
+// default keeps the smallest count whose observation span is a multiple of 16 bytes, which measured best.
 int meda_warp_envs(const meda_cfg_t& cfg)
 {
     const int A = cfg.n_agents;
