@@ -227,10 +227,12 @@ __device__ __forceinline__ void meda_paint_warp(const meda_cfg_t& cfg, const uin
 // of the destination leaves as ONE TMA bulk store issued by lane 0, whatever the alignment of the destination; the
 // < 16 head and tail bytes are ordinary stores.  Returns true when a bulk store is in flight: lane 0 must
 // tma_store_wait_read_all() before the tile is written again or the CTA exits.
+template <bool PHASED>
 __device__ __forceinline__ bool store_tile_warp(int8_t* __restrict__ gdst, const int8_t* tile, uint32_t nbytes)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t head = min((16u - (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u)) & 15u, nbytes);
+    // PHASED = false: the host saw that every warp's destination is 16-byte aligned (no head)
+    const uint32_t head = PHASED ? min((16u - (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u)) & 15u, nbytes) : 0u;
     const uint32_t bulk = (nbytes - head) & ~15u;
     fence_proxy_async_smem();
     __syncwarp();
@@ -238,7 +240,7 @@ __device__ __forceinline__ bool store_tile_warp(int8_t* __restrict__ gdst, const
         tma_store_1d(gdst + head, tile + head, bulk);
         tma_store_commit();
     }
-    if (lane < head) gdst[lane] = tile[lane];
+    if (PHASED && lane < head) gdst[lane] = tile[lane];
     for (uint32_t b = head + bulk + lane; b < nbytes; b += 32u) gdst[b] = tile[b];
     return bulk != 0;
 }
@@ -327,7 +329,7 @@ __device__ __forceinline__ DropIn meda_load_inputs(const meda_state_t& st, const
 // MEDAEnv.step (meda.py:513-539).  Warp w of the grid takes group w of EW consecutive envs (EW * A <= 32).
 // (A persistent variant - grid capped at the resident CTAs, every warp looping over groups with its next inputs
 // prefetched and the TMA drain overlapped - was measured slower, 115 vs 100 us, and removed.)
-template <int VER, int A_T, int FOV_T>
+template <int VER, int A_T, int FOV_T, bool PHASED>
 __global__ void __launch_bounds__(kThreads)
 meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, const void* __restrict__ actions, int aes,
                  const double* __restrict__ u, uint64_t seed, uint32_t flags, const uint8_t* __restrict__ set_order,
@@ -355,7 +357,7 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
         const int64_t n0 = (int64_t)grp * EW;
         // the tile starts at the 16-byte phase of its destination, so that the middle of it can leave by TMA
         int8_t* const gobs = out.obs + (size_t)n0 * A * D;
-        int8_t* const tile = region + (reinterpret_cast<uintptr_t>(gobs) & 15u);
+        int8_t* const tile = PHASED ? region + (reinterpret_cast<uintptr_t>(gobs) & 15u) : region;
         const int ev = (int)min((int64_t)EW, (int64_t)st.n_envs - n0);
         const bool mine = lane < ev * A;
         const int e = mine ? lane / A : 0, i = lane - e * A;
@@ -485,7 +487,7 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
         }
         __syncwarp();
         meda_paint_warp<VER, A_T, FOV_T>(cfg, s_word, s_flag, tile, ev, set_order);
-        if (store_tile_warp(gobs, tile, (uint32_t)(ev * A * D)) && lane == 0)
+        if (store_tile_warp<PHASED>(gobs, tile, (uint32_t)(ev * A * D)) && lane == 0)
             tma_store_wait_read_all();                        // shared memory must outlive the bulk read
     }
 }
@@ -709,11 +711,13 @@ int meda_launch_step_t(const meda_cfg_t* cfg, const meda_state_t* st, const void
     if (forced_wpc >= 1 && forced_wpc <= kThreads / 32) wpc = forced_wpc;
     while (wpc > 1 && StepLayout(*cfg, EW, wpc).total > 200u * 1024u) wpc >>= 1;
     const StepLayout L(*cfg, EW, wpc);
-    auto kern = meda_step_kernel<VER, A_T, FOV_T>;
-    static thread_local uint32_t smem_set = 0;
-    if (L.total > 48 * 1024 && L.total > smem_set) {
+    // every warp's destination is 16-byte aligned when the tensor is and a group's span is a multiple of 16 bytes
+    const bool phased = (reinterpret_cast<uintptr_t>(out->obs) & 15u) != 0 || (EW * cfg->n_agents * cfg->obs_dim) % 16 != 0;
+    auto kern = phased ? meda_step_kernel<VER, A_T, FOV_T, true> : meda_step_kernel<VER, A_T, FOV_T, false>;
+    static thread_local uint32_t smem_set[2] = {0, 0};        // per kernel instance (phased or not)
+    if (L.total > 48 * 1024 && L.total > smem_set[phased]) {
         DMFB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        smem_set = L.total;
+        smem_set[phased] = L.total;
     }
     const int n_groups = (st->n_envs + EW - 1) / EW;          // one group of EW envs per warp
     const int grid = (n_groups + wpc - 1) / wpc;
