@@ -35,11 +35,14 @@ inline int gcd_int(int a, int b)
 // Smallest number of envs whose rows (row_bytes each) form a span that is a multiple of 16 bytes,
 // scaled up to roughly `target_bytes` per tile.  Tiles of that many envs start 16-byte aligned when
 // the tensor base is, which is what the TMA bulk store needs.
-inline int pick_tile_envs(int row_bytes, int target_bytes, int max_envs)
+// Rows so long (and odd) that even one alignment unit of them would not fit `limit_bytes` of shared memory get a
+// smaller tile; its tiles then start unaligned and leave through the ordinary-store path of store_tile().
+inline int pick_tile_envs(int row_bytes, int target_bytes, int max_envs, int limit_bytes = 160 * 1024)
 {
     int unit = 16 / gcd_int(16, row_bytes);
     int e = unit;
     while (e * 2 <= max_envs && (e * 2) * row_bytes <= target_bytes) e *= 2;
+    while (e > 1 && (long long)e * row_bytes > limit_bytes) e >>= 1;
     return e;
 }
 

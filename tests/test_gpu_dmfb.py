@@ -94,6 +94,8 @@ CASES = [
     (1, 10, 10, 4, 9, True, True),
     (20, 128, 128, 32, 19, True, True),          # the library's maxima: chip side, droplets, fov
     (24, 60, 60, 8, 9, True, False, 32),         # ... and obstacles
+    (40, 30, 30, 25, 19, True, False),           # odd, long observation rows: 16 of them would not fit shared memory
+    (10, 127, 127, 4, 9, True, True),            # odd global-state rows (3 * 127 * 127 bytes)
     (500, 10, 10, 4, 9, True, False, 0, 1),      # DMFBenv_v0_1 through the fused step kernel
     (200, 20, 20, 10, 9, True, True, 0, 1),      # >= 10 droplets: own goal not projected (dmfb.py:756-761)
     (150, 14, 14, 5, 7, True, False, 6, 1),

@@ -80,6 +80,8 @@ CASES = [
     (1, 30, 60, 4, 19, False, 2),
     (9, 128, 128, 32, 19, True, 0),    # the library's maxima: chip side, droplets (one env per warp)
     (7, 120, 120, 16, 19, False, 2),   # largest python-set order table (2^16 rows)
+    (20, 90, 90, 15, 19, True, 0),     # long observation rows: the reset tile is capped by shared memory
+    (20, 75, 90, 15, 21, False, 1),
     (300, 30, 60, 4, 19, False, 1),    # MEDAEnv_v0_1 through the step kernel (specialised instance)
     (33, 80, 80, 10, 19, True, 1),     # ... and the generic instance with the python-set order table
     (70, 45, 30, 3, 9, False, 1),
