@@ -98,6 +98,11 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b)
 
 enum : uint32_t { kStreamMove = 1, kStreamLayout = 2, kStreamDegrade = 3, kStreamBlocks = 4 };
 
+// The reference's task / obstacle generators redraw until the draw is legal, i.e. for ever when the requested density
+// cannot be placed (dmfb.py:212-224,246-250, meda.py:213-233).  A kernel that never ends takes the GPU with it, so the
+// device generators abort the launch (CUDA error, reported through the return code) after this many rounds.
+constexpr uint32_t kMaxSamplerRounds = 1u << 22;
+
 // splitmix64 finaliser (Steele/Lea/Flood 2014): cheap counter-based generator for the task sampler
 __device__ __forceinline__ uint64_t mix64(uint64_t z)
 {

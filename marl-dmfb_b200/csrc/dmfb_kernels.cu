@@ -208,6 +208,7 @@ __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const
         base += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)epi << 32 | (uint32_t)g.i) * 0xDA942042E4DD58B5ull;
         base = mix64(base);
         for (uint32_t round = 0;; ++round) {
+            if (round >= kMaxSamplerRounds) __trap();             // density that cannot be placed
             const uint64_t k = (uint64_t)round * NG + (uint64_t)my_group;
             uint32_t w = 0;
             if (lane_in) {
@@ -254,7 +255,9 @@ __device__ __forceinline__ void generate_blocks(const dmfb_cfg_t& cfg, const dmf
     const int sx = word & 255u, sy = (word >> 8) & 255u, tx = (word >> 16) & 255u, ty = word >> 24;
     for (int b = 0; b < nb; ++b) {
         bool pending = want;
+        uint32_t rounds = 0;
         while (__any_sync(kFull, pending)) {
+            if (++rounds >= kMaxSamplerRounds) __trap();          // obstacles that cannot be placed
             uint32_t cand = 0;
             if (pending && g.i == 0) {
                 const uint64_t z = mix64(state += 0x9E3779B97F4A7C15ull);

@@ -503,7 +503,8 @@ __device__ void meda_generate_tasks(const meda_cfg_t& cfg, uint64_t seed, int64_
     state = mix64(state);
     for (int i = 0; i < A; ++i) {
         uint32_t sx, sy, tx, ty;
-        for (;;) {
+        for (uint32_t rounds = 0;; ++rounds) {
+            if (rounds >= kMaxSamplerRounds) __trap();            // droplets that cannot be placed
             const uint64_t z = mix64(state += 0x9E3779B97F4A7C15ull);
             sy = kRad + __umulhi((uint32_t)z, (uint32_t)(W - 2 * kRad));
             sx = kRad + __umulhi((uint32_t)(z >> 32), (uint32_t)(Lc - 2 * kRad));
@@ -514,7 +515,8 @@ __device__ void meda_generate_tasks(const meda_cfg_t& cfg, uint64_t seed, int64_
             }
             if (ok) break;
         }
-        for (;;) {
+        for (uint32_t rounds = 0;; ++rounds) {
+            if (rounds >= kMaxSamplerRounds) __trap();
             const uint64_t z = mix64(state += 0x9E3779B97F4A7C15ull);
             ty = kRad + __umulhi((uint32_t)z, (uint32_t)(W - 2 * kRad));
             tx = kRad + __umulhi((uint32_t)(z >> 32), (uint32_t)(Lc - 2 * kRad));

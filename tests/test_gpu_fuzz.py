@@ -22,9 +22,8 @@ def dmfb_case(P, O, rng):
         fov -= 2
     # droplet density bounded so that the whole-set rejection sampler of the oracle accepts within ~e^4 attempts
     A = int(rng.integers(2, max(2, min(32, int(0.6 * np.sqrt(W * L)))) + 1))
-    nb = int(rng.integers(0, 4)) * int(rng.integers(0, 2))
-    if nb * 4 / (W * L) > 0.2:
-        nb = 0
+    # obstacles only where they can always be placed (GenRandomBlocks retries for ever otherwise, dmfb.py:246-250)
+    nb = int(rng.integers(0, 4)) * int(rng.integers(0, 2)) if min(W, L) >= 12 else 0
     stall, deg, ver = bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), int(rng.integers(0, 2))
     N = int(rng.integers(1, 200))
     cfg = dict(kind="dmfb", N=N, W=W, L=L, A=A, fov=fov, nb=nb, stall=stall, deg=deg, ver=ver)
