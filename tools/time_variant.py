@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """CUDA-event timing of the DMFB step for an arbitrary configuration (experiment knob for DESIGN.md's breakdowns).
-usage: python tools/time_variant.py W L A fov degrade(0|1) track_usage(0|1) [n_envs] [health<1 fraction]"""
+usage: python tools/time_variant.py W L A fov degrade(0|1) track_usage(0|1) [n_envs] [health<1 fraction] [obs_version]"""
 import importlib
 import os
 import sys
@@ -13,8 +13,9 @@ pkg = importlib.import_module("marl-dmfb_b200")
 W, L, A, fov, deg, track = [int(x) for x in sys.argv[1:7]]
 N = int(sys.argv[7]) if len(sys.argv) > 7 else 65536
 frac = float(sys.argv[8]) if len(sys.argv) > 8 else 0.0
+ver = int(sys.argv[9]) if len(sys.argv) > 9 else 0
 env = pkg.BatchedDMFB(N, W, L, A, fov=fov, b_degrade=bool(deg), per_degrade=1.0, device="cuda:0", seed=1,
-                      track_usage=bool(track))
+                      track_usage=bool(track), obs_version=ver)
 env.reset(new=True)
 if deg and frac > 0:
     g = torch.Generator(device="cuda:0").manual_seed(2)
@@ -41,4 +42,4 @@ with torch.cuda.stream(s):
     e1.record(s)
     s.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / (5 * slots)
-print(f"DMFB {W}x{L} A={A} fov={fov} deg={deg} usage={track} degraded-cells={frac}: step {us:8.2f} us")
+print(f"DMFB {W}x{L} A={A} fov={fov} deg={deg} usage={track} degraded-cells={frac} obs_version={ver}: step {us:8.2f} us")
