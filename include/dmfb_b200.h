@@ -228,6 +228,10 @@ typedef struct meda_state {
      * droplet whose 5x5 footprint it would increment (x | y<<8, 0xFFFF = none); meda_reset / meda_flush_usage replay it. */
     uint16_t* usage_log;    /* [N, usage_log_cap, A] */
     int32_t* usage_log_len; /* [N] */
+    /* Optional scratch for DMFB_STEP_AUTO_RESET (both NULL = a masked meda_reset over the whole batch after the step):
+     * the step appends the envs that just terminated to reset_list, and a small second kernel resets exactly those. */
+    int32_t* reset_list;    /* [N] */
+    int32_t* reset_count;   /* [2], zero-initialised: entries in reset_list, finished-CTA ticket */
 } meda_state_t;
 
 typedef struct meda_out {

@@ -66,7 +66,7 @@ class MedaState(C.Structure):
         ("drop", C.c_void_p), ("start", C.c_void_p), ("status", C.c_void_p), ("step_count", C.c_void_p),
         ("fails", C.c_void_p), ("terminated", C.c_void_p), ("episode", C.c_void_p),
         ("usage", C.c_void_p), ("health", C.c_void_p), ("degrade", C.c_void_p),
-        ("usage_log", C.c_void_p), ("usage_log_len", C.c_void_p),
+        ("usage_log", C.c_void_p), ("usage_log_len", C.c_void_p), ("reset_list", C.c_void_p), ("reset_count", C.c_void_p),
     ]
 
 

@@ -459,6 +459,8 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
                     st.terminated[n] = (uint8_t)term;
                     st.fails[n] = fails;
                     st.step_count[n] = sc;
+                    if (term && (flags & DMFB_STEP_AUTO_RESET) && st.reset_list != nullptr)
+                        st.reset_list[atomicAdd(st.reset_count, 1)] = (int32_t)n;
                 }
                 s_flag[e] = frozen ? 0 : kEnvSelected;
             }
@@ -655,6 +657,108 @@ meda_flush_usage_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state
     if ((threadIdx.x & 31) == 0) st.usage_log_len[n] = 0;
 }
 
+// DMFB_STEP_AUTO_RESET, second half: MEDAEnv.reset() (meda.py:541-550) for exactly the envs the step just appended to
+// st.reset_list.  One small CTA per env, a few hundred envs per step, instead of a masked sweep over the whole batch:
+// thread 0 draws the task, all threads replay the usage log and run updateHealth, warp 0 paints the first
+// observation of the new episode and stores it with a (phase-matched) TMA bulk store.  The last CTA to finish empties
+// the list.
+template <int VER>
+__global__ void __launch_bounds__(128)
+meda_reset_list_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, uint64_t seed,
+                       const uint8_t* __restrict__ set_order, int8_t* __restrict__ obs)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int A = cfg.n_agents, D = cfg.obs_dim, cells = cfg.width * cfg.length;
+    const int tid = (int)threadIdx.x, nthreads = (int)blockDim.x;
+    const uint32_t region_bytes = (((uint32_t)(A * D) + 15u) & ~15u) + 16u;
+    int8_t* const region = reinterpret_cast<int8_t*>(smem_raw);
+    uint32_t* const s_word = reinterpret_cast<uint32_t*>(smem_raw + region_bytes);
+    uint8_t* const s_flag = smem_raw + region_bytes + (size_t)A * 4;
+    const int count = st.reset_count[0];
+    for (int k = blockIdx.x; k < count; k += gridDim.x) {
+        const int64_t n = st.reset_list[k];
+        for (int q = tid; q < (int)(region_bytes >> 4); q += nthreads) reinterpret_cast<uint4*>(region)[q] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid == 0) {
+            const uint32_t episode = st.episode ? st.episode[n] + 1u : 0u;
+            if (st.episode) st.episode[n] = episode;
+            meda_generate_tasks(cfg, seed, cfg.env_base + n, episode, s_word);
+            uint32_t* gdrop = reinterpret_cast<uint32_t*>(st.drop) + (size_t)n * A;
+            for (int i = 0; i < A; ++i) {
+                gdrop[i] = s_word[i];
+                st.status[(size_t)n * A + i] = 0;
+                if (st.start) reinterpret_cast<uint16_t*>(st.start)[(size_t)n * A + i] = (uint16_t)(s_word[i] & 0xFFFFu);
+            }
+            st.step_count[n] = 0;
+            st.fails[n] = 0;
+            st.terminated[n] = 0;
+            s_flag[0] = kEnvSelected;
+        }
+        if (st.usage && st.usage_log != nullptr && st.usage_log_len != nullptr) {   // m_usage is about to be read
+            meda_replay_usage_log(cfg, st, n, tid, nthreads);
+            __syncthreads();
+            if (tid == 0) st.usage_log_len[n] = 0;
+        }
+        if (cfg.b_degrade && st.usage && st.health) {            // updateHealth (meda.py:600-605)
+            uint32_t* usage = st.usage + (size_t)n * cells;
+            double* health = st.health + (size_t)n * cells;
+            const double* degrade = st.degrade ? st.degrade + (size_t)n * cells : nullptr;
+            for (int c = tid; c < cells; c += nthreads)
+                if (usage[c] > 50) {
+                    health[c] = health[c] * (degrade ? degrade[c] : 1.0);
+                    usage[c] = 0;
+                }
+        }
+        __syncthreads();                                          // task words and the zeroed tile before the paint
+        if (tid < 32) {
+            int8_t* const gobs = obs + (size_t)n * A * D;
+            int8_t* const tile = region + (reinterpret_cast<uintptr_t>(gobs) & 15u);
+            meda_paint_warp<VER, 0, 0>(cfg, s_word, s_flag, tile, 1, set_order);
+            if (store_tile_warp<true>(gobs, tile, (uint32_t)(A * D)) && tid == 0) tma_store_wait_read_all();
+        }
+        __syncthreads();                                          // the tile is free again
+    }
+    // the last CTA out empties the list for the next step
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(st.reset_count + 1, 1) == (int)gridDim.x - 1) {
+            st.reset_count[0] = 0;
+            st.reset_count[1] = 0;
+        }
+    }
+}
+
+int meda_launch_reset_list(const meda_cfg_t* cfg, const meda_state_t* st, uint64_t seed, const uint8_t* set_order, int8_t* obs,
+                           void* stream)
+{
+    const uint32_t region = ((((uint32_t)(cfg->n_agents * cfg->obs_dim) + 15u) & ~15u) + 16u);
+    const uint32_t smem = region + cfg->n_agents * 4 + 16;
+    static thread_local int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        DMFB_CUDA_TRY(cudaGetDevice(&dev));
+        DMFB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int grid = st->n_envs;                                        // never more CTAs than envs
+    if (grid > 8 * sms) grid = 8 * sms;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define MEDA_RESET_LIST(V)                                                                                         \
+    {                                                                                                              \
+        static thread_local uint32_t smem_set = 0;                                                                 \
+        if (smem > 48 * 1024 && smem > smem_set) {                                                                 \
+            DMFB_CUDA_TRY(cudaFuncSetAttribute(meda_reset_list_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            smem_set = smem;                                                                                       \
+        }                                                                                                          \
+        meda_reset_list_kernel<V><<<grid, 128, smem, s>>>(*cfg, *st, seed, set_order, obs);                        \
+    }
+    if (cfg->obs_version == MEDA_OBS_V02) MEDA_RESET_LIST(MEDA_OBS_V02)
+    else if (cfg->obs_version == MEDA_OBS_V01) MEDA_RESET_LIST(MEDA_OBS_V01)
+    else MEDA_RESET_LIST(MEDA_OBS_BASE)
+#undef MEDA_RESET_LIST
+    g_launches.fetch_add(1);
+    DMFB_CUDA_TRY(cudaGetLastError());
+    return DMFB_OK;
+}
+
 int meda_tile_envs(const meda_cfg_t& cfg)
 {
     const int row = cfg.n_agents * cfg.obs_dim;
@@ -795,8 +899,11 @@ int meda_step(const meda_cfg_t* cfg, const meda_state_t* state, const void* acti
     if (state->n_envs == 0) return DMFB_OK;
     rc = meda_launch_step(cfg, state, actions, action_elem_size, u_inject, seed, flags, set_order, out, stream);
     if (rc) return rc;
-    if (flags & DMFB_STEP_AUTO_RESET)
+    if (flags & DMFB_STEP_AUTO_RESET) {
+        if (state->reset_list && state->reset_count)
+            return meda_launch_reset_list(cfg, state, seed, set_order, out->obs, stream);
         return meda_launch_reset(cfg, state, state->terminated, 0, 0, nullptr, nullptr, seed, set_order, out->obs, stream);
+    }
     return DMFB_OK;
 }
 

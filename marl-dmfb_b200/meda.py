@@ -49,7 +49,7 @@ class BatchedMEDA:
 
     def __init__(self, n_envs, width, length, n_agents, fov=19, b_degrade=False, per_degrade=0.1, obs_version=2,
                  device="cuda", seed=0, env_base=0, reward_f64=False, degrade=None, layouts=None, track_usage=None,
-                 usage_log=True):
+                 usage_log=True, reset_list=True):
         # track_usage: keep the m_usage actuation counters (addUsage, meda.py:591-598).  Nothing reads them unless the
         # chip degrades (updateHealth runs only `if self.b_degrade`, meda.py:547-548), so like BatchedDMFB the default
         # is `b_degrade`; the N=1 adapters always track them because `m_usage` is a visible attribute there.
@@ -91,7 +91,13 @@ class BatchedMEDA:
         self._usage_log = bool(usage_log) and self.usage is not None
         self.usage_log = z(N, self.max_step, A, dtype=torch.int16) if self._usage_log else None
         self.usage_log_len = z(N, dtype=torch.int32) if self._usage_log else None
+        # auto_reset: the step lists the envs that terminated and a small kernel resets exactly those (reset_list=False:
+        # a masked reset sweeps the whole batch after every step instead)
+        self.reset_list = z(N, dtype=torch.int32) if reset_list else None
+        self.reset_count = z(2, dtype=torch.int32) if reset_list else None
         self.state = nat.MedaState(
+            reset_list=self.reset_list.data_ptr() if reset_list else None,
+            reset_count=self.reset_count.data_ptr() if reset_list else None,
             n_envs=N, usage_log_cap=self.max_step if self._usage_log else 0,
             usage_log=self.usage_log.data_ptr() if self._usage_log else None,
             usage_log_len=self.usage_log_len.data_ptr() if self._usage_log else None, drop=self.drop.data_ptr(), start=self.start.data_ptr(), status=self.status.data_ptr(),

@@ -250,3 +250,38 @@ def test_meda_usage_log_is_transparent():
     b.reset()
     assert torch.equal(a.health, b.health)
     run(30, "after reset", auto_reset=True)
+
+
+@pytest.mark.parametrize("ver,deg,A,W,L", [(0, False, 4, 30, 60), (2, True, 4, 30, 60), (1, True, 6, 45, 60), (2, False, 10, 80, 80)])
+def test_meda_listed_auto_reset_equals_masked_reset(ver, deg, A, W, L):
+    """auto_reset resets exactly the envs the step listed as terminated (meda_state_t.reset_list, one warp per env);
+    without the list a masked meda_reset sweeps the batch.  Same tasks, observations, health and counters."""
+    P = pkg()
+    N = 1500
+    rng = np.random.default_rng(ver + A)
+    kw = dict(fov=19, b_degrade=deg, per_degrade=1.0, obs_version=ver, device="cuda:0", seed=77, reward_f64=True, track_usage=True)
+    a = P.BatchedMEDA(N, W, L, A, reset_list=True, **kw)
+    b = P.BatchedMEDA(N, W, L, A, reset_list=False, **kw)
+    assert a.reset_list is not None and b.reset_list is None and torch.equal(a.drop, b.drop)
+    for env in (a, b):
+        env.usage.fill_(46)
+        env.step_count.copy_(torch.arange(N, device="cuda:0", dtype=torch.int32) % env.max_step)   # staggered episodes
+    n_resets = 0
+    for t in range(W + L + 25):
+        d = a.drop.to(torch.int32)
+        dx, dy = d[..., 2] - d[..., 0], d[..., 3] - d[..., 1]
+        toward = torch.where(dx.abs() >= dy.abs(), torch.where(dx > 0, 1, 3), torch.where(dy > 0, 2, 0)).to(torch.int8)
+        rnd = torch.as_tensor(rng.integers(0, 9, (N, A)).astype(np.int8), device="cuda:0")
+        acts = torch.where(torch.as_tensor(rng.random((N, A)) < 0.8, device="cuda:0"), toward, rnd)
+        ep0 = a.episode.clone()
+        oa, ra, da, ia = a.step(acts, auto_reset=True)
+        ob, rb, db, ib = b.step(acts, auto_reset=True)
+        n_resets += int((a.episode != ep0).sum())
+        assert torch.equal(a.drop, b.drop) and torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), f"t{t}"
+        assert torch.equal(a.episode, b.episode) and torch.equal(a.step_count, b.step_count)
+        assert torch.equal(a.status, b.status) and torch.equal(a.fails, b.fails) and torch.equal(a.start, b.start)
+        assert int(a.terminated.sum()) == 0 and int(a.reset_count.abs().sum()) == 0
+        if deg:
+            assert torch.equal(a.health, b.health), f"t{t} health"
+    assert n_resets > N
+    assert torch.equal(a.usage_counts(), b.usage_counts())
