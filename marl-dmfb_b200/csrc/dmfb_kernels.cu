@@ -176,6 +176,60 @@ struct Group {
 // threads per CTA for E envs with G lanes per env
 __host__ __device__ constexpr int cta_threads(int E, int G) { return ((E + 32 / G - 1) / (32 / G)) * 32; }
 
+// _Generate_Start_End for a compile-time droplet count: EVERY LANE tests a whole attempt of its own, 32 attempts per
+// warp round instead of 32/G, with the 2*A_T points and all pair tests in registers (fully unrolled).  pt[j] packs
+// start_j | goal_j << 16, i.e. the final droplet word.  The geometric tail of the sampler - the unluckiest of the envs
+// that reset in a step keeps its whole tile waiting - shrinks by the same factor.  Attempt k of (seed, env, episode)
+// is a pure function of those values; the lowest accepted attempt of a round wins.
+template <int G, int A_T>
+__device__ __noinline__ uint32_t generate_layout_regs(const dmfb_cfg_t& cfg, const Group<G>& g, uint64_t seed, int64_t env0,
+                                                      uint32_t episode, unsigned todo, uint32_t keep)
+{
+    const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
+    uint32_t word = keep;
+    while (todo) {
+        const int src = __ffs(todo) - 1;                          // leader lane of the group served now
+        todo &= todo - 1;
+        const int64_t env = env0 + src / G;
+        const uint32_t epi = __shfl_sync(kFull, episode, src);
+        uint64_t base = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
+        base += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)epi << 32) * 0xDA942042E4DD58B5ull;
+        base = mix64(base ^ 0xA5A5A5A5A5A5A5A5ull);
+        for (uint32_t round = 0;; ++round) {
+            if (round >= kMaxSamplerRounds) __trap();             // density that cannot be placed
+            const uint64_t k = (uint64_t)round * 32u + (uint64_t)g.lane;
+            const uint64_t ctr = base + k * (uint64_t)(2 * A_T) * 0x9E3779B97F4A7C15ull;
+            uint32_t pt[A_T];
+#pragma unroll
+            for (int j = 0; j < A_T; ++j) {
+                const uint64_t z0 = mix64(ctr + (uint64_t)(2 * j + 1) * 0x9E3779B97F4A7C15ull);
+                const uint64_t z1 = mix64(ctr + (uint64_t)(2 * j + 2) * 0x9E3779B97F4A7C15ull);
+                pt[j] = __umulhi((uint32_t)z0, W) | (__umulhi((uint32_t)(z0 >> 32), Lc) << 8) |
+                        (__umulhi((uint32_t)z1, W) << 16) | (__umulhi((uint32_t)(z1 >> 32), Lc) << 24);
+            }
+            uint32_t bad = 0;
+#pragma unroll
+            for (int a = 0; a < A_T; ++a) {
+                bad |= near_pair(pt[a], pt[a] >> 16) & 1u;        // own start vs own goal
+#pragma unroll
+                for (int b = a + 1; b < A_T; ++b)                 // start-start, goal-goal | start-goal, goal-start
+                    bad |= near_pair(pt[a], pt[b]) | near_pair(pt[a], __byte_perm(pt[b], 0u, 0x1032));
+            }
+            const unsigned okm = __ballot_sync(kFull, bad == 0u);
+            if (okm) {
+                const int win = __ffs(okm) - 1;                   // lowest attempt number of this round
+#pragma unroll
+                for (int j = 0; j < A_T; ++j) {
+                    const uint32_t w = __shfl_sync(kFull, pt[j], win);
+                    if (g.idx == src / G && g.i == j) word = w;
+                }
+                break;
+            }
+        }
+    }
+    return word;
+}
+
 // _Generate_Start_End (dmfb.py:207-226): 2A uniform cells, the whole set is redrawn until every pairwise
 // squared distance is > 2.  Attempt number k for (seed, env, episode) is a pure function of those four values:
 // lane i draws (start_i, goal_i) of the attempt from a counter-based generator and the group rejects the
@@ -195,6 +249,11 @@ __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const
     uint32_t word = keep;
     unsigned todo = __ballot_sync(kFull, want && g.i == 0);      // leader lanes of the requesting groups
     if (todo == 0u) return word;
+    // 10 droplets (C2 / C3): one attempt per LANE.  The choice depends on A only, so every kernel instance draws the
+    // same task for the same (seed, env, episode).  Measured at 64K envs: C2 staggered auto-reset 105 -> 69 us per
+    // step, reset-all 890 -> 434 us.  Not used for 4 droplets: acceptance is 8 % there, the tail is short, and the
+    // callee's registers cost the C1 step 0.4 us.
+    if (A == 10) return generate_layout_regs<G, 10>(cfg, g, seed, env0, episode, todo, keep);
     const int my_group = g.idx;
     const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
     const bool lane_in = g.valid && g.i < A;
