@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""End-to-end VDN training on GPU-resident envs (BASELINE config #5 when launched on 8 GPUs).
+"""End-to-end VDN / QMIX training on GPU-resident envs (BASELINE config #5 when launched on 8 GPUs).
 
   python tools/train_vdn.py --envs 4096 --iters 50
+  python tools/train_vdn.py --alg qmix --envs 2048 --iters 50      # mixer over the global state (get_state kernel)
   python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/train_vdn.py --envs 32768
 
 Batched counterpart of `python train.py dmfb --drop_num=4 --fov=9` (train.py:32-93): every iteration collects one
@@ -22,6 +23,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--alg", choices=["vdn", "qmix"], default="vdn")
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--width", type=int, default=10)
@@ -44,12 +46,18 @@ def main():
     env = P.BatchedDMFB(args.envs, args.width, args.length, args.drop_num, fov=args.fov, device=dev, seed=1234,
                         env_base=rank * args.envs)
     info = env.get_env_info()
-    learner = P.VDNLearner(info["obs_shape"], info["n_agents"], info["n_actions"], dev, world_size=world, seed=0)
+    qmix = args.alg == "qmix"
+    state_dim = 3 * args.width * args.length if qmix else 0     # getglobalobs (dmfb.py:368-392), flattened
+    if qmix:
+        learner = P.QMIXLearner(info["obs_shape"], info["n_agents"], info["n_actions"], state_dim, dev, world_size=world, seed=0)
+    else:
+        learner = P.VDNLearner(info["obs_shape"], info["n_agents"], info["n_actions"], dev, world_size=world, seed=0)
     agents = P.BatchedAgents(learner.eval_rnn, info["n_agents"], info["n_actions"], dev, seed=100 + rank)
-    worker = P.BatchedRolloutWorker(env, agents, anneal_steps=args.anneal_steps)
+    worker = P.BatchedRolloutWorker(env, agents, anneal_steps=args.anneal_steps, record_state=qmix)
     buf = P.ReplayBufferGPU(max(args.buffer_size, args.envs), info["episode_limit"], info["n_agents"], info["obs_shape"][-1],
-                            info["n_actions"], dev, seed=200 + rank)
-    ep = P.EpisodeBatch(args.envs, info["episode_limit"], info["n_agents"], info["obs_shape"][-1], info["n_actions"], dev)
+                            info["n_actions"], dev, seed=200 + rank, state_dim=state_dim)
+    ep = P.EpisodeBatch(args.envs, info["episode_limit"], info["n_agents"], info["obs_shape"][-1], info["n_actions"], dev,
+                        state_dim=state_dim)
     train_step, t0, env_steps = 0, time.time(), 0
     for it in range(args.iters):
         ep, stats = worker.generate_episodes(batch=ep)
