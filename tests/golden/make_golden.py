@@ -65,6 +65,12 @@ DMFB_SCENARIOS = {
     # at ABSOLUTE coordinates and in the global state
     "dmfb_blocks_12x12": dict(W=12, L=12, A=3, fov=9, stall=True, b_degrade=False, per_degrade=0.1, n_blocks=5,
                               K=6, n_ep=6, T=50, seed=111, p_goal=0.6, state_every=5),
+    # C2 / obstacle traces in which episodes really END IN SUCCESS (the +10/+10 bonus and info['success'], dmfb.py:293-296,
+    # 579-580): a constraint-avoiding policy (see _dmfb_safe_policy) instead of the mostly-greedy one
+    "dmfb_c2_success": dict(W=20, L=20, A=10, fov=9, stall=True, b_degrade=False, per_degrade=0.1,
+                            K=6, n_ep=3, T=84, seed=113, p_goal=1.0, state_every=12, obs_every=3, policy="safe"),
+    "dmfb_blocks_success": dict(W=20, L=16, A=5, fov=5, stall=True, b_degrade=False, per_degrade=0.1, n_blocks=8,
+                                K=4, n_ep=4, T=74, seed=114, p_goal=1.0, state_every=9, obs_every=3, policy="safe"),
     "dmfb_blocks_20x16_f5": dict(W=20, L=16, A=5, fov=5, stall=True, b_degrade=True, per_degrade=1.0, n_blocks=8,
                                  K=4, n_ep=4, T=74, seed=112, p_goal=0.7, state_every=9, obs_every=2),
 }
@@ -78,6 +84,17 @@ MEDA_SCENARIOS = {
                        K=2, n_ep=2, T=162, seed=203, p_goal=0.85, obs_every=9),
     "meda_45x30_f9": dict(W=45, L=30, A=3, fov=9, b_degrade=False, per_degrade=0.1,
                           K=3, n_ep=3, T=76, seed=204, p_goal=0.8, obs_every=2),
+    # Degradation that really happens (meda.py:302-309 getMoveProb < 1, :280 failed draws, :600-605 updateHealth):
+    # the C4 chip pre-aged to usage 48 on every microelectrode (state set on the reference object after construction,
+    # recorded as usage0), so that the first resets already degrade every cell a droplet has crossed three times ...
+    "meda_c4_aged": dict(W=30, L=60, A=4, fov=19, b_degrade=True, per_degrade=1.0,
+                         K=4, n_ep=14, T=90, seed=205, p_goal=0.75, obs_every=15, pre_usage=48),
+    # ... a small chip aged the natural way, by 70 short episodes from usage 0 ...
+    "meda_30x30_aged": dict(W=30, L=30, A=4, fov=19, b_degrade=True, per_degrade=0.8,
+                            K=3, n_ep=70, T=60, seed=206, p_goal=0.7, obs_every=30),
+    # ... and the 10-droplet set-order case on an aged 80x80 chip
+    "meda_80x80_aged": dict(W=80, L=80, A=10, fov=19, b_degrade=True, per_degrade=1.0,
+                            K=2, n_ep=5, T=160, seed=207, p_goal=0.8, obs_every=40, pre_usage=49),
 }
 
 
@@ -101,8 +118,52 @@ def _dmfb_policy(rng, env, p_goal):
     return acts
 
 
+def _dmfb_safe_policy(rng, env, p_goal):
+    """Droplets are planned in index order; each takes the goal-ward move (else any move, else STALL) whose target
+    cell keeps a Chebyshev distance >= 2 from every other droplet's old cell and from the cells already planned, and
+    does not touch an obstacle: no static / dynamic constraint (dmfb.py:254-271) is ever incurred, so an episode that
+    gets every droplet home within the step limit ends with success = 1."""
+    rm = env.routing_manager
+    old = [(d.x, d.y) for d in rm.droplets]
+    new = list(old)
+    acts = []
+    delta = {0: (0, 0), 1: (1, 0), 2: (-1, 0), 3: (0, -1), 4: (0, 1)}
+
+    def ok(i, c):
+        if not (0 <= c[0] < env.width and 0 <= c[1] < env.length):
+            return False
+        for b in rm.blocks:
+            if b.x_min <= c[0] <= b.x_max and b.y_min <= c[1] <= b.y_max:
+                return False
+        for j in range(len(old)):
+            if j == i:
+                continue
+            for q in (old[j], new[j]):
+                if abs(q[0] - c[0]) <= 1 and abs(q[1] - c[1]) <= 1:
+                    return False
+        return True
+
+    for i, d in enumerate(rm.droplets):
+        if (d.x, d.y) == (d.des_x, d.des_y):
+            acts.append(int(rng.integers(5)))      # done droplets ignore their action when stall=True
+            continue
+        dist = lambda c: abs(c[0] - d.des_x) + abs(c[1] - d.des_y)  # noqa: E731
+        order = sorted(range(1, 5), key=lambda a: (dist((d.x + delta[a][0], d.y + delta[a][1])), rng.random()))
+        if rng.random() > p_goal:
+            rng.shuffle(order)
+        a = 0
+        for cand in order:
+            c = (d.x + delta[cand][0], d.y + delta[cand][1])
+            if ok(i, c) and (dist(c) < dist(old[i]) or rng.random() < 0.35):
+                a = cand
+                break
+        new[i] = (d.x + delta[a][0], d.y + delta[a][1])
+        acts.append(a)
+    return acts
+
+
 def gen_dmfb(name, W, L, A, fov, stall, b_degrade, per_degrade, K, n_ep, T, seed, p_goal,
-             state_every=1, obs_every=1, n_blocks=0):
+             state_every=1, obs_every=1, n_blocks=0, policy="greedy"):
     rng = np.random.default_rng(seed)
     np.random.seed(seed)  # the reference draws layouts/degrade from the global numpy RNG
     import random as pyrandom
@@ -176,7 +237,7 @@ def gen_dmfb(name, W, L, A, fov, stall, b_degrade, per_degrade, K, n_ep, T, seed
             out["usage_reset"][ep, k] = rm.m_usage
         for t in range(T):
             for k, e in enumerate(envs):
-                acts = _dmfb_policy(rng, e, p_goal)
+                acts = (_dmfb_safe_policy if policy == "safe" else _dmfb_policy)(rng, e, p_goal)
                 out["actions"][ep, t, k] = acts
                 obs, rew, done, info = injs[k].step(e, acts, out["draws"][ep, t, k])
                 out["draws_used"][ep, t, k] = injs[k].consumed
@@ -216,7 +277,7 @@ def _meda_policy(rng, env, p_goal):
     return acts
 
 
-def gen_meda(name, W, L, A, fov, b_degrade, per_degrade, K, n_ep, T, seed, p_goal, obs_every=1):
+def gen_meda(name, W, L, A, fov, b_degrade, per_degrade, K, n_ep, T, seed, p_goal, obs_every=1, pre_usage=0):
     import random as pyrandom
     rng = np.random.default_rng(seed)
     np.random.seed(seed)
@@ -226,8 +287,20 @@ def gen_meda(name, W, L, A, fov, b_degrade, per_degrade, K, n_ep, T, seed, p_goa
         # taken from the same object through MEDAEnv.getOneObs (meda.py:613-674).
         e = ref_meda.MEDAEnv_v0_2(W, L, A, fov=fov, b_degrade=b_degrade, per_degrade=per_degrade)
         pyrandom.seed(seed * 1000 + k)  # task generator uses python's random (meda.py:224-227)
+        if pre_usage:
+            e.m_usage[...] = float(pre_usage)   # aged chip: m_usage is plain env state (meda.py:495)
         envs.append(e)
         injs.append(ref_shim.DrawInjector(ref_meda, e.routing_manager))
+    # bookkeeping for the printout only: the probabilities getMoveProb returned (instance wrapper, class untouched)
+    probs_seen = []
+    for e in envs:
+        def _wrap(orig):
+            def f(droplet, m_health):
+                p = orig(droplet, m_health)
+                probs_seen.append(p)
+                return p
+            return f
+        e.routing_manager.getMoveProb = _wrap(e.routing_manager.getMoveProb)
     D0 = 4 * fov * fov + 2
     D2 = 3 * fov * fov + 2
     t_obs = list(range(0, T, obs_every))
@@ -256,6 +329,7 @@ def gen_meda(name, W, L, A, fov, b_degrade, per_degrade, K, n_ep, T, seed, p_goa
         kind="meda", W=W, L=L, A=A, fov=fov, b_degrade=int(b_degrade), per_degrade=per_degrade,
         K=K, n_ep=n_ep, T=T, episode_limit=envs[0].max_step, n_actions=9,
         degrade=np.stack([e.m_degrade for e in envs]),
+        usage0=np.stack([e.m_usage for e in envs]),   # state before the first reset (nonzero for pre-aged chips)
         layouts=np.zeros((n_ep, K, A, 4), np.int16),  # x_c, y_c, goal x_c, goal y_c
         actions=np.zeros((n_ep, T, K, A), np.int8),
         draws=rng.random((n_ep, T, K, A)),
@@ -309,6 +383,11 @@ def gen_meda(name, W, L, A, fov, b_degrade, per_degrade, K, n_ep, T, seed, p_goa
         for k, e in enumerate(envs):
             out["usage_end"][ep, k] = e.m_usage
     out["health_final"] = np.stack([e.m_health for e in envs])
+    # draws are consumed in the order getMoveProb was called: one per True entry of draws_used, (ep, t, k, i) order
+    used = out["draws"][out["draws_used"] > 0]
+    assert len(used) == len(probs_seen)
+    out["_failed_draws"] = int((used > np.array(probs_seen)).sum())
+    out["_min_prob"] = float(min(probs_seen)) if probs_seen else 1.0
     return out
 
 
@@ -327,11 +406,13 @@ def main(argv):
         if want and name not in want:
             continue
         data = gen_meda(name, **kw)
+        failed, min_prob = data.pop("_failed_draws"), data.pop("_min_prob")
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **data)
         print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB  success-steps={int(data['success'].sum())} "
               f"punish-steps={int((data['constraints'] < 0).sum())} "
-              f"min-health={data['health_final'].min():.3g}")
+              f"min-health={data['health_final'].min():.3g} degraded-cells={int((data['health_final'] < 1).sum())} "
+              f"failed-draws={failed} min-move-prob={min_prob:.3g}")
 
 
 if __name__ == "__main__":

@@ -22,13 +22,25 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
-@pytest.mark.parametrize("name", golden_names("dmfb"))
-def test_dmfb_cuda_matches_reference_trace(name):
+def _trace_params():
+    """Every reference trace with the usage counters kept (kernel instances <..., DEG=true>) and, for the chips that do
+    not degrade, also WITHOUT any degradation state (track_usage=False: health / usage / log all NULL), which is what
+    selects the <..., DEG=false> instances that bench.py times (dmfb_kernels.cu StepLaunch)."""
+    out = []
+    for name in golden_names("dmfb"):
+        out.append((name, True))
+        if not load_golden(name)["b_degrade"]:
+            out.append((name, False))
+    return out
+
+
+@pytest.mark.parametrize("name,track", _trace_params())
+def test_dmfb_cuda_matches_reference_trace(name, track):
     g = load_golden(name)
     K, A, W, L = g["K"], g["A"], g["W"], g["L"]
     nb = int(g.get("n_blocks", 0))
     env = pkg().BatchedDMFB(K, W, L, A, nb, fov=g["fov"], stall=bool(g["stall"]), b_degrade=bool(g["b_degrade"]),
-                            per_degrade=g["per_degrade"], device="cuda:0", track_usage=True, reward_f64=True,
+                            per_degrade=g["per_degrade"], device="cuda:0", track_usage=track, reward_f64=True,
                             degrade=g["degrade"] if g["b_degrade"] else None, layouts=g["layouts"][0],
                             block_layouts=g["blocks"][0] if nb else None)
     obs_t, state_t = list(g["obs_t"]), list(g["state_t"])
@@ -51,7 +63,10 @@ def test_dmfb_cuda_matches_reference_trace(name):
         check_v01(g["obs1_reset"][ep], g["dir1_reset"][ep], f"{name} reset ep{ep}")
         if g["b_degrade"]:
             np.testing.assert_array_equal(_np(env.health), g["health_reset"][ep], err_msg=f"health ep{ep}")
-        np.testing.assert_array_equal(_np(env.usage_counts()), g["usage_reset"][ep], err_msg=f"usage ep{ep}")
+        if track:
+            np.testing.assert_array_equal(_np(env.usage_counts()), g["usage_reset"][ep], err_msg=f"usage ep{ep}")
+        else:
+            assert env.usage is None and env.health is None and env.usage_log is None
         for t in range(g["T"]):
             acts = torch.as_tensor(g["actions"][ep, t], device="cuda:0")
             obs, rew, done, info = env.step(acts, draws=g["draws"][ep, t])
@@ -71,10 +86,13 @@ def test_dmfb_cuda_matches_reference_trace(name):
             if t in state_t:
                 np.testing.assert_array_equal(_np(env.get_state()), g["state"][ep, state_t.index(t)],
                                               err_msg=msg + " state")
-        np.testing.assert_array_equal(_np(env.usage_counts()), g["usage_end"][ep], err_msg=f"usage end ep{ep}")
+        if track:
+            np.testing.assert_array_equal(_np(env.usage_counts()), g["usage_end"][ep], err_msg=f"usage end ep{ep}")
     if g["b_degrade"]:
         np.testing.assert_array_equal(_np(env.health), g["health_final"])
     assert _np(env.get_avail_actions()).min() == 1
+    if name.endswith("_success"):
+        assert g["success"].sum() > 100      # these traces exist for the +10/+10 bonus and info['success']
 
 
 CASES = [
@@ -103,8 +121,13 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", CASES)
-def test_dmfb_cuda_matches_oracle_random(oracle_lib, case):
+def _case_params():
+    # chips that do not degrade also run without any degradation state: the <..., DEG=false> kernel instances
+    return [(c, True) for c in CASES] + [(c, False) for c in CASES if not c[6]]
+
+
+@pytest.mark.parametrize("case,track", _case_params())
+def test_dmfb_cuda_matches_oracle_random(oracle_lib, case, track):
     N, W, L, A, fov, stall, deg = case[:7]
     nb = case[7] if len(case) > 7 else 0
     ver = case[8] if len(case) > 8 else 0
@@ -114,7 +137,7 @@ def test_dmfb_cuda_matches_oracle_random(oracle_lib, case):
     layouts = ref.gen_layouts(seed=N)
     blocks = ref.gen_blocks(N, layouts) if nb else None
     env = pkg().BatchedDMFB(N, W, L, A, nb, fov=fov, stall=stall, b_degrade=deg, per_degrade=1.0, device="cuda:0",
-                            track_usage=True, reward_f64=True, degrade=degrade, layouts=layouts, block_layouts=blocks,
+                            track_usage=track, reward_f64=True, degrade=degrade, layouts=layouts, block_layouts=blocks,
                             obs_version=ver)
     if deg:
         ref.degrade[...] = degrade
@@ -159,10 +182,64 @@ def test_dmfb_cuda_matches_oracle_random(oracle_lib, case):
             np.testing.assert_array_equal(_np(info["success"]), succ, err_msg=msg + " success")
             np.testing.assert_array_equal(_np(env.step_count), ref.step_count)
             np.testing.assert_array_equal(_np(env.constraints_cum), ref.constraints)
-        np.testing.assert_array_equal(_np(env.usage_counts()), ref.usage, err_msg=f"usage ep{ep}")
+        if track:
+            np.testing.assert_array_equal(_np(env.usage_counts()), ref.usage, err_msg=f"usage ep{ep}")
         np.testing.assert_array_equal(_np(env.get_state()), ref.global_state())
         if deg:
             np.testing.assert_array_equal(_np(env.health), ref.health)
+
+
+@pytest.mark.parametrize("N,W,L,A,steps", [(65536, 10, 10, 4, 90), (16384, 20, 20, 10, 100)])
+def test_benched_instances_with_fused_auto_reset_match_oracle_at_full_size(oracle_lib, N, W, L, A, steps):
+    """Exactly what bench.py launches - dmfb_step_kernel<9,4,4,16,false> (C1, 65,536 envs) and <9,10,10,8,false> (C2):
+    no degradation state, DMFB_STEP_AUTO_RESET, staggered episode phases - replayed env for env through the oracle.
+    The oracle has no task generator of its own in this test: after every step the tasks the DEVICE drew for the envs
+    that terminated are read back and injected into the oracle's masked reset (the generator itself is pinned by the
+    rejection-rule / uniformity tests).  Every byte of every step's output is compared."""
+    fov = 9
+    env = pkg().BatchedDMFB(N, W, L, A, fov=fov, stall=True, b_degrade=False, device="cuda:0", seed=1234, reward_f64=True)
+    assert env.usage is None and env.health is None and env.usage_log is None      # => DEG = false instance
+    ref = oracle_lib.OracleDMFB(N, W, L, A, fov=fov, stall=True, b_degrade=False)
+    obs0 = env.reset()
+    np.testing.assert_array_equal(ref.reset(_np(env.drop)), _np(obs0))
+    phase = (np.arange(N) % env.max_step).astype(np.int32)       # bench.py's staggered episode phases
+    env.step_count.copy_(torch.as_tensor(phase))
+    ref.step_count[...] = phase
+    rng = np.random.default_rng(N + A)
+    n_term, n_succ, last_obs = 0, 0, _np(obs0).copy()
+    for t in range(steps):
+        acts = rng.integers(0, 5, (N, A)).astype(np.int8)
+        if t % 3 != 0:   # goal-ward moves two steps out of three, so that episodes also end by success
+            d = ref.drop.astype(np.int32)
+            dx, dy = d[..., 2] - d[..., 0], d[..., 3] - d[..., 1]
+            toward = np.where(np.abs(dx) >= np.abs(dy), np.where(dx > 0, 1, 2), np.where(dy > 0, 4, 3))
+            acts = np.where((dx == 0) & (dy == 0), 0, toward).astype(np.int8)
+        o_ref, r_ref, d_ref, c_ref, s_ref = ref.step(acts)
+        o, r, d, info = env.step(torch.as_tensor(acts, device="cuda:0"), auto_reset=True)
+        msg = f"t{t}"
+        term = d_ref.all(-1)
+        np.testing.assert_array_equal(_np(info["terminated"]), term, err_msg=msg + " terminated")
+        np.testing.assert_array_equal(_np(env.reward_f64), r_ref, err_msg=msg + " reward")
+        np.testing.assert_array_equal(_np(d).astype(np.uint8), d_ref, err_msg=msg + " done")
+        np.testing.assert_array_equal(_np(info["constraints"]), c_ref, err_msg=msg + " constraints")
+        np.testing.assert_array_equal(_np(info["success"]), s_ref, err_msg=msg + " success")
+        np.testing.assert_allclose(_np(info["team_reward"]), r_ref.sum(-1) / A, rtol=1e-6, atol=1e-6)
+        drop = _np(env.drop)
+        # envs that terminated were reset inside the same launch: hand the oracle the tasks the device drew
+        o_reset = ref.reset(drop, mask=term.astype(np.uint8))
+        want = np.where(term[:, None, None], o_reset, o_ref)
+        np.testing.assert_array_equal(_np(o), want, err_msg=msg + " obs")
+        np.testing.assert_array_equal(drop, ref.drop, err_msg=msg + " drop")
+        np.testing.assert_array_equal(_np(env.step_count), ref.step_count, err_msg=msg + " step_count")
+        np.testing.assert_array_equal(_np(env.constraints_cum), ref.constraints, err_msg=msg + " cum constraints")
+        # the new tasks obey _Generate_Start_End's rule (dmfb.py:220) and are new
+        if term.any():
+            pts = drop[term].astype(np.int32).reshape(-1, A, 2, 2).transpose(0, 2, 1, 3).reshape(-1, 2 * A, 2)
+            cheb = np.abs(pts[:, :, None, :] - pts[:, None, :, :]).max(-1) + 9 * np.eye(2 * A, dtype=np.int32)
+            assert cheb.min() >= 2, msg
+        n_term += int(term.sum())
+        n_succ += int(s_ref.sum())
+    assert n_term > 2 * N and (n_succ > 0 or A > 4)   # on average every env went through two fused resets
 
 
 def test_dmfb_known_answers():

@@ -38,6 +38,7 @@ def test_meda_cuda_matches_reference_trace(name):
         np.testing.assert_array_equal(o[..., -1] / L, dirs[..., 1], err_msg=msg + " obs v0_1 dir x")
 
     obs_t = list(g["obs_t"])
+    env.usage.copy_(torch.as_tensor(g["usage0"].astype(np.int32)))   # pre-aged chips (meda_*_aged)
     for ep in range(g["n_ep"]):
         obs = env.reset(layouts=g["layouts"][ep])
         np.testing.assert_array_equal(_np(obs), g["obs2_reset"][ep], err_msg=f"{name} v0_2 reset obs ep{ep}")

@@ -68,6 +68,7 @@ def test_meda_oracle_matches_reference_trace(oracle_lib, name):
         np.testing.assert_array_equal(o[..., -1] / L, dirs[..., 1], err_msg=msg + " obs v0_1 dir x")
 
     env.degrade[...] = g["degrade"]
+    env.usage[...] = g["usage0"]          # pre-aged chips (meda_*_aged) start with m_usage > 0
     obs_t = list(g["obs_t"])
     for ep in range(g["n_ep"]):
         # the reference updates health AFTER computing the reset observation (meda.py:547-548); the golden
@@ -93,6 +94,9 @@ def test_meda_oracle_matches_reference_trace(oracle_lib, name):
                 check_v01(env1.observe(), g["obs1"][ep, obs_t.index(t)], g["dir1"][ep, obs_t.index(t)], msg)
         np.testing.assert_array_equal(env.usage, g["usage_end"][ep], err_msg=f"usage end ep{ep}")
     np.testing.assert_array_equal(env.health, g["health_final"])
+    if name.endswith("_aged"):
+        # these traces exist to pin getMoveProb < 1 / failed draws / updateHealth (meda.py:302-309,280,600-605)
+        assert g["health_final"].min() < 0.7 and (g["health_final"] < 1.0).sum() > 1000
 
 
 def test_set_order_emulation_matches_this_cpython(oracle_lib):
