@@ -53,8 +53,12 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-clocks", action="store_true")
+    p.add_argument("--quick", action="store_true", help="short roofline / e2e legs (profiling runs under ncu)")
     p.add_argument("--no-others", action="store_true", help="skip the context timings of the other BASELINE configs")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--ref-seconds", type=float, default=20.0, help="--impl reference: wall time of the timed call")
+    p.add_argument("--window-ms", type=float, default=100.0, help="minimum length of one timed window")
+    p.add_argument("--windows", type=int, default=7, help="timed windows; the median is reported")
     return p.parse_args()
 
 
@@ -132,33 +136,66 @@ def cpu_baseline(seconds, threads=None):
 
 
 # ------------------------------------------------------------ reference arm --
+REF_PY_FILE = os.path.join(ROOT, "profiles", "reference_python_cpu.json")
+
+
+def reference_python_context():
+    """The reference's own Python env (unmodified, behind the import shim) timed in the BUILD container by
+    tools/time_reference_python.py - it cannot travel to the GPU box (/root/reference does not exist there), so the
+    committed measurement is quoted with its provenance, as context only."""
+    try:
+        with open(REF_PY_FILE) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def run_reference(args, rank, world):
+    """CPU arm: the C oracle port of DMFBenv.step on every host thread, same config as the own arm (65,536 chips,
+    uniform random actions, auto-reset, the full observation written every env-step).  One bench "step" = S env-steps
+    of all 65,536 chips (S sized so that the whole run takes ~20 s); the K timed steps run in ONE call, so that no
+    thread start-up sits inside a step."""
     if rank != 0:
         return
     import oracle
     oracle.build()
     threads = os.cpu_count() or 1
-    n_envs = 256 * threads
-    steps_per = 40  # one bench "step" here = 40 lock-step env steps over the sample (one episode length)
-    for _ in range(max(args.warmup, 1)):
-        oracle.dmfb_rollout(W, L, A, FOV, True, False, n_envs, steps_per, seed=3, threads=threads)
+    n_envs = args.envs
     t0 = time.perf_counter()
-    total = 0
-    for k in range(args.steps):
-        n, _ = oracle.dmfb_rollout(W, L, A, FOV, True, False, n_envs, steps_per, seed=10 + k, threads=threads)
-        total += n
+    oracle.dmfb_rollout(W, L, A, FOV, True, False, n_envs, 8, seed=3, threads=threads)       # calibration: the slope
+    t1 = time.perf_counter()
+    oracle.dmfb_rollout(W, L, A, FOV, True, False, n_envs, 48, seed=3, threads=threads)
+    per_env_step = max((time.perf_counter() - t1) - (t1 - t0), 1e-4) / 40
+    S = max(1, int(round(args.ref_seconds / max(args.steps, 1) / max(per_env_step, 1e-6))))
+    S = min(S, 4000)
+    if args.warmup > 0:
+        oracle.dmfb_rollout(W, L, A, FOV, True, False, n_envs, min(S * args.warmup, 3 * S), seed=4, threads=threads)
+    t0 = time.perf_counter()
+    total, _ = oracle.dmfb_rollout(W, L, A, FOV, True, False, n_envs, S * args.steps, seed=10, threads=threads)
     dt = time.perf_counter() - t0
     value = total / dt
-    sample = (f"each step = {n_envs} envs x {steps_per} env-steps of the C oracle port of the reference env on "
-              f"{threads} host threads")
+    sample = (f"each step = {S} env-steps of all {n_envs} chips ({S * n_envs * A} agent-steps), C oracle port of the "
+              f"reference env on {threads} host threads, the {args.steps} steps in one call ({dt:.1f} s)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "DMFB 10x10 chip, 4 droplets, fov 9, random actions, auto-reset", "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": workload_config(n_envs, 1, extra={"sample": sample}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "reference_python": reference_python_context()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def workload_config(n_envs, world, extra=None):
+    """`config` of both arms (kept identical so that the two lines describe the same workload)."""
+    slots = EP_LEN
+    cfg = {"workload": f"DMFB {W}x{L} chip, {A} droplets, fov {FOV}, {n_envs} envs/GPU, random actions, "
+                       f"auto-reset with staggered episode phases, obs to rotating [{slots + 1},N,A,{D}] buffer",
+           "envs_per_gpu": n_envs, "parallelism": f"env-shard x{world} (no collective)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
 
 
 # ------------------------------------------------------------------ own arm --
@@ -209,46 +246,82 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- capture `chunk` consecutive steps in one CUDA graph (launch-bound otherwise: ~15 us kernels) ----
-    chunk = min(args.steps, slots) if not args.no_graph else 0
-    graph = None
+    # ---- CUDA graphs: the step kernels are ~15 us, so a run is launch-bound unless they are replayed from a graph.
+    # The timed region is a whole number R of passes of `--steps` steps: n_full replays of a graph of GRAPH_STEPS steps (a
+    # multiple of the rotating buffer, so every replay continues where the last one ended) + one graph with the rest.
+    GRAPH_STEPS = slots * 6
+    graph_unit = graph_rem = None
     with torch.cuda.stream(stream):
         do_steps(0, max(args.warmup, 3))  # warm-up (also triggers cudaFuncSetAttribute / module load)
         stream.synchronize()
-        if chunk:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=stream):
-                do_steps(0, chunk)
-            graph.replay()
+        if not args.no_graph:
+            graph_unit = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_unit, stream=stream):
+                do_steps(0, GRAPH_STEPS)
+            graph_unit.replay()
+            # calibration: how many steps fill one window
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            for _ in range(4):
+                graph_unit.replay()
+            c1.record(stream)
+            stream.synchronize()
+            est_ms_per_step = c0.elapsed_time(c1) / (4 * GRAPH_STEPS)
+        else:
+            est_ms_per_step = 0.03
+    repeats = max(1, -(-int(args.window_ms / est_ms_per_step) // args.steps))      # ceil
+    if dist is not None:     # same R on every rank
+        r_all = torch.tensor([repeats], device=dev, dtype=torch.int64)
+        dist.all_reduce(r_all, op=dist.ReduceOp.MAX)
+        repeats = int(r_all.item())
+    total_steps = args.steps * repeats
+    n_full, rem = (total_steps // GRAPH_STEPS, total_steps % GRAPH_STEPS) if graph_unit is not None else (0, total_steps)
+    if graph_unit is not None and rem:
+        with torch.cuda.stream(stream):
+            graph_rem = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_rem, stream=stream):
+                do_steps(0, rem)
+            graph_rem.replay()
             stream.synchronize()
 
     def timed_region():
-        n_graph = (args.steps // chunk) if chunk else 0
-        rem = args.steps - n_graph * chunk
-        for _ in range(n_graph):
-            graph.replay()
+        if graph_unit is None:
+            do_steps(0, total_steps)
+            return
+        for _ in range(n_full):
+            graph_unit.replay()
         if rem:
-            do_steps(n_graph * chunk, rem)
+            graph_rem.replay()
 
+    # Windows: the GPU is kept busy across ev0 (one untimed replay is queued first) and nothing synchronises with the
+    # host between ev0 and ev1, so neither launch latency nor the host sits inside the window; `--windows` windows,
+    # the median is reported.  nvidia-smi is polled on rank 0 only.
     barrier()
     launches0 = lib.dmfb_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks = ClockSampler(local_rank)
-    if not args.no_clocks:
+    sample_clocks = (not args.no_clocks) and rank == 0
+    if sample_clocks:
         clocks.__enter__()
+    window_ms = []
     with torch.cuda.stream(stream):
-        ev0.record(stream)
-        timed_region()
-        ev1.record(stream)
+        for _ in range(max(1, args.windows)):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if graph_unit is not None:
+                graph_unit.replay()                  # untimed: the window starts on a busy GPU
+            ev0.record(stream)
+            timed_region()
+            ev1.record(stream)
+            stream.synchronize()
+            window_ms.append(ev0.elapsed_time(ev1))
     barrier()
-    ms = ev0.elapsed_time(ev1)
-    gpu_launches = args.steps  # one fused step(+auto-reset) kernel per step (graph replays included)
+    ms = statistics.median(window_ms)
+    gpu_launches = total_steps  # one fused step(+auto-reset) kernel per step, per window (graph replays included)
     _ = lib.dmfb_launch_count() - launches0
     t_all = torch.tensor([ms], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     ms_max = float(t_all.item())
-    value = world * N * A * args.steps / (ms_max * 1e-3)
+    value = world * N * A * total_steps / (ms_max * 1e-3)
 
     # ---- roofline of the dominant kernel: the step kernel alone (no auto-reset), CUDA events on its stream ----
     roof = None
@@ -265,7 +338,7 @@ def run_b200(args, rank, world, local_rank):
             g2.replay()
             stream.synchronize()
             # ~0.6 s so that nvidia-smi samples clocks under load; short when the caller asked for a short run (ncu)
-            reps = max(2, min(int(0.6 / (slots * 20e-6)), args.steps // slots))
+            reps = 2 if args.quick else int(0.6 / (slots * 20e-6))
             e0.record(stream)
             for _ in range(reps):
                 g2.replay()
@@ -284,7 +357,7 @@ def run_b200(args, rank, world, local_rank):
                     roof["traffic"] = json.load(f).get("dram_bytes_per_launch")
             except Exception:
                 pass
-    if not args.no_clocks:
+    if sample_clocks:
         clocks.__exit__(None, None, None)
     env.reset()
 
@@ -391,14 +464,17 @@ def run_b200(args, rank, world, local_rank):
 
     if rank == 0:
         cpu = None if args.no_cpu else cpu_baseline(args.cpu_seconds)
+        if cpu is not None:
+            cpu["reference_python"] = reference_python_context()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_max / total_steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"DMFB {W}x{L} chip, {A} droplets, fov {FOV}, {N} envs/GPU, random actions, "
-                                       f"auto-reset with staggered episode phases, obs to rotating [{slots + 1},N,A,{D}] buffer",
-                           "envs_per_gpu": N, "parallelism": f"env-shard x{world} (no collective)",
-                           "l2": f"outputs rotate over {(slots + 1) * N * A * D / 1e9:.2f} GB > L2 (no explicit flush)",
-                           "cuda_graph_steps": chunk},
+                "repeats": repeats, "windows_ms": window_ms,
+                "config": workload_config(N, world, extra={
+                    "l2": f"outputs rotate over {(slots + 1) * N * A * D / 1e9:.2f} GB > L2 (no explicit flush)",
+                    "timing": f"{len(window_ms)} windows of {repeats} x {args.steps} steps = {total_steps} steps each "
+                              f"(CUDA graphs of {GRAPH_STEPS} steps, GPU busy at the start event, no host sync inside), "
+                              f"median window, max over ranks"}),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": gpu_launches,
                 "roofline": roof, "cpu_baseline": cpu, "other_configs": others}
         print(json.dumps(line), flush=True)
