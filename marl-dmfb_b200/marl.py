@@ -144,39 +144,60 @@ class BatchedAgents:
 
 # --------------------------------------------------------------- episode batch --
 class EpisodeBatch:
-    """N lock-step episodes of T = episode_limit transitions in the reference's wire format
-    (common/replay_buffer.py:17-26), on the device.  `o` and `avail_u` are stored for T+1 steps; o_next[t] = o[t+1],
-    avail_u_next[t] = avail_u[t+1].  (One deliberate difference: at the terminating transition the reference stores
-    avail_u_next = ones, here it is zeros like the padding that follows; the learner multiplies that target by
-    (1 - terminated) = 0, so the loss is identical.)"""
+    """n lock-step episodes of T = episode_limit transitions, on the device, stored TIME-MAJOR: `o_all[t]` is one
+    contiguous [n, A, D] slice, so the env step kernel writes the observation of step t straight into the buffer
+    (`env.step(out=ep.o_all[t + 1])`) and the learner's per-transition reads are contiguous too.  `o` and `avail_u` are
+    stored for T+1 steps: o_next[t] = o[t+1], avail_u_next[t] = avail_u[t+1].
+
+    as_dict()       the keys and [B, T, ...] shapes of the reference's episode dict (common/replay_buffer.py:17-26),
+                    as transposed VIEWS of the time-major storage.  Loss-equivalent, not byte-identical, to what the
+                    reference stores: at the first padded step `o` still shows the terminal observation (reference:
+                    zeros) and at the terminating transition `avail_u_next` is zeros (reference: ones); both entries
+                    are multiplied by the padding mask / by (1 - terminated) in the loss (vdn.py:105-118).
+    to_reference()  the reference's wire format bit for bit (rollout.py:101-150 incl. the padding rules :131-141 and
+                    the dtypes of replay_buffer.py:17-26), materialised as numpy arrays - for exchanging episodes
+                    with the reference's own ReplayBuffer / learner and for the differential tests."""
 
     KEYS = ("o", "u", "r", "avail_u", "avail_u_next", "u_onehot", "padded", "terminated")
+    _FIELDS = ("o_all", "u", "r", "avail_all", "u_onehot", "padded", "terminated")
 
     def __init__(self, n, T, A, D, n_actions, device, state_dim=0):
         z = lambda *s, dtype: torch.zeros(*s, dtype=dtype, device=device)  # noqa: E731
         self.n, self.T, self.A, self.D, self.n_actions = n, T, A, D, n_actions
         # QMIX only: global state for T+1 steps (s_next[t] = s[t+1]), the flattened (3,W,L) get_state tensor
         self.state_dim = state_dim
-        self.s_all = z(n, T + 1, state_dim, dtype=torch.int8) if state_dim else None
-        self.o_all = z(n, T + 1, A, D, dtype=torch.int8)
-        self.u = z(n, T, A, 1, dtype=torch.int8)
-        self.r = z(n, T, 1, dtype=torch.float32)
-        self.avail_all = z(n, T + 1, A, n_actions, dtype=torch.int8)
-        self.u_onehot = z(n, T, A, n_actions, dtype=torch.int8)
-        self.padded = torch.ones(n, T, 1, dtype=torch.bool, device=device)
-        self.terminated = torch.ones(n, T, 1, dtype=torch.bool, device=device)
+        self.s_all = z(T + 1, n, state_dim, dtype=torch.int8) if state_dim else None
+        self.o_all = z(T + 1, n, A, D, dtype=torch.int8)
+        self.u = z(T, n, A, 1, dtype=torch.int8)
+        self.r = z(T, n, 1, dtype=torch.float32)
+        self.avail_all = z(T + 1, n, A, n_actions, dtype=torch.int8)
+        self.u_onehot = z(T, n, A, n_actions, dtype=torch.int8)
+        self.padded = torch.ones(T, n, 1, dtype=torch.bool, device=device)
+        self.terminated = torch.ones(T, n, 1, dtype=torch.bool, device=device)
 
     def as_dict(self, idx=None, T=None):
-        """The dict ReplayBuffer.sample returns (replay_buffer.py:51-56), as views (optionally rows idx, first T steps)."""
         T = self.T if T is None else T
-        s = (lambda x: x) if idx is None else (lambda x: x[idx])
-        d = {"o": s(self.o_all)[:, :T], "o_next": s(self.o_all)[:, 1:T + 1], "u": s(self.u)[:, :T],
-             "r": s(self.r)[:, :T], "avail_u": s(self.avail_all)[:, :T], "avail_u_next": s(self.avail_all)[:, 1:T + 1],
-             "u_onehot": s(self.u_onehot)[:, :T], "padded": s(self.padded)[:, :T],
-             "terminated": s(self.terminated)[:, :T]}
+        s = (lambda x: x) if idx is None else (lambda x: x[:, idx])          # episodes live on dim 1
+        v = lambda x, a, b: s(x)[a:b].transpose(0, 1)                        # noqa: E731  -> [B, T, ...] view
+        d = {"o": v(self.o_all, 0, T), "o_next": v(self.o_all, 1, T + 1), "u": v(self.u, 0, T), "r": v(self.r, 0, T),
+             "avail_u": v(self.avail_all, 0, T), "avail_u_next": v(self.avail_all, 1, T + 1),
+             "u_onehot": v(self.u_onehot, 0, T), "padded": v(self.padded, 0, T), "terminated": v(self.terminated, 0, T)}
         if self.s_all is not None:
-            d["s"], d["s_next"] = s(self.s_all)[:, :T], s(self.s_all)[:, 1:T + 1]
+            d["s"], d["s_next"] = v(self.s_all, 0, T), v(self.s_all, 1, T + 1)
         return d
+
+    def to_reference(self, idx=None):
+        d = {k: v.cpu().numpy() for k, v in self.as_dict(idx).items()}
+        live = ~d["padded"]                                                   # [B, T, 1]
+        out = {"o": (d["o"] * live[..., None]).astype("int8"), "u": d["u"].astype("int8"),
+               "r": d["r"].astype("float64"), "o_next": d["o_next"].astype("int8"),
+               "avail_u": d["avail_u"].astype("int8"),
+               "avail_u_next": (live[..., None] * (d["avail_u"] * 0 + 1)).astype("int8"),   # ones on every live step
+               "u_onehot": d["u_onehot"].astype("int8"), "padded": d["padded"].astype(bool),
+               "terminated": d["terminated"].astype(bool)}
+        if "s" in d:
+            out["s"], out["s_next"] = d["s"], d["s_next"]
+        return out
 
 
 class ReplayBufferGPU(EpisodeBatch):
@@ -208,10 +229,11 @@ class ReplayBufferGPU(EpisodeBatch):
         if ep.n > self.size:
             raise ValueError("more episodes than the buffer holds")
         idx = self._storage_idx(ep.n)
-        for name in ("o_all", "u", "r", "avail_all", "u_onehot", "padded", "terminated"):
-            getattr(self, name)[idx] = getattr(ep, name)
+        for name in self._FIELDS:
+            getattr(self, name).index_copy_(1, idx, getattr(ep, name))
         if self.s_all is not None:
-            self.s_all[idx] = ep.s_all
+            self.s_all.index_copy_(1, idx, ep.s_all)
+        return idx
 
     def sample(self, batch_size):
         idx = torch.randint(0, self.current_size, (batch_size,), device=self.o_all.device, generator=self.gen)
@@ -223,10 +245,17 @@ class BatchedRolloutWorker:
     """RolloutWorker.generate_episode (rollout.py:101-150) for all N envs of a batched env in lock step.
 
     Finished envs are frozen by the env kernel (`freeze_terminated`), which emits exactly the zero padding the
-    reference appends (rollout.py:131-141); the loop stops as soon as every env is done."""
+    reference appends (rollout.py:131-141); the loop stops as soon as every env is done.  The step kernel writes each
+    observation directly into the episode buffer slice `ep.o_all[t + 1]`.
+
+    Epsilon: the reference anneals once per ENV step (rollout.py:126-127).  Here all N envs of a lock-step iteration act
+    under the same epsilon, which is then annealed by the number of env-steps that iteration really made (the live
+    envs), with the reference's stopping rule (no further decrement once epsilon <= min_epsilon) - i.e. after the same
+    total number of env-steps epsilon is where the reference's would be.  It lives on the device, so annealing costs no
+    host synchronisation; `self.epsilon` is read back once per rollout."""
 
     def __init__(self, env, agents, epsilon=1.0, min_epsilon=0.05, anneal_steps=150000, epsilon_anneal_scale="step",
-                 record_state=False):
+                 record_state=False, sync_every=8):
         self.env, self.agents = env, agents
         self.record_state = record_state      # QMIX: store get_state() of every step as `s` / `s_next`
         info = env.get_env_info()
@@ -234,6 +263,14 @@ class BatchedRolloutWorker:
         self.epsilon, self.min_epsilon = epsilon, min_epsilon
         self.anneal_epsilon = (epsilon - min_epsilon) / anneal_steps
         self.epsilon_anneal_scale = epsilon_anneal_scale
+        self.sync_every = sync_every
+
+    def _anneal(self, eps, count):
+        """`count` applications of `eps = eps - anneal if eps > min_epsilon else eps` (rollout.py:115,127), closed form."""
+        if self.anneal_epsilon <= 0:
+            return eps
+        k = torch.clamp(torch.ceil((eps - self.min_epsilon) / self.anneal_epsilon), min=0)
+        return eps - torch.minimum(k, count.to(eps.dtype)) * self.anneal_epsilon
 
     @torch.no_grad()
     def generate_episodes(self, evaluate=False, batch=None):
@@ -244,12 +281,12 @@ class BatchedRolloutWorker:
         state_dim = 3 * env.W * env.L if self.record_state else 0
         ep = batch if batch is not None else EpisodeBatch(N, T, A, self.D, self.n_actions, dev, state_dim=state_dim)
         ep.padded.fill_(True); ep.terminated.fill_(True)
-        ep.u.zero_(); ep.u_onehot.zero_(); ep.r.zero_(); ep.avail_all.zero_(); ep.o_all[:, 1:].zero_()
-        ep.o_all[:, 0].copy_(env.reset())
+        ep.u.zero_(); ep.u_onehot.zero_(); ep.r.zero_(); ep.avail_all.zero_(); ep.o_all[1:].zero_()
+        env.reset(out=ep.o_all[0])
         if ep.s_all is not None:
-            ep.s_all[:, 1:].zero_()
-            ep.s_all[:, 0].copy_(env.get_state().reshape(N, -1))
-        ep.avail_all[:, 0] = 1
+            ep.s_all[1:].zero_()
+            env.get_state(out=ep.s_all[0].view(N, 3, env.W, env.L))
+        ep.avail_all[0] = 1
         hidden = self.agents.init_hidden(N)
         last = torch.zeros(N, A, self.n_actions, device=dev)
         reward = torch.zeros(N, device=dev)
@@ -257,24 +294,23 @@ class BatchedRolloutWorker:
         success = torch.zeros(N, device=dev, dtype=torch.int64)
         steps = torch.zeros(N, device=dev, dtype=torch.int64)
         alive = torch.ones(N, dtype=torch.bool, device=dev)
-        eps = 0.0 if evaluate else self.epsilon
+        eps = torch.full((), 0.0 if evaluate else float(self.epsilon), device=dev, dtype=torch.float64)
         if not evaluate and self.epsilon_anneal_scale == "episode":
-            eps = eps - self.anneal_epsilon if eps > self.min_epsilon else eps
-        obs_t = torch.empty(N, A, self.D, dtype=torch.int8, device=dev)
+            eps = self._anneal(eps, torch.tensor(N, device=dev))
         for t in range(T):
-            actions, hidden = self.agents.choose_actions(ep.o_all[:, t], last, hidden, ep.avail_all[:, t], eps)
-            obs, _, _, info = env.step(actions, freeze_terminated=True, out=obs_t)
+            actions, hidden = self.agents.choose_actions(ep.o_all[t], last, hidden, ep.avail_all[t], eps)
+            _, _, _, info = env.step(actions, freeze_terminated=True, out=ep.o_all[t + 1])   # written in place
             live = alive & ~info["padded"]
             onehot = F.one_hot(actions, self.n_actions).to(torch.int8) * live[:, None, None]
-            ep.o_all[:, t + 1] = obs
             if ep.s_all is not None:                            # padded steps keep the zero state, like the zero obs
-                ep.s_all[:, t + 1] = env.get_state().reshape(N, -1) * live[:, None]
-            ep.u[:, t, :, 0] = (actions * live[:, None]).to(torch.int8)
-            ep.u_onehot[:, t] = onehot
-            ep.r[:, t, 0] = info["team_reward"]
-            ep.avail_all[:, t + 1] = env.get_avail_actions() * (live & ~info["terminated"])[:, None, None]
-            ep.padded[:, t, 0] = ~live
-            ep.terminated[:, t, 0] = info["terminated"] | ~live
+                env.get_state(out=ep.s_all[t + 1].view(N, 3, env.W, env.L))
+                ep.s_all[t + 1] *= live[:, None]
+            ep.u[t, :, :, 0] = (actions * live[:, None]).to(torch.int8)
+            ep.u_onehot[t] = onehot
+            ep.r[t, :, 0] = info["team_reward"]
+            ep.avail_all[t + 1] = env.get_avail_actions() * (live & ~info["terminated"])[:, None, None]
+            ep.padded[t, :, 0] = ~live
+            ep.terminated[t, :, 0] = info["terminated"] | ~live
             reward += info["team_reward"] * live
             constraints += info["constraints"].to(torch.int64) * live
             success += info["success"].to(torch.int64) * live
@@ -282,16 +318,28 @@ class BatchedRolloutWorker:
             last = onehot.to(torch.float32)
             alive = live & ~info["terminated"]
             if not evaluate and self.epsilon_anneal_scale == "step":
-                eps = eps - self.anneal_epsilon if eps > self.min_epsilon else eps
-            if t % 8 == 7 and not bool(alive.any()):        # one host sync every 8 steps
-                break
+                eps = self._anneal(eps, live.sum())
+            if self.sync_every and t % self.sync_every == self.sync_every - 1 and not bool(alive.any()):
+                break                                        # one host sync every `sync_every` steps
         if not evaluate:
-            self.epsilon = eps
+            self.epsilon = float(eps)
         steps = torch.where(success > 0, steps, torch.full_like(steps, T))
         return ep, {"reward": reward, "steps": steps, "constraints": constraints, "success": (success > 0).to(torch.int64)}
 
 
 # -------------------------------------------------------------------- learner --
+def global_mask_sum(mask_sum, world_size):
+    """Number of valid transitions over ALL ranks.  Each rank scales its loss by world_size / global count, so that the
+    rank-averaged gradient is the gradient of the mean over every valid transition of the global batch ("data parallel
+    == one large batch" also when the ranks hold different numbers of valid transitions)."""
+    if world_size <= 1:
+        return mask_sum
+    import torch.distributed as dist
+    total = mask_sum.detach().clone()
+    dist.all_reduce(total)
+    return total
+
+
 def allreduce_gradients(params, world_size):
     """One flat fp32 bucket, summed over ranks and divided by the world size (290,765 parameters =
     1.16 MB per learn step; latency-bound on NVLink, so a single bucket)."""
@@ -370,7 +418,8 @@ class VDNLearner:
         q_total_target = q_targets.sum(dim=2, keepdim=True)
         targets = r + self.gamma * q_total_target * (1.0 - terminated)
         masked_td = mask * (targets.detach() - q_total_eval)
-        loss = (masked_td ** 2).sum() / mask.sum().clamp_min(1.0)
+        denom = global_mask_sum(mask.sum(), self.world_size).clamp_min(1.0)
+        loss = (masked_td ** 2).sum() * (float(self.world_size) / denom)     # world_size 1: sum / mask.sum() (vdn.py:116)
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
         allreduce_gradients(self.eval_parameters, self.world_size)
@@ -421,7 +470,8 @@ class QMIXLearner(VDNLearner):
             q_total_target = self.target_qmix_net(q_targets, s_next)
         targets = r + self.gamma * q_total_target * (1.0 - terminated)
         masked_td = mask * (q_total_eval - targets.detach())
-        loss = (masked_td ** 2).sum() / mask.sum().clamp_min(1.0)
+        denom = global_mask_sum(mask.sum(), self.world_size).clamp_min(1.0)
+        loss = (masked_td ** 2).sum() * (float(self.world_size) / denom)
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
         allreduce_gradients(self.eval_parameters, self.world_size)

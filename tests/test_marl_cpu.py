@@ -139,7 +139,7 @@ def test_replay_buffer_ring_and_sampling(P):
         buf.store_episodes(ep)
     # reference _get_storage_idx: 0-1, 2-3, then [4, 0] (wrap), then 1-2
     assert buf.current_size == 5 and buf.current_idx == 3
-    assert buf.r[:, 0, 0].tolist() == [2.0, 3.0, 3.0, 1.0, 2.0]
+    assert buf.r[0, :, 0].tolist() == [2.0, 3.0, 3.0, 1.0, 2.0]
     s = buf.sample(64)
     assert s["o"].shape == (64, T, A, D) and s["o_next"].shape == (64, T, A, D) and s["u"].dtype == torch.int8
     assert set(s["r"][:, 0, 0].tolist()) <= {1.0, 2.0, 3.0}
