@@ -13,8 +13,8 @@ from .build import build  # noqa: F401
 from .dmfb import BatchedDMFB, DMFBenv, DMFBenv_v0_1  # noqa: F401
 from .host import HostDMFB  # noqa: F401
 from .sharding import shard_range  # noqa: F401
-from .marl import (CRNN, RNN, BatchedAgents, BatchedRolloutWorker, EpisodeBatch, QMixNet, QMIXLearner,  # noqa: F401
-                   ReplayBufferGPU, VDNLearner, allreduce_gradients)
+from .marl import (CRNN, RNN, BatchedAgents, BatchedRolloutWorker, EpisodeBatch, PhaseTimer, QMixNet,  # noqa: F401
+                   QMIXLearner, ReplayBufferGPU, VDNLearner, allreduce_gradients)
 
 try:  # MEDA kernels are part of the same library
     from .meda import BatchedMEDA, MEDAEnv, MEDAEnv_v0_1, MEDAEnv_v0_2  # noqa: F401

@@ -113,6 +113,46 @@ class QMixNet(nn.Module):
         return (torch.bmm(hidden, w2) + b2).view(B, -1, 1)
 
 
+# ------------------------------------------------------------------- timing --
+class PhaseTimer:
+    """CUDA-event stopwatch per named phase (env step / policy forward / learner / all-reduce), on the current stream.
+    Nothing synchronises until summary(); with enabled=False every call is a no-op."""
+
+    def __init__(self, enabled=True):
+        self.enabled, self.pairs = enabled, {}
+
+    class _Span:
+        def __init__(self, timer, name):
+            self.t, self.name = timer, name
+
+        def __enter__(self):
+            if self.t.enabled:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *a):
+            if self.t.enabled:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.t.pairs.setdefault(self.name, []).append((self.e0, e1))
+
+    def __call__(self, name):
+        return PhaseTimer._Span(self, name)
+
+    def summary(self, reset=True):
+        """{phase: total milliseconds since the last summary}"""
+        if not self.enabled:
+            return {}
+        torch.cuda.synchronize()
+        out = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in self.pairs.items()}
+        if reset:
+            self.pairs = {}
+        return out
+
+
+_NO_TIMER = PhaseTimer(enabled=False)
+
+
 # ------------------------------------------------------------ action selection --
 class BatchedAgents:
     """Agents.choose_action (agent/agent.py:22-48) for all N*A agents in one forward pass, on the device."""
@@ -255,8 +295,9 @@ class BatchedRolloutWorker:
     host synchronisation; `self.epsilon` is read back once per rollout."""
 
     def __init__(self, env, agents, epsilon=1.0, min_epsilon=0.05, anneal_steps=150000, epsilon_anneal_scale="step",
-                 record_state=False, sync_every=8):
+                 record_state=False, sync_every=8, timer=None):
         self.env, self.agents = env, agents
+        self.timer = timer or _NO_TIMER
         self.record_state = record_state      # QMIX: store get_state() of every step as `s` / `s_next`
         info = env.get_env_info()
         self.T, self.A, self.n_actions, self.D = info["episode_limit"], info["n_agents"], info["n_actions"], info["obs_shape"][-1]
@@ -269,20 +310,23 @@ class BatchedRolloutWorker:
         """`count` applications of `eps = eps - anneal if eps > min_epsilon else eps` (rollout.py:115,127), closed form."""
         if self.anneal_epsilon <= 0:
             return eps
-        k = torch.clamp(torch.ceil((eps - self.min_epsilon) / self.anneal_epsilon), min=0)
+        # decrements until eps <= min_epsilon; a quotient within 1e-6 of an integer is that integer (the reference gets
+        # there by repeated float subtraction, which lands a few ulps on either side of min_epsilon)
+        k = torch.clamp(torch.ceil((eps - self.min_epsilon) / self.anneal_epsilon - 1e-6), min=0)
         return eps - torch.minimum(k, count.to(eps.dtype)) * self.anneal_epsilon
 
     @torch.no_grad()
-    def generate_episodes(self, evaluate=False, batch=None):
+    def generate_episodes(self, evaluate=False, batch=None, reset_kwargs=None):
         """Returns (EpisodeBatch, stats) with stats = per-env episode reward, steps (episode_limit when not successful,
-        rollout.py:148-149), constraints and success, all device tensors."""
+        rollout.py:148-149), constraints and success, all device tensors.  `reset_kwargs` go to env.reset (e.g.
+        injected `layouts`)."""
         env, N, A, T = self.env, self.env.N, self.A, self.T
         dev = env.device
         state_dim = 3 * env.W * env.L if self.record_state else 0
         ep = batch if batch is not None else EpisodeBatch(N, T, A, self.D, self.n_actions, dev, state_dim=state_dim)
         ep.padded.fill_(True); ep.terminated.fill_(True)
         ep.u.zero_(); ep.u_onehot.zero_(); ep.r.zero_(); ep.avail_all.zero_(); ep.o_all[1:].zero_()
-        env.reset(out=ep.o_all[0])
+        env.reset(out=ep.o_all[0], **(reset_kwargs or {}))
         if ep.s_all is not None:
             ep.s_all[1:].zero_()
             env.get_state(out=ep.s_all[0].view(N, 3, env.W, env.L))
@@ -298,8 +342,10 @@ class BatchedRolloutWorker:
         if not evaluate and self.epsilon_anneal_scale == "episode":
             eps = self._anneal(eps, torch.tensor(N, device=dev))
         for t in range(T):
-            actions, hidden = self.agents.choose_actions(ep.o_all[t], last, hidden, ep.avail_all[t], eps)
-            _, _, _, info = env.step(actions, freeze_terminated=True, out=ep.o_all[t + 1])   # written in place
+            with self.timer("policy_forward"):
+                actions, hidden = self.agents.choose_actions(ep.o_all[t], last, hidden, ep.avail_all[t], eps)
+            with self.timer("env_step"):
+                _, _, _, info = env.step(actions, freeze_terminated=True, out=ep.o_all[t + 1])   # written in place
             live = alive & ~info["padded"]
             onehot = F.one_hot(actions, self.n_actions).to(torch.int8) * live[:, None, None]
             if ep.s_all is not None:                            # padded steps keep the zero state, like the zero obs
@@ -358,8 +404,9 @@ class VDNLearner:
     """policy/vdn.py: eval/target CRNN, sum mixer, Adam(0.9, 0.99), grad-norm clip, periodic target sync."""
 
     def __init__(self, obs_shape, n_agents, n_actions, device, lr=5e-4, gamma=0.99, grad_norm_clip=9.0,
-                 target_update_cycle=200, rnn_hidden_dim=128, hyper_hidden_dim=24, world_size=1, seed=0):
+                 target_update_cycle=200, rnn_hidden_dim=128, hyper_hidden_dim=24, world_size=1, seed=0, timer=None):
         torch.manual_seed(seed)
+        self.timer = timer or _NO_TIMER
         self.device = torch.device(device)
         self.n_agents, self.n_actions = n_agents, n_actions
         self.eval_rnn = CRNN(obs_shape, n_actions, rnn_hidden_dim, hyper_hidden_dim).to(self.device)
@@ -422,7 +469,8 @@ class VDNLearner:
         loss = (masked_td ** 2).sum() * (float(self.world_size) / denom)     # world_size 1: sum / mask.sum() (vdn.py:116)
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
-        allreduce_gradients(self.eval_parameters, self.world_size)
+        with self.timer("grad_allreduce"):
+            allreduce_gradients(self.eval_parameters, self.world_size)
         torch.nn.utils.clip_grad_norm_(self.eval_parameters, self.grad_norm_clip)
         self.optimizer.step()
         if train_step > 0 and train_step % self.target_update_cycle == 0:

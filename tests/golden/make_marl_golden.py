@@ -122,6 +122,12 @@ def gen_rollout(name, kind, K, seed, p_goal, **kw):
         n_actions = 9
     pyrandom.seed(seed)
     info = env.get_env_info()
+    if kind == "meda":
+        # the reference's MEDA get_env_info returns the flat length (meda.py:676-681) although RolloutWorker / CRNN index
+        # a tuple (rollout.py:94, base_net.py:38-40): as shipped `train.py meda` cannot start.  The tuple a working
+        # configuration needs is the DMFB-style one.
+        assert info["obs_shape"] == 4 * kw["fov"] ** 2 + 2
+        info["obs_shape"] = (4, kw["fov"], kw["fov"], 2, info["obs_shape"])
     A, T, D = info["n_agents"], info["episode_limit"], info["obs_shape"][-1]
     args = types.SimpleNamespace(episode_limit=T, n_actions=n_actions, obs_shape=info["obs_shape"],
                                  epsilon_anneal_scale="step", epsilon=1.0, min_epsilon=0.05, anneal_steps=120)
@@ -170,6 +176,19 @@ def gen_rollout(name, kind, K, seed, p_goal, **kw):
                 else:
                     a = int(rng.integers(n_actions))
                 script[t, i] = a
+        if kind == "dmfb" and k % 2 == 0:
+            # every other episode: a closed-loop, constraint-avoiding plan (make_golden._dmfb_safe_policy) recorded on
+            # the peeked task, so that some episodes END IN SUCCESS; the env is deterministic here (health == 1), so
+            # replaying the recorded actions after the RNG restore reproduces the same trajectory
+            import make_golden
+            st2_np, st2_py = np.random.get_state(), pyrandom.getstate()
+            env.reset()
+            for t in range(T):
+                acts = make_golden._dmfb_safe_policy(rng, env, 1.0)
+                script[t] = acts
+                env.step(acts)
+            np.random.set_state(st2_np)
+            pyrandom.setstate(st2_py)
         out["script"][k] = script
         agents.start(script)
         reward, step, constraints, success, episode = worker.generate_episode()
@@ -247,7 +266,7 @@ def gen_replay_idx():
 
 if __name__ == "__main__":
     gen_vdn_learn()
-    gen_rollout("marl_rollout_c1", "dmfb", K=8, seed=31, p_goal=0.85, W=10, L=10, A=4, fov=9)
+    gen_rollout("marl_rollout_c1", "dmfb", K=10, seed=31, p_goal=0.85, W=10, L=10, A=4, fov=9)
     gen_rollout("marl_rollout_meda", "meda", K=4, seed=32, p_goal=0.85, W=30, L=60, A=4, fov=19)
     gen_evaluator()
     gen_replay_idx()

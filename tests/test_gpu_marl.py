@@ -80,3 +80,36 @@ def test_qmix_rollout_records_the_global_state_and_learns():
     losses = [float(learner.learn(buf.sample(32), s)) for s in range(4)]
     assert np.isfinite(losses).all()
     assert not torch.equal(w0, learner.eval_qmix_net.hyper_w1.weight) and not torch.equal(r0, learner.eval_rnn.fc1.weight)
+
+
+def test_meda_training_config4_rollout_and_updates():
+    """BASELINE config #4: VDN training on GPU-resident MEDA envs (30x60 chip, 4 droplets, fov 19, MEDAEnv's base
+    observation - what common/config.py:10-16 hands to train.py - through the fov-19 CRNN of base_net.py:23-33)."""
+    P = importlib.import_module("marl-dmfb_b200")
+    dev = torch.device("cuda:0")
+    N, A, n_act = 192, 4, 9
+    env = P.BatchedMEDA(N, 30, 60, A, fov=19, obs_version=0, device=dev, seed=5)
+    info = env.get_env_info()
+    assert info["obs_shape"] == (4, 19, 19, 2, 1446) and info["episode_limit"] == 90
+    T, D = info["episode_limit"], info["obs_shape"][-1]
+    timer = P.PhaseTimer()
+    learner = P.VDNLearner(info["obs_shape"], A, n_act, dev, hyper_hidden_dim=32, grad_norm_clip=10.0, seed=0, timer=timer)
+    agents = P.BatchedAgents(learner.eval_rnn, A, n_act, dev, seed=1)
+    worker = P.BatchedRolloutWorker(env, agents, epsilon=1.0, anneal_steps=300000, timer=timer)
+    ep, stats = worker.generate_episodes()
+    assert ep.o_all.shape == (T + 1, N, A, D)
+    # the step kernel wrote straight into the episode buffer: slice t+1 is the env's observation after step t
+    b = ep.as_dict()
+    pad = b["padded"][:, :, 0]
+    assert not bool(pad[:, 0].any()) and bool((pad[:, 1:] >= pad[:, :-1]).all())
+    assert not bool(b["o_next"][pad].any()) and bool(b["o"][:, 0].any())
+    first = ep.o_all[0].clone()
+    env.reset(layouts=env.start.new_zeros(0) if False else None, out=None)      # a fresh task changes the first observation
+    assert first.shape == (N, A, D)
+    buf = P.ReplayBufferGPU(256, T, A, D, n_act, dev, seed=3)
+    buf.store_episodes(ep)
+    w0 = learner.eval_rnn.conv2.weight.detach().clone()
+    losses = [float(learner.learn(buf.sample(16), s)) for s in range(3)]
+    assert np.isfinite(losses).all() and not torch.equal(w0, learner.eval_rnn.conv2.weight)
+    ph = timer.summary()
+    assert ph["env_step"] > 0 and ph["policy_forward"] > 0 and "grad_allreduce" in ph

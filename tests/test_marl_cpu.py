@@ -151,12 +151,23 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _ragged_batch():
+    """4 episodes of 3 transitions; the two episodes of rank 1 are shorter (1 and 2 live transitions), so the two ranks
+    hold different numbers of valid transitions (6 vs 3)."""
+    full = _synthetic_batch(4, 3, 4, 245, 5, seed=9)
+    for b, n in ((2, 1), (3, 2)):
+        full["padded"][b, n:] = True
+        full["terminated"][b, n - 1:] = True
+        full["r"][b, n:] = 0
+    return full
+
+
 def _ddp_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     P = importlib.import_module("marl-dmfb_b200")
     learner = P.VDNLearner(OBS_SHAPE, 4, 5, "cpu", seed=3, world_size=world)
-    full = _synthetic_batch(4, 3, 4, 245, 5, seed=9)
+    full = _ragged_batch()
     mine = {k: v[rank * 2:(rank + 1) * 2] for k, v in full.items()}     # 2 episodes per rank
     learner.learn(mine, 0)
     flat = torch.cat([p.detach().flatten() for p in learner.eval_rnn.parameters()])
@@ -178,8 +189,9 @@ def test_gradient_allreduce_equals_large_batch(P):
         assert p.exitcode == 0
     # both ranks end with identical parameters ...
     np.testing.assert_array_equal(out[0], out[1])
-    # ... equal to one process learning on the concatenated batch (equal mask sums per rank -> mean of means)
+    # ... equal to one process learning on the concatenated batch, although the ranks hold different numbers of valid
+    # transitions: every rank normalises by the GLOBAL count (marl.global_mask_sum)
     single = P.VDNLearner(OBS_SHAPE, 4, 5, "cpu", seed=3)
-    single.learn(_synthetic_batch(4, 3, 4, 245, 5, seed=9), 0)
+    single.learn(_ragged_batch(), 0)
     flat = torch.cat([p.detach().flatten() for p in single.eval_rnn.parameters()]).numpy()
     np.testing.assert_allclose(out[0], flat, rtol=2e-4, atol=2e-6)
