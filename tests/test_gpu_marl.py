@@ -103,9 +103,6 @@ def test_meda_training_config4_rollout_and_updates():
     pad = b["padded"][:, :, 0]
     assert not bool(pad[:, 0].any()) and bool((pad[:, 1:] >= pad[:, :-1]).all())
     assert not bool(b["o_next"][pad].any()) and bool(b["o"][:, 0].any())
-    first = ep.o_all[0].clone()
-    env.reset(layouts=env.start.new_zeros(0) if False else None, out=None)      # a fresh task changes the first observation
-    assert first.shape == (N, A, D)
     buf = P.ReplayBufferGPU(256, T, A, D, n_act, dev, seed=3)
     buf.store_episodes(ep)
     w0 = learner.eval_rnn.conv2.weight.detach().clone()
