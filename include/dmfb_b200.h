@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DMFB_ABI_VERSION 2
+#define DMFB_ABI_VERSION 3
 #define DMFB_MAX_DIM 128    /* max chip width / length (cells) */
 #define DMFB_MAX_AGENTS 32  /* max droplets per chip */
 #define DMFB_MAX_FOV 19     /* max field of view (cells) */
@@ -54,6 +54,12 @@ enum dmfb_status {
     DMFB_ERR_CUDA = 5,               /* launch / runtime error (see dmfb_last_cuda_error) */
     DMFB_ERR_CHIP_TOO_SMALL = 6      /* AssertionError: width >= 5 and length >= 5     dmfb.py:489 */
 };
+
+/* sticky status bits (dmfb_out_t.status / meda_out_t.status, dmfb_state_t.gen_status / meda_state_t.gen_status) */
+#define DMFB_STATUS_ILLEGAL_ACTION 1  /* an action outside the action set was applied: TypeError (dmfb.py:115-116) */
+#define DMFB_STATUS_SAMPLER_GAVE_UP 2 /* a task / obstacle generator found no legal draw within its attempt budget (the
+                                         reference would loop for ever, dmfb.py:212-224,246-250, meda.py:213-233): the env
+                                         keeps its previous layout; the host layer raises RuntimeError */
 
 /* step flags */
 #define DMFB_STEP_RECORD_USAGE 1u  /* DMFBenv.step(record=True): addUsage, dmfb.py:570-571 */
@@ -115,6 +121,15 @@ typedef struct dmfb_state {
      * m_usage; dmfb_flush_usage() folds the log in for a reader.  A full log falls back to direct increments. */
     uint16_t* usage_log;    /* [N, usage_log_cap, A] */
     int32_t* usage_log_len; /* [N] entries in use */
+    /* Optional (both NULL = off) task prefetch for DMFB_STEP_AUTO_RESET.  _Generate_Start_End redraws the whole point set
+     * until it is legal (dmfb.py:212-224), a geometric number of attempts whose tail would keep the whole launch waiting
+     * for the unluckiest of the envs that reset in a step.  Attempt k of (seed, env, episode) is a pure function, so the
+     * search for the NEXT episode's task can run ahead: every step examines at most one round of attempts per warp for
+     * an env whose next task is not known yet and parks the first accepted one here; the reset then only picks it up
+     * (or finishes the search where it stopped).  The task drawn is the same first accepted attempt either way. */
+    uint32_t* next_task;    /* [N,A] packed x | y<<8 | goal_x<<16 | goal_y<<24 of the next episode's task */
+    uint32_t* next_cursor;  /* [N] zero-initialised: attempts already examined; bit 31 = next_task is valid */
+    int32_t* gen_status;    /* [1] sticky DMFB_STATUS_* bits raised by the generators, may be NULL */
 } dmfb_state_t;
 
 /* Per-step outputs, device pointers; any pointer except `obs` may be NULL. */
@@ -129,7 +144,7 @@ typedef struct dmfb_out {
     uint8_t* success;       /* [N]             info['success'], dmfb.py:579-580 */
     uint8_t* terminated;    /* [N]             all(dones), rollout.py:34-35 */
     uint8_t* padded;        /* [N]             1 when the env was frozen (DMFB_STEP_FREEZE_TERM) */
-    int32_t* status;        /* [1]             sticky bit 0: an illegal action was applied (TypeError, dmfb.py:115-116) */
+    int32_t* status;        /* [1]             sticky DMFB_STATUS_ILLEGAL_ACTION (TypeError, dmfb.py:115-116) */
 } dmfb_out_t;
 
 /* Validate arguments like DMFBenv.__init__/RoutingTaskManager.__init__ (dmfb.py:128-155,
@@ -232,6 +247,7 @@ typedef struct meda_state {
      * the step appends the envs that just terminated to reset_list, and a small second kernel resets exactly those. */
     int32_t* reset_list;    /* [N] */
     int32_t* reset_count;   /* [2], zero-initialised: entries in reset_list, finished-CTA ticket */
+    int32_t* gen_status;    /* [1] sticky DMFB_STATUS_* bits raised by the task generator, may be NULL */
 } meda_state_t;
 
 typedef struct meda_out {

@@ -13,6 +13,8 @@ DMFB_L2_WORDS = 12
 STEP_RECORD_USAGE = 1
 STEP_FREEZE_TERM = 2
 STEP_AUTO_RESET = 4
+STATUS_ILLEGAL_ACTION = 1
+STATUS_SAMPLER_GAVE_UP = 2
 
 DMFB_OBS_BASE = 0
 DMFB_OBS_V01 = 1
@@ -39,6 +41,7 @@ class DmfbState(C.Structure):
         ("drop", C.c_void_p), ("start", C.c_void_p), ("step_count", C.c_void_p), ("constraints", C.c_void_p),
         ("terminated", C.c_void_p), ("episode", C.c_void_p), ("usage", C.c_void_p), ("health", C.c_void_p),
         ("degrade", C.c_void_p), ("blocks", C.c_void_p), ("usage_log", C.c_void_p), ("usage_log_len", C.c_void_p),
+        ("next_task", C.c_void_p), ("next_cursor", C.c_void_p), ("gen_status", C.c_void_p),
     ]
 
 
@@ -67,6 +70,7 @@ class MedaState(C.Structure):
         ("fails", C.c_void_p), ("terminated", C.c_void_p), ("episode", C.c_void_p),
         ("usage", C.c_void_p), ("health", C.c_void_p), ("degrade", C.c_void_p),
         ("usage_log", C.c_void_p), ("usage_log_len", C.c_void_p), ("reset_list", C.c_void_p), ("reset_count", C.c_void_p),
+        ("gen_status", C.c_void_p),
     ]
 
 

@@ -176,120 +176,120 @@ struct Group {
 // threads per CTA for E envs with G lanes per env
 __host__ __device__ constexpr int cta_threads(int E, int G) { return ((E + 32 / G - 1) / (32 / G)) * 32; }
 
-// _Generate_Start_End for a compile-time droplet count: EVERY LANE tests a whole attempt of its own, 32 attempts per
-// warp round instead of 32/G, with the 2*A_T points and all pair tests in registers (fully unrolled).  pt[j] packs
-// start_j | goal_j << 16, i.e. the final droplet word.  The geometric tail of the sampler - the unluckiest of the envs
-// that reset in a step keeps its whole tile waiting - shrinks by the same factor.  Attempt k of (seed, env, episode)
-// is a pure function of those values; the lowest accepted attempt of a round wins.
+// ---- _Generate_Start_End (dmfb.py:207-226) -------------------------------------------------------------------------
+// 2A uniform cells; the whole set is redrawn until every pairwise squared distance is > 2.  Attempt number k for
+// (seed, env, episode) is a pure function of those values, and the task is the FIRST accepted attempt - the same
+// accept/reject rule on the same proposal distribution as the reference, so tasks are distributed exactly like the
+// reference's, independent of sharding (cfg.env_base) and of who examines which attempt when.
+//
+// The search is organised in ROUNDS: the whole warp examines kAttemptsPerRound consecutive attempts of ONE env and
+// hands the lowest accepted one to the lanes of the group `dst` that holds that env (lane i gets the word of droplet
+// i).  Two flavours, chosen by A alone (so every kernel instance draws the same task for the same key):
+//   A == 10  one attempt per LANE, all 20 points and the 190 pair tests in registers, fully unrolled (32 per round);
+//   else     one attempt per lane GROUP, points exchanged by shuffles (32/G per round).
+constexpr uint32_t kTaskReady = 0x80000000u;   // dmfb_state_t.next_cursor: next_task holds the next episode's task
+
+template <int G>
+__device__ __forceinline__ int attempts_per_round(int A) { return A == 10 ? 32 : Group<G>::kPerWarp; }
+
+// One round for env `env` (global index), episode `epi`, attempts [first, first + attempts_per_round).  All 32 lanes
+// call with warp-uniform arguments.  Returns true if an attempt was accepted; then `word` of the lanes of group `dst`
+// (lane i < A) is the task, other lanes keep theirs.
 template <int G, int A_T>
-__device__ __noinline__ uint32_t generate_layout_regs(const dmfb_cfg_t& cfg, const Group<G>& g, uint64_t seed, int64_t env0,
-                                                      uint32_t episode, unsigned todo, uint32_t keep)
+__device__ __noinline__ bool sample_round_regs(const dmfb_cfg_t& cfg, const Group<G>& g, uint64_t seed, int64_t env,
+                                               uint32_t epi, uint32_t first, int dst, uint32_t& word)
 {
     const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
-    uint32_t word = keep;
-    while (todo) {
-        const int src = __ffs(todo) - 1;                          // leader lane of the group served now
-        todo &= todo - 1;
-        const int64_t env = env0 + src / G;
-        const uint32_t epi = __shfl_sync(kFull, episode, src);
-        uint64_t base = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
-        base += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)epi << 32) * 0xDA942042E4DD58B5ull;
-        base = mix64(base ^ 0xA5A5A5A5A5A5A5A5ull);
-        for (uint32_t round = 0;; ++round) {
-            if (round >= kMaxSamplerRounds) __trap();             // density that cannot be placed
-            const uint64_t k = (uint64_t)round * 32u + (uint64_t)g.lane;
-            const uint64_t ctr = base + k * (uint64_t)(2 * A_T) * 0x9E3779B97F4A7C15ull;
-            uint32_t pt[A_T];
+    uint64_t base = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
+    base += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)epi << 32) * 0xDA942042E4DD58B5ull;
+    base = mix64(base ^ 0xA5A5A5A5A5A5A5A5ull);
+    const uint64_t k = (uint64_t)first + (uint64_t)g.lane;
+    const uint64_t ctr = base + k * (uint64_t)(2 * A_T) * 0x9E3779B97F4A7C15ull;
+    uint32_t pt[A_T];                                         // pt[j] = start_j | goal_j << 16: the final droplet word
 #pragma unroll
-            for (int j = 0; j < A_T; ++j) {
-                const uint64_t z0 = mix64(ctr + (uint64_t)(2 * j + 1) * 0x9E3779B97F4A7C15ull);
-                const uint64_t z1 = mix64(ctr + (uint64_t)(2 * j + 2) * 0x9E3779B97F4A7C15ull);
-                pt[j] = __umulhi((uint32_t)z0, W) | (__umulhi((uint32_t)(z0 >> 32), Lc) << 8) |
-                        (__umulhi((uint32_t)z1, W) << 16) | (__umulhi((uint32_t)(z1 >> 32), Lc) << 24);
-            }
-            uint32_t bad = 0;
-#pragma unroll
-            for (int a = 0; a < A_T; ++a) {
-                bad |= near_pair(pt[a], pt[a] >> 16) & 1u;        // own start vs own goal
-#pragma unroll
-                for (int b = a + 1; b < A_T; ++b)                 // start-start, goal-goal | start-goal, goal-start
-                    bad |= near_pair(pt[a], pt[b]) | near_pair(pt[a], __byte_perm(pt[b], 0u, 0x1032));
-            }
-            const unsigned okm = __ballot_sync(kFull, bad == 0u);
-            if (okm) {
-                const int win = __ffs(okm) - 1;                   // lowest attempt number of this round
-#pragma unroll
-                for (int j = 0; j < A_T; ++j) {
-                    const uint32_t w = __shfl_sync(kFull, pt[j], win);
-                    if (g.idx == src / G && g.i == j) word = w;
-                }
-                break;
-            }
-        }
+    for (int j = 0; j < A_T; ++j) {
+        const uint64_t z0 = mix64(ctr + (uint64_t)(2 * j + 1) * 0x9E3779B97F4A7C15ull);
+        const uint64_t z1 = mix64(ctr + (uint64_t)(2 * j + 2) * 0x9E3779B97F4A7C15ull);
+        pt[j] = __umulhi((uint32_t)z0, W) | (__umulhi((uint32_t)(z0 >> 32), Lc) << 8) |
+                (__umulhi((uint32_t)z1, W) << 16) | (__umulhi((uint32_t)(z1 >> 32), Lc) << 24);
     }
-    return word;
+    uint32_t bad = 0;
+#pragma unroll
+    for (int a = 0; a < A_T; ++a) {
+        bad |= near_pair(pt[a], pt[a] >> 16) & 1u;            // own start vs own goal
+#pragma unroll
+        for (int b = a + 1; b < A_T; ++b)                     // start-start, goal-goal | start-goal, goal-start
+            bad |= near_pair(pt[a], pt[b]) | near_pair(pt[a], __byte_perm(pt[b], 0u, 0x1032));
+    }
+    const unsigned okm = __ballot_sync(kFull, bad == 0u);
+    if (okm == 0u) return false;
+    const int win = __ffs(okm) - 1;                           // lowest attempt number of this round
+#pragma unroll
+    for (int j = 0; j < A_T; ++j) {
+        const uint32_t w = __shfl_sync(kFull, pt[j], win);
+        if (g.idx == dst && g.i == j) word = w;
+    }
+    return true;
 }
 
-// _Generate_Start_End (dmfb.py:207-226): 2A uniform cells, the whole set is redrawn until every pairwise
-// squared distance is > 2.  Attempt number k for (seed, env, episode) is a pure function of those four values:
-// lane i draws (start_i, goal_i) of the attempt from a counter-based generator and the group rejects the
-// attempt if any two of its 2A points are within one cell of each other; the task is the first accepted
-// attempt — the same accept/reject rule on the same proposal distribution as the reference, so tasks are
-// distributed exactly like the reference's.
-// The WHOLE WARP works on one requesting env at a time: its 32/G lane groups evaluate 32/G consecutive
-// attempts in parallel, the lowest accepted attempt wins and is handed to the requesting group.  (One group
-// looping alone would leave the other lanes of the warp idle for ~1/p_accept rounds.)
-// Every lane of the warp must call; `want` and `episode` are uniform per group; env0 = global env index of
-// the warp's group 0.
 template <int G>
-__device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const Group<G>& g, int A, uint64_t seed,
-                                                    int64_t env0, uint32_t episode, bool want, uint32_t keep)
+__device__ __forceinline__ bool sample_round(const dmfb_cfg_t& cfg, const Group<G>& g, int A, uint64_t seed, int64_t env,
+                                             uint32_t epi, uint32_t first, int dst, uint32_t& word)
 {
-    constexpr int NG = Group<G>::kPerWarp;
+    if (A == 10) return sample_round_regs<G, 10>(cfg, g, seed, env, epi, first, dst, word);
+    const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
+    const bool lane_in = g.valid && g.i < A;
+    // per-(env, episode, droplet) stream; attempt k uses counters 2k+1, 2k+2
+    uint64_t base = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
+    base += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)epi << 32 | (uint32_t)g.i) * 0xDA942042E4DD58B5ull;
+    base = mix64(base);
+    const uint64_t k = (uint64_t)first + (uint64_t)g.idx;
+    uint32_t w = 0;
+    if (lane_in) {
+        const uint64_t z0 = mix64(base + (2 * k + 1) * 0x9E3779B97F4A7C15ull);
+        const uint64_t z1 = mix64(base + (2 * k + 2) * 0x9E3779B97F4A7C15ull);
+        w = __umulhi((uint32_t)z0, W) | (__umulhi((uint32_t)(z0 >> 32), Lc) << 8) |
+            (__umulhi((uint32_t)z1, W) << 16) | (__umulhi((uint32_t)(z1 >> 32), Lc) << 24);
+    }
+    uint32_t bad = near_pair(w, w >> 16) & 1u;                // own start vs own goal
+    for (int j = 0; j < A; ++j) {
+        const uint32_t o = g.get(w, j);
+        const uint32_t hit = near_pair(w, dup_lo(o)) | near_pair(w, dup_hi(o));  // my 2 points vs theirs
+        if (j != g.i) bad |= hit;
+    }
+    const unsigned gb = g.ballot(bad != 0u && lane_in);
+    const unsigned okm = __ballot_sync(kFull, g.valid && gb == 0u && g.i == 0);   // leaders of accepting groups
+    if (okm == 0u) return false;
+    const int win = __ffs(okm) - 1;                           // lowest attempt number of this round
+    const uint32_t wsel = __shfl_sync(kFull, w, win + g.i);
+    if (g.idx == dst) word = wsel;
+    return true;
+}
+
+// Complete searches for the groups whose leader has `want` set, each starting at attempt `first` (uniform per group;
+// 0 or the cursor of a search that already ran ahead).  Every lane of the warp must call; env0 = global env index of
+// the warp's group 0.  A density that cannot be placed makes the reference loop for ever (dmfb.py:212-224); here the
+// search gives up after kMaxSamplerRounds rounds, raises DMFB_STATUS_SAMPLER_GAVE_UP and keeps the previous layout.
+template <int G>
+__device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const Group<G>& g, int A,
+                                                    uint64_t seed, int64_t env0, uint32_t episode, bool want,
+                                                    uint32_t first, uint32_t keep)
+{
     uint32_t word = keep;
     unsigned todo = __ballot_sync(kFull, want && g.i == 0);      // leader lanes of the requesting groups
     if (todo == 0u) return word;
-    // 10 droplets (C2 / C3): one attempt per LANE.  The choice depends on A only, so every kernel instance draws the
-    // same task for the same (seed, env, episode).  Measured at 64K envs: C2 staggered auto-reset 105 -> 69 us per
-    // step, reset-all 890 -> 434 us.  Not used for 4 droplets: acceptance is 8 % there, the tail is short, and the
-    // callee's registers cost the C1 step 0.4 us.
-    if (A == 10) return generate_layout_regs<G, 10>(cfg, g, seed, env0, episode, todo, keep);
-    const int my_group = g.idx;
-    const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
-    const bool lane_in = g.valid && g.i < A;
+    const uint32_t per_round = (uint32_t)attempts_per_round<G>(A);
     while (todo) {
         const int src = __ffs(todo) - 1;                          // leader lane of the group served now
         todo &= todo - 1;
-        const int64_t env = env0 + src / G;
         const uint32_t epi = __shfl_sync(kFull, episode, src);
-        // per-(env, episode, droplet) stream; attempt k uses counters 2k+1, 2k+2
-        uint64_t base = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
-        base += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)epi << 32 | (uint32_t)g.i) * 0xDA942042E4DD58B5ull;
-        base = mix64(base);
-        for (uint32_t round = 0;; ++round) {
-            if (round >= kMaxSamplerRounds) __trap();             // density that cannot be placed
-            const uint64_t k = (uint64_t)round * NG + (uint64_t)my_group;
-            uint32_t w = 0;
-            if (lane_in) {
-                const uint64_t z0 = mix64(base + (2 * k + 1) * 0x9E3779B97F4A7C15ull);
-                const uint64_t z1 = mix64(base + (2 * k + 2) * 0x9E3779B97F4A7C15ull);
-                w = __umulhi((uint32_t)z0, W) | (__umulhi((uint32_t)(z0 >> 32), Lc) << 8) |
-                    (__umulhi((uint32_t)z1, W) << 16) | (__umulhi((uint32_t)(z1 >> 32), Lc) << 24);
-            }
-            uint32_t bad = near_pair(w, w >> 16) & 1u;            // own start vs own goal
-            for (int j = 0; j < A; ++j) {
-                const uint32_t o = g.get(w, j);
-                const uint32_t hit = near_pair(w, dup_lo(o)) | near_pair(w, dup_hi(o));  // my 2 points vs theirs
-                if (j != g.i) bad |= hit;
-            }
-            const unsigned gb = g.ballot(bad != 0u && lane_in);
-            const unsigned okm = __ballot_sync(kFull, g.valid && gb == 0u && g.i == 0);   // leaders of accepting groups
-            if (okm) {
-                const int win = __ffs(okm) - 1;                   // lowest attempt number of this round
-                const uint32_t wsel = __shfl_sync(kFull, w, win + g.i);
-                if (my_group == src / G) word = wsel;
+        uint32_t at = __shfl_sync(kFull, first, src);
+        for (uint32_t round = 0;; ++round, at += per_round) {
+            if (round >= kMaxSamplerRounds) {                     // density that cannot be placed
+                if (st.gen_status && g.lane == 0) atomicOr(st.gen_status, DMFB_STATUS_SAMPLER_GAVE_UP);
                 break;
             }
+            if (sample_round<G>(cfg, g, A, seed, env0 + src / G, epi, at, src / G, word)) break;
         }
     }
     return word;
@@ -316,7 +316,10 @@ __device__ __forceinline__ void generate_blocks(const dmfb_cfg_t& cfg, const dmf
         bool pending = want;
         uint32_t rounds = 0;
         while (__any_sync(kFull, pending)) {
-            if (++rounds >= kMaxSamplerRounds) __trap();          // obstacles that cannot be placed
+            if (++rounds >= kMaxSamplerRounds) {                  // obstacles that cannot be placed: previous ones stay
+                if (st.gen_status && g.lane == 0) atomicOr(st.gen_status, DMFB_STATUS_SAMPLER_GAVE_UP);
+                return;
+            }
             uint32_t cand = 0;
             if (pending && g.i == 0) {
                 const uint64_t z = mix64(state += 0x9E3779B97F4A7C15ull);
@@ -585,6 +588,7 @@ struct LaneIn {
     int sc_in, cum_in;  // leader lane only: step_count, cumulative constraints
     uint32_t episode;   // leader lane only
     int frozen_i;       // leader lane only
+    uint32_t next_cur;  // leader lane only: task-prefetch cursor (dmfb_state_t.next_cursor)
 };
 
 struct LaneOut {
@@ -604,7 +608,7 @@ __device__ __forceinline__ LaneIn load_lane_inputs(const dmfb_state_t& st, const
                                                    bool lane_on, bool leader)
 {
     LaneIn in;
-    in.d = 0; in.a = 0; in.draw = 0.0; in.sc_in = 0; in.cum_in = 0; in.episode = 0; in.frozen_i = 0;
+    in.d = 0; in.a = 0; in.draw = 0.0; in.sc_in = 0; in.cum_in = 0; in.episode = 0; in.frozen_i = 0; in.next_cur = 0;
     if (lane_on) {
         in.d = reinterpret_cast<const uint32_t*>(st.drop)[ja];
         in.a = load_action(actions, aes, ja);
@@ -615,6 +619,7 @@ __device__ __forceinline__ LaneIn load_lane_inputs(const dmfb_state_t& st, const
         in.cum_in = st.constraints[n];
         if (st.episode) in.episode = st.episode[n];
         if (flags & DMFB_STEP_FREEZE_TERM) in.frozen_i = st.terminated[n];
+        if ((flags & DMFB_STEP_AUTO_RESET) && st.next_cursor) in.next_cur = st.next_cursor[n];
     }
     return in;
 }
@@ -755,12 +760,46 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
     o.word = (d & 0xFFFF0000u) | cur;
     o.do_reset = (flags & DMFB_STEP_AUTO_RESET) && o.term && !frozen && env_on;
     if (flags & DMFB_STEP_AUTO_RESET) {
-        o.word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.idx, episode + 1u, o.do_reset, o.word);
+        const bool prefetch = st.next_task != nullptr && st.next_cursor != nullptr;
+        uint32_t cur = prefetch ? g.get(in.next_cur, 0) : 0u;     // search state of THIS env's next task
+        const uint32_t cur_in = cur;
+        bool need = o.do_reset;
+        if (prefetch && need && (cur & kTaskReady)) {             // the search ran ahead and is finished: pick it up
+            if (lane_on) o.word = st.next_task[ja];
+            need = false;
+        }
+        // otherwise finish it now, from the first attempt nobody has examined yet
+        o.word = generate_layout<G>(cfg, st, g, A, seed, cfg.env_base + n - g.idx, episode + 1u, need, cur & ~kTaskReady, o.word);
+        if (o.do_reset) cur = 0u;                                 // the search for the episode after the new one starts over
         if (A_T == 0) generate_blocks<G>(cfg, st, g, seed, n, episode + 1u, o.do_reset, lane_on, o.word);
         if (o.do_reset) {
             o.sc_out = 0;
             o.cum = 0;
             if (lane_on && st.start) reinterpret_cast<uint16_t*>(st.start)[ja] = (uint16_t)(o.word & 0xFFFFu);
+        }
+        if (prefetch) {
+            // Run ahead: ONE round of attempts per warp and step, for the first env of the warp whose next task is not
+            // known yet.  An env needs 1/p_accept attempts per episode (about 12 for 4 droplets on 10x10, 70 for 10 on
+            // 20x20) and has a whole episode of steps to find them, so the searches finish long before they are needed
+            // and no launch ever waits for the tail of the geometric distribution.
+            const unsigned open = __ballot_sync(kFull, env_on && g.i == 0 && !(cur & kTaskReady) &&
+                                                       cur < kMaxSamplerRounds * (uint32_t)attempts_per_round<G>(A));
+            if (open) {
+                const int src = __ffs(open) - 1, dst = src / G;
+                const uint32_t epi = __shfl_sync(kFull, episode + 1u + (o.do_reset ? 1u : 0u), src);
+                const uint32_t at = __shfl_sync(kFull, cur, src);
+                uint32_t task = 0;
+                const bool hit = sample_round<G>(cfg, g, A, seed, cfg.env_base + n - g.idx + dst, epi, at, dst, task);
+                if (g.idx == dst) {
+                    if (hit) {
+                        if (lane_on) st.next_task[ja] = task;
+                        cur = kTaskReady;
+                    } else {
+                        cur = at + (uint32_t)attempts_per_round<G>(A);
+                    }
+                }
+            }
+            if (env_on && g.i == 0 && cur != cur_in) st.next_cursor[n] = cur;
         }
     }
     return o;
@@ -909,8 +948,20 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
         if (layouts) {
             if (lane_on && selected) word = reinterpret_cast<const uint32_t*>(layouts)[ja];
         } else {
-            word = generate_layout<G>(cfg, g, A, seed, cfg.env_base + n - g.idx, episode, selected && env_on, word);
+            // a search that ran ahead (dmfb_state_t.next_task) is for exactly this episode: pick it up or resume it
+            const bool prefetch = st.next_task != nullptr && st.next_cursor != nullptr;
+            uint32_t cur = 0;
+            if (prefetch && leader && selected) cur = st.next_cursor[n];
+            cur = g.get(cur, 0);
+            bool need = selected && env_on;
+            if (need && (cur & kTaskReady)) {
+                if (lane_on) word = st.next_task[ja];
+                need = false;
+            }
+            word = generate_layout<G>(cfg, st, g, A, seed, cfg.env_base + n - g.idx, episode, need, cur & ~kTaskReady, word);
         }
+        // the episode number moves on: whatever was prefetched for it is used up (or overridden by an injected task)
+        if (leader && selected && st.next_cursor) st.next_cursor[n] = 0u;
         if (cfg.n_blocks) {   // refresh() regenerates the obstacles with every task (dmfb.py:174-177)
             if (block_layouts) {
                 if (leader && selected)

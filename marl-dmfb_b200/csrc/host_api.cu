@@ -29,6 +29,8 @@ struct dmfb_host_env {
     uint8_t* blocks = nullptr;
     uint16_t* usage_log = nullptr;      // [N, max_step, A] actuated cells since the last reset (dmfb_state_t)
     int32_t* usage_log_len = nullptr;
+    uint32_t* next_task = nullptr;      // task prefetch (dmfb_state_t.next_task / next_cursor)
+    uint32_t* next_cursor = nullptr;
     double *health = nullptr, *degrade = nullptr;
     // device staging of per-step inputs / outputs
     int8_t* d_actions = nullptr;
@@ -81,6 +83,8 @@ dmfb_state_t sub_state(const dmfb_host_env* h, int lo, int hi)
     s.usage_log_cap = h->usage_log ? h->cfg.max_step : 0;
     s.usage_log = h->usage_log ? h->usage_log + (size_t)lo * h->cfg.max_step * A : nullptr;
     s.usage_log_len = h->usage_log_len ? h->usage_log_len + lo : nullptr;
+    s.next_task = h->next_task + (size_t)lo * A;
+    s.next_cursor = h->next_cursor + lo;
     return s;
 }
 
@@ -156,6 +160,8 @@ int dmfb_host_create(const dmfb_cfg_t* cfg, int n_envs, int device, int n_chunks
     TRY_ALLOC(step_count, N)
     TRY_ALLOC(constraints, N)
     TRY_ALLOC(episode, N)
+    TRY_ALLOC(next_task, N * A)
+    TRY_ALLOC(next_cursor, N)
     if (cfg->n_blocks) TRY_ALLOC(blocks, N * (size_t)cfg->n_blocks * 2)
     if (cfg->b_degrade) {
         TRY_ALLOC(usage, N * cells)
@@ -195,7 +201,7 @@ void dmfb_host_destroy(dmfb_host_env_t* h)
     if (h->d_packed) cudaFree(h->d_packed);
     if (h->h_packed) cudaFreeHost(h->h_packed);
     void* ptrs[] = {h->drop, h->start, h->terminated, h->step_count, h->constraints, h->episode, h->usage, h->health,
-                    h->degrade, h->blocks, h->usage_log, h->usage_log_len, h->d_actions, h->d_u, h->d_obs, h->d_reward, h->d_done, h->d_cons, h->d_succ,
+                    h->degrade, h->blocks, h->usage_log, h->usage_log_len, h->next_task, h->next_cursor, h->d_actions, h->d_u, h->d_obs, h->d_reward, h->d_done, h->d_cons, h->d_succ,
                     h->d_layouts};
     for (void* p : ptrs)
         if (p) cudaFree(p);

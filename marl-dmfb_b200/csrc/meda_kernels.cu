@@ -497,7 +497,10 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
 // refresh/addTask/_genLegalDroplet (meda.py:161-185,213-233): centres uniform in [r, dim-r-1]; a droplet
 // (destination) is redrawn while its centre is closer than 1.5*(2+2+2) = 9 to an earlier droplet (destination);
 // the destination is also redrawn while it overlaps its own droplet.  One thread per env (sequential by nature).
-__device__ void meda_generate_tasks(const meda_cfg_t& cfg, uint64_t seed, int64_t env, uint32_t episode, uint32_t* words)
+// Droplets that cannot be placed make the reference loop for ever (meda.py:213-233); here the generator gives up after
+// kMaxSamplerRounds redraws of one droplet, restores `words` from `prev` (the env's current layout) and returns false.
+__device__ bool meda_generate_tasks(const meda_cfg_t& cfg, uint64_t seed, int64_t env, uint32_t episode, uint32_t* words,
+                                    const uint32_t* prev)
 {
     const int A = cfg.n_agents, W = cfg.width, Lc = cfg.length;
     uint64_t state = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
@@ -506,7 +509,10 @@ __device__ void meda_generate_tasks(const meda_cfg_t& cfg, uint64_t seed, int64_
     for (int i = 0; i < A; ++i) {
         uint32_t sx, sy, tx, ty;
         for (uint32_t rounds = 0;; ++rounds) {
-            if (rounds >= kMaxSamplerRounds) __trap();            // droplets that cannot be placed
+            if (rounds >= kMaxSamplerRounds) {                    // droplets that cannot be placed
+                for (int j = 0; j < A; ++j) words[j] = prev[j];
+                return false;
+            }
             const uint64_t z = mix64(state += 0x9E3779B97F4A7C15ull);
             sy = kRad + __umulhi((uint32_t)z, (uint32_t)(W - 2 * kRad));
             sx = kRad + __umulhi((uint32_t)(z >> 32), (uint32_t)(Lc - 2 * kRad));
@@ -518,7 +524,10 @@ __device__ void meda_generate_tasks(const meda_cfg_t& cfg, uint64_t seed, int64_
             if (ok) break;
         }
         for (uint32_t rounds = 0;; ++rounds) {
-            if (rounds >= kMaxSamplerRounds) __trap();
+            if (rounds >= kMaxSamplerRounds) {
+                for (int j = 0; j < A; ++j) words[j] = prev[j];
+                return false;
+            }
             const uint64_t z = mix64(state += 0x9E3779B97F4A7C15ull);
             ty = kRad + __umulhi((uint32_t)z, (uint32_t)(W - 2 * kRad));
             tx = kRad + __umulhi((uint32_t)(z >> 32), (uint32_t)(Lc - 2 * kRad));
@@ -533,6 +542,7 @@ __device__ void meda_generate_tasks(const meda_cfg_t& cfg, uint64_t seed, int64_
         }
         words[i] = sx | (sy << 8) | (tx << 16) | (ty << 24);
     }
+    return true;
 }
 
 // mode 0: reset, mode 1: restart (droplets back to their start cells, meda.py:170-173,552-561), mode 2: observe only
@@ -570,7 +580,8 @@ meda_reset_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st,
                 const uint32_t* lay = reinterpret_cast<const uint32_t*>(layouts) + (size_t)n * A;
                 for (int i = 0; i < A; ++i) words[i] = lay[i];
             } else {
-                meda_generate_tasks(cfg, seed, cfg.env_base + n, episode, words);
+                if (!meda_generate_tasks(cfg, seed, cfg.env_base + n, episode, words, gdrop) && st.gen_status)
+                    atomicOr(st.gen_status, DMFB_STATUS_SAMPLER_GAVE_UP);
             }
             for (int i = 0; i < A; ++i) {
                 gdrop[i] = words[i];
@@ -681,8 +692,9 @@ meda_reset_list_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_
         if (tid == 0) {
             const uint32_t episode = st.episode ? st.episode[n] + 1u : 0u;
             if (st.episode) st.episode[n] = episode;
-            meda_generate_tasks(cfg, seed, cfg.env_base + n, episode, s_word);
             uint32_t* gdrop = reinterpret_cast<uint32_t*>(st.drop) + (size_t)n * A;
+            if (!meda_generate_tasks(cfg, seed, cfg.env_base + n, episode, s_word, gdrop) && st.gen_status)
+                atomicOr(st.gen_status, DMFB_STATUS_SAMPLER_GAVE_UP);
             for (int i = 0; i < A; ++i) {
                 gdrop[i] = s_word[i];
                 st.status[(size_t)n * A + i] = 0;

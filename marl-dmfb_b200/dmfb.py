@@ -32,7 +32,7 @@ class BatchedDMFB:
 
     def __init__(self, n_envs, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False,
                  per_degrade=0.1, device="cuda", seed=0, env_base=0, track_usage=None, reward_f64=False,
-                 degrade=None, layouts=None, block_layouts=None, obs_version=0, usage_log=True):
+                 degrade=None, layouts=None, block_layouts=None, obs_version=0, usage_log=True, task_prefetch=True):
         self.lib = nat.load()
         self.cfg = nat.DmfbCfg()
         nat.check(self.lib.dmfb_cfg_init(C.byref(self.cfg), width, length, n_agents, n_blocks, fov, int(bool(stall)),
@@ -77,7 +77,15 @@ class BatchedDMFB:
         self._usage_log = bool(usage_log) and track_usage
         self.usage_log = z(N, self.max_step, A, dtype=torch.int16) if self._usage_log else None
         self.usage_log_len = z(N, dtype=torch.int32) if self._usage_log else None
+        # task prefetch for auto_reset (dmfb_state_t.next_task): the search for the next episode's task runs ahead, one
+        # round of attempts per warp and step; the tasks drawn are the same with or without it
+        self._prefetch = bool(task_prefetch)
+        self.next_task = z(N, A, dtype=torch.int32) if self._prefetch else None
+        self.next_cursor = z(N, dtype=torch.int32) if self._prefetch else None
+        self.status = z(1, dtype=torch.int32)          # sticky DMFB_STATUS_* bits (illegal action, sampler gave up)
         self.state = nat.DmfbState(
+            next_task=self.next_task.data_ptr() if self._prefetch else None,
+            next_cursor=self.next_cursor.data_ptr() if self._prefetch else None, gen_status=self.status.data_ptr(),
             n_envs=N, usage_log_cap=self.max_step if self._usage_log else 0,
             usage_log=self.usage_log.data_ptr() if self._usage_log else None,
             usage_log_len=self.usage_log_len.data_ptr() if self._usage_log else None, drop=self.drop.data_ptr(), start=self.start.data_ptr(), step_count=self.step_count.data_ptr(),
@@ -97,7 +105,6 @@ class BatchedDMFB:
         self.success = z(N, dtype=torch.uint8)
         self.term_out = z(N, dtype=torch.uint8)
         self.padded = z(N, dtype=torch.uint8)
-        self.status = z(1, dtype=torch.int32)
         self._out = self._make_out(self.obs)
         # the reference constructor draws the degradation matrix and a first task (dmfb.py:151-155)
         self.reset(new=True, layouts=layouts, degrade=degrade, block_layouts=block_layouts)
@@ -213,11 +220,18 @@ class BatchedDMFB:
                 "episode_limit": self.max_step}
 
     def check_actions(self):
-        """Raises the reference's TypeError if an illegal action was applied since the last check
-        (device -> host sync; dmfb.py:115-116)."""
-        if int(self.status.item()) & 1:
+        """Raises the reference's TypeError if an illegal action was applied since the last check (dmfb.py:115-116),
+        and RuntimeError if a task / obstacle generator gave up on a density that cannot be placed (the reference
+        would loop for ever there, dmfb.py:212-224,246-250; the env kept its previous layout).  Device -> host sync."""
+        st = int(self.status.item())
+        if st:
             self.status.zero_()
+        if st & nat.STATUS_ILLEGAL_ACTION:
             raise TypeError("action is illegal")
+        if st & nat.STATUS_SAMPLER_GAVE_UP:
+            raise RuntimeError("the task generator found no legal layout for this chip size / droplet count / obstacles")
+
+    check = check_actions
 
     # convenience views
     @property

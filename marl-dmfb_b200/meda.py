@@ -95,7 +95,9 @@ class BatchedMEDA:
         # a masked reset sweeps the whole batch after every step instead)
         self.reset_list = z(N, dtype=torch.int32) if reset_list else None
         self.reset_count = z(2, dtype=torch.int32) if reset_list else None
+        self.gen_status = z(1, dtype=torch.int32)      # sticky DMFB_STATUS_SAMPLER_GAVE_UP
         self.state = nat.MedaState(
+            gen_status=self.gen_status.data_ptr(),
             reset_list=self.reset_list.data_ptr() if reset_list else None,
             reset_count=self.reset_count.data_ptr() if reset_list else None,
             n_envs=N, usage_log_cap=self.max_step if self._usage_log else 0,
@@ -201,6 +203,13 @@ class BatchedMEDA:
 
     def get_avail_actions(self):
         return self.avail
+
+    def check(self):
+        """RuntimeError if the task generator gave up since the last check (droplets that cannot be placed; the
+        reference would loop for ever, meda.py:213-233; the env kept its previous layout).  Device -> host sync."""
+        if int(self.gen_status.item()) & nat.STATUS_SAMPLER_GAVE_UP:
+            self.gen_status.zero_()
+            raise RuntimeError("the task generator found no legal droplet placement for this chip")
 
     def get_env_info(self):
         c = 3 if self.obs_version == nat.MEDA_OBS_V02 else 4

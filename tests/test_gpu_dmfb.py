@@ -607,3 +607,68 @@ def test_usage_log_is_transparent():
     a.reset(new=True)
     b.reset(new=True)
     assert int(a.usage_counts().max()) == 0 and torch.equal(a.health, b.health)
+
+
+@pytest.mark.parametrize("W,L,A,fov,nb", [(10, 10, 4, 9, 0), (20, 20, 10, 9, 0), (14, 14, 4, 7, 5), (12, 12, 6, 5, 0)])
+def test_task_prefetch_is_transparent(W, L, A, fov, nb):
+    """dmfb_state_t.next_task / next_cursor: with auto-reset the search for the next episode's task runs ahead, one
+    round of attempts per warp and step, and the reset picks the result up (or finishes the search where it stopped).
+    The task is the first accepted attempt of (seed, env, episode) either way: trajectories with and without the
+    prefetch are identical - through fused resets, explicit generator resets, masked resets with injected tasks (which
+    use up an episode number and so invalidate what was prefetched) and restarts."""
+    P = pkg()
+    N = 3000
+    kw = dict(fov=fov, device="cuda:0", seed=99)
+    a = P.BatchedDMFB(N, W, L, A, nb, task_prefetch=True, **kw)
+    b = P.BatchedDMFB(N, W, L, A, nb, task_prefetch=False, **kw)
+    assert a.next_task is not None and b.next_task is None and torch.equal(a.drop, b.drop)
+    gen = torch.Generator(device="cuda:0").manual_seed(6)
+    ready_seen = 0
+
+    def run(steps, tag):
+        nonlocal ready_seen
+        for t in range(steps):
+            d = a.drop.to(torch.int32)
+            dx, dy = d[..., 2] - d[..., 0], d[..., 3] - d[..., 1]
+            toward = torch.where(dx.abs() >= dy.abs(), torch.where(dx > 0, 1, 2), torch.where(dy > 0, 4, 3))
+            rnd = torch.randint(0, 5, (N, A), device="cuda:0", generator=gen)
+            acts = torch.where(torch.rand(N, A, device="cuda:0", generator=gen) < 0.6, toward, rnd).to(torch.int8)
+            oa, ra, da, ia = a.step(acts, auto_reset=True)
+            ob, rb, db, ib = b.step(acts, auto_reset=True)
+            assert torch.equal(a.drop, b.drop), f"{tag} t{t}"
+            assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(a.step_count, b.step_count), f"{tag} t{t}"
+            assert torch.equal(a.episode, b.episode) and torch.equal(a.start, b.start)
+            if nb:
+                assert torch.equal(a.blocks, b.blocks)
+            ready_seen = max(ready_seen, int((a.next_cursor < 0).sum()))      # bit 31 = next task known
+
+    run(2 * (W + L) + 20, "fused resets")
+    assert ready_seen > 0.9 * N                       # the searches do finish ahead of time
+    assert torch.equal(a.reset(), b.reset()) and torch.equal(a.drop, b.drop)          # explicit reset picks them up too
+    run(25, "after reset-all")
+    mask = (torch.arange(N, device="cuda:0") % 3 == 0).to(torch.uint8)
+    lay = a.drop.roll(1, dims=0).clone()
+    a.reset(mask=mask, layouts=lay)
+    b.reset(mask=mask, layouts=lay)
+    run(2 * (W + L) + 5, "after injected tasks")
+    a.restart()
+    b.restart()
+    run(20, "after restart")
+    a.check()
+    b.check()
+
+
+def test_task_generator_gives_up_recoverably_on_an_impossible_density():
+    """8x8 with 9 droplets passes the reference's density check (dmfb.py:144-146) but 18 points that are pairwise not
+    within one cell do not fit an 8x8 chip (at most 16 do): the reference would redraw for ever.  The device generator
+    gives up, raises DMFB_STATUS_SAMPLER_GAVE_UP (RuntimeError at check time) and leaves the CUDA context usable
+    (no __trap)."""
+    P = pkg()
+    env = P.BatchedDMFB(1, 8, 8, 9, fov=5, device="cuda:0", seed=1)
+    with pytest.raises(RuntimeError, match="no legal layout"):
+        env.check()
+    env.check()                                        # the flag was cleared
+    ok = P.BatchedDMFB(64, 10, 10, 4, fov=9, device="cuda:0", seed=1)     # the context is alive
+    ok.step(torch.zeros(64, 4, dtype=torch.int8, device="cuda:0"), auto_reset=True)
+    ok.check()
+    assert int(ok.step_count.max()) == 1
