@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DMFB_ABI_VERSION 3
+#define DMFB_ABI_VERSION 4
 #define DMFB_MAX_DIM 128    /* max chip width / length (cells) */
 #define DMFB_MAX_AGENTS 32  /* max droplets per chip */
 #define DMFB_MAX_FOV 19     /* max field of view (cells) */
@@ -130,6 +130,12 @@ typedef struct dmfb_state {
     uint32_t* next_task;    /* [N,A] packed x | y<<8 | goal_x<<16 | goal_y<<24 of the next episode's task */
     uint32_t* next_cursor;  /* [N] zero-initialised: attempts already examined; bit 31 = next_task is valid */
     int32_t* gen_status;    /* [1] sticky DMFB_STATUS_* bits raised by the generators, may be NULL */
+    /* Optional (NULL = off) bit map of the degraded cells: bit k (k = x*length + y) of an env's ceil(W*L/32) words is set
+     * iff health[k] != 1.0.  getMoveProb (dmfb.py:361-363) reads one float64 per droplet and step at a random place of an
+     * array that cannot live in L2 (1.3 GB for 64K 50x50 chips); the bit map can (20 MB), and a clear bit answers
+     * "1.0" without touching the array.  dmfb_reset keeps it in step with health (new_task clears it, updateHealth sets
+     * bits); a caller that writes `health` itself calls dmfb_sync_health_bits() afterwards. */
+    uint32_t* health_bits;  /* [N, ceil(W*L/32)] */
 } dmfb_state_t;
 
 /* Per-step outputs, device pointers; any pointer except `obs` may be NULL. */
@@ -188,6 +194,9 @@ int dmfb_reset(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const uint8_t* 
 
 /* Folds state->usage_log into state->usage for every env and empties the log (no-op without a log). */
 int dmfb_flush_usage(const dmfb_cfg_t* cfg, const dmfb_state_t* state, void* stream);
+
+/* Rebuilds state->health_bits from state->health (no-op when either is NULL). */
+int dmfb_sync_health_bits(const dmfb_cfg_t* cfg, const dmfb_state_t* state, void* stream);
 
 /* DMFBenv.getObs() of the current state for all envs (dmfb.py:614-626). */
 int dmfb_observe(const dmfb_cfg_t* cfg, const dmfb_state_t* state, int8_t* obs, void* stream);
@@ -248,6 +257,10 @@ typedef struct meda_state {
     int32_t* reset_list;    /* [N] */
     int32_t* reset_count;   /* [2], zero-initialised: entries in reset_list, finished-CTA ticket */
     int32_t* gen_status;    /* [1] sticky DMFB_STATUS_* bits raised by the task generator, may be NULL */
+    /* Optional (NULL = off) bit map of the degraded cells, bit y*length + x set iff health[y][x] != 1.0 (same idea as
+     * dmfb_state_t.health_bits): getMoveProb (meda.py:302-309) averages 25 float64 cells per droplet and step; 25 clear
+     * bits answer "1.0" (25 ones sum to 25.0 exactly) without the gather.  meda_sync_health_bits() after writing health. */
+    uint32_t* health_bits;  /* [N, ceil(W*L/32)] */
 } meda_state_t;
 
 typedef struct meda_out {
@@ -282,6 +295,8 @@ int meda_restart(const meda_cfg_t* cfg, const meda_state_t* state, const uint8_t
                  int8_t* obs, void* stream);
 /* Folds state->usage_log into state->usage for every env and empties the log (no-op without a log). */
 int meda_flush_usage(const meda_cfg_t* cfg, const meda_state_t* state, void* stream);
+/* Rebuilds state->health_bits from state->health (no-op when either is NULL). */
+int meda_sync_health_bits(const meda_cfg_t* cfg, const meda_state_t* state, void* stream);
 /* Host helper: iteration order of the CPython set {i : bit i of mask_bits} built by ascending insertion
  * (MEDAEnv_v0_2 iterates such a set, meda.py:862-872).  out[0..n_max) = elements in iteration order, 0xFF padded.
  * The device table `set_order` is [2^A][A] uint8 with row m = meda_set_order(m, A, ...). */

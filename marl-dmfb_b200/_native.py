@@ -42,6 +42,7 @@ class DmfbState(C.Structure):
         ("terminated", C.c_void_p), ("episode", C.c_void_p), ("usage", C.c_void_p), ("health", C.c_void_p),
         ("degrade", C.c_void_p), ("blocks", C.c_void_p), ("usage_log", C.c_void_p), ("usage_log_len", C.c_void_p),
         ("next_task", C.c_void_p), ("next_cursor", C.c_void_p), ("gen_status", C.c_void_p),
+        ("health_bits", C.c_void_p),
     ]
 
 
@@ -70,7 +71,7 @@ class MedaState(C.Structure):
         ("fails", C.c_void_p), ("terminated", C.c_void_p), ("episode", C.c_void_p),
         ("usage", C.c_void_p), ("health", C.c_void_p), ("degrade", C.c_void_p),
         ("usage_log", C.c_void_p), ("usage_log_len", C.c_void_p), ("reset_list", C.c_void_p), ("reset_count", C.c_void_p),
-        ("gen_status", C.c_void_p),
+        ("gen_status", C.c_void_p), ("health_bits", C.c_void_p),
     ]
 
 
@@ -78,8 +79,8 @@ MedaOut = DmfbOut  # same field list (include/dmfb_b200.h: meda_out_t)
 
 # every symbol include/dmfb_b200.h declares
 EXPORTS = [
-    "dmfb_cfg_init", "dmfb_cfg_set_obs_version", "dmfb_flush_usage", "dmfb_step", "dmfb_reset", "dmfb_observe", "dmfb_global_state", "dmfb_restart",
-    "meda_cfg_init", "meda_step", "meda_reset", "meda_observe", "meda_restart", "meda_set_order", "meda_flush_usage",
+    "dmfb_cfg_init", "dmfb_cfg_set_obs_version", "dmfb_flush_usage", "dmfb_sync_health_bits", "dmfb_step", "dmfb_reset", "dmfb_observe", "dmfb_global_state", "dmfb_restart",
+    "meda_cfg_init", "meda_step", "meda_reset", "meda_observe", "meda_restart", "meda_set_order", "meda_flush_usage", "meda_sync_health_bits",
     "dmfb_abi_version", "dmfb_last_cuda_error", "dmfb_launch_count",
     "dmfb_host_create", "dmfb_host_destroy", "dmfb_host_reset", "dmfb_host_step", "dmfb_host_set_transfer", "dmfb_host_unpack_records",
     "dmfb_host_alloc_pinned", "dmfb_host_free_pinned",
@@ -89,7 +90,8 @@ _lib = None
 
 
 def lib_path():
-    return _build.LIB
+    # DMFB_B200_LIB: an alternative build of the library (kernel experiments: tools/build_variants.py)
+    return os.environ.get("DMFB_B200_LIB") or _build.LIB
 
 
 def load():
@@ -114,6 +116,7 @@ def load():
     lib.dmfb_restart.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dmfb_observe.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p, C.c_void_p]
     lib.dmfb_flush_usage.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p]
+    lib.dmfb_sync_health_bits.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p]
     lib.dmfb_global_state.argtypes = [C.POINTER(DmfbCfg), C.POINTER(DmfbState), C.c_void_p, C.c_void_p]
     if hasattr(lib, "meda_cfg_init"):
         lib.meda_cfg_init.argtypes = [C.POINTER(MedaCfg)] + [C.c_int] * 5 + [C.c_double, C.c_int]
@@ -124,6 +127,7 @@ def load():
         lib.meda_observe.argtypes = [C.POINTER(MedaCfg), C.POINTER(MedaState), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.meda_set_order.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
         lib.meda_flush_usage.argtypes = [C.POINTER(MedaCfg), C.POINTER(MedaState), C.c_void_p]
+        lib.meda_sync_health_bits.argtypes = [C.POINTER(MedaCfg), C.POINTER(MedaState), C.c_void_p]
         lib.meda_restart.argtypes = [C.POINTER(MedaCfg), C.POINTER(MedaState), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]
     if hasattr(lib, "dmfb_host_create"):

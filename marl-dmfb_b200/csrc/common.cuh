@@ -54,6 +54,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p)
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Shared-memory stores by 32-bit shared address (a generic pointer can make the compiler rebuild the shared window
+// base in front of a predicated store).
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+
 // Make this thread's generic-proxy shared-memory writes visible to the async (TMA) proxy.
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
@@ -63,8 +74,30 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 // TMA 1-D bulk store shared -> global (UBLKCP in SASS).  dst/src 16-byte aligned, bytes % 16 == 0.
 __device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes)
 {
+#ifdef DMFB_OBS_EVICT_FIRST
+    // the observation stream is written once and not read again by this library: let it leave L2 first, so that the
+    // small state arrays that every step re-reads stay resident
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes), "l"(policy) : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+#endif
+}
+// 32-bit load that asks L2 to keep the line (small, hot, randomly accessed tables)
+__device__ __forceinline__ uint32_t ldg_u32_keep(const uint32_t* p)
+{
+#ifdef DMFB_BITS_EVICT_LAST
+    uint64_t policy;
+    uint32_t v;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+#else
+    return *p;
+#endif
 }
 __device__ __forceinline__ void tma_store_commit()
 {

@@ -539,8 +539,14 @@ __device__ __noinline__ void paint_agent_v01(const dmfb_cfg_t& cfg, const TileLa
     rec[4 * f2 + 1] = (int8_t)(gx - x);
 }
 
+// Words of the optional degraded-cell bit map per env (dmfb_state_t.health_bits)
+__host__ __device__ __forceinline__ int health_bit_words(const dmfb_cfg_t& cfg) { return (cfg.width * cfg.length + 31) >> 5; }
+
 // Folds the usage log of env n into its counters (threads tid, tid + nthreads, ... of the caller cooperate).  The
-// caller synchronises before anyone reads the counters and clears usage_log_len afterwards.
+// caller synchronises before anyone reads the counters and clears usage_log_len afterwards.  The log is read 8 entries
+// per load where the env's slice is 16-byte aligned, and a thread issues all its loads before the first increment: a
+// reset inside a step kernel sits on that launch's critical path, so what counts is the number of dependent DRAM round
+// trips, not the bytes.
 __device__ __forceinline__ void replay_usage_log(const dmfb_cfg_t& cfg, const dmfb_state_t& st, int64_t n, int tid,
                                                  int nthreads)
 {
@@ -548,17 +554,86 @@ __device__ __forceinline__ void replay_usage_log(const dmfb_cfg_t& cfg, const dm
     const int len = min(st.usage_log_len[n], st.usage_log_cap);
     const uint16_t* log = st.usage_log + (size_t)n * st.usage_log_cap * A;
     uint32_t* usage = st.usage + (size_t)n * cfg.width * Lc;
-    for (int k = tid; k < len * A; k += nthreads) {
+    const int total = len * A;
+    int done = 0;
+    if ((reinterpret_cast<uintptr_t>(log) & 15u) == 0) {
+        const uint4* log4 = reinterpret_cast<const uint4*>(log);
+        const int n4 = total >> 3;
+        constexpr int kBatch = 4;
+        for (int base = 0; base < n4; base += kBatch * nthreads) {
+            uint4 v[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int k = base + b * nthreads + tid;
+                v[b] = k < n4 ? __ldcg(log4 + k) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const uint32_t w[4] = {v[b].x, v[b].y, v[b].z, v[b].w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t c = (w[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
+                    if (c != 0xFFFFu) atomicAdd(usage + (c & 255u) * Lc + (c >> 8), 1u);
+                }
+            }
+        }
+        done = n4 << 3;
+    }
+    for (int k = done + tid; k < total; k += nthreads) {
         const uint32_t c = log[k];
         if (c != 0xFFFFu) atomicAdd(usage + (c & 255u) * Lc + (c >> 8), 1u);
     }
 }
 
-// updateHealth (dmfb.py:465-471) for the envs of the tile flagged kFlagNewTask; whole CTA cooperates.
+// updateHealth (dmfb.py:465-471) of env n: cells with usage > 50 get health *= degrade (one IEEE multiply) and
+// usage = 0.  Threads tid, tid + nthreads, ... cooperate.  The counters are scanned four cells per load, a batch of
+// loads in flight per thread (see replay_usage_log); cells over the threshold are rare.
+__device__ __forceinline__ void update_health_env(const dmfb_cfg_t& cfg, const dmfb_state_t& st, int64_t n, int tid, int nthreads)
+{
+    const int cells = cfg.width * cfg.length;
+    uint32_t* usage = st.usage + (size_t)n * cells;
+    double* health = st.health ? st.health + (size_t)n * cells : nullptr;
+    const double* degrade = st.degrade ? st.degrade + (size_t)n * cells : nullptr;
+    uint32_t* bits = st.health_bits ? st.health_bits + (size_t)n * health_bit_words(cfg) : nullptr;
+    auto hit = [&](int k) {
+        if (health) {
+            const double h = health[k] * (degrade ? degrade[k] : 1.0);
+            health[k] = h;
+            if (bits && h != 1.0) atomicOr(bits + (k >> 5), 1u << (k & 31));
+        }
+        usage[k] = 0;
+    };
+    int done = 0;
+    if ((reinterpret_cast<uintptr_t>(usage) & 15u) == 0) {
+        const uint4* u4 = reinterpret_cast<const uint4*>(usage);
+        const int n4 = cells >> 2;
+        constexpr int kBatch = 4;
+        for (int base = 0; base < n4; base += kBatch * nthreads) {
+            uint4 v[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int k = base + b * nthreads + tid;
+                v[b] = k < n4 ? __ldcg(u4 + k) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int k = 4 * (base + b * nthreads + tid);
+                if (v[b].x > 50u) hit(k);
+                if (v[b].y > 50u) hit(k + 1);
+                if (v[b].z > 50u) hit(k + 2);
+                if (v[b].w > 50u) hit(k + 3);
+            }
+        }
+        done = n4 << 2;
+    }
+    for (int k = done + tid; k < cells; k += nthreads)
+        if (__ldcg(usage + k) > 50u) hit(k);
+}
+
+// updateHealth for the envs of the tile flagged kFlagNewTask; whole CTA cooperates.
 __device__ __forceinline__ void update_health_flagged(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const TileSmem& S,
                                                       int64_t n0, int e_valid)
 {
-    const int cells = cfg.width * cfg.length;
     if (st.usage_log != nullptr && st.usage_log_len != nullptr) {   // the counters are read below: fold the log in first
         for (int e = 0; e < e_valid; ++e)
             if (S.flag[e] & kFlagNewTask) replay_usage_log(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x);
@@ -566,17 +641,8 @@ __device__ __forceinline__ void update_health_flagged(const dmfb_cfg_t& cfg, con
         for (int e = (int)threadIdx.x; e < e_valid; e += (int)blockDim.x)
             if (S.flag[e] & kFlagNewTask) st.usage_log_len[n0 + e] = 0;
     }
-    for (int e = 0; e < e_valid; ++e) {
-        if (!(S.flag[e] & kFlagNewTask)) continue;
-        uint32_t* usage = st.usage + (size_t)(n0 + e) * cells;
-        double* health = st.health ? st.health + (size_t)(n0 + e) * cells : nullptr;
-        const double* degrade = st.degrade ? st.degrade + (size_t)(n0 + e) * cells : nullptr;
-        for (int k = threadIdx.x; k < cells; k += blockDim.x)
-            if (usage[k] > 50) {
-                if (health) health[k] = health[k] * (degrade ? degrade[k] : 1.0);
-                usage[k] = 0;
-            }
-    }
+    for (int e = 0; e < e_valid; ++e)
+        if (S.flag[e] & kFlagNewTask) update_health_env(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x);
 }
 
 // ------------------------------------------------------------------------ step --
@@ -638,8 +704,14 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
     const int a = in.a;
     double prob = 1.0, draw = in.draw;
     const bool have_prob = DEG_T && st.health != nullptr;
-    if (have_prob && lane_on)  // getMoveProb (:361-363): the cell occupied at the start of the step
-        prob = st.health[((size_t)n * W + (d & 255u)) * Lc + ((d >> 8) & 255u)];
+    if (have_prob && lane_on) {  // getMoveProb (:361-363): the cell occupied at the start of the step
+        const uint32_t cell = (d & 255u) * (uint32_t)Lc + ((d >> 8) & 255u);
+        // a clear bit in the (L2-sized) degraded-cell map means health == 1.0 exactly: no gather from the big array
+        bool degraded = true;
+        if (st.health_bits)
+            degraded = (st.health_bits[(size_t)n * health_bit_words(cfg) + (cell >> 5)] >> (cell & 31u)) & 1u;
+        if (degraded) prob = st.health[(size_t)n * W * Lc + cell];
+    }
     const int sc_in = g.get(in.sc_in, 0);
     const int cum_in = g.get(in.cum_in, 0);
     const uint32_t episode = g.get(in.episode, 0);
@@ -998,6 +1070,9 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
                 double* degrade = st.degrade ? st.degrade + (size_t)nn * cells : nullptr;
                 const uint32_t episode = st.episode ? st.episode[nn] : 0u;
                 if (threadIdx.x == 0 && st.usage_log_len) st.usage_log_len[nn] = 0;   // usage = 0: the log goes with it
+                if (st.health_bits && health)
+                    for (int k = threadIdx.x; k < health_bit_words(cfg); k += blockDim.x)
+                        st.health_bits[(size_t)nn * health_bit_words(cfg) + k] = 0u;
                 for (int k = threadIdx.x; k < cells; k += blockDim.x) {
                     if (usage) usage[k] = 0;
                     if (health) health[k] = 1.0;
@@ -1040,6 +1115,23 @@ dmfb_flush_usage_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state
     replay_usage_log(cfg, st, n, (int)(threadIdx.x & 31), 32);
     __syncwarp();
     if ((threadIdx.x & 31) == 0) st.usage_log_len[n] = 0;
+}
+
+// ---------------------------------------------------------- health bit map --
+// Rebuilds dmfb_state_t.health_bits from health (bit k of an env = health[k] != 1.0): one warp per env.
+__global__ void __launch_bounds__(128)
+dmfb_health_bits_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st)
+{
+    const int64_t n = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (n >= st.n_envs) return;
+    const int lane = threadIdx.x & 31, cells = cfg.width * cfg.length, nw = health_bit_words(cfg);
+    const double* health = st.health + (size_t)n * cells;
+    uint32_t* bits = st.health_bits + (size_t)n * nw;
+    for (int w = 0; w < nw; ++w) {
+        const int k = w * 32 + lane;
+        const unsigned m = __ballot_sync(kFull, k < cells && health[k] != 1.0);
+        if (lane == 0) bits[w] = m;
+    }
 }
 
 // ----------------------------------------------------------------- get_state --
@@ -1279,6 +1371,17 @@ int dmfb_flush_usage(const dmfb_cfg_t* cfg, const dmfb_state_t* state, void* str
     if (rc) return rc;
     if (state->n_envs == 0 || !state->usage || !state->usage_log || !state->usage_log_len) return DMFB_OK;
     dmfb_flush_usage_kernel<<<(state->n_envs + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, *state);
+    g_launches.fetch_add(1);
+    DMFB_CUDA_TRY(cudaGetLastError());
+    return DMFB_OK;
+}
+
+int dmfb_sync_health_bits(const dmfb_cfg_t* cfg, const dmfb_state_t* state, void* stream)
+{
+    int rc = check_common(cfg, state);
+    if (rc) return rc;
+    if (state->n_envs == 0 || !state->health || !state->health_bits) return DMFB_OK;
+    dmfb_health_bits_kernel<<<(state->n_envs + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, *state);
     g_launches.fetch_add(1);
     DMFB_CUDA_TRY(cudaGetLastError());
     return DMFB_OK;

@@ -81,17 +81,6 @@ __device__ __forceinline__ FootRect foot_rect(int fov, int ox, int oy, int X, in
     return r;
 }
 
-// Shared-memory stores by 32-bit shared address: a generic pointer makes the compiler rebuild the shared
-// window base in front of every predicated store.
-__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v)
-{
-    asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
-{
-    asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
-}
-
 // One lane fills the rectangle (at most 5x5) with `val`: 25 predicated byte stores at immediate offsets.
 __device__ __forceinline__ void fill_rect(uint32_t layer, int fov, const FootRect& r, int val, bool active)
 {
@@ -263,23 +252,60 @@ __device__ __forceinline__ void meda_replay_usage_log(const meda_cfg_t& cfg, con
     }
 }
 
-// updateHealth (meda.py:600-605) for the flagged envs of the tile
+// Words of the optional degraded-cell bit map per env (meda_state_t.health_bits): bit y*length + x
+__host__ __device__ __forceinline__ int meda_bit_words(const meda_cfg_t& cfg) { return (cfg.width * cfg.length + 31) >> 5; }
+
+// updateHealth (meda.py:600-605) of env n: cells with usage > 50 get health *= degrade and usage = 0.  Threads tid,
+// tid + nthreads, ... cooperate; four cells per load and a batch of loads in flight per thread, because inside a
+// step launch (auto-reset) the dependent DRAM round trips of this scan are on the critical path.
+__device__ __forceinline__ void meda_update_health_env(const meda_cfg_t& cfg, const meda_state_t& st, int64_t n, int tid,
+                                                       int nthreads)
+{
+    const int cells = cfg.width * cfg.length;
+    uint32_t* usage = st.usage + (size_t)n * cells;
+    double* health = st.health + (size_t)n * cells;
+    const double* degrade = st.degrade ? st.degrade + (size_t)n * cells : nullptr;
+    uint32_t* bits = st.health_bits ? st.health_bits + (size_t)n * meda_bit_words(cfg) : nullptr;
+    auto hit = [&](int k) {
+        const double h = health[k] * (degrade ? degrade[k] : 1.0);
+        health[k] = h;
+        if (bits && h != 1.0) atomicOr(bits + (k >> 5), 1u << (k & 31));
+        usage[k] = 0;
+    };
+    int done = 0;
+    if ((reinterpret_cast<uintptr_t>(usage) & 15u) == 0) {
+        const uint4* u4 = reinterpret_cast<const uint4*>(usage);
+        const int n4 = cells >> 2;
+        constexpr int kBatch = 4;
+        for (int base = 0; base < n4; base += kBatch * nthreads) {
+            uint4 v[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int k = base + b * nthreads + tid;
+                v[b] = k < n4 ? __ldcg(u4 + k) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int k = 4 * (base + b * nthreads + tid);
+                if (v[b].x > 50u) hit(k);
+                if (v[b].y > 50u) hit(k + 1);
+                if (v[b].z > 50u) hit(k + 2);
+                if (v[b].w > 50u) hit(k + 3);
+            }
+        }
+        done = n4 << 2;
+    }
+    for (int k = done + tid; k < cells; k += nthreads)
+        if (__ldcg(usage + k) > 50u) hit(k);
+}
+
+// updateHealth for the flagged envs of the tile
 __device__ __forceinline__ void meda_update_health(const meda_cfg_t& cfg, const meda_state_t& st, const MedaSmem& S,
                                                    int64_t n0, int e_valid)
 {
     if (!cfg.b_degrade || !st.usage || !st.health) return;
-    const int cells = cfg.width * cfg.length;
-    for (int e = 0; e < e_valid; ++e) {
-        if (!(S.flag[e] & kEnvSelected)) continue;
-        uint32_t* usage = st.usage + (size_t)(n0 + e) * cells;
-        double* health = st.health + (size_t)(n0 + e) * cells;
-        const double* degrade = st.degrade ? st.degrade + (size_t)(n0 + e) * cells : nullptr;
-        for (int k = threadIdx.x; k < cells; k += blockDim.x)
-            if (usage[k] > 50) {
-                health[k] = health[k] * (degrade ? degrade[k] : 1.0);
-                usage[k] = 0;
-            }
-    }
+    for (int e = 0; e < e_valid; ++e)
+        if (S.flag[e] & kEnvSelected) meda_update_health_env(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x);
 }
 
 // Shared memory of the step kernel: per warp a tile of EW envs' observations, their packed droplet words and
@@ -381,10 +407,27 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
                 bool move = true;
                 if (st.health) {                              // getMoveProb (:302-309): sequential float64 mean of 25 cells
                     const double* h = st.health + (size_t)n * cells;
+                    // the (L2-sized) degraded-cell bit map first: five clear bits in each of the five rows mean 25
+                    // cells of exactly 1.0, whose sequential sum is 25.0 and whose mean is 1.0 - no gather
+                    uint32_t any_degraded = 1u;
+                    if (st.health_bits) {
+                        const int nw = meda_bit_words(cfg);
+                        const uint32_t* hb = st.health_bits + (size_t)n * nw;
+                        any_degraded = 0u;
+#pragma unroll
+                        for (int dy = -kRad; dy <= kRad; ++dy) {
+                            const int k0 = (yc + dy) * Lc + xc - kRad, w0 = k0 >> 5;
+                            any_degraded |= __funnelshift_r(hb[w0], hb[min(w0 + 1, nw - 1)], k0 & 31) & 31u;
+                        }
+                    }
                     double prob = 0.0;
-                    for (int y = yc - kRad; y <= yc + kRad; ++y)
-                        for (int x = xc - kRad; x <= xc + kRad; ++x) prob += h[y * Lc + x];
-                    prob = prob / 25.0;
+                    if (any_degraded) {
+                        for (int y = yc - kRad; y <= yc + kRad; ++y)
+                            for (int x = xc - kRad; x <= xc + kRad; ++x) prob += h[y * Lc + x];
+                        prob = prob / 25.0;
+                    } else {
+                        prob = 1.0;
+                    }
                     double draw;
                     if (u) draw = u[ja];
                     else {
@@ -611,6 +654,9 @@ meda_reset_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st,
                 const int64_t n = n0 + e;
                 const uint32_t episode = st.episode ? st.episode[n] : 0u;
                 if (threadIdx.x == 0 && st.usage_log_len) st.usage_log_len[n] = 0;   // usage = 0: the log goes with it
+                if (st.health_bits && st.health)
+                    for (int k = threadIdx.x; k < meda_bit_words(cfg); k += blockDim.x)
+                        st.health_bits[(size_t)n * meda_bit_words(cfg) + k] = 0u;
                 for (int k = threadIdx.x; k < cells; k += blockDim.x) {
                     if (st.usage) st.usage[(size_t)n * cells + k] = 0;
                     if (st.health) st.health[(size_t)n * cells + k] = 1.0;
@@ -668,6 +714,22 @@ meda_flush_usage_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state
     if ((threadIdx.x & 31) == 0) st.usage_log_len[n] = 0;
 }
 
+// Rebuilds meda_state_t.health_bits from health (bit k of an env = health[k] != 1.0): one warp per env.
+__global__ void __launch_bounds__(128)
+meda_health_bits_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st)
+{
+    const int64_t n = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (n >= st.n_envs) return;
+    const int lane = threadIdx.x & 31, cells = cfg.width * cfg.length, nw = meda_bit_words(cfg);
+    const double* health = st.health + (size_t)n * cells;
+    uint32_t* bits = st.health_bits + (size_t)n * nw;
+    for (int w = 0; w < nw; ++w) {
+        const int k = w * 32 + lane;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, k < cells && health[k] != 1.0);
+        if (lane == 0) bits[w] = m;
+    }
+}
+
 // DMFB_STEP_AUTO_RESET, second half: MEDAEnv.reset() (meda.py:541-550) for exactly the envs the step just appended to
 // st.reset_list.  One small CTA per env, a few hundred envs per step, instead of a masked sweep over the whole batch:
 // thread 0 draws the task, all threads replay the usage log and run updateHealth, warp 0 paints the first
@@ -710,16 +772,7 @@ meda_reset_list_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_
             __syncthreads();
             if (tid == 0) st.usage_log_len[n] = 0;
         }
-        if (cfg.b_degrade && st.usage && st.health) {            // updateHealth (meda.py:600-605)
-            uint32_t* usage = st.usage + (size_t)n * cells;
-            double* health = st.health + (size_t)n * cells;
-            const double* degrade = st.degrade ? st.degrade + (size_t)n * cells : nullptr;
-            for (int c = tid; c < cells; c += nthreads)
-                if (usage[c] > 50) {
-                    health[c] = health[c] * (degrade ? degrade[c] : 1.0);
-                    usage[c] = 0;
-                }
-        }
+        if (cfg.b_degrade && st.usage && st.health) meda_update_health_env(cfg, st, n, tid, nthreads);   // (meda.py:600-605)
         __syncthreads();                                          // task words and the zeroed tile before the paint
         if (tid < 32) {
             int8_t* const gobs = obs + (size_t)n * A * D;
@@ -948,6 +1001,17 @@ int meda_flush_usage(const meda_cfg_t* cfg, const meda_state_t* state, void* str
     if (rc) return rc;
     if (state->n_envs == 0 || !state->usage || !state->usage_log || !state->usage_log_len) return DMFB_OK;
     meda_flush_usage_kernel<<<(state->n_envs + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, *state);
+    g_launches.fetch_add(1);
+    DMFB_CUDA_TRY(cudaGetLastError());
+    return DMFB_OK;
+}
+
+int meda_sync_health_bits(const meda_cfg_t* cfg, const meda_state_t* state, void* stream)
+{
+    int rc = meda_check(cfg, state);
+    if (rc) return rc;
+    if (state->n_envs == 0 || !state->health || !state->health_bits) return DMFB_OK;
+    meda_health_bits_kernel<<<(state->n_envs + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, *state);
     g_launches.fetch_add(1);
     DMFB_CUDA_TRY(cudaGetLastError());
     return DMFB_OK;

@@ -32,7 +32,8 @@ class BatchedDMFB:
 
     def __init__(self, n_envs, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False,
                  per_degrade=0.1, device="cuda", seed=0, env_base=0, track_usage=None, reward_f64=False,
-                 degrade=None, layouts=None, block_layouts=None, obs_version=0, usage_log=True, task_prefetch=True):
+                 degrade=None, layouts=None, block_layouts=None, obs_version=0, usage_log=True, task_prefetch=True,
+                 health_bitmap=True):
         self.lib = nat.load()
         self.cfg = nat.DmfbCfg()
         nat.check(self.lib.dmfb_cfg_init(C.byref(self.cfg), width, length, n_agents, n_blocks, fov, int(bool(stall)),
@@ -70,7 +71,13 @@ class BatchedDMFB:
         self.episode = z(N, dtype=torch.int32)
         self.usage = z(N, width, length, dtype=torch.int32) if track_usage else None
         self.blocks = z(N, self.n_blocks, 2, dtype=torch.uint8) if self.n_blocks else None   # (x_min, y_min) of 2x2 blocks
-        self.health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
+        self._health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
+        # degraded-cell bit map (dmfb_state_t.health_bits): lets the step skip the float64 gather on healthy cells.
+        # Kernels keep it in step with `health`; `env.health` hands the tensor out and may be written through, so every
+        # access marks the map stale and the next call rebuilds it first.
+        self._health_bits = (z(N, (width * length + 31) // 32, dtype=torch.int32)
+                             if (self.b_degrade and health_bitmap) else None)
+        self._health_dirty = False
         self.degrade = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         # Steps append the actuated cells to a per-env log instead of incrementing `usage` in place; resets (and
         # usage_counts()) fold the log in.  `usage` alone is therefore NOT m_usage between resets: read usage_counts().
@@ -91,7 +98,8 @@ class BatchedDMFB:
             usage_log_len=self.usage_log_len.data_ptr() if self._usage_log else None, drop=self.drop.data_ptr(), start=self.start.data_ptr(), step_count=self.step_count.data_ptr(),
             constraints=self.constraints_cum.data_ptr(), terminated=self.terminated.data_ptr(),
             episode=self.episode.data_ptr(), usage=self.usage.data_ptr() if track_usage else None,
-            health=self.health.data_ptr() if self.b_degrade else None,
+            health=self._health.data_ptr() if self.b_degrade else None,
+            health_bits=self._health_bits.data_ptr() if self._health_bits is not None else None,
             degrade=self.degrade.data_ptr() if self.b_degrade else None,
             blocks=self.blocks.data_ptr() if self.n_blocks else None)
         # ---- per-step outputs ----
@@ -121,6 +129,21 @@ class BatchedDMFB:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    @property
+    def health(self):
+        """m_health [N,W,L] float64 (None without degradation).  The tensor may be written through; the degraded-cell
+        bit map is rebuilt before the next kernel that reads it."""
+        if self._health_bits is not None:
+            self._health_dirty = True
+        return self._health
+
+    def _sync_health(self):
+        if self._health_dirty:
+            self._health_dirty = False
+            with torch.cuda.device(self.device):
+                rc = self.lib.dmfb_sync_health_bits(C.byref(self.cfg), C.byref(self.state), self._stream())
+            nat.check(rc, "dmfb_sync_health_bits")
+
     def _as(self, t, dtype, shape, name):
         if t is None:
             return None
@@ -143,6 +166,7 @@ class BatchedDMFB:
         deg_t = self._as(degrade, torch.float64, (self.N, self.W, self.L), "degrade")
         blk_t = self._as(block_layouts, torch.uint8, (self.N, self.n_blocks, 2), "block_layouts") if self.n_blocks else None
         obs = self.obs if out is None else out
+        self._sync_health()
         with torch.cuda.device(self.device):
             rc = self.lib.dmfb_reset(C.byref(self.cfg), C.byref(self.state), _ptr(mask_t), int(bool(new)), _ptr(lay_t),
                                      _ptr(blk_t), _ptr(deg_t), self.seed, _ptr(obs), self._stream())
@@ -184,6 +208,7 @@ class BatchedDMFB:
             obs, o = self.obs, self._out
         else:
             obs, o = out, self._make_out(out)
+        self._sync_health()
         with torch.cuda.device(self.device):
             rc = self.lib.dmfb_step(C.byref(self.cfg), C.byref(self.state), _ptr(actions), actions.element_size(),
                                     _ptr(draws_t), self.seed, flags, C.byref(o), self._stream())

@@ -49,7 +49,7 @@ class BatchedMEDA:
 
     def __init__(self, n_envs, width, length, n_agents, fov=19, b_degrade=False, per_degrade=0.1, obs_version=2,
                  device="cuda", seed=0, env_base=0, reward_f64=False, degrade=None, layouts=None, track_usage=None,
-                 usage_log=True, reset_list=True):
+                 usage_log=True, reset_list=True, health_bitmap=True):
         # track_usage: keep the m_usage actuation counters (addUsage, meda.py:591-598).  Nothing reads them unless the
         # chip degrades (updateHealth runs only `if self.b_degrade`, meda.py:547-548), so like BatchedDMFB the default
         # is `b_degrade`; the N=1 adapters always track them because `m_usage` is a visible attribute there.
@@ -85,7 +85,13 @@ class BatchedMEDA:
         if track_usage is None:
             track_usage = self.b_degrade
         self.usage = z(N, width, length, dtype=torch.int32) if (track_usage or self.b_degrade) else None
-        self.health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
+        self._health = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
+        # degraded-cell bit map (meda_state_t.health_bits): 25 clear bits under a droplet skip the float64 gather.  Kept
+        # in step with `health` by the kernels; reading `env.health` marks it stale (the tensor may be written through)
+        # and the next call rebuilds it first.
+        self._health_bits = (z(N, (width * length + 31) // 32, dtype=torch.int32)
+                             if (self.b_degrade and health_bitmap) else None)
+        self._health_dirty = False
         self.degrade = torch.ones(N, width, length, dtype=torch.float64, device=dev) if self.b_degrade else None
         # steps log the actuated droplets; resets and usage_counts() fold the log into `usage` (meda_state_t.usage_log)
         self._usage_log = bool(usage_log) and self.usage is not None
@@ -106,7 +112,8 @@ class BatchedMEDA:
             step_count=self.step_count.data_ptr(), fails=self.fails.data_ptr(),
             terminated=self.terminated.data_ptr(), episode=self.episode.data_ptr(),
             usage=self.usage.data_ptr() if self.usage is not None else None,
-            health=self.health.data_ptr() if self.b_degrade else None,
+            health=self._health.data_ptr() if self.b_degrade else None,
+            health_bits=self._health_bits.data_ptr() if self._health_bits is not None else None,
             degrade=self.degrade.data_ptr() if self.b_degrade else None)
         self.set_order = None
         if self.obs_version != nat.MEDA_OBS_BASE and A > 16:
@@ -138,6 +145,20 @@ class BatchedMEDA:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    @property
+    def health(self):
+        """m_health [N,W,L] float64 (None without degradation); may be written through."""
+        if self._health_bits is not None:
+            self._health_dirty = True
+        return self._health
+
+    def _sync_health(self):
+        if self._health_dirty:
+            self._health_dirty = False
+            with torch.cuda.device(self.device):
+                rc = self.lib.meda_sync_health_bits(C.byref(self.cfg), C.byref(self.state), self._stream())
+            nat.check(rc, "meda_sync_health_bits")
+
     def _as(self, t, dtype, shape, name):
         if t is None:
             return None
@@ -155,6 +176,7 @@ class BatchedMEDA:
         lay_t = self._as(layouts, torch.uint8, (self.N, self.A, 4), "layouts")
         deg_t = self._as(degrade, torch.float64, (self.N, self.W, self.L), "degrade")
         obs = self.obs if out is None else out
+        self._sync_health()
         with torch.cuda.device(self.device):
             rc = self.lib.meda_reset(C.byref(self.cfg), C.byref(self.state), _ptr(mask_t), int(bool(new_chip)),
                                      _ptr(lay_t), _ptr(deg_t), self.seed, _ptr(self.set_order), _ptr(obs),
@@ -185,6 +207,7 @@ class BatchedMEDA:
         draws_t = self._as(draws, torch.float64, (self.N, self.A), "draws")
         flags = (nat.STEP_FREEZE_TERM if freeze_terminated else 0) | (nat.STEP_AUTO_RESET if auto_reset else 0)
         obs, o = (self.obs, self._out) if out is None else (out, self._make_out(out))
+        self._sync_health()
         with torch.cuda.device(self.device):
             rc = self.lib.meda_step(C.byref(self.cfg), C.byref(self.state), _ptr(actions), actions.element_size(),
                                     _ptr(draws_t), self.seed, flags, _ptr(self.set_order), C.byref(o), self._stream())

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(P):
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, f"symbols declared in include/dmfb_b200.h but not exported: {missing}"
     assert set(P._native.EXPORTS) <= declared
-    assert lib.dmfb_abi_version() == 3
+    assert lib.dmfb_abi_version() == 4
 
 
 def test_ctypes_mirrors_match_c_layout(P, tmp_path):

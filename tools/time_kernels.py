@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """CUDA-event timing of the individual entry points at benchmark size.
-usage: python tools/time_kernels.py [c1|c2|c3] [n_envs]"""
+usage: python tools/time_kernels.py [c1|c2|c3] [n_envs] [short]   (short: the two step timings only)"""
 import importlib
 import os
 import sys
@@ -17,7 +17,9 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 c = CFG[name]
 T = 2 * (c["W"] + c["L"])
 env = pkg.BatchedDMFB(N, c["W"], c["L"], c["A"], fov=c["fov"], b_degrade=c["deg"], per_degrade=1.0,
-                      device="cuda:0", seed=1234)
+                      device="cuda:0", seed=1234, usage_log=os.environ.get("TK_USAGE_LOG", "1") != "0",
+                      task_prefetch=os.environ.get("TK_PREFETCH", "1") != "0",
+                      health_bitmap=os.environ.get("TK_BITMAP", "1") != "0")
 slots = min(T, max(8, int(2.6e9 // (N * c["A"] * env.D))))
 obs_buf = torch.empty(slots + 1, N, c["A"], env.D, dtype=torch.int8, device="cuda:0")
 gen = torch.Generator(device="cuda:0").manual_seed(1)
@@ -61,13 +63,16 @@ def graph_time(fn, n):
 env.reset()
 us = graph_time(lambda i: env.step(actions[i % slots], out=obs_buf[i % slots + 1]), slots)
 print(f"{name} N={N}: step (no reset, graph)       {us:8.2f} us  {alg * N / us / 1e3:8.1f} GB/s alg")
-env.reset()
-us = graph_time(lambda i: env.step(actions[i % slots], auto_reset=True, out=obs_buf[i % slots + 1]), T)
-print(f"{name} N={N}: step (auto-reset, graph of T) {us:8.2f} us  {N * c['A'] / us / 1e3:8.2f} G agent-steps/s")
+if not (len(sys.argv) > 3 and sys.argv[3] == "short"):
+    env.reset()
+    us = graph_time(lambda i: env.step(actions[i % slots], auto_reset=True, out=obs_buf[i % slots + 1]), T)
+    print(f"{name} N={N}: step (auto-reset, graph of T) {us:8.2f} us  {N * c['A'] / us / 1e3:8.2f} G agent-steps/s")
 env.reset()
 env.step_count.copy_(torch.arange(N, device="cuda:0", dtype=torch.int32) % T)   # stagger the episode phases
 us = graph_time(lambda i: env.step(actions[i % slots], auto_reset=True, out=obs_buf[i % slots + 1]), T)
 print(f"{name} N={N}: step (auto-reset, staggered)  {us:8.2f} us  {N * c['A'] / us / 1e3:8.2f} G agent-steps/s")
+if len(sys.argv) > 3 and sys.argv[3] == "short":
+    sys.exit(0)
 us = timeit(lambda i: env.reset(out=obs_buf[i % slots]), 20)
 print(f"{name} N={N}: reset all (device generator)  {us:8.2f} us")
 lay = env.drop.clone()
