@@ -954,6 +954,21 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
         zero_tile(L, S, tid, (int)blockDim.x);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const LaneIn in = load_lane_inputs<DEG_T>(st, actions, aes, u, flags, n, ja, lane_on, leader);
+    if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) {
+        // An env on its last step before the limit is reset in this launch for certain: updateHealth will then scan its
+        // counters (and replay its usage log), a chain of dependent DRAM round trips at the very end of the CTA - the
+        // tail of the whole launch.  Ask L2 for those lines now, while the dynamics run.
+        const int sc_now = g.get(in.sc_in, 0);
+        if (env_on && sc_now + 1 >= cfg.max_step) {
+            const char* ub = reinterpret_cast<const char*>(st.usage + (size_t)n * W * Lc);
+            for (int k = g.i * 128; k < W * Lc * 4; k += A * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(ub + k));
+            if (st.usage_log != nullptr) {
+                const char* lb = reinterpret_cast<const char*>(st.usage_log + (size_t)n * st.usage_log_cap * A);
+                for (int k = g.i * 128; k < st.usage_log_cap * A * 2; k += A * 128)
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(lb + k));
+            }
+        }
+    }
 
     const LaneOut o = dmfb_dynamics<G, A_T, DEG_T>(cfg, st, g, A, n, ja, env_on, lane_on, in, u, seed, flags, out.status);
     write_back_lane(st, out, o, n, ja, g.i, lane_on, leader);

@@ -308,6 +308,91 @@ __device__ __forceinline__ void meda_update_health(const meda_cfg_t& cfg, const 
         if (S.flag[e] & kEnvSelected) meda_update_health_env(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x);
 }
 
+// refresh/addTask/_genLegalDroplet (meda.py:161-185,213-233): centres uniform in [r, dim-r-1]; a droplet
+// (destination) is redrawn while its centre is closer than 1.5*(2+2+2) = 9 to an earlier droplet (destination);
+// the destination is also redrawn while it overlaps its own droplet.  One thread per env (sequential by nature).
+// Droplets that cannot be placed make the reference loop for ever (meda.py:213-233); here the generator gives up after
+// kMaxSamplerRounds redraws of one droplet, restores `words` from `prev` (the env's current layout) and returns false.
+__device__ bool meda_generate_tasks(const meda_cfg_t& cfg, uint64_t seed, int64_t env, uint32_t episode, uint32_t* words,
+                                    const uint32_t* prev)
+{
+    const int A = cfg.n_agents, W = cfg.width, Lc = cfg.length;
+    uint64_t state = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
+    state += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)episode << 32) * 0xDA942042E4DD58B5ull;
+    state = mix64(state);
+    for (int i = 0; i < A; ++i) {
+        uint32_t sx, sy, tx, ty;
+        for (uint32_t rounds = 0;; ++rounds) {
+            if (rounds >= kMaxSamplerRounds) {                    // droplets that cannot be placed
+                for (int j = 0; j < A; ++j) words[j] = prev[j];
+                return false;
+            }
+            const uint64_t z = mix64(state += 0x9E3779B97F4A7C15ull);
+            sy = kRad + __umulhi((uint32_t)z, (uint32_t)(W - 2 * kRad));
+            sx = kRad + __umulhi((uint32_t)(z >> 32), (uint32_t)(Lc - 2 * kRad));
+            bool ok = true;
+            for (int j = 0; j < i; ++j) {
+                const int dx = (int)sx - (int)(words[j] & 255u), dy = (int)sy - (int)((words[j] >> 8) & 255u);
+                if (dx * dx + dy * dy < 81) { ok = false; break; }
+            }
+            if (ok) break;
+        }
+        for (uint32_t rounds = 0;; ++rounds) {
+            if (rounds >= kMaxSamplerRounds) {
+                for (int j = 0; j < A; ++j) words[j] = prev[j];
+                return false;
+            }
+            const uint64_t z = mix64(state += 0x9E3779B97F4A7C15ull);
+            ty = kRad + __umulhi((uint32_t)z, (uint32_t)(W - 2 * kRad));
+            tx = kRad + __umulhi((uint32_t)(z >> 32), (uint32_t)(Lc - 2 * kRad));
+            bool ok = true;
+            for (int j = 0; j < i; ++j) {
+                const int dx = (int)tx - (int)((words[j] >> 16) & 255u), dy = (int)ty - (int)(words[j] >> 24);
+                if (dx * dx + dy * dy < 81) { ok = false; break; }
+            }
+            if (!ok) continue;
+            if (abs((int)tx - (int)sx) <= 2 * kRad && abs((int)ty - (int)sy) <= 2 * kRad) continue;  // isDropletOverlap
+            break;
+        }
+        words[i] = sx | (sy << 8) | (tx << 16) | (ty << 24);
+    }
+    return true;
+}
+
+// DMFB_STEP_AUTO_RESET inside the step launch: MEDAEnv.reset() (meda.py:541-550) of env n by the warp that just stepped
+// it.  Lane `src` draws the task (sequential by nature) into `words` (the env's slice of the warp's shared droplet words,
+// which the paint reads next) and resets the env's scalars; with degradation all 32 lanes then replay the usage log and
+// run updateHealth.  All lanes call with uniform n / src.
+__device__ __forceinline__ void meda_reset_env_warp(const meda_cfg_t& cfg, const meda_state_t& st, int64_t n, uint64_t seed,
+                                                    uint32_t* words, int src)
+{
+    const int lane = threadIdx.x & 31, A = cfg.n_agents;
+    if (lane == src) {
+        const uint32_t episode = st.episode ? st.episode[n] + 1u : 0u;
+        if (st.episode) st.episode[n] = episode;
+        uint32_t* gdrop = reinterpret_cast<uint32_t*>(st.drop) + (size_t)n * A;
+        uint32_t prev[DMFB_MAX_AGENTS];
+        for (int i = 0; i < A; ++i) prev[i] = words[i];               // the layout after the step (= what gdrop holds)
+        if (!meda_generate_tasks(cfg, seed, cfg.env_base + n, episode, words, prev) && st.gen_status)
+            atomicOr(st.gen_status, DMFB_STATUS_SAMPLER_GAVE_UP);
+        for (int i = 0; i < A; ++i) {
+            gdrop[i] = words[i];
+            st.status[(size_t)n * A + i] = 0;
+            if (st.start) reinterpret_cast<uint16_t*>(st.start)[(size_t)n * A + i] = (uint16_t)(words[i] & 0xFFFFu);
+        }
+        st.step_count[n] = 0;
+        st.fails[n] = 0;
+        st.terminated[n] = 0;
+    }
+    if (st.usage && st.usage_log != nullptr && st.usage_log_len != nullptr) {   // m_usage is about to be read
+        meda_replay_usage_log(cfg, st, n, lane, 32);
+        __syncwarp();
+        if (lane == 0) st.usage_log_len[n] = 0;
+    }
+    if (cfg.b_degrade && st.usage && st.health) meda_update_health_env(cfg, st, n, lane, 32);   // (meda.py:600-605)
+    __syncwarp();
+}
+
 // Shared memory of the step kernel: per warp a tile of EW envs' observations, their packed droplet words and
 // per-env flags.
 struct StepLayout {
@@ -531,61 +616,19 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
             }
         }
         __syncwarp();
+        if ((flags & DMFB_STEP_AUTO_RESET) && st.reset_list == nullptr) {
+            // fused auto-reset: the envs of this warp that just terminated start their next episode here; their rows
+            // then show its first observation (reward / done / info stay those of the finished step)
+            const int term_env = (mine && i == 0 && !frozen && (in_time ? all : 1)) ? 1 : 0;
+            for (uint32_t m = __ballot_sync(0xFFFFFFFFu, term_env); m; m &= m - 1u) {
+                const int src = __ffs(m) - 1;                 // first lane of the env
+                meda_reset_env_warp(cfg, st, n0 + src / A, seed, s_word + src, src);
+            }
+        }
         meda_paint_warp<VER, A_T, FOV_T>(cfg, s_word, s_flag, tile, ev, set_order);
         if (store_tile_warp<PHASED>(gobs, tile, (uint32_t)(ev * A * D)) && lane == 0)
             tma_store_wait_read_all();                        // shared memory must outlive the bulk read
     }
-}
-
-// refresh/addTask/_genLegalDroplet (meda.py:161-185,213-233): centres uniform in [r, dim-r-1]; a droplet
-// (destination) is redrawn while its centre is closer than 1.5*(2+2+2) = 9 to an earlier droplet (destination);
-// the destination is also redrawn while it overlaps its own droplet.  One thread per env (sequential by nature).
-// Droplets that cannot be placed make the reference loop for ever (meda.py:213-233); here the generator gives up after
-// kMaxSamplerRounds redraws of one droplet, restores `words` from `prev` (the env's current layout) and returns false.
-__device__ bool meda_generate_tasks(const meda_cfg_t& cfg, uint64_t seed, int64_t env, uint32_t episode, uint32_t* words,
-                                    const uint32_t* prev)
-{
-    const int A = cfg.n_agents, W = cfg.width, Lc = cfg.length;
-    uint64_t state = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
-    state += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)episode << 32) * 0xDA942042E4DD58B5ull;
-    state = mix64(state);
-    for (int i = 0; i < A; ++i) {
-        uint32_t sx, sy, tx, ty;
-        for (uint32_t rounds = 0;; ++rounds) {
-            if (rounds >= kMaxSamplerRounds) {                    // droplets that cannot be placed
-                for (int j = 0; j < A; ++j) words[j] = prev[j];
-                return false;
-            }
-            const uint64_t z = mix64(state += 0x9E3779B97F4A7C15ull);
-            sy = kRad + __umulhi((uint32_t)z, (uint32_t)(W - 2 * kRad));
-            sx = kRad + __umulhi((uint32_t)(z >> 32), (uint32_t)(Lc - 2 * kRad));
-            bool ok = true;
-            for (int j = 0; j < i; ++j) {
-                const int dx = (int)sx - (int)(words[j] & 255u), dy = (int)sy - (int)((words[j] >> 8) & 255u);
-                if (dx * dx + dy * dy < 81) { ok = false; break; }
-            }
-            if (ok) break;
-        }
-        for (uint32_t rounds = 0;; ++rounds) {
-            if (rounds >= kMaxSamplerRounds) {
-                for (int j = 0; j < A; ++j) words[j] = prev[j];
-                return false;
-            }
-            const uint64_t z = mix64(state += 0x9E3779B97F4A7C15ull);
-            ty = kRad + __umulhi((uint32_t)z, (uint32_t)(W - 2 * kRad));
-            tx = kRad + __umulhi((uint32_t)(z >> 32), (uint32_t)(Lc - 2 * kRad));
-            bool ok = true;
-            for (int j = 0; j < i; ++j) {
-                const int dx = (int)tx - (int)((words[j] >> 16) & 255u), dy = (int)ty - (int)(words[j] >> 24);
-                if (dx * dx + dy * dy < 81) { ok = false; break; }
-            }
-            if (!ok) continue;
-            if (abs((int)tx - (int)sx) <= 2 * kRad && abs((int)ty - (int)sy) <= 2 * kRad) continue;  // isDropletOverlap
-            break;
-        }
-        words[i] = sx | (sy << 8) | (tx << 16) | (ty << 24);
-    }
-    return true;
 }
 
 // mode 0: reset, mode 1: restart (droplets back to their start cells, meda.py:170-173,552-561), mode 2: observe only
@@ -964,11 +1007,10 @@ int meda_step(const meda_cfg_t* cfg, const meda_state_t* state, const void* acti
     if (state->n_envs == 0) return DMFB_OK;
     rc = meda_launch_step(cfg, state, actions, action_elem_size, u_inject, seed, flags, set_order, out, stream);
     if (rc) return rc;
-    if (flags & DMFB_STEP_AUTO_RESET) {
-        if (state->reset_list && state->reset_count)
-            return meda_launch_reset_list(cfg, state, seed, set_order, out->obs, stream);
-        return meda_launch_reset(cfg, state, state->terminated, 0, 0, nullptr, nullptr, seed, set_order, out->obs, stream);
-    }
+    // DMFB_STEP_AUTO_RESET: fused into the step kernel, unless the caller supplied the reset list: then the step only
+    // lists the envs that terminated and a second, small kernel resets exactly those
+    if ((flags & DMFB_STEP_AUTO_RESET) && state->reset_list && state->reset_count)
+        return meda_launch_reset_list(cfg, state, seed, set_order, out->obs, stream);
     return DMFB_OK;
 }
 

@@ -49,7 +49,7 @@ class BatchedMEDA:
 
     def __init__(self, n_envs, width, length, n_agents, fov=19, b_degrade=False, per_degrade=0.1, obs_version=2,
                  device="cuda", seed=0, env_base=0, reward_f64=False, degrade=None, layouts=None, track_usage=None,
-                 usage_log=True, reset_list=True, health_bitmap=True):
+                 usage_log=True, reset_list=False, health_bitmap=True):
         # track_usage: keep the m_usage actuation counters (addUsage, meda.py:591-598).  Nothing reads them unless the
         # chip degrades (updateHealth runs only `if self.b_degrade`, meda.py:547-548), so like BatchedDMFB the default
         # is `b_degrade`; the N=1 adapters always track them because `m_usage` is a visible attribute there.
@@ -97,7 +97,8 @@ class BatchedMEDA:
         self._usage_log = bool(usage_log) and self.usage is not None
         self.usage_log = z(N, self.max_step, A, dtype=torch.int16) if self._usage_log else None
         self.usage_log_len = z(N, dtype=torch.int32) if self._usage_log else None
-        # auto_reset: the step lists the envs that terminated and a small kernel resets exactly those (reset_list=False:
+        # auto_reset is fused into the step kernel (the warp that stepped an env resets it); reset_list=True: the step
+        # only lists the envs that terminated and a second, small kernel resets exactly those (
         # a masked reset sweeps the whole batch after every step instead)
         self.reset_list = z(N, dtype=torch.int32) if reset_list else None
         self.reset_count = z(2, dtype=torch.int32) if reset_list else None

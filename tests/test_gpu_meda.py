@@ -255,16 +255,18 @@ def test_meda_usage_log_is_transparent():
 
 @pytest.mark.parametrize("ver,deg,A,W,L", [(0, False, 4, 30, 60), (2, True, 4, 30, 60), (1, True, 6, 45, 60), (2, False, 10, 80, 80)])
 def test_meda_listed_auto_reset_equals_masked_reset(ver, deg, A, W, L):
-    """auto_reset resets exactly the envs the step listed as terminated (meda_state_t.reset_list, one warp per env);
-    without the list a masked meda_reset sweeps the batch.  Same tasks, observations, health and counters."""
+    """auto_reset is fused into the step kernel (env b); with meda_state_t.reset_list the step only lists the envs that
+    terminated and a second kernel resets exactly those (env a); env c steps without auto_reset and then runs a masked
+    meda_reset over the envs the step reported as terminated.  Same tasks, observations, health and counters."""
     P = pkg()
     N = 1500
     rng = np.random.default_rng(ver + A)
     kw = dict(fov=19, b_degrade=deg, per_degrade=1.0, obs_version=ver, device="cuda:0", seed=77, reward_f64=True, track_usage=True)
     a = P.BatchedMEDA(N, W, L, A, reset_list=True, **kw)
     b = P.BatchedMEDA(N, W, L, A, reset_list=False, **kw)
-    assert a.reset_list is not None and b.reset_list is None and torch.equal(a.drop, b.drop)
-    for env in (a, b):
+    c = P.BatchedMEDA(N, W, L, A, reset_list=False, **kw)
+    assert a.reset_list is not None and b.reset_list is None and torch.equal(a.drop, b.drop) and torch.equal(a.drop, c.drop)
+    for env in (a, b, c):
         env.usage.fill_(46)
         env.step_count.copy_(torch.arange(N, device="cuda:0", dtype=torch.int32) % env.max_step)   # staggered episodes
     n_resets = 0
@@ -277,12 +279,16 @@ def test_meda_listed_auto_reset_equals_masked_reset(ver, deg, A, W, L):
         ep0 = a.episode.clone()
         oa, ra, da, ia = a.step(acts, auto_reset=True)
         ob, rb, db, ib = b.step(acts, auto_reset=True)
+        oc, rc_, dc, ic = c.step(acts)
+        oc = c.reset(mask=ic["terminated"].to(torch.uint8))
+        assert torch.equal(ob, oc) and torch.equal(rb, rc_) and torch.equal(db, dc) and torch.equal(b.drop, c.drop), f"t{t} (fused vs masked)"
+        assert torch.equal(b.episode, c.episode) and torch.equal(b.step_count, c.step_count) and torch.equal(b.fails, c.fails)
         n_resets += int((a.episode != ep0).sum())
         assert torch.equal(a.drop, b.drop) and torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), f"t{t}"
         assert torch.equal(a.episode, b.episode) and torch.equal(a.step_count, b.step_count)
         assert torch.equal(a.status, b.status) and torch.equal(a.fails, b.fails) and torch.equal(a.start, b.start)
         assert int(a.terminated.sum()) == 0 and int(a.reset_count.abs().sum()) == 0
         if deg:
-            assert torch.equal(a.health, b.health), f"t{t} health"
+            assert torch.equal(a.health, b.health) and torch.equal(b.health, c.health), f"t{t} health"
     assert n_resets > N
-    assert torch.equal(a.usage_counts(), b.usage_counts())
+    assert torch.equal(a.usage_counts(), b.usage_counts()) and torch.equal(b.usage_counts(), c.usage_counts())
