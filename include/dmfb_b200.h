@@ -335,6 +335,18 @@ int dmfb_host_set_transfer(dmfb_host_env_t* h, int n_threads, int dma_percent);
  * contiguous int8 records of cells+2 bytes with n_threads threads. */
 int dmfb_host_unpack_records(const uint8_t* packed, size_t packed_stride, int8_t* out, int cells, size_t n_records,
                              int n_threads);
+/* The same for MEDA: MEDAEnv.step / reset (meda.py:513-550) with host buffers.  obs [N,A,obs_dim] int8; `constraints`
+ * is the punish COUNT of the step (info['constraints'] == -0.6 * count, meda.py:256,538).  DMFB_STEP_AUTO_RESET resets
+ * the envs that terminate inside the step launch.  The handle builds the CPython-set order table itself when the
+ * observation variant needs one (v0_1 / v0_2 with more than 8 droplets; at most 16 droplets then). */
+typedef struct meda_host_env meda_host_env_t;
+int meda_host_create(const meda_cfg_t* cfg, int n_envs, int device, meda_host_env_t** out);
+void meda_host_destroy(meda_host_env_t* h);
+int meda_host_reset(meda_host_env_t* h, int new_chip, const uint8_t* layouts, const double* degrade, uint64_t seed,
+                    int8_t* obs);
+int meda_host_step(meda_host_env_t* h, const int8_t* actions, const double* u_inject, uint64_t seed, uint32_t flags,
+                   int8_t* obs, float* reward, uint8_t* done, int32_t* constraints, uint8_t* success);
+
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so that callers outside torch can
  * give the copies a DMA-able buffer */
 void* dmfb_host_alloc_pinned(size_t bytes);

@@ -11,7 +11,7 @@ or through the alias module at the repo root:  `import marl_dmfb_b200`.
 from . import _native  # noqa: F401
 from .build import build  # noqa: F401
 from .dmfb import BatchedDMFB, DMFBenv, DMFBenv_v0_1  # noqa: F401
-from .host import HostDMFB  # noqa: F401
+from .host import HostDMFB, HostMEDA  # noqa: F401
 from .sharding import shard_range  # noqa: F401
 from .marl import (CRNN, RNN, BatchedAgents, BatchedRolloutWorker, EpisodeBatch, PhaseTimer, QMixNet,  # noqa: F401
                    QMIXLearner, ReplayBufferGPU, VDNLearner, allreduce_gradients)
@@ -21,4 +21,4 @@ try:  # MEDA kernels are part of the same library
 except ImportError:  # pragma: no cover - only while the package is being bootstrapped
     pass
 
-__all__ = ["BatchedDMFB", "DMFBenv", "DMFBenv_v0_1", "HostDMFB", "BatchedMEDA", "MEDAEnv", "MEDAEnv_v0_1", "MEDAEnv_v0_2", "shard_range", "build"]
+__all__ = ["BatchedDMFB", "DMFBenv", "DMFBenv_v0_1", "HostDMFB", "HostMEDA", "BatchedMEDA", "MEDAEnv", "MEDAEnv_v0_1", "MEDAEnv_v0_2", "shard_range", "build"]

@@ -84,6 +84,7 @@ EXPORTS = [
     "dmfb_abi_version", "dmfb_last_cuda_error", "dmfb_launch_count",
     "dmfb_host_create", "dmfb_host_destroy", "dmfb_host_reset", "dmfb_host_step", "dmfb_host_set_transfer", "dmfb_host_unpack_records",
     "dmfb_host_alloc_pinned", "dmfb_host_free_pinned",
+    "meda_host_create", "meda_host_destroy", "meda_host_reset", "meda_host_step",
 ]
 
 _lib = None
@@ -142,6 +143,12 @@ def load():
         lib.dmfb_host_alloc_pinned.argtypes = [C.c_size_t]
         lib.dmfb_host_free_pinned.argtypes = [C.c_void_p]
         lib.dmfb_host_free_pinned.restype = None
+    if hasattr(lib, "meda_host_create"):
+        lib.meda_host_create.argtypes = [C.POINTER(MedaCfg), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        lib.meda_host_destroy.argtypes = [C.c_void_p]
+        lib.meda_host_destroy.restype = None
+        lib.meda_host_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.meda_host_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_void_p] * 5
     _lib = lib
     return lib
 

@@ -34,7 +34,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 // Shared-memory carve-up of one tile, computed identically on host and device.
 struct TileLayout {
     int E, A, D, nw, ncodes;
-    uint32_t tile_bytes, off_l2row, off_l2col, off_flag, off_dirx, off_diry, off_sink, total;
+    uint32_t tile_bytes, off_l2row, off_l2col, off_flag, off_dirx, off_diry, off_sink, off_sets, total;
     __host__ __device__ TileLayout(int E_, int A_, int fov, int W, int Lc, int D_) {
         E = E_; A = A_; D = D_; nw = (fov * fov + 31) / 32; ncodes = 2 * (fov / 2) + 1;
         tile_bytes = ((uint32_t)(E * A * D) + 15u) & ~15u;
@@ -45,6 +45,7 @@ struct TileLayout {
         off_dirx = o; o += ((uint32_t)(2 * W) + 3u) & ~3u;
         off_diry = o; o += ((uint32_t)(2 * Lc) + 3u) & ~3u;
         off_sink = o; o += 16u;
+        off_sets = o; o += (uint32_t)E * 4u * (((uint32_t)A + 3u) & ~3u);   // CoordSets: 16-byte aligned per env
         total = (o + 15u) & ~15u;
     }
     __host__ __device__ TileLayout(const dmfb_cfg_t& c, int E_)
@@ -63,6 +64,7 @@ struct TileSmem {
     int8_t* dirx;
     int8_t* diry;
     int8_t* sink;     // predicated-off byte stores go here (keeps the paint code branch-free)
+    uint8_t* sets;    // [E][4][slots] coordinate sets of the specialised instances (CoordSets)
     __device__ TileSmem(unsigned char* base, const TileLayout& L) {
         tile = reinterpret_cast<int8_t*>(base);
         l2row = reinterpret_cast<uint32_t*>(base + L.off_l2row);
@@ -71,6 +73,7 @@ struct TileSmem {
         dirx = reinterpret_cast<int8_t*>(base + L.off_dirx);
         diry = reinterpret_cast<int8_t*>(base + L.off_diry);
         sink = reinterpret_cast<int8_t*>(base + L.off_sink);
+        sets = base + L.off_sets;
     }
 };
 
@@ -132,6 +135,63 @@ __device__ __forceinline__ uint32_t near_pair(uint32_t a, uint32_t b)
 __device__ __forceinline__ uint32_t dup_lo(uint32_t w) { return __byte_perm(w, 0, 0x1010); }  // cell0 | cell0<<16
 __device__ __forceinline__ uint32_t dup_hi(uint32_t w) { return __byte_perm(w, 0, 0x3232); }  // cell1 | cell1<<16
 
+// Coordinate sets of one env in shared memory (instances with a compile-time droplet count): the x and the y
+// coordinates of all droplets as byte arrays, padded to whole words - CX, CY after the moves, PX, PY before.  A lane
+// then tests its droplet against FOUR others per VABSDIFF4 (the byte-replicated own coordinate against a word of the
+// set) instead of one per shuffle: the pairwise constraint counts and the visibility test of the observation drop from
+// ~17 and 4 instructions per PAIR to ~9 and 3 per WORD.  Pad slots hold 128 + fov/2: further than any window reaches
+// and more than one cell from every real coordinate (< 128), yet small enough that "difference + bias" stays a byte.
+template <int A_T>
+struct CoordSets {
+    static constexpr int kSlots = (A_T + 3) & ~3, kWords = kSlots / 4, kBytes = 4 * kSlots;
+    uint8_t* p;                                                  // the env's block: [CX | CY | PX | PY], kSlots bytes each
+    uint32_t x[kWords], y[kWords];                               // CX / CY once loaded
+    __device__ CoordSets(uint8_t* sets, int env_in_tile) : p(sets + env_in_tile * kBytes) {}
+    // lane i publishes its coordinates in the sets sx / sy (0: CX, 1: CY, 2: PX, 3: PY); lanes i < kSlots - A_T also pad
+    __device__ __forceinline__ void put(int sx, int sy, int i, uint32_t vx, uint32_t vy, uint32_t pad_byte) const {
+        p[sx * kSlots + i] = (uint8_t)vx;
+        p[sy * kSlots + i] = (uint8_t)vy;
+        if (A_T + i < kSlots) {
+            p[sx * kSlots + A_T + i] = (uint8_t)pad_byte;
+            p[sy * kSlots + A_T + i] = (uint8_t)pad_byte;
+        }
+    }
+    __device__ __forceinline__ uint32_t word(int s, int w) const { return reinterpret_cast<const uint32_t*>(p)[s * kWords + w]; }
+    __device__ __forceinline__ void load_current() {
+#pragma unroll
+        for (int w = 0; w < kWords; ++w) { x[w] = word(0, w); y[w] = word(1, w); }
+    }
+    // number of slots within one cell (|dx| <= 1 and |dy| <= 1) of (vx, vy) among the words (sx, sy); pads never are
+    __device__ __forceinline__ static int count_near(uint32_t vx, uint32_t vy, const uint32_t* sx, const uint32_t* sy) {
+        const uint32_t mx = vx * 0x01010101u, my = vy * 0x01010101u;
+        int far = 0;
+#pragma unroll
+        for (int w = 0; w < kWords; ++w) {
+            const uint32_t t = __vabsdiffu4(mx, sx[w]) | __vabsdiffu4(my, sy[w]);
+            const uint32_t h = (t >> 1) & 0x7F7F7F7Fu;            // a byte is zero iff both differences are <= 1
+            far += __popc((h + 0x7F7F7F7Fu) & 0x80808080u);       // bit 7 of a byte: nonzero
+        }
+        return kSlots - far;
+    }
+    // bit j set iff droplet j (current sets) lies in the window of half-width hf around (vx, vy):
+    // 2|dx| < fov and 2|dy| < fov for odd fov
+    __device__ __forceinline__ uint32_t visible(uint32_t vx, uint32_t vy, int hf) const {
+        const uint32_t mx = vx * 0x01010101u, my = vy * 0x01010101u;
+        const uint32_t bias = (uint32_t)(0x7F - hf) * 0x01010101u; // byte + bias sets bit 7 iff byte > hf (no carry: byte <= 128 + hf)
+        uint32_t hidden = 0;
+#pragma unroll
+        for (int w = 0; w < kWords; ++w) {
+            const uint32_t nv = ((__vabsdiffu4(mx, x[w]) + bias) | (__vabsdiffu4(my, y[w]) + bias)) & 0x80808080u;
+            hidden |= (((nv >> 7) * 0x01020408u) >> 24) << (4 * w);   // bits 0, 8, 16, 24 -> one nibble
+        }
+        return ~hidden & ((1u << A_T) - 1u);
+    }
+};
+template <>
+struct CoordSets<0> {                                            // run-time droplet count: shuffles, no sets
+    __device__ CoordSets(uint8_t*, int) {}
+};
+
 // A lane group = the G consecutive lanes of a warp that hold the droplets of one env.  G is a power of two
 // (4, 8, 16, 32) or, to avoid idle lanes, exactly the droplet count (G = 10: three envs per warp, lanes 30-31 idle).
 template <int G>
@@ -185,50 +245,54 @@ __host__ __device__ constexpr int cta_threads(int E, int G) { return ((E + 32 / 
 // The search is organised in ROUNDS: the whole warp examines kAttemptsPerRound consecutive attempts of ONE env and
 // hands the lowest accepted one to the lanes of the group `dst` that holds that env (lane i gets the word of droplet
 // i).  Two flavours, chosen by A alone (so every kernel instance draws the same task for the same key):
-//   A == 10  one attempt per LANE, all 20 points and the 190 pair tests in registers, fully unrolled (32 per round);
+//   A == 10  one attempt per WARP and round: lane = point, the 190 pair tests by shuffles with early exit;
 //   else     one attempt per lane GROUP, points exchanged by shuffles (32/G per round).
 constexpr uint32_t kTaskReady = 0x80000000u;   // dmfb_state_t.next_cursor: next_task holds the next episode's task
 
 template <int G>
-__device__ __forceinline__ int attempts_per_round(int A) { return A == 10 ? 32 : Group<G>::kPerWarp; }
+__device__ __forceinline__ int attempts_per_round(int A) { return A == 10 ? 1 : Group<G>::kPerWarp; }
+// rounds of the run-ahead search per warp and step (fused auto-reset): enough to keep up with the demand - three envs
+// per warp that each need about 70 attempts (10 droplets, 20x20) per episode of 80 steps = 2.6 per step
+__device__ __forceinline__ int prefetch_rounds(int A) { return A == 10 ? 4 : 1; }
 
 // One round for env `env` (global index), episode `epi`, attempts [first, first + attempts_per_round).  All 32 lanes
 // call with warp-uniform arguments.  Returns true if an attempt was accepted; then `word` of the lanes of group `dst`
 // (lane i < A) is the task, other lanes keep theirs.
+//
+// A == 10: ONE attempt per round, spread over the warp.  Lane p < 20 draws point p (point 2j = start of droplet j,
+// 2j+1 = its goal) and tests it against the points p+1 .. p+10 (mod 20) - all 190 pairs - stopping at the first
+// offset at which any lane saw a conflict (an attempt on a 20x20 chip fails with 98.6 %, after 2.5 offsets on average).
+// A round is ~60 instructions: what a step that runs ahead adds is small and the same for every warp.  (One attempt
+// per LANE with all points in registers, 32 per round, costs the same per attempt but ~3,000 instructions per round:
+// the few warps that ran a round in a step kept the whole launch waiting, +11 us at 64K envs of 10 droplets.)
 template <int G, int A_T>
-__device__ __noinline__ bool sample_round_regs(const dmfb_cfg_t& cfg, const Group<G>& g, uint64_t seed, int64_t env,
-                                               uint32_t epi, uint32_t first, int dst, uint32_t& word)
+__device__ __forceinline__ bool sample_round_warp(const dmfb_cfg_t& cfg, const Group<G>& g, uint64_t seed, int64_t env,
+                                                  uint32_t epi, uint32_t first, int dst, uint32_t& word)
 {
+    constexpr int P = 2 * A_T;                                    // points of one attempt, P <= 32
     const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
     uint64_t base = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
     base += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)epi << 32) * 0xDA942042E4DD58B5ull;
     base = mix64(base ^ 0xA5A5A5A5A5A5A5A5ull);
-    const uint64_t k = (uint64_t)first + (uint64_t)g.lane;
-    const uint64_t ctr = base + k * (uint64_t)(2 * A_T) * 0x9E3779B97F4A7C15ull;
-    uint32_t pt[A_T];                                         // pt[j] = start_j | goal_j << 16: the final droplet word
-#pragma unroll
-    for (int j = 0; j < A_T; ++j) {
-        const uint64_t z0 = mix64(ctr + (uint64_t)(2 * j + 1) * 0x9E3779B97F4A7C15ull);
-        const uint64_t z1 = mix64(ctr + (uint64_t)(2 * j + 2) * 0x9E3779B97F4A7C15ull);
-        pt[j] = __umulhi((uint32_t)z0, W) | (__umulhi((uint32_t)(z0 >> 32), Lc) << 8) |
-                (__umulhi((uint32_t)z1, W) << 16) | (__umulhi((uint32_t)(z1 >> 32), Lc) << 24);
+    const uint64_t ctr = base + (uint64_t)first * (uint64_t)P * 0x9E3779B97F4A7C15ull;
+    const int p = g.lane;
+    const bool on = p < P;
+    const uint64_t z = mix64(ctr + (uint64_t)(p + 1) * 0x9E3779B97F4A7C15ull);
+    // idle lanes hold distinct far-away cells
+    const uint32_t cell = on ? (__umulhi((uint32_t)z, W) | (__umulhi((uint32_t)(z >> 32), Lc) << 8)) : (0xFF00u | (uint32_t)p);
+    bool bad = false;
+#pragma unroll 1
+    for (int o = 1; o <= P / 2; ++o) {
+        int q = p + o;
+        if (q >= P) q -= P;
+        const uint32_t other = __shfl_sync(kFull, cell, on ? q : p);
+        if (on && (__vabsdiffu4(cell, other) & 0xFEFEu) == 0u) bad = true;   // |dx| <= 1 && |dy| <= 1
+        if (__any_sync(kFull, bad)) return false;
     }
-    uint32_t bad = 0;
-#pragma unroll
-    for (int a = 0; a < A_T; ++a) {
-        bad |= near_pair(pt[a], pt[a] >> 16) & 1u;            // own start vs own goal
-#pragma unroll
-        for (int b = a + 1; b < A_T; ++b)                     // start-start, goal-goal | start-goal, goal-start
-            bad |= near_pair(pt[a], pt[b]) | near_pair(pt[a], __byte_perm(pt[b], 0u, 0x1032));
-    }
-    const unsigned okm = __ballot_sync(kFull, bad == 0u);
-    if (okm == 0u) return false;
-    const int win = __ffs(okm) - 1;                           // lowest attempt number of this round
-#pragma unroll
-    for (int j = 0; j < A_T; ++j) {
-        const uint32_t w = __shfl_sync(kFull, pt[j], win);
-        if (g.idx == dst && g.i == j) word = w;
-    }
+    // accepted: droplet i = start (point 2i) | goal (point 2i+1) << 16
+    const int i2 = (g.i < A_T) ? 2 * g.i : 0;
+    const uint32_t w = __shfl_sync(kFull, cell, i2) | (__shfl_sync(kFull, cell, i2 + 1) << 16);
+    if (g.idx == dst && g.i < A_T) word = w;
     return true;
 }
 
@@ -236,7 +300,7 @@ template <int G>
 __device__ __forceinline__ bool sample_round(const dmfb_cfg_t& cfg, const Group<G>& g, int A, uint64_t seed, int64_t env,
                                              uint32_t epi, uint32_t first, int dst, uint32_t& word)
 {
-    if (A == 10) return sample_round_regs<G, 10>(cfg, g, seed, env, epi, first, dst, word);
+    if (A == 10) return sample_round_warp<G, 10>(cfg, g, seed, env, epi, first, dst, word);
     const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
     const bool lane_in = g.valid && g.i < A;
     // per-(env, episode, droplet) stream; attempt k uses counters 2k+1, 2k+2
@@ -276,6 +340,9 @@ __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const
                                                     uint32_t first, uint32_t keep)
 {
     uint32_t word = keep;
+#ifdef DMFB_WHATIF_NOSAMPLE
+    return word;
+#endif
     unsigned todo = __ballot_sync(kFull, want && g.i == 0);      // leader lanes of the requesting groups
     if (todo == 0u) return word;
     const uint32_t per_round = (uint32_t)attempts_per_round<G>(A);
@@ -354,7 +421,7 @@ __device__ __forceinline__ void generate_blocks(const dmfb_cfg_t& cfg, const dmf
 template <int FOV_T, int A_T, typename GetWord>
 __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLayout& L, const TileSmem& S,
                                             int agent_in_tile, int i, uint32_t me, bool on, GetWord get,
-                                            const uint8_t* __restrict__ env_blocks = nullptr)
+                                            const CoordSets<A_T>& cs, const uint8_t* __restrict__ env_blocks = nullptr)
 {
     const int fov = FOV_T ? FOV_T : cfg.fov;
     const int hf = fov >> 1, f2 = fov * fov;
@@ -425,6 +492,25 @@ __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLay
     // ---- layer 0: droplets inside the window (:408-413); layer 1: clipped goals of the other droplets
     //      with |dx| < fov/2 and |dy| < fov/2 (:416-420) --------------------------------------------------
     const int ox = x - hf, oy = y - hf;
+    if constexpr (A_T == 10) {
+        // Ten droplets, few of them inside any one window: the visible ones come out of the coordinate sets as a bit
+        // mask (three VABSDIFF4 pairs instead of ten per-droplet tests) and only those are painted, in ascending
+        // order.  The trip count is the largest number of visible droplets over the warp (4-5 on a 20x20 chip).
+        static_assert(FOV_T & 1, "the window test below is the odd-fov one");
+        uint32_t m = on ? cs.visible((uint32_t)x, (uint32_t)y, hf) : 0u;
+        while (__any_sync(kFull, m != 0u)) {
+            const bool act = m != 0u;
+            const int j = act ? __ffs(m) - 1 : 0;
+            m &= m - 1u;
+            const uint32_t d = get(j);
+            const int rx = (int)(d & 255u) - ox, ry = (int)((d >> 8) & 255u) - oy;
+            *(act ? rec + rx * fov + ry : S.sink) = (int8_t)(j + 1);
+            int cx = (int)((d >> 16) & 255u) - ox, cy = (int)(d >> 24) - oy;
+            cx = min(max(cx, 0), fov - 1);
+            cy = min(max(cy, 0), fov - 1);
+            *((act && j != i) ? rec + f2 + cx * fov + cy : S.sink) = (int8_t)(j + 1);      // ascending j: later index overwrites
+        }
+    } else {
     const uint32_t vis_bias = (uint32_t)(0x7F - ((fov - 1) >> 1)) * 0x0101u;  // byte + bias sets bit 7 iff byte > (fov-1)/2
 #pragma unroll
     for (int j = 0; j < A; ++j) {
@@ -439,6 +525,7 @@ __device__ __forceinline__ void paint_agent(const dmfb_cfg_t& cfg, const TileLay
         cx = min(max(cx, 0), fov - 1);
         cy = min(max(cy, 0), fov - 1);
         *((on && vis && j != i) ? rec + f2 + cx * fov + cy : S.sink) = (int8_t)(j + 1);  // ascending j: later index overwrites
+    }
     }
     // ---- direction bytes (:442-454) from the host-built table -------------------------------------------
     const int dxi = on ? gx - x + W - 1 : 0, dyi = on ? gy - y + Lc - 1 : 0;
@@ -696,7 +783,7 @@ template <int G, int A_T, bool DEG_T>
 __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const Group<G>& g, int A,
                                                  int64_t n, size_t ja, bool env_on, bool lane_on, LaneIn in,
                                                  const double* __restrict__ u, uint64_t seed, uint32_t flags,
-                                                 int32_t* status_flag)
+                                                 int32_t* status_flag, CoordSets<A_T>& cs)
 {
     const int W = cfg.width, Lc = cfg.length;
     const uint32_t all_mask = (A >= 32) ? 0xFFFFFFFFu : ((1u << A) - 1u);
@@ -771,16 +858,34 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
     else r = -0.4;
 
     // ---- comflic_static / comflic_dynamic (:254-271): final vs final, saved vs final ---------------
-    const uint32_t both = cur | (start_cell << 16);   // my (current, past) cells
     int sta = 0, dyn = 0;
+    if constexpr (A_T != 0) {
+        // all droplets of the env at once: coordinates published in shared memory, four others per VABSDIFF4
+        const uint32_t pad = 128u + (uint32_t)(cfg.fov >> 1);
+        if (lane_on) {
+            cs.put(0, 1, g.i, (uint32_t)nx, (uint32_t)ny, pad);
+            cs.put(2, 3, g.i, (uint32_t)x, (uint32_t)y, pad);
+        }
+        __syncwarp();
+        cs.load_current();
+        uint32_t px[CoordSets<A_T>::kWords], py[CoordSets<A_T>::kWords];
 #pragma unroll
-    for (int j = 0; j < A; ++j) {
-        const uint32_t bj = g.get(both, j);                 // (current_j, past_j)
-        const uint32_t h1 = near_pair(both, dup_lo(bj));    // bit0: cur_me~cur_j, bit1: past_me~cur_j
-        const uint32_t h2 = near_pair(both, dup_hi(bj));    // bit0: cur_me~past_j
-        const uint32_t other = (j != g.i) ? 1u : 0u;
-        sta += (int)(h1 & other);
-        dyn += (int)((h1 >> 1) & other) + (int)(h2 & other);
+        for (int w = 0; w < CoordSets<A_T>::kWords; ++w) { px[w] = cs.word(2, w); py[w] = cs.word(3, w); }
+        // a droplet is always within one cell of itself and of its own past cell: the three "- 1"
+        sta = CoordSets<A_T>::count_near((uint32_t)nx, (uint32_t)ny, cs.x, cs.y) - 1;              // cur_me ~ cur_j
+        dyn = CoordSets<A_T>::count_near((uint32_t)x, (uint32_t)y, cs.x, cs.y) - 1                 // past_me ~ cur_j
+              + CoordSets<A_T>::count_near((uint32_t)nx, (uint32_t)ny, px, py) - 1;                // cur_me ~ past_j
+    } else {
+        const uint32_t both = cur | (start_cell << 16);   // my (current, past) cells
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            const uint32_t bj = g.get(both, j);                 // (current_j, past_j)
+            const uint32_t h1 = near_pair(both, dup_lo(bj));    // bit0: cur_me~cur_j, bit1: past_me~cur_j
+            const uint32_t h2 = near_pair(both, dup_hi(bj));    // bit0: cur_me~past_j
+            const uint32_t other = (j != g.i) ? 1u : 0u;
+            sta += (int)(h1 & other);
+            dyn += (int)((h1 >> 1) & other) + (int)(h2 & other);
+        }
     }
     if (!lane_on) { sta = 0; dyn = 0; }
     const int constraints = g.sum(sta + dyn);                              // (:287)
@@ -850,14 +955,26 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
             if (lane_on && st.start) reinterpret_cast<uint16_t*>(st.start)[ja] = (uint16_t)(o.word & 0xFFFFu);
         }
         if (prefetch) {
-            // Run ahead: ONE round of attempts per warp and step, for the first env of the warp whose next task is not
-            // known yet.  An env needs 1/p_accept attempts per episode (about 12 for 4 droplets on 10x10, 70 for 10 on
+            // Run ahead: prefetch_rounds() rounds of attempts per warp and step, for the first envs of the warp whose next
+            // task is not known yet.  An env needs 1/p_accept attempts per episode (about 12 for 4 droplets on 10x10, 70 for 10 on
             // 20x20) and has a whole episode of steps to find them, so the searches finish long before they are needed
             // and no launch ever waits for the tail of the geometric distribution.
-            const unsigned open = __ballot_sync(kFull, env_on && g.i == 0 && !(cur & kTaskReady) &&
-                                                       cur < kMaxSamplerRounds * (uint32_t)attempts_per_round<G>(A));
-            if (open) {
-                const int src = __ffs(open) - 1, dst = src / G;
+            // The env closest to its step limit goes first, and when that is about to need its task (it has 8 steps
+            // left) the budget rises, so that what is left of the search is spread over its last steps instead of
+            // running inside the launch that resets it.
+            const uint32_t rem = (uint32_t)max(cfg.max_step - o.sc_out, 0);
+            int rounds = prefetch_rounds(A);
+#ifdef DMFB_WHATIF_NOSAMPLE
+            rounds = 0;
+#endif
+#pragma unroll 1
+            for (int r = 0; r < rounds; ++r) {
+                const bool open = env_on && g.i == 0 && !(cur & kTaskReady) &&
+                                  cur < kMaxSamplerRounds * (uint32_t)attempts_per_round<G>(A);
+                const uint32_t best = __reduce_min_sync(kFull, open ? ((rem << 5) | (uint32_t)g.lane) : 0xFFFFFFFFu);
+                if (best == 0xFFFFFFFFu) break;
+                if (r == 0 && (best >> 5) <= 8u) rounds = 8 * prefetch_rounds(A);
+                const int src = (int)(best & 31u), dst = src / G;
                 const uint32_t epi = __shfl_sync(kFull, episode + 1u + (o.do_reset ? 1u : 0u), src);
                 const uint32_t at = __shfl_sync(kFull, cur, src);
                 uint32_t task = 0;
@@ -970,7 +1087,18 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
         }
     }
 
-    const LaneOut o = dmfb_dynamics<G, A_T, DEG_T>(cfg, st, g, A, n, ja, env_on, lane_on, in, u, seed, flags, out.status);
+    CoordSets<A_T> cs(S.sets, env_on ? e : 0);
+    const LaneOut o = dmfb_dynamics<G, A_T, DEG_T>(cfg, st, g, A, n, ja, env_on, lane_on, in, u, seed, flags, out.status, cs);
+    if constexpr (A_T == 10) {
+        // the paint reads the current positions from the sets: an env that was just reset has new ones
+        if ((flags & DMFB_STEP_AUTO_RESET) && __any_sync(kFull, o.do_reset)) {
+            __syncwarp();
+            if (lane_on && o.do_reset)
+                cs.put(0, 1, g.i, o.word & 255u, (o.word >> 8) & 255u, 128u + (uint32_t)(cfg.fov >> 1));
+            __syncwarp();
+            cs.load_current();
+        }
+    }
     write_back_lane(st, out, o, n, ja, g.i, lane_on, leader);
     if (leader) S.flag[e] = (uint8_t)(o.do_reset ? kFlagNewTask : 0);
     const int any_frozen = __syncthreads_or(o.frozen && env_on);   // also the zero-fill / table barrier
@@ -978,7 +1106,9 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     write_avail(cfg, out, A, n0, e_valid, any_frozen, tid, (int)blockDim.x, agent, lane_on, o.frozen);
     if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) {
         // rare: only tiles in which an env was just reset scan its electrodes (updateHealth, dmfb.py:465-471)
+#ifndef DMFB_WHATIF_NOHEALTH
         if (__syncthreads_or(o.do_reset)) update_health_flagged(cfg, st, S, n0, e_valid);
+#endif
     }
 
     const uint32_t word = o.word;
@@ -989,7 +1119,7 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
         paint_agent_v01(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); }, env_blocks);
     else
         paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); },
-                                env_blocks);
+                                cs, env_blocks);
     store_tile(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
 }
 
@@ -1115,7 +1245,7 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
     bool v01 = false;
     if constexpr (FOV_T == 0) v01 = cfg.obs_version == DMFB_OBS_V01;
     if (v01) paint_agent_v01(cfg, L, S, e * A + g.i, g.i, word, on, get, env_blocks);
-    else paint_agent<FOV_T, 0>(cfg, L, S, e * A + g.i, g.i, word, on, get, env_blocks);
+    else paint_agent<FOV_T, 0>(cfg, L, S, e * A + g.i, g.i, word, on, get, CoordSets<0>(nullptr, 0), env_blocks);
     int8_t* gobs = obs + (size_t)n0 * A * L.D;
     if (n_selected == e_valid) store_tile(gobs, S.tile, (uint32_t)(e_valid * A * L.D));
     else store_rows_masked(gobs, S.tile, e_valid, A * L.D, S.flag);

@@ -98,3 +98,66 @@ class HostDMFB:
             self.close()
         except Exception:
             pass
+
+
+class HostMEDA:
+    """The MEDA hot path behind HOST buffers (meda_host_* of include/dmfb_b200.h): MEDAEnv.step / reset (meda.py:513-550)
+    for N chips with numpy arrays in and out.  `constraints` is the punish count of the step (the reference's
+    info['constraints'] is -0.6 * count)."""
+
+    n_actions = 9
+
+    def __init__(self, n_envs, width, length, n_agents, fov=19, b_degrade=False, per_degrade=0.1, obs_version=2,
+                 device=0, seed=0, env_base=0):
+        self.lib = nat.load()
+        self.cfg = nat.MedaCfg()
+        rc = self.lib.meda_cfg_init(C.byref(self.cfg), width, length, n_agents, fov, int(bool(b_degrade)),
+                                    float(per_degrade), int(obs_version))
+        if rc == 2:  # meda.py:151-154
+            raise RuntimeError("Too many droplets in the " + str(width) + "x" + str(length) + " MEDA array")
+        nat.check(rc, "meda_cfg_init")
+        self.cfg.env_base = int(env_base)
+        self.N, self.A, self.D = int(n_envs), n_agents, self.cfg.obs_dim
+        self.max_step = self.cfg.max_step
+        self.seed = int(seed)
+        self._h = C.c_void_p()
+        nat.check(self.lib.meda_host_create(C.byref(self.cfg), self.N, int(device), C.byref(self._h)), "meda_host_create")
+        N, A = self.N, self.A
+        self._pins = {k: _Pinned(self.lib, s, d) for k, (s, d) in dict(
+            actions=((N, A), np.int8), obs=((N, A, self.D), np.int8), reward=((N, A), np.float32),
+            done=((N, A), np.uint8), constraints=((N,), np.int32), success=((N,), np.uint8)).items()}
+        for k, v in self._pins.items():
+            setattr(self, k, v.array)
+        self.h2d_bytes_per_step = N * A
+        self.d2h_bytes_per_step = N * A * self.D + N * A * 4 + N * A + N * 4 + N
+
+    def _p(self, a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    def reset(self, new_chip=False, layouts=None, degrade=None):
+        lay = None if layouts is None else np.ascontiguousarray(layouts, np.uint8)
+        deg = None if degrade is None else np.ascontiguousarray(degrade, np.float64)
+        nat.check(self.lib.meda_host_reset(self._h, int(bool(new_chip)), self._p(lay), self._p(deg), self.seed,
+                                           self._p(self.obs)), "meda_host_reset")
+        return self.obs
+
+    def step(self, actions=None, draws=None, auto_reset=False):
+        if actions is not None and actions is not self.actions:
+            self.actions[...] = actions
+        u = None if draws is None else np.ascontiguousarray(draws, np.float64)
+        flags = nat.STEP_AUTO_RESET if auto_reset else 0
+        nat.check(self.lib.meda_host_step(self._h, self._p(self.actions), self._p(u), self.seed, flags,
+                                          self._p(self.obs), self._p(self.reward), self._p(self.done),
+                                          self._p(self.constraints), self._p(self.success)), "meda_host_step")
+        return self.obs, self.reward, self.done.view(np.bool_), {"constraints": self.constraints, "success": self.success}
+
+    def close(self):
+        if self._h:
+            self.lib.meda_host_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

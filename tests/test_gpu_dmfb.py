@@ -645,7 +645,7 @@ def test_task_prefetch_is_transparent(W, L, A, fov, nb):
     run(2 * (W + L) + 20, "fused resets")
     # the searches do finish ahead of time (the goal-biased policy here ends episodes after ~15 steps and a warp of 8
     # 4-droplet envs advances one search per step, so not every env is ready at any one moment)
-    assert ready_seen > (0.75 if (A == 4 and nb == 0) or A == 10 else 0.2) * N
+    assert ready_seen > (0.75 if (A == 4 and nb == 0) else 0.2) * N
     assert torch.equal(a.reset(), b.reset()) and torch.equal(a.drop, b.drop)          # explicit reset picks them up too
     run(25, "after reset-all")
     mask = (torch.arange(N, device="cuda:0") % 3 == 0).to(torch.uint8)

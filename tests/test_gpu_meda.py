@@ -292,3 +292,30 @@ def test_meda_listed_auto_reset_equals_masked_reset(ver, deg, A, W, L):
             assert torch.equal(a.health, b.health) and torch.equal(b.health, c.health), f"t{t} health"
     assert n_resets > N
     assert torch.equal(a.usage_counts(), b.usage_counts()) and torch.equal(b.usage_counts(), c.usage_counts())
+
+
+@pytest.mark.parametrize("n_envs,W,L,A,ver,deg", [(500, 30, 60, 4, 0, False), (200, 30, 60, 4, 2, True), (64, 80, 80, 10, 2, False)])
+def test_meda_host_buffer_path_equals_device_path(n_envs, W, L, A, ver, deg):
+    """meda_host_step / meda_host_reset (host buffers in and out, the reference-facing call shape of MEDAEnv.step,
+    meda.py:513-550) return exactly what the device-resident API returns, through fused auto-resets and with the
+    CPython-set order table the handle builds for more than 8 droplets."""
+    P = pkg()
+    rng = np.random.default_rng(n_envs)
+    dev = P.BatchedMEDA(n_envs, W, L, A, fov=19, obs_version=ver, b_degrade=deg, per_degrade=1.0, device="cuda:0", seed=31)
+    host = P.HostMEDA(n_envs, W, L, A, fov=19, obs_version=ver, b_degrade=deg, per_degrade=1.0, device=0, seed=31)
+    o_dev = _np(dev.reset(new_chip=True))
+    for _ in range(int(dev.episode[0])):       # tasks are keyed by (seed, env, episode): same number of resets
+        o_host = host.reset(new_chip=True)
+    np.testing.assert_array_equal(o_host, o_dev)
+    for t in range(W + L + 10):
+        acts = rng.integers(0, 9, (n_envs, A)).astype(np.int8)
+        draws = rng.random((n_envs, A)) if deg else None
+        o, r, d, info = dev.step(torch.as_tensor(acts, device="cuda:0"), draws=draws, auto_reset=True)
+        ho, hr, hd, hinfo = host.step(acts, draws=draws, auto_reset=True)
+        np.testing.assert_array_equal(ho, _np(o), err_msg=f"obs t{t}")
+        np.testing.assert_array_equal(hr, _np(r), err_msg=f"reward t{t}")
+        np.testing.assert_array_equal(hd, _np(d), err_msg=f"done t{t}")
+        np.testing.assert_array_equal(hinfo["constraints"], _np(info["constraints"]))
+        np.testing.assert_array_equal(hinfo["success"], _np(info["success"]))
+    assert int(dev.episode.max()) > int(dev.episode.min()) or int(dev.episode.max()) > 1   # resets did happen
+    host.close()

@@ -1,12 +1,14 @@
 #!/bin/bash
 # ncu captures of the DMFB step kernel at benchmark size (run under gpurun; reports land in gpurun_out/).
-# usage: tools/ncu_capture.sh <tag> [c1 c2 c3 ...]; c1 = fused auto-reset as bench.py issues it, others without reset
+# usage: tools/ncu_capture.sh <tag> [c1 c2 c3 c2r c3r ...]; c1 = fused auto-reset as bench.py issues it, c2 / c3 without
+# reset, c2r / c3r with fused auto-reset and staggered episodes
 set -u
 tag=$1; shift
 for c in "$@"; do
   mode=""; [ "$c" != "c1" ] && mode="noreset"
-  python tools/prof_step.py $c 14 $mode > gpurun_out/plain_$c.log 2>&1 &&
+  cfg=$c; case "$c" in *r) cfg=${c%r}; mode="";; esac
+  python tools/prof_step.py $cfg 14 $mode > gpurun_out/plain_$c.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:dmfb_step_kernel -s 10 -c 2 \
-      -f -o gpurun_out/${tag}_step_$c python tools/prof_step.py $c 14 $mode > gpurun_out/ncu_$c.log 2>&1
+      -f -o gpurun_out/${tag}_step_$c python tools/prof_step.py $cfg 14 $mode > gpurun_out/ncu_$c.log 2>&1
   echo "$c rc=$?"
 done
