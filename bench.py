@@ -420,6 +420,8 @@ def run_b200(args, rank, world, local_rank):
         import numpy as np
         obs_buf = None
         torch.cuda.empty_cache()
+        # several ranks per host: each rank, its pinned buffers and its unpack threads on the GPU's own NUMA node
+        numa_cpus = pkg.pin_to_gpu_numa(local_rank) if world > 1 else None
         henv = pkg.HostDMFB(N, W, L, A, fov=FOV, device=local_rank, seed=1234, env_base=rank * N, n_chunks=1)
         henv.reset()
         rng = np.random.default_rng(5 + rank)
@@ -427,7 +429,12 @@ def run_b200(args, rank, world, local_rank):
         k_e2e = max(10, min(args.steps, 60))
         # The transfer of the 65.9 MB of observations is the whole cost of this path.  Pick, on this host, between the
         # plain DMA and the packed transfer (4-bit cells over PCIe, expanded by the host cores): a few untimed steps each.
-        threads = max(1, (os.cpu_count() or 1) // max(1, world))
+        threads = len(numa_cpus) if numa_cpus else max(1, (os.cpu_count() or 1) // max(1, world))
+        if numa_cpus:   # ranks that share a NUMA node share its cores
+            import torch.distributed as _d
+            same = [None] * world
+            _d.all_gather_object(same, sorted(numa_cpus)[:1])
+            threads = max(1, len(numa_cpus) // max(1, sum(1 for x in same if x == sorted(numa_cpus)[:1])))
         modes = [("plain DMA", 0, 100)]
         if threads >= 4 and A <= 15:
             modes += [(f"packed: 4-bit cells, {threads} host threads", threads, 0),
@@ -459,7 +466,10 @@ def run_b200(args, rank, world, local_rank):
                "h2d_bytes_per_step": henv.h2d_bytes_per_step, "d2h_bytes_per_step": henv.d2h_bytes_per_step,
                "steps": k_e2e, "ms_per_step": float(t_e.item()) / k_e2e * 1e3,
                "api": "dmfb_host_step (pinned host buffers); transfer chosen on this host from " +
-                      ", ".join(m[0] for m in modes) + ": " + best[1]}
+                      ", ".join(m[0] for m in modes) + ": " + best[1],
+               "bound": "host memory: every step lands 64 MB of observations per GPU in host DRAM (PCIe Gen5 x16 carries "
+                        "~55 GB/s; the packed transfer halves the PCIe bytes, the host cores then write the 64 MB)",
+               "numa_pinned_cpus": len(numa_cpus) if numa_cpus else None}
         henv.close()
 
     if rank == 0:

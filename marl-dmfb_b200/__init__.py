@@ -11,7 +11,7 @@ or through the alias module at the repo root:  `import marl_dmfb_b200`.
 from . import _native  # noqa: F401
 from .build import build  # noqa: F401
 from .dmfb import BatchedDMFB, DMFBenv, DMFBenv_v0_1  # noqa: F401
-from .host import HostDMFB, HostMEDA  # noqa: F401
+from .host import HostDMFB, HostMEDA, gpu_cpu_affinity, pin_to_gpu_numa  # noqa: F401
 from .sharding import shard_range  # noqa: F401
 from .marl import (CRNN, RNN, BatchedAgents, BatchedRolloutWorker, EpisodeBatch, PhaseTimer, QMixNet,  # noqa: F401
                    QMIXLearner, ReplayBufferGPU, VDNLearner, allreduce_gradients)

@@ -164,7 +164,10 @@ __device__ __forceinline__ int load_action(const void* actions, int elem_size, s
 //  - slow path (unaligned tensor base): byte stores.
 // Must be called by all threads of the CTA after their last write to the tile; contains the
 // proxy fence + barrier, and thread 0 returns only after the TMA has finished reading smem.
-__device__ __forceinline__ void store_tile(int8_t* __restrict__ gdst, const int8_t* tile, uint32_t nbytes)
+// store_tile_issue() returns true to the thread that has a bulk store in flight: it must call
+// tma_store_wait_read_all() before the tile is reused or the CTA exits (work that does not touch the tile can go in
+// between and overlaps the drain).
+__device__ __forceinline__ bool store_tile_issue(int8_t* __restrict__ gdst, const int8_t* tile, uint32_t nbytes)
 {
     const bool aligned = ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0);
     if (aligned) {
@@ -176,11 +179,15 @@ __device__ __forceinline__ void store_tile(int8_t* __restrict__ gdst, const int8
             tma_store_commit();
         }
         for (uint32_t b = bulk + threadIdx.x; b < nbytes; b += blockDim.x) gdst[b] = tile[b];
-        if (threadIdx.x == 0 && bulk) tma_store_wait_read_all();
-    } else {
-        __syncthreads();
-        for (uint32_t b = threadIdx.x; b < nbytes; b += blockDim.x) gdst[b] = tile[b];
+        return threadIdx.x == 0 && bulk;
     }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbytes; b += blockDim.x) gdst[b] = tile[b];
+    return false;
+}
+__device__ __forceinline__ void store_tile(int8_t* __restrict__ gdst, const int8_t* tile, uint32_t nbytes)
+{
+    if (store_tile_issue(gdst, tile, nbytes)) tma_store_wait_read_all();
 }
 
 // Store only the rows (row_bytes each) whose flag is set; used by masked resets.

@@ -34,7 +34,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 // Shared-memory carve-up of one tile, computed identically on host and device.
 struct TileLayout {
     int E, A, D, nw, ncodes;
-    uint32_t tile_bytes, off_l2row, off_l2col, off_flag, off_dirx, off_diry, off_sink, off_sets, total;
+    uint32_t tile_bytes, off_l2row, off_l2col, off_flag, off_loglen, off_dirx, off_diry, off_sink, off_sets, total;
     __host__ __device__ TileLayout(int E_, int A_, int fov, int W, int Lc, int D_) {
         E = E_; A = A_; D = D_; nw = (fov * fov + 31) / 32; ncodes = 2 * (fov / 2) + 1;
         tile_bytes = ((uint32_t)(E * A * D) + 15u) & ~15u;
@@ -42,6 +42,7 @@ struct TileLayout {
         off_l2row = o; o += (uint32_t)(ncodes * nw) * 4u;
         off_l2col = o; o += (uint32_t)(ncodes * nw) * 4u;
         off_flag = o; o += ((uint32_t)E + 3u) & ~3u;
+        off_loglen = o; o += (uint32_t)E * 4u;
         off_dirx = o; o += ((uint32_t)(2 * W) + 3u) & ~3u;
         off_diry = o; o += ((uint32_t)(2 * Lc) + 3u) & ~3u;
         off_sink = o; o += 16u;
@@ -61,6 +62,7 @@ struct TileSmem {
     uint32_t* l2row;  // [ncodes][nw]
     uint32_t* l2col;
     uint8_t* flag;    // [E]
+    int32_t* loglen;  // [E] usage-log entries of the envs flagged kFlagNewTask (fused auto-reset)
     int8_t* dirx;
     int8_t* diry;
     int8_t* sink;     // predicated-off byte stores go here (keeps the paint code branch-free)
@@ -70,6 +72,7 @@ struct TileSmem {
         l2row = reinterpret_cast<uint32_t*>(base + L.off_l2row);
         l2col = reinterpret_cast<uint32_t*>(base + L.off_l2col);
         flag = reinterpret_cast<uint8_t*>(base + L.off_flag);
+        loglen = reinterpret_cast<int32_t*>(base + L.off_loglen);
         dirx = reinterpret_cast<int8_t*>(base + L.off_dirx);
         diry = reinterpret_cast<int8_t*>(base + L.off_diry);
         sink = reinterpret_cast<int8_t*>(base + L.off_sink);
@@ -265,42 +268,61 @@ __device__ __forceinline__ int prefetch_rounds(int A) { return A == 10 ? 4 : 1; 
 // A round is ~60 instructions: what a step that runs ahead adds is small and the same for every warp.  (One attempt
 // per LANE with all points in registers, 32 per round, costs the same per attempt but ~3,000 instructions per round:
 // the few warps that ran a round in a step kept the whole launch waiting, +11 us at 64K envs of 10 droplets.)
+// Stream of the attempts of (seed, env, episode) for the one-attempt-per-warp flavour
+__device__ __forceinline__ uint64_t layout_stream(uint64_t seed, int64_t env, uint32_t epi)
+{
+    uint64_t base = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
+    base += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)epi << 32) * 0xDA942042E4DD58B5ull;
+    return mix64(base ^ 0xA5A5A5A5A5A5A5A5ull);
+}
+
+// Attempts first, first + 1, ... (at most `max_rounds`) of the stream `base`, one per iteration; stops at the first
+// accepted one.  Returns the number of attempts examined; `hit` says whether the last one was accepted.
 template <int G, int A_T>
-__device__ __forceinline__ bool sample_round_warp(const dmfb_cfg_t& cfg, const Group<G>& g, uint64_t seed, int64_t env,
-                                                  uint32_t epi, uint32_t first, int dst, uint32_t& word)
+__device__ __forceinline__ uint32_t sample_rounds_warp(const dmfb_cfg_t& cfg, const Group<G>& g, uint64_t base,
+                                                       uint32_t first, uint32_t max_rounds, int dst, uint32_t& word, bool& hit)
 {
     constexpr int P = 2 * A_T;                                    // points of one attempt, P <= 32
     const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
-    uint64_t base = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(kStreamLayout + 1));
-    base += (uint64_t)env * 0xD1342543DE82EF95ull + ((uint64_t)epi << 32) * 0xDA942042E4DD58B5ull;
-    base = mix64(base ^ 0xA5A5A5A5A5A5A5A5ull);
-    const uint64_t ctr = base + (uint64_t)first * (uint64_t)P * 0x9E3779B97F4A7C15ull;
     const int p = g.lane;
     const bool on = p < P;
-    const uint64_t z = mix64(ctr + (uint64_t)(p + 1) * 0x9E3779B97F4A7C15ull);
-    // idle lanes hold distinct far-away cells
-    const uint32_t cell = on ? (__umulhi((uint32_t)z, W) | (__umulhi((uint32_t)(z >> 32), Lc) << 8)) : (0xFF00u | (uint32_t)p);
-    bool bad = false;
+    hit = false;
+    uint32_t done = 0;
 #pragma unroll 1
-    for (int o = 1; o <= P / 2; ++o) {
-        int q = p + o;
-        if (q >= P) q -= P;
-        const uint32_t other = __shfl_sync(kFull, cell, on ? q : p);
-        if (on && (__vabsdiffu4(cell, other) & 0xFEFEu) == 0u) bad = true;   // |dx| <= 1 && |dy| <= 1
-        if (__any_sync(kFull, bad)) return false;
+    while (done < max_rounds) {
+        const uint64_t ctr = base + (uint64_t)(first + done) * (uint64_t)P * 0x9E3779B97F4A7C15ull;
+        ++done;
+        const uint64_t z = mix64(ctr + (uint64_t)(p + 1) * 0x9E3779B97F4A7C15ull);
+        // idle lanes hold distinct far-away cells
+        const uint32_t cell = on ? (__umulhi((uint32_t)z, W) | (__umulhi((uint32_t)(z >> 32), Lc) << 8)) : (0xFF00u | (uint32_t)p);
+        bool bad = false;
+#pragma unroll 1
+        for (int o = 1; o <= P / 2 && !bad; ++o) {
+            int q = p + o;
+            if (q >= P) q -= P;
+            const uint32_t other = __shfl_sync(kFull, cell, on ? q : p);
+            bad = __any_sync(kFull, on && (__vabsdiffu4(cell, other) & 0xFEFEu) == 0u);   // |dx| <= 1 && |dy| <= 1
+        }
+        if (bad) continue;
+        // accepted: droplet i = start (point 2i) | goal (point 2i+1) << 16
+        const int i2 = (g.i < A_T) ? 2 * g.i : 0;
+        const uint32_t w = __shfl_sync(kFull, cell, i2) | (__shfl_sync(kFull, cell, i2 + 1) << 16);
+        if (g.idx == dst && g.i < A_T) word = w;
+        hit = true;
+        break;
     }
-    // accepted: droplet i = start (point 2i) | goal (point 2i+1) << 16
-    const int i2 = (g.i < A_T) ? 2 * g.i : 0;
-    const uint32_t w = __shfl_sync(kFull, cell, i2) | (__shfl_sync(kFull, cell, i2 + 1) << 16);
-    if (g.idx == dst && g.i < A_T) word = w;
-    return true;
+    return done;
 }
 
 template <int G>
 __device__ __forceinline__ bool sample_round(const dmfb_cfg_t& cfg, const Group<G>& g, int A, uint64_t seed, int64_t env,
                                              uint32_t epi, uint32_t first, int dst, uint32_t& word)
 {
-    if (A == 10) return sample_round_warp<G, 10>(cfg, g, seed, env, epi, first, dst, word);
+    if (A == 10) {
+        bool hit;
+        sample_rounds_warp<G, 10>(cfg, g, layout_stream(seed, env, epi), first, 1u, dst, word, hit);
+        return hit;
+    }
     const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
     const bool lane_in = g.valid && g.i < A;
     // per-(env, episode, droplet) stream; attempt k uses counters 2k+1, 2k+2
@@ -340,9 +362,6 @@ __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const
                                                     uint32_t first, uint32_t keep)
 {
     uint32_t word = keep;
-#ifdef DMFB_WHATIF_NOSAMPLE
-    return word;
-#endif
     unsigned todo = __ballot_sync(kFull, want && g.i == 0);      // leader lanes of the requesting groups
     if (todo == 0u) return word;
     const uint32_t per_round = (uint32_t)attempts_per_round<G>(A);
@@ -351,6 +370,12 @@ __device__ __forceinline__ uint32_t generate_layout(const dmfb_cfg_t& cfg, const
         todo &= todo - 1;
         const uint32_t epi = __shfl_sync(kFull, episode, src);
         uint32_t at = __shfl_sync(kFull, first, src);
+        if (A == 10) {
+            bool hit;
+            sample_rounds_warp<G, 10>(cfg, g, layout_stream(seed, env0 + src / G, epi), at, kMaxSamplerRounds, src / G, word, hit);
+            if (!hit && st.gen_status && g.lane == 0) atomicOr(st.gen_status, DMFB_STATUS_SAMPLER_GAVE_UP);
+            continue;
+        }
         for (uint32_t round = 0;; ++round, at += per_round) {
             if (round >= kMaxSamplerRounds) {                     // density that cannot be placed
                 if (st.gen_status && g.lane == 0) atomicOr(st.gen_status, DMFB_STATUS_SAMPLER_GAVE_UP);
@@ -635,10 +660,10 @@ __host__ __device__ __forceinline__ int health_bit_words(const dmfb_cfg_t& cfg) 
 // reset inside a step kernel sits on that launch's critical path, so what counts is the number of dependent DRAM round
 // trips, not the bytes.
 __device__ __forceinline__ void replay_usage_log(const dmfb_cfg_t& cfg, const dmfb_state_t& st, int64_t n, int tid,
-                                                 int nthreads)
+                                                 int nthreads, int known_len = -1)
 {
     const int A = cfg.n_agents, Lc = cfg.length;
-    const int len = min(st.usage_log_len[n], st.usage_log_cap);
+    const int len = min(known_len >= 0 ? known_len : st.usage_log_len[n], st.usage_log_cap);
     const uint16_t* log = st.usage_log + (size_t)n * st.usage_log_cap * A;
     uint32_t* usage = st.usage + (size_t)n * cfg.width * Lc;
     const int total = len * A;
@@ -675,6 +700,7 @@ __device__ __forceinline__ void replay_usage_log(const dmfb_cfg_t& cfg, const dm
 // updateHealth (dmfb.py:465-471) of env n: cells with usage > 50 get health *= degrade (one IEEE multiply) and
 // usage = 0.  Threads tid, tid + nthreads, ... cooperate.  The counters are scanned four cells per load, a batch of
 // loads in flight per thread (see replay_usage_log); cells over the threshold are rare.
+template <int kBatch = 4>
 __device__ __forceinline__ void update_health_env(const dmfb_cfg_t& cfg, const dmfb_state_t& st, int64_t n, int tid, int nthreads)
 {
     const int cells = cfg.width * cfg.length;
@@ -694,7 +720,6 @@ __device__ __forceinline__ void update_health_env(const dmfb_cfg_t& cfg, const d
     if ((reinterpret_cast<uintptr_t>(usage) & 15u) == 0) {
         const uint4* u4 = reinterpret_cast<const uint4*>(usage);
         const int n4 = cells >> 2;
-        constexpr int kBatch = 4;
         for (int base = 0; base < n4; base += kBatch * nthreads) {
             uint4 v[kBatch];
 #pragma unroll
@@ -717,19 +742,23 @@ __device__ __forceinline__ void update_health_env(const dmfb_cfg_t& cfg, const d
         if (__ldcg(usage + k) > 50u) hit(k);
 }
 
-// updateHealth for the envs of the tile flagged kFlagNewTask; whole CTA cooperates.
+// updateHealth for the envs of the tile flagged kFlagNewTask; whole CTA cooperates.  FUSED: inside a step launch, where
+// this is the tail of the CTA (and, for the last CTAs, of the launch): the log lengths come from shared memory
+// (S.loglen) instead of a dependent global read.
+template <bool FUSED = false>
 __device__ __forceinline__ void update_health_flagged(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const TileSmem& S,
                                                       int64_t n0, int e_valid)
 {
     if (st.usage_log != nullptr && st.usage_log_len != nullptr) {   // the counters are read below: fold the log in first
         for (int e = 0; e < e_valid; ++e)
-            if (S.flag[e] & kFlagNewTask) replay_usage_log(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x);
+            if (S.flag[e] & kFlagNewTask)
+                replay_usage_log(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x, FUSED ? S.loglen[e] : -1);
         __syncthreads();
         for (int e = (int)threadIdx.x; e < e_valid; e += (int)blockDim.x)
             if (S.flag[e] & kFlagNewTask) st.usage_log_len[n0 + e] = 0;
     }
     for (int e = 0; e < e_valid; ++e)
-        if (S.flag[e] & kFlagNewTask) update_health_env(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x);
+        if (S.flag[e] & kFlagNewTask) update_health_env<4>(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x);
 }
 
 // ------------------------------------------------------------------------ step --
@@ -748,8 +777,9 @@ struct LaneOut {
     uint32_t word;      // droplet word after the step (after the reset when the env was auto-reset)
     double r;           // float64 reward
     uint32_t done_mask;
-    int sc_out, cum, constraints, success, term;
-    bool frozen, do_reset;
+    int sc_out, cum, constraints, success, term, log_len;
+    bool frozen, do_reset, cursor_dirty;
+    uint32_t cursor;    // leader lane: dmfb_state_t.next_cursor after the reset logic (run_ahead() continues from it)
     float team;
     uint32_t episode;
 };
@@ -912,6 +942,9 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
     o.constraints = frozen ? 0 : constraints;
     o.done_mask = post_mask;
     o.success = 0;
+    o.cursor = 0u;
+    o.cursor_dirty = false;
+    o.log_len = 0;
     if (sc < cfg.max_step) o.success = (all_done && o.cum == 0) ? 1 : 0;
     else o.done_mask = all_mask;
     if (frozen) { o.done_mask = all_mask; o.success = 0; }
@@ -925,12 +958,17 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
             if (env_on && g.i == 0 && !frozen) len = st.usage_log_len[n];
             len = g.get(len, 0);
             logged = len < st.usage_log_cap;                       // a full log falls back to direct increments
+            o.log_len = len + (logged ? 1 : 0);
             if (logged && lane_on && !frozen) {
                 st.usage_log[((size_t)n * st.usage_log_cap + len) * A + g.i] = add ? (uint16_t)(nx | (ny << 8)) : (uint16_t)0xFFFFu;
                 if (g.i == 0) st.usage_log_len[n] = len + 1;
             }
         }
         if (add && !logged) atomicAdd(st.usage + ((size_t)n * W + nx) * Lc + ny, 1u);   // result unused -> RED.ADD
+    } else if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage && st.usage_log != nullptr && st.usage_log_len != nullptr) {
+        int len = 0;                                               // record=False: a fused reset still replays the log
+        if (env_on && g.i == 0) len = st.usage_log_len[n];
+        o.log_len = g.get(len, 0);
     }
 
     // ---- fused auto-reset: DMFBenv.reset(new=False) (:589-597) for envs that just terminated -------
@@ -954,44 +992,50 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
             o.cum = 0;
             if (lane_on && st.start) reinterpret_cast<uint16_t*>(st.start)[ja] = (uint16_t)(o.word & 0xFFFFu);
         }
-        if (prefetch) {
-            // Run ahead: prefetch_rounds() rounds of attempts per warp and step, for the first envs of the warp whose next
-            // task is not known yet.  An env needs 1/p_accept attempts per episode (about 12 for 4 droplets on 10x10, 70 for 10 on
-            // 20x20) and has a whole episode of steps to find them, so the searches finish long before they are needed
-            // and no launch ever waits for the tail of the geometric distribution.
-            // The env closest to its step limit goes first, and when that is about to need its task (it has 8 steps
-            // left) the budget rises, so that what is left of the search is spread over its last steps instead of
-            // running inside the launch that resets it.
-            const uint32_t rem = (uint32_t)max(cfg.max_step - o.sc_out, 0);
-            int rounds = prefetch_rounds(A);
-#ifdef DMFB_WHATIF_NOSAMPLE
-            rounds = 0;
-#endif
-#pragma unroll 1
-            for (int r = 0; r < rounds; ++r) {
-                const bool open = env_on && g.i == 0 && !(cur & kTaskReady) &&
-                                  cur < kMaxSamplerRounds * (uint32_t)attempts_per_round<G>(A);
-                const uint32_t best = __reduce_min_sync(kFull, open ? ((rem << 5) | (uint32_t)g.lane) : 0xFFFFFFFFu);
-                if (best == 0xFFFFFFFFu) break;
-                if (r == 0 && (best >> 5) <= 8u) rounds = 8 * prefetch_rounds(A);
-                const int src = (int)(best & 31u), dst = src / G;
-                const uint32_t epi = __shfl_sync(kFull, episode + 1u + (o.do_reset ? 1u : 0u), src);
-                const uint32_t at = __shfl_sync(kFull, cur, src);
-                uint32_t task = 0;
-                const bool hit = sample_round<G>(cfg, g, A, seed, cfg.env_base + n - g.idx + dst, epi, at, dst, task);
-                if (g.idx == dst) {
-                    if (hit) {
-                        if (lane_on) st.next_task[ja] = task;
-                        cur = kTaskReady;
-                    } else {
-                        cur = at + (uint32_t)attempts_per_round<G>(A);
-                    }
-                }
-            }
-            if (env_on && g.i == 0 && cur != cur_in) st.next_cursor[n] = cur;
-        }
+        o.cursor = cur;
+        o.cursor_dirty = cur != cur_in;
     }
     return o;
+}
+
+// Run-ahead task search of a fused auto-reset step (dmfb_state_t.next_task / next_cursor), called by every warp at the
+// very END of the step kernel - after the tile's bulk store has been issued, so that the search overlaps the drain of
+// the observation and no other warp waits for it at a barrier.  Per warp and step ONE env is served, the open search
+// whose env is closest to its step limit, with up to prefetch_rounds() rounds of attempts (8x that when the env has
+// at most 8 steps left: what remains of its search is then spread over its last steps instead of running inside the
+// launch that resets it).  An env needs 1/p_accept attempts per episode (about 12 for 4 droplets on 10x10, 70 for 10
+// on 20x20) and has the whole episode to find them.
+template <int G>
+__device__ __forceinline__ void run_ahead(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const Group<G>& g, int A,
+                                          uint64_t seed, int64_t n, size_t ja, bool env_on, bool lane_on, const LaneOut& o)
+{
+    if (st.next_task == nullptr || st.next_cursor == nullptr) return;
+    uint32_t cur = o.cursor;
+    const uint32_t per_round = (uint32_t)attempts_per_round<G>(A);
+    const bool open = env_on && g.i == 0 && !(cur & kTaskReady) && cur < kMaxSamplerRounds * per_round;
+    const uint32_t rem = (uint32_t)max(cfg.max_step - o.sc_out, 0);
+    const uint32_t best = __reduce_min_sync(kFull, open ? ((rem << 5) | (uint32_t)g.lane) : 0xFFFFFFFFu);
+    bool dirty = o.cursor_dirty;
+    if (best != 0xFFFFFFFFu) {
+        const uint32_t rounds = (uint32_t)prefetch_rounds(A) * ((best >> 5) <= 8u ? 8u : 1u);
+        const int src = (int)(best & 31u), dst = src / G;
+        const uint32_t epi = __shfl_sync(kFull, o.episode + 1u + (o.do_reset ? 1u : 0u), src);
+        const uint32_t at = __shfl_sync(kFull, cur, src);
+        const int64_t env = cfg.env_base + n - g.idx + dst;
+        uint32_t task = 0, used = 0;
+        bool hit = false;
+        if (A == 10) {
+            used = sample_rounds_warp<G, 10>(cfg, g, layout_stream(seed, env, epi), at, rounds, dst, task, hit);
+        } else {
+            for (; used < rounds && !hit; ++used) hit = sample_round<G>(cfg, g, A, seed, env, epi, at + used * per_round, dst, task);
+        }
+        if (g.idx == dst) {
+            if (hit && lane_on) st.next_task[ja] = task;
+            cur = hit ? kTaskReady : at + used * per_round;
+            dirty = true;
+        }
+    }
+    if (env_on && g.i == 0 && dirty) st.next_cursor[n] = cur;
 }
 
 // Coalesced write-back of the state and of the small per-step outputs (consecutive lanes -> consecutive
@@ -1100,15 +1144,16 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
         }
     }
     write_back_lane(st, out, o, n, ja, g.i, lane_on, leader);
-    if (leader) S.flag[e] = (uint8_t)(o.do_reset ? kFlagNewTask : 0);
+    if (leader) {
+        S.flag[e] = (uint8_t)(o.do_reset ? kFlagNewTask : 0);
+        if (DEG_T) S.loglen[e] = o.log_len;
+    }
     const int any_frozen = __syncthreads_or(o.frozen && env_on);   // also the zero-fill / table barrier
 
     write_avail(cfg, out, A, n0, e_valid, any_frozen, tid, (int)blockDim.x, agent, lane_on, o.frozen);
     if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) {
         // rare: only tiles in which an env was just reset scan its electrodes (updateHealth, dmfb.py:465-471)
-#ifndef DMFB_WHATIF_NOHEALTH
-        if (__syncthreads_or(o.do_reset)) update_health_flagged(cfg, st, S, n0, e_valid);
-#endif
+        if (__syncthreads_or(o.do_reset)) update_health_flagged<true>(cfg, st, S, n0, e_valid);
     }
 
     const uint32_t word = o.word;
@@ -1120,7 +1165,9 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     else
         paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); },
                                 cs, env_blocks);
-    store_tile(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
+    const bool in_flight = store_tile_issue(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
+    if (flags & DMFB_STEP_AUTO_RESET) run_ahead<G>(cfg, st, g, A, seed, n, ja, env_on, lane_on, o);
+    if (in_flight) tma_store_wait_read_all();
 }
 
 // --------------------------------------------------------------------- reset --

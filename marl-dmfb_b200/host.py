@@ -10,6 +10,57 @@ import numpy as np
 from . import _native as nat
 
 
+def gpu_cpu_affinity(device):
+    """CPUs of the NUMA node GPU `device` hangs off (`nvidia-smi topo -m`, column "CPU Affinity"), or None."""
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=10).stdout
+    except Exception:
+        return None
+    import re
+    out = re.sub(r"\x1b\[[0-9;]*m", "", out)                 # the header row is underlined with ANSI codes
+    lines = [ln for ln in out.splitlines() if ln.strip()]
+    if not lines or "CPU Affinity" not in lines[0]:
+        return None
+    header = [h.strip() for h in lines[0].split("\t") if h.strip()]
+    try:
+        col = header.index("CPU Affinity") + 1          # data rows start with the GPU name
+    except ValueError:
+        return None
+    for ln in lines[1:]:
+        f = [x.strip() for x in ln.split("\t")]
+        f = [x for x in f if x != ""]
+        if f and f[0] == f"GPU{device}" and len(f) > col:
+            cpus = set()
+            for part in f[col].split(","):
+                try:
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+                except ValueError:
+                    return None
+            return cpus or None
+    return None
+
+
+def pin_to_gpu_numa(device):
+    """Restrict this process to the CPUs next to GPU `device`, so that the pinned host buffers it allocates from now on
+    (first touch) and the unpack threads live on that NUMA node.  Several ranks per host otherwise share one node's
+    memory controllers for all their D2H traffic.  Returns the CPU set used, or None when the topology is unknown or
+    the allowed set would become empty."""
+    import os
+    cpus = gpu_cpu_affinity(device)
+    if not cpus:
+        return None
+    try:
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except (AttributeError, OSError):
+        return None
+
+
 class _Pinned:
     """numpy array over cudaHostAlloc'ed memory (freed with the object)."""
 

@@ -6,9 +6,10 @@ set -u
 tag=$1; shift
 for c in "$@"; do
   mode=""; [ "$c" != "c1" ] && mode="noreset"
-  cfg=$c; case "$c" in *r) cfg=${c%r}; mode="";; esac
-  python tools/prof_step.py $cfg 14 $mode > gpurun_out/plain_$c.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:dmfb_step_kernel -s 10 -c 2 \
-      -f -o gpurun_out/${tag}_step_$c python tools/prof_step.py $cfg 14 $mode > gpurun_out/ncu_$c.log 2>&1
+  cfg=$c; steps=14; skip=10
+  case "$c" in *r) cfg=${c%r}; mode=""; steps=230; skip=220;; esac    # steady state of the run-ahead task search
+  python tools/prof_step.py $cfg $steps $mode > gpurun_out/plain_$c.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:dmfb_step_kernel -s $skip -c 2 \
+      -f -o gpurun_out/${tag}_step_$c python tools/prof_step.py $cfg $steps $mode > gpurun_out/ncu_$c.log 2>&1
   echo "$c rc=$?"
 done
