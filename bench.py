@@ -57,6 +57,8 @@ def parse():
     p.add_argument("--no-others", action="store_true", help="skip the context timings of the other BASELINE configs")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--ref-seconds", type=float, default=20.0, help="--impl reference: wall time of the timed call")
+    p.add_argument("--sub-batches", type=int, default=4,
+                   help="the batch of every GPU is stepped as this many sub-batches on as many streams (1 = one launch per step)")
     p.add_argument("--window-ms", type=float, default=100.0, help="minimum length of one timed window")
     p.add_argument("--windows", type=int, default=7, help="timed windows; the median is reported")
     return p.parse_args()
@@ -188,7 +190,8 @@ def run_reference(args, rank, world):
 
 
 def workload_config(n_envs, world, extra=None):
-    """`config` of both arms (kept identical so that the two lines describe the same workload)."""
+    """`config` of both arms (kept identical so that the two lines describe the same workload; how each arm schedules
+    the batch - host threads there, sub-batches on streams here - goes into `extra`)."""
     slots = EP_LEN
     cfg = {"workload": f"DMFB {W}x{L} chip, {A} droplets, fov {FOV}, {n_envs} envs/GPU, random actions, "
                        f"auto-reset with staggered episode phases, obs to rotating [{slots + 1},N,A,{D}] buffer",
@@ -223,8 +226,10 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     lib = pkg._native.load()
     N = args.envs
+    K = max(1, args.sub_batches)
     env = pkg.BatchedDMFB(N, W, L, A, fov=FOV, stall=True, b_degrade=False, device=dev, seed=1234,
-                          env_base=rank * N)
+                          env_base=rank * N, sub_batches=K)
+    K = len(env._sub.ranges) if env._sub is not None else 1
     slots = EP_LEN
     obs_buf = torch.empty(slots + 1, N, A, D, dtype=torch.int8, device=dev)
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
@@ -236,9 +241,12 @@ def run_b200(args, rank, world, local_rank):
     stream = torch.cuda.Stream(device=dev)
 
     def do_steps(t0, k):
+        # consecutive steps are chained without a join: while one sub-batch waits for its own previous step to drain,
+        # the kernels of the other sub-batches keep HBM busy (marl-dmfb_b200/pipeline.py); one join at the end
         for t in range(t0, t0 + k):
             s = t % slots
-            env.step(actions[s], auto_reset=True, out=obs_buf[s + 1])
+            env.step(actions[s], auto_reset=True, out=obs_buf[s + 1], join=False)
+        env.join()
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -315,7 +323,7 @@ def run_b200(args, rank, world, local_rank):
             window_ms.append(ev0.elapsed_time(ev1))
     barrier()
     ms = statistics.median(window_ms)
-    gpu_launches = total_steps  # one fused step(+auto-reset) kernel per step, per window (graph replays included)
+    gpu_launches = total_steps * K  # one fused step(+auto-reset) kernel per sub-batch and step, per window
     _ = lib.dmfb_launch_count() - launches0
     t_all = torch.tensor([ms], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -333,28 +341,40 @@ def run_b200(args, rank, world, local_rank):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2, stream=stream):
-                for t in range(slots):
-                    env.step(actions[t], out=obs_buf[t + 1])
+                for r in range(6):
+                    for t in range(slots):
+                        env.step(actions[t], out=obs_buf[t + 1], join=False)
+                env.join()
             g2.replay()
             stream.synchronize()
             # ~0.6 s so that nvidia-smi samples clocks under load; short when the caller asked for a short run (ncu)
-            reps = 2 if args.quick else int(0.6 / (slots * 20e-6))
+            reps = 2 if args.quick else int(0.6 / (6 * slots * 20e-6))
             e0.record(stream)
             for _ in range(reps):
                 g2.replay()
             e1.record(stream)
             stream.synchronize()
-        per_launch_s = e0.elapsed_time(e1) * 1e-3 / (reps * slots)
+        per_step_s = e0.elapsed_time(e1) * 1e-3 / (reps * 6 * slots)
         alg_bytes = ALG_BYTES_PER_ENV_STEP * N
-        achieved = alg_bytes / per_launch_s / 1e9
+        achieved = alg_bytes / per_step_s / 1e9
+        # K launches (one per sub-batch) make one step of the batch; they overlap, so a launch has no duration of its own:
+        # achieved = algorithmic bytes of ALL launches of the window / the window = bytes per launch / (window / launches)
         roof = {"bound": "hbm", "kernel": "dmfb_step_kernel<fov=9,G=4,A=4,E=16,deg=false>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "alg_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "launches_timed": reps * slots}
+                "alg_bytes_per_launch": alg_bytes // K, "us_per_launch": per_step_s * 1e6 / K,
+                "launches_timed": reps * 6 * slots * K, "concurrent_launches": K,
+                "alg_bytes_per_step": alg_bytes, "us_per_step": per_step_s * 1e6,
+                "note": f"{K} launches (sub-batches of {N // K} envs on {K} streams) per step of the batch; us_per_launch = "
+                        "window / launches.  A frac a little above 1 is possible: the peak is a COPY (read + write), this "
+                        "kernel is 99 % writes"}
         tr = os.path.join(ROOT, "profiles", "traffic_step_kernel.json")
         if os.path.exists(tr):
             try:
                 with open(tr) as f:
-                    roof["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                    tj = json.load(f)
+                    # measured on whole-batch launches (one launch = one step of 65,536 envs): per step of the batch
+                    roof["traffic_per_step"] = tj.get("dram_bytes_per_launch")
+                    roof["traffic"] = tj.get("dram_bytes_per_launch") / K
             except Exception:
                 pass
     if sample_clocks:
@@ -368,7 +388,7 @@ def run_b200(args, rank, world, local_rank):
         del obs_buf
         torch.cuda.empty_cache()
 
-        def quick(make, n_act, alg_bytes, slots2=8):
+        def quick(make, n_act, alg_bytes, slots2=16):
             e2 = make()
             buf = torch.empty(slots2 + 1, e2.N, e2.A, e2.D, dtype=torch.int8, device=dev)
             acts = torch.randint(0, n_act, (slots2, e2.N, e2.A), device=dev, generator=gen, dtype=torch.int8)
@@ -379,7 +399,8 @@ def run_b200(args, rank, world, local_rank):
                 gq = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gq, stream=stream):
                     for t in range(slots2):
-                        e2.step(acts[t], out=buf[t + 1])
+                        e2.step(acts[t], out=buf[t + 1], join=False)
+                    e2.join()
                 gq.replay()
                 stream.synchronize()
                 q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -392,16 +413,17 @@ def run_b200(args, rank, world, local_rank):
             return {"us_per_step": us, "agent_steps_per_s": e2.N * e2.A / (us * 1e-6),
                     "alg_GBps": alg_bytes * e2.N / (us * 1e-6) / 1e9, "frac_of_peak": alg_bytes * e2.N / (us * 1e-6) / 1e9 / peak}
 
-        others["C2 DMFB 20x20 10d fov9"] = quick(lambda: pkg.BatchedDMFB(N, 20, 20, 10, fov=9, device=dev, seed=1), 5, 2641)
+        others["C2 DMFB 20x20 10d fov9"] = quick(lambda: pkg.BatchedDMFB(N, 20, 20, 10, fov=9, device=dev, seed=1, sub_batches=K), 5, 2641, slots2=16)
         torch.cuda.empty_cache()
         others["C3 DMFB 50x50 10d fov9 degrade"] = quick(lambda: pkg.BatchedDMFB(N, 50, 50, 10, fov=9, b_degrade=True,
-                                                                                  per_degrade=1.0, device=dev, seed=1), 5, 2761)
+                                                                                  per_degrade=1.0, device=dev, seed=1,
+                                                                                  sub_batches=K), 5, 2761, slots2=16)
         torch.cuda.empty_cache()
         # MEDA: without degradation nothing reads the usage counters, so they are not kept (BatchedMEDA default); the
         # "usage" / "degrade" lines add the counters (a 2-byte usage-log entry per droplet-step, replayed at reset)
         # and the 25-cell float64 health gather
         def meda(ver, **kw):
-            return lambda: pkg.BatchedMEDA(N, 30, 60, 4, fov=19, obs_version=ver, device=dev, seed=1, **kw)
+            return lambda: pkg.BatchedMEDA(N, 30, 60, 4, fov=19, obs_version=ver, device=dev, seed=1, sub_batches=K, **kw)
 
         others["C4 MEDA 30x60 4d fov19 (base obs, int8)"] = quick(meda(0), 9, 5897)
         torch.cuda.empty_cache()
@@ -482,6 +504,9 @@ def run_b200(args, rank, world, local_rank):
                 "repeats": repeats, "windows_ms": window_ms,
                 "config": workload_config(N, world, extra={
                     "l2": f"outputs rotate over {(slots + 1) * N * A * D / 1e9:.2f} GB > L2 (no explicit flush)",
+                    "sub_batches": f"every step of the {N} envs of a GPU is {K} launches (sub-batches of {N // K} envs on {K} "
+                                   f"streams, chained without a join inside a graph): the kernels of one sub-batch fill the "
+                                   f"bubble between two dependent launches of another",
                     "timing": f"{len(window_ms)} windows of {repeats} x {args.steps} steps = {total_steps} steps each "
                               f"(CUDA graphs of {GRAPH_STEPS} steps, GPU busy at the start event, no host sync inside), "
                               f"median window, max over ranks"}),

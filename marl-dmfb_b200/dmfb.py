@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
+from .pipeline import SubBatches, offset_ptr
 
 
 def _ptr(t):
@@ -33,7 +34,9 @@ class BatchedDMFB:
     def __init__(self, n_envs, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False,
                  per_degrade=0.1, device="cuda", seed=0, env_base=0, track_usage=None, reward_f64=False,
                  degrade=None, layouts=None, block_layouts=None, obs_version=0, usage_log=True, task_prefetch=True,
-                 health_bitmap=True):
+                 health_bitmap=True, sub_batches=1):
+        # sub_batches: K > 1 steps the batch as K sub-batches on K streams (pipeline.py): consecutive steps issued with
+        # step(..., join=False) then overlap - the results are the same, env for env
         self.lib = nat.load()
         self.cfg = nat.DmfbCfg()
         nat.check(self.lib.dmfb_cfg_init(C.byref(self.cfg), width, length, n_agents, n_blocks, fov, int(bool(stall)),
@@ -90,18 +93,8 @@ class BatchedDMFB:
         self.next_task = z(N, A, dtype=torch.int32) if self._prefetch else None
         self.next_cursor = z(N, dtype=torch.int32) if self._prefetch else None
         self.status = z(1, dtype=torch.int32)          # sticky DMFB_STATUS_* bits (illegal action, sampler gave up)
-        self.state = nat.DmfbState(
-            next_task=self.next_task.data_ptr() if self._prefetch else None,
-            next_cursor=self.next_cursor.data_ptr() if self._prefetch else None, gen_status=self.status.data_ptr(),
-            n_envs=N, usage_log_cap=self.max_step if self._usage_log else 0,
-            usage_log=self.usage_log.data_ptr() if self._usage_log else None,
-            usage_log_len=self.usage_log_len.data_ptr() if self._usage_log else None, drop=self.drop.data_ptr(), start=self.start.data_ptr(), step_count=self.step_count.data_ptr(),
-            constraints=self.constraints_cum.data_ptr(), terminated=self.terminated.data_ptr(),
-            episode=self.episode.data_ptr(), usage=self.usage.data_ptr() if track_usage else None,
-            health=self._health.data_ptr() if self.b_degrade else None,
-            health_bits=self._health_bits.data_ptr() if self._health_bits is not None else None,
-            degrade=self.degrade.data_ptr() if self.b_degrade else None,
-            blocks=self.blocks.data_ptr() if self.n_blocks else None)
+        self._track_usage = bool(track_usage)
+        self.state = self._make_state(0, N)
         # ---- per-step outputs ----
         self.obs = z(N, A, self.D, dtype=torch.int8)
         self.reward = z(N, A, dtype=torch.float32)
@@ -114,17 +107,43 @@ class BatchedDMFB:
         self.term_out = z(N, dtype=torch.uint8)
         self.padded = z(N, dtype=torch.uint8)
         self._out = self._make_out(self.obs)
+        self._sub = SubBatches(self.device, N, sub_batches) if int(sub_batches) > 1 else None
+        if self._sub is not None:
+            self._sub_cfg, self._sub_state = [], []
+            for lo, hi in self._sub.ranges:
+                cfg = nat.DmfbCfg.from_buffer_copy(self.cfg)
+                cfg.env_base = self.cfg.env_base + lo            # RNG streams are functions of the GLOBAL env index
+                self._sub_cfg.append(cfg)
+                self._sub_state.append(self._make_state(lo, hi))
+            self._sub_out = [self._make_out(self.obs, lo) for lo, _ in self._sub.ranges]
         # the reference constructor draws the degradation matrix and a first task (dmfb.py:151-155)
         self.reset(new=True, layouts=layouts, degrade=degrade, block_layouts=block_layouts)
 
     # ------------------------------------------------------------------ helpers --
-    def _make_out(self, obs):
+    def _make_state(self, lo, hi):
+        """dmfb_state_t over the envs [lo, hi) of the batch (pointers offset into the same tensors)."""
+        p = offset_ptr
+        return nat.DmfbState(
+            n_envs=hi - lo, usage_log_cap=self.max_step if self._usage_log else 0,
+            drop=p(self.drop, lo), start=p(self.start, lo), step_count=p(self.step_count, lo),
+            constraints=p(self.constraints_cum, lo), terminated=p(self.terminated, lo), episode=p(self.episode, lo),
+            usage=p(self.usage, lo) if self._track_usage else None, health=p(self._health, lo),
+            degrade=p(self.degrade, lo), blocks=p(self.blocks, lo), usage_log=p(self.usage_log, lo),
+            usage_log_len=p(self.usage_log_len, lo), next_task=p(self.next_task, lo), next_cursor=p(self.next_cursor, lo),
+            gen_status=self.status.data_ptr(), health_bits=p(self._health_bits, lo))
+
+    def _make_out(self, obs, lo=0):
+        p = offset_ptr
         return nat.DmfbOut(
-            obs=obs.data_ptr(), reward=self.reward.data_ptr(),
-            reward_f64=self.reward_f64.data_ptr() if self.reward_f64 is not None else None,
-            team_reward=self.team_reward.data_ptr(), done=self.done.data_ptr(), avail=self.avail.data_ptr(),
-            constraints=self.constraints.data_ptr(), success=self.success.data_ptr(),
-            terminated=self.term_out.data_ptr(), padded=self.padded.data_ptr(), status=self.status.data_ptr())
+            obs=p(obs, lo), reward=p(self.reward, lo), reward_f64=p(self.reward_f64, lo),
+            team_reward=p(self.team_reward, lo), done=p(self.done, lo), avail=p(self.avail, lo),
+            constraints=p(self.constraints, lo), success=p(self.success, lo),
+            terminated=p(self.term_out, lo), padded=p(self.padded, lo), status=self.status.data_ptr())
+
+    def join(self):
+        """Makes the caller's stream wait for sub-batch steps issued with join=False (no-op otherwise)."""
+        if self._sub is not None:
+            self._sub.join()
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -139,6 +158,7 @@ class BatchedDMFB:
 
     def _sync_health(self):
         if self._health_dirty:
+            self.join()
             self._health_dirty = False
             with torch.cuda.device(self.device):
                 rc = self.lib.dmfb_sync_health_bits(C.byref(self.cfg), C.byref(self.state), self._stream())
@@ -161,6 +181,7 @@ class BatchedDMFB:
         layouts: optional [N,A,4] (x, y, goal_x, goal_y) injected tasks; default: on-device generator
         equivalent to _Generate_Start_End (dmfb.py:207-226).  degrade: optional [N,W,L] float64 factors
         (only used with new=True)."""
+        self.join()
         mask_t = self._as(mask, torch.uint8, (self.N,), "mask")
         lay_t = self._as(layouts, torch.uint8, (self.N, self.A, 4), "layouts")
         deg_t = self._as(degrade, torch.float64, (self.N, self.W, self.L), "degrade")
@@ -175,6 +196,7 @@ class BatchedDMFB:
 
     def restart(self, mask=None):
         """DMFBenv.restart (dmfb.py:599-605)."""
+        self.join()
         mask_t = self._as(mask, torch.uint8, (self.N,), "mask")
         with torch.cuda.device(self.device):
             rc = self.lib.dmfb_restart(C.byref(self.cfg), C.byref(self.state), _ptr(mask_t), _ptr(self.obs),
@@ -182,7 +204,7 @@ class BatchedDMFB:
         nat.check(rc, "dmfb_restart")
         return self.obs
 
-    def step(self, actions, draws=None, record=True, freeze_terminated=False, auto_reset=False, out=None):
+    def step(self, actions, draws=None, record=True, freeze_terminated=False, auto_reset=False, out=None, join=True):
         """DMFBenv.step (dmfb.py:560-587) on every env.
 
         actions: [N,A] integer tensor (int8 / int32 / int64) on this device.
@@ -191,7 +213,10 @@ class BatchedDMFB:
         auto_reset: envs that terminate in this step are reset (new task, updateHealth) right after it;
                  their obs rows hold the first observation of the next episode.
         out:     optional int8 [N,A,D] tensor that receives the observation (e.g. a slice of an
-                 episode buffer) instead of ``self.obs``."""
+                 episode buffer) instead of ``self.obs``.
+        join:    with sub_batches > 1 only.  False leaves the sub-batch streams running, so that the next step's
+                 kernels overlap this one's; the returned tensors are then valid on the caller's stream after join()
+                 (every other method joins first).  Keep `actions` / `draws` alive until then."""
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.ascontiguousarray(actions))
         if actions.device != self.device:
@@ -209,16 +234,31 @@ class BatchedDMFB:
         else:
             obs, o = out, self._make_out(out)
         self._sync_health()
-        with torch.cuda.device(self.device):
-            rc = self.lib.dmfb_step(C.byref(self.cfg), C.byref(self.state), _ptr(actions), actions.element_size(),
-                                    _ptr(draws_t), self.seed, flags, C.byref(o), self._stream())
-        nat.check(rc, "dmfb_step")
+        if self._sub is None:
+            with torch.cuda.device(self.device):
+                rc = self.lib.dmfb_step(C.byref(self.cfg), C.byref(self.state), _ptr(actions), actions.element_size(),
+                                        _ptr(draws_t), self.seed, flags, C.byref(o), self._stream())
+            nat.check(rc, "dmfb_step")
+        else:
+            sub, es = self._sub, actions.element_size()
+            sub.fork(keep_alive=(actions, draws_t, out))
+            with torch.cuda.device(self.device):
+                for k, ((lo, hi), stream) in enumerate(zip(sub.ranges, sub.handles())):
+                    o_k = self._sub_out[k] if out is None else self._make_out(out, lo)
+                    rc = self.lib.dmfb_step(C.byref(self._sub_cfg[k]), C.byref(self._sub_state[k]),
+                                            C.c_void_p(actions.data_ptr() + lo * self.A * es), es,
+                                            None if draws_t is None else C.c_void_p(draws_t.data_ptr() + lo * self.A * 8),
+                                            self.seed, flags, C.byref(o_k), stream)
+                    nat.check(rc, "dmfb_step")
+            if join:
+                sub.join()
         info = {"constraints": self.constraints, "success": self.success, "terminated": self.term_out.view(torch.bool),
                 "team_reward": self.team_reward, "padded": self.padded.view(torch.bool)}
         return obs, self.reward, self.done.view(torch.bool), info
 
     def get_obs(self, out=None):
         """getObs() of the current state (dmfb.py:622-626), recomputed from the droplet positions."""
+        self.join()
         obs = self.obs if out is None else out
         with torch.cuda.device(self.device):
             rc = self.lib.dmfb_observe(C.byref(self.cfg), C.byref(self.state), _ptr(obs), self._stream())
@@ -227,6 +267,7 @@ class BatchedDMFB:
 
     def get_state(self, out=None):
         """getglobalobs() (dmfb.py:368-392) as int8 [N,3,W,L]."""
+        self.join()
         if out is None:
             out = torch.empty(self.N, 3, self.W, self.L, dtype=torch.int8, device=self.device)
         with torch.cuda.device(self.device):
@@ -248,6 +289,7 @@ class BatchedDMFB:
         """Raises the reference's TypeError if an illegal action was applied since the last check (dmfb.py:115-116),
         and RuntimeError if a task / obstacle generator gave up on a density that cannot be placed (the reference
         would loop for ever there, dmfb.py:212-224,246-250; the env kept its previous layout).  Device -> host sync."""
+        self.join()
         st = int(self.status.item())
         if st:
             self.status.zero_()
@@ -269,6 +311,7 @@ class BatchedDMFB:
 
     def usage_counts(self):
         """m_usage as an integer tensor (folds the usage log into the counters first)."""
+        self.join()
         if self._usage_log:
             with torch.cuda.device(self.device):
                 rc = self.lib.dmfb_flush_usage(C.byref(self.cfg), C.byref(self.state), self._stream())

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
+from .pipeline import SubBatches, offset_ptr
 
 
 def _ptr(t):
@@ -49,7 +50,7 @@ class BatchedMEDA:
 
     def __init__(self, n_envs, width, length, n_agents, fov=19, b_degrade=False, per_degrade=0.1, obs_version=2,
                  device="cuda", seed=0, env_base=0, reward_f64=False, degrade=None, layouts=None, track_usage=None,
-                 usage_log=True, reset_list=False, health_bitmap=True):
+                 usage_log=True, reset_list=False, health_bitmap=True, sub_batches=1):
         # track_usage: keep the m_usage actuation counters (addUsage, meda.py:591-598).  Nothing reads them unless the
         # chip degrades (updateHealth runs only `if self.b_degrade`, meda.py:547-548), so like BatchedDMFB the default
         # is `b_degrade`; the N=1 adapters always track them because `m_usage` is a visible attribute there.
@@ -103,19 +104,7 @@ class BatchedMEDA:
         self.reset_list = z(N, dtype=torch.int32) if reset_list else None
         self.reset_count = z(2, dtype=torch.int32) if reset_list else None
         self.gen_status = z(1, dtype=torch.int32)      # sticky DMFB_STATUS_SAMPLER_GAVE_UP
-        self.state = nat.MedaState(
-            gen_status=self.gen_status.data_ptr(),
-            reset_list=self.reset_list.data_ptr() if reset_list else None,
-            reset_count=self.reset_count.data_ptr() if reset_list else None,
-            n_envs=N, usage_log_cap=self.max_step if self._usage_log else 0,
-            usage_log=self.usage_log.data_ptr() if self._usage_log else None,
-            usage_log_len=self.usage_log_len.data_ptr() if self._usage_log else None, drop=self.drop.data_ptr(), start=self.start.data_ptr(), status=self.status.data_ptr(),
-            step_count=self.step_count.data_ptr(), fails=self.fails.data_ptr(),
-            terminated=self.terminated.data_ptr(), episode=self.episode.data_ptr(),
-            usage=self.usage.data_ptr() if self.usage is not None else None,
-            health=self._health.data_ptr() if self.b_degrade else None,
-            health_bits=self._health_bits.data_ptr() if self._health_bits is not None else None,
-            degrade=self.degrade.data_ptr() if self.b_degrade else None)
+        self.state = self._make_state(0, N)
         self.set_order = None
         if self.obs_version != nat.MEDA_OBS_BASE and A > 16:
             # the others' goals are painted in CPython-set iteration order (meda.py:862-878), served from a [2^A][A] table
@@ -133,15 +122,44 @@ class BatchedMEDA:
         self.term_out = z(N, dtype=torch.uint8)
         self.padded = z(N, dtype=torch.uint8)
         self._out = self._make_out(self.obs)
+        # sub_batches: K > 1 steps the batch as K sub-batches on K streams (pipeline.py)
+        self._sub = SubBatches(self.device, N, sub_batches) if int(sub_batches) > 1 and not reset_list else None
+        if self._sub is not None:
+            self._sub_cfg, self._sub_state = [], []
+            for lo, hi in self._sub.ranges:
+                cfg = nat.MedaCfg.from_buffer_copy(self.cfg)
+                cfg.env_base = self.cfg.env_base + lo
+                self._sub_cfg.append(cfg)
+                self._sub_state.append(self._make_state(lo, hi))
+            self._sub_out = [self._make_out(self.obs, lo) for lo, _ in self._sub.ranges]
         self.reset(new_chip=True, layouts=layouts, degrade=degrade)
 
-    def _make_out(self, obs):
+    def _make_state(self, lo, hi):
+        """meda_state_t over the envs [lo, hi) of the batch (pointers offset into the same tensors)."""
+        p = offset_ptr
+        whole = lo == 0 and hi == self.N
+        return nat.MedaState(
+            n_envs=hi - lo, usage_log_cap=self.max_step if self._usage_log else 0,
+            drop=p(self.drop, lo), start=p(self.start, lo), status=p(self.status, lo), step_count=p(self.step_count, lo),
+            fails=p(self.fails, lo), terminated=p(self.terminated, lo), episode=p(self.episode, lo),
+            usage=p(self.usage, lo), health=p(self._health, lo), degrade=p(self.degrade, lo),
+            usage_log=p(self.usage_log, lo), usage_log_len=p(self.usage_log_len, lo),
+            reset_list=self.reset_list.data_ptr() if (whole and self.reset_list is not None) else None,
+            reset_count=self.reset_count.data_ptr() if (whole and self.reset_count is not None) else None,
+            gen_status=self.gen_status.data_ptr(), health_bits=p(self._health_bits, lo))
+
+    def _make_out(self, obs, lo=0):
+        p = offset_ptr
         return nat.MedaOut(
-            obs=obs.data_ptr(), reward=self.reward.data_ptr(),
-            reward_f64=self.reward_f64.data_ptr() if self.reward_f64 is not None else None,
-            team_reward=self.team_reward.data_ptr(), done=self.done.data_ptr(), avail=self.avail.data_ptr(),
-            constraints=self.constraints.data_ptr(), success=self.success.data_ptr(),
-            terminated=self.term_out.data_ptr(), padded=self.padded.data_ptr(), status=None)
+            obs=p(obs, lo), reward=p(self.reward, lo), reward_f64=p(self.reward_f64, lo),
+            team_reward=p(self.team_reward, lo), done=p(self.done, lo), avail=p(self.avail, lo),
+            constraints=p(self.constraints, lo), success=p(self.success, lo),
+            terminated=p(self.term_out, lo), padded=p(self.padded, lo), status=None)
+
+    def join(self):
+        """Makes the caller's stream wait for sub-batch steps issued with join=False (no-op otherwise)."""
+        if self._sub is not None:
+            self._sub.join()
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -155,6 +173,7 @@ class BatchedMEDA:
 
     def _sync_health(self):
         if self._health_dirty:
+            self.join()
             self._health_dirty = False
             with torch.cuda.device(self.device):
                 rc = self.lib.meda_sync_health_bits(C.byref(self.cfg), C.byref(self.state), self._stream())
@@ -173,6 +192,7 @@ class BatchedMEDA:
     def reset(self, mask=None, layouts=None, new_chip=False, degrade=None, out=None):
         """MEDAEnv.reset (meda.py:541-550): new tasks, observation, then updateHealth.
         layouts: optional [N,A,4] (x_c, y_c, goal x_c, goal y_c) with centres in [2, dim-3]."""
+        self.join()
         mask_t = self._as(mask, torch.uint8, (self.N,), "mask")
         lay_t = self._as(layouts, torch.uint8, (self.N, self.A, 4), "layouts")
         deg_t = self._as(degrade, torch.float64, (self.N, self.W, self.L), "degrade")
@@ -187,6 +207,7 @@ class BatchedMEDA:
 
     def restart(self, mask=None):
         """MEDAEnv.restart (meda.py:552-561): droplets back to their start squares; `fails` is kept."""
+        self.join()
         mask_t = self._as(mask, torch.uint8, (self.N,), "mask")
         with torch.cuda.device(self.device):
             rc = self.lib.meda_restart(C.byref(self.cfg), C.byref(self.state), _ptr(mask_t), _ptr(self.set_order),
@@ -194,7 +215,7 @@ class BatchedMEDA:
         nat.check(rc, "meda_restart")
         return self.obs
 
-    def step(self, actions, draws=None, freeze_terminated=False, auto_reset=False, out=None):
+    def step(self, actions, draws=None, freeze_terminated=False, auto_reset=False, out=None, join=True):
         """MEDAEnv.step (meda.py:513-539) on every env; actions [N,A] in 0..8."""
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.ascontiguousarray(actions))
@@ -209,15 +230,30 @@ class BatchedMEDA:
         flags = (nat.STEP_FREEZE_TERM if freeze_terminated else 0) | (nat.STEP_AUTO_RESET if auto_reset else 0)
         obs, o = (self.obs, self._out) if out is None else (out, self._make_out(out))
         self._sync_health()
-        with torch.cuda.device(self.device):
-            rc = self.lib.meda_step(C.byref(self.cfg), C.byref(self.state), _ptr(actions), actions.element_size(),
-                                    _ptr(draws_t), self.seed, flags, _ptr(self.set_order), C.byref(o), self._stream())
-        nat.check(rc, "meda_step")
+        if self._sub is None:
+            with torch.cuda.device(self.device):
+                rc = self.lib.meda_step(C.byref(self.cfg), C.byref(self.state), _ptr(actions), actions.element_size(),
+                                        _ptr(draws_t), self.seed, flags, _ptr(self.set_order), C.byref(o), self._stream())
+            nat.check(rc, "meda_step")
+        else:       # K sub-batches on K streams; join=False lets the next step's kernels overlap these (pipeline.py)
+            sub, es = self._sub, actions.element_size()
+            sub.fork(keep_alive=(actions, draws_t, out))
+            with torch.cuda.device(self.device):
+                for k, ((lo, hi), stream) in enumerate(zip(sub.ranges, sub.handles())):
+                    o_k = self._sub_out[k] if out is None else self._make_out(out, lo)
+                    rc = self.lib.meda_step(C.byref(self._sub_cfg[k]), C.byref(self._sub_state[k]),
+                                            C.c_void_p(actions.data_ptr() + lo * self.A * es), es,
+                                            None if draws_t is None else C.c_void_p(draws_t.data_ptr() + lo * self.A * 8),
+                                            self.seed, flags, _ptr(self.set_order), C.byref(o_k), stream)
+                    nat.check(rc, "meda_step")
+            if join:
+                sub.join()
         info = {"constraints": self.constraints, "success": self.success, "terminated": self.term_out.view(torch.bool),
                 "team_reward": self.team_reward, "padded": self.padded.view(torch.bool)}
         return obs, self.reward, self.done.view(torch.bool), info
 
     def get_obs(self, out=None):
+        self.join()
         obs = self.obs if out is None else out
         with torch.cuda.device(self.device):
             rc = self.lib.meda_observe(C.byref(self.cfg), C.byref(self.state), _ptr(self.set_order), _ptr(obs),
@@ -231,6 +267,7 @@ class BatchedMEDA:
     def check(self):
         """RuntimeError if the task generator gave up since the last check (droplets that cannot be placed; the
         reference would loop for ever, meda.py:213-233; the env kept its previous layout).  Device -> host sync."""
+        self.join()
         if int(self.gen_status.item()) & nat.STATUS_SAMPLER_GAVE_UP:
             self.gen_status.zero_()
             raise RuntimeError("the task generator found no legal droplet placement for this chip")
@@ -242,6 +279,7 @@ class BatchedMEDA:
 
     def usage_counts(self):
         """m_usage (folds the usage log into the counters first)."""
+        self.join()
         if self._usage_log:
             with torch.cuda.device(self.device):
                 rc = self.lib.meda_flush_usage(C.byref(self.cfg), C.byref(self.state), self._stream())

@@ -674,3 +674,56 @@ def test_task_generator_gives_up_recoverably_on_an_impossible_density():
     ok.step(torch.zeros(64, 4, dtype=torch.int8, device="cuda:0"), auto_reset=True)
     ok.check()
     assert int(ok.step_count.max()) == 1
+
+
+@pytest.mark.parametrize("W,L,A,fov,deg,K", [(10, 10, 4, 9, False, 4), (20, 20, 10, 9, False, 2), (12, 12, 6, 5, True, 3)])
+def test_sub_batch_pipelining_is_transparent(W, L, A, fov, deg, K):
+    """BatchedDMFB(sub_batches=K) steps the batch as K sub-batches on K streams (pipeline.py).  Env for env the
+    trajectories equal the single-launch batch: same tasks (RNG streams follow the global env index), observations,
+    rewards, health - with a join after every step, with steps chained without a join, and replayed from a CUDA graph."""
+    P = pkg()
+    N = 1000                                  # not a multiple of the 64-env sub-batch unit
+    kw = dict(fov=fov, b_degrade=deg, per_degrade=1.0, device="cuda:0", seed=5, reward_f64=True)
+    a = P.BatchedDMFB(N, W, L, A, **kw)
+    b = P.BatchedDMFB(N, W, L, A, sub_batches=K, **kw)
+    assert b._sub is not None and len(b._sub.ranges) == K and b._sub.ranges[-1][1] == N
+    assert torch.equal(a.drop, b.drop) and torch.equal(a.obs, b.obs)
+    gen = torch.Generator(device="cuda:0").manual_seed(3)
+    T = 2 * (W + L)
+    acts = torch.randint(0, 5, (T + 6, N, A), device="cuda:0", generator=gen, dtype=torch.int8)
+
+    def same(tag):
+        b.join()
+        torch.cuda.synchronize()
+        assert torch.equal(a.drop, b.drop) and torch.equal(a.obs, b.obs), tag
+        assert torch.equal(a.reward_f64, b.reward_f64) and torch.equal(a.done, b.done), tag
+        assert torch.equal(a.step_count, b.step_count) and torch.equal(a.episode, b.episode), tag
+        assert torch.equal(a.constraints, b.constraints) and torch.equal(a.success, b.success), tag
+        if deg:
+            assert torch.equal(a.health, b.health) and torch.equal(a.usage_counts(), b.usage_counts()), tag
+
+    for t in range(8):                        # joined after every step
+        a.step(acts[t], auto_reset=True)
+        b.step(acts[t], auto_reset=True)
+        same(f"joined t{t}")
+    for t in range(8, T + 6):                 # chained: the sub-batch streams run ahead of each other
+        a.step(acts[t], auto_reset=True)
+        b.step(acts[t], auto_reset=True, join=False)
+    same("chained")
+    assert int(a.episode.max()) >= 2                        # fused resets did happen
+    # the same chain inside a CUDA graph (how bench.py issues it)
+    buf_a = torch.zeros(6, N, A, a.D, dtype=torch.int8, device="cuda:0")
+    buf_b = torch.zeros_like(buf_a)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for t in range(6):
+                b.step(acts[t], auto_reset=True, out=buf_b[t], join=False)
+            b.join()
+        for t in range(6):
+            a.step(acts[t], auto_reset=True, out=buf_a[t])
+        g.replay()
+        s.synchronize()
+    assert torch.equal(buf_a, buf_b) and torch.equal(a.drop, b.drop) and torch.equal(a.reward_f64, b.reward_f64)
+    assert torch.equal(b.reset(), a.reset())

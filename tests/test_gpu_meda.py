@@ -319,3 +319,24 @@ def test_meda_host_buffer_path_equals_device_path(n_envs, W, L, A, ver, deg):
         np.testing.assert_array_equal(hinfo["success"], _np(info["success"]))
     assert int(dev.episode.max()) > int(dev.episode.min()) or int(dev.episode.max()) > 1   # resets did happen
     host.close()
+
+
+def test_meda_sub_batch_pipelining_is_transparent():
+    """BatchedMEDA(sub_batches=K): K sub-batches on K streams, env for env the single-launch trajectories."""
+    P = pkg()
+    N, W, L, A = 700, 30, 60, 4
+    kw = dict(fov=19, obs_version=2, b_degrade=True, per_degrade=1.0, device="cuda:0", seed=9, reward_f64=True)
+    a = P.BatchedMEDA(N, W, L, A, **kw)
+    b = P.BatchedMEDA(N, W, L, A, sub_batches=3, **kw)
+    assert b._sub is not None and torch.equal(a.drop, b.drop) and torch.equal(a.obs, b.obs)
+    gen = torch.Generator(device="cuda:0").manual_seed(4)
+    acts = torch.randint(0, 9, (W + L + 12, N, A), device="cuda:0", generator=gen, dtype=torch.int8)
+    for t in range(acts.shape[0]):
+        a.step(acts[t], auto_reset=True)
+        b.step(acts[t], auto_reset=True, join=(t % 7 == 0))
+    b.join()
+    torch.cuda.synchronize()
+    assert torch.equal(a.drop, b.drop) and torch.equal(a.obs, b.obs) and torch.equal(a.reward_f64, b.reward_f64)
+    assert torch.equal(a.episode, b.episode) and torch.equal(a.fails, b.fails) and torch.equal(a.status, b.status)
+    assert torch.equal(a.health, b.health) and torch.equal(a.usage_counts(), b.usage_counts())
+    assert int(a.episode.max()) > 1

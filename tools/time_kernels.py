@@ -19,7 +19,9 @@ T = 2 * (c["W"] + c["L"])
 env = pkg.BatchedDMFB(N, c["W"], c["L"], c["A"], fov=c["fov"], b_degrade=c["deg"], per_degrade=1.0,
                       device="cuda:0", seed=1234, usage_log=os.environ.get("TK_USAGE_LOG", "1") != "0",
                       task_prefetch=os.environ.get("TK_PREFETCH", "1") != "0",
-                      health_bitmap=os.environ.get("TK_BITMAP", "1") != "0")
+                      health_bitmap=os.environ.get("TK_BITMAP", "1") != "0",
+                      sub_batches=int(os.environ.get("TK_SUB", "1")))
+JOIN = int(os.environ.get("TK_SUB", "1")) == 1
 slots = min(T, max(8, int(2.6e9 // (N * c["A"] * env.D))))
 obs_buf = torch.empty(slots + 1, N, c["A"], env.D, dtype=torch.int8, device="cuda:0")
 gen = torch.Generator(device="cuda:0").manual_seed(1)
@@ -45,11 +47,13 @@ def graph_time(fn, n):
     with torch.cuda.stream(s):
         for i in range(3):
             fn(i)
+        env.join()
         s.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=s):
             for i in range(n):
                 fn(i)
+            env.join()
         g.replay(); s.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(s)
@@ -61,15 +65,15 @@ def graph_time(fn, n):
 
 
 env.reset()
-us = graph_time(lambda i: env.step(actions[i % slots], out=obs_buf[i % slots + 1]), slots)
+us = graph_time(lambda i: env.step(actions[i % slots], out=obs_buf[i % slots + 1], join=JOIN), slots)
 print(f"{name} N={N}: step (no reset, graph)       {us:8.2f} us  {alg * N / us / 1e3:8.1f} GB/s alg")
 if not (len(sys.argv) > 3 and sys.argv[3] == "short"):
     env.reset()
-    us = graph_time(lambda i: env.step(actions[i % slots], auto_reset=True, out=obs_buf[i % slots + 1]), T)
+    us = graph_time(lambda i: env.step(actions[i % slots], auto_reset=True, out=obs_buf[i % slots + 1], join=JOIN), T)
     print(f"{name} N={N}: step (auto-reset, graph of T) {us:8.2f} us  {N * c['A'] / us / 1e3:8.2f} G agent-steps/s")
 env.reset()
 env.step_count.copy_(torch.arange(N, device="cuda:0", dtype=torch.int32) % T)   # stagger the episode phases
-us = graph_time(lambda i: env.step(actions[i % slots], auto_reset=True, out=obs_buf[i % slots + 1]), T)
+us = graph_time(lambda i: env.step(actions[i % slots], auto_reset=True, out=obs_buf[i % slots + 1], join=JOIN), T)
 print(f"{name} N={N}: step (auto-reset, staggered)  {us:8.2f} us  {N * c['A'] / us / 1e3:8.2f} G agent-steps/s")
 if len(sys.argv) > 3 and sys.argv[3] == "short":
     sys.exit(0)

@@ -17,7 +17,8 @@ deg = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
 W, L, A, fov = 30, 60, 4, 19
 usage = bool(int(sys.argv[4])) if len(sys.argv) > 4 else True
 env = pkg.BatchedMEDA(N, W, L, A, fov=fov, obs_version=ver, b_degrade=deg, per_degrade=1.0, device="cuda:0", seed=1,
-                      track_usage=usage)
+                      track_usage=usage, sub_batches=int(os.environ.get("TK_SUB", "1")))
+JOIN = int(os.environ.get("TK_SUB", "1")) == 1
 auto = bool(int(sys.argv[5])) if len(sys.argv) > 5 else False
 if auto:   # steady state of a long rollout: episode phases spread uniformly
     env.step_count.copy_(torch.arange(N, device="cuda:0", dtype=torch.int32) % env.max_step)
@@ -28,12 +29,14 @@ actions = torch.randint(0, 9, (slots, N, A), device="cuda:0", generator=gen, dty
 s = torch.cuda.Stream()
 with torch.cuda.stream(s):
     for i in range(3):
-        env.step(actions[i], out=obs_buf[i + 1], auto_reset=auto)
+        env.step(actions[i], out=obs_buf[i + 1], auto_reset=auto, join=JOIN)
+    env.join()
     s.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g, stream=s):
         for i in range(slots):
-            env.step(actions[i], out=obs_buf[i + 1], auto_reset=auto)
+            env.step(actions[i], out=obs_buf[i + 1], auto_reset=auto, join=JOIN)
+        env.join()
     g.replay(); s.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(s)
