@@ -370,10 +370,8 @@ __device__ __forceinline__ void meda_reset_env_warp(const meda_cfg_t& cfg, const
     if (lane == src) {
         const uint32_t episode = st.episode ? st.episode[n] + 1u : 0u;
         if (st.episode) st.episode[n] = episode;
-        uint32_t* gdrop = reinterpret_cast<uint32_t*>(st.drop) + (size_t)n * A;
-        uint32_t prev[DMFB_MAX_AGENTS];
-        for (int i = 0; i < A; ++i) prev[i] = words[i];               // the layout after the step (= what gdrop holds)
-        if (!meda_generate_tasks(cfg, seed, cfg.env_base + n, episode, words, prev) && st.gen_status)
+        uint32_t* gdrop = reinterpret_cast<uint32_t*>(st.drop) + (size_t)n * A;   // holds the layout after the step
+        if (!meda_generate_tasks(cfg, seed, cfg.env_base + n, episode, words, gdrop) && st.gen_status)
             atomicOr(st.gen_status, DMFB_STATUS_SAMPLER_GAVE_UP);
         for (int i = 0; i < A; ++i) {
             gdrop[i] = words[i];

@@ -328,6 +328,7 @@ class MEDAEnv:
         self.mode = None
         self.rewards = {a: 0.0 for a in self.agents}
         self.dones = {a: False for a in self.agents}
+        self._fails_f = 0
         self.routing_manager = _MedaRoutingView(self)
 
     # reference attributes
@@ -337,7 +338,22 @@ class MEDAEnv:
 
     @property
     def fails(self):
-        return -0.6 * int(self._b.fails[0].item())
+        """The reference's running float `self.fails += fail` (meda.py:521), accumulated in its order."""
+        return self._fails_f
+
+    def _punish_sum(self):
+        """`np.sum(calPunish())` (meda.py:256,321-330) in the reference's accumulation order: -0.6 subtracted once per
+        close pair from both droplets, then summed over the droplets - so that `info['constraints']` and `fails` are
+        the reference's floats to the last bit, not just -0.6 * count."""
+        d = self._b.drop[0, :, 0:2].cpu().numpy().astype(np.int64)
+        n = len(self.agents)
+        punish = [0] * n
+        for i in range(n - 1):
+            for j in range(i + 1, n):
+                if int(((d[i] - d[j]) ** 2).sum()) < 36:      # centre distance < 1.5 * (r_i + r_j) = 6
+                    punish[i] -= 0.6
+                    punish[j] -= 0.6
+        return np.sum(punish)
 
     @property
     def m_health(self):
@@ -379,13 +395,16 @@ class MEDAEnv:
         for k, name in enumerate(self.agents):
             self.rewards[name] = float(r[k])
             self.dones[name] = bool(d[k])
-        cnt = int(info["constraints"][0].item())
-        out_info = {"constraints": -0.6 * cnt if cnt else 0, "success": int(info["success"][0].item())}
+        fail = self._punish_sum()
+        assert round(float(fail) / -0.6) == int(info["constraints"][0].item())   # the kernel's punish count
+        self._fails_f += fail
+        out_info = {"constraints": fail, "success": int(info["success"][0].item())}
         return self._obs_list(obs), self.rewards, self.dones, out_info
 
     def reset(self, layouts=None):
         self.rewards = {a: 0.0 for a in self.agents}
         self.dones = {a: False for a in self.agents}
+        self._fails_f = 0                                         # meda.py:544
         return self._obs_list(self._b.reset(layouts=None if layouts is None else np.asarray(layouts)[None]))
 
     def restart(self, index=None):

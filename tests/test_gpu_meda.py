@@ -159,6 +159,19 @@ def test_meda_adapter_types_and_generator():
     want = np.concatenate([g["obs1_reset"][0, 0].astype(np.float64), g["dir1_reset"][0, 0]], axis=-1)
     np.testing.assert_array_equal(np.stack(obs), want)
     assert env1.get_env_info()["obs_shape"] == (4, 19, 19, 2, 1446)
+    # info['constraints'] and `fails` are the reference's FLOATS (sums of -0.6 in its accumulation order), bit for bit
+    g8 = load_golden("meda_80x80")            # 10 droplets: several close pairs per step
+    k = 0
+    envg = P.MEDAEnv_v0_2(g8["W"], g8["L"], g8["A"], fov=g8["fov"], layouts=g8["layouts"][0][k])
+    envg.reset(layouts=g8["layouts"][0][k])
+    fails, n_pun = 0, 0
+    for t in range(g8["T"]):
+        _, _, _, info = envg.step([int(x) for x in g8["actions"][0, t, k]])
+        assert info["constraints"] == g8["constraints"][0, t, k], t
+        fails += g8["constraints"][0, t, k]
+        assert envg.fails == fails
+        n_pun += int(g8["constraints"][0, t, k] != 0)
+    assert n_pun > 0
     with pytest.raises(RuntimeError, match="Too many droplets"):
         P.MEDAEnv(30, 60, 9)
     # device task generator: the reference's rejection rules (meda.py:78-81,179-182)
