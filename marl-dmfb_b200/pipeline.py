@@ -16,14 +16,21 @@ import ctypes as C
 import torch
 
 
+def sub_batch_ranges(n_envs, k, unit=64):
+    """[lo, hi) env ranges of at most k sub-batches that cover [0, n_envs); every boundary but the last is a multiple of
+    `unit` envs, which keeps each sub-batch's observation rows 16-byte aligned (the TMA bulk store needs that) and the
+    tiles of the step kernel whole."""
+    units = (n_envs + unit - 1) // unit
+    k = max(1, min(int(k), units))
+    b = [min(n_envs, (units * c // k) * unit) for c in range(k + 1)]
+    b[k] = n_envs
+    return [(b[c], b[c + 1]) for c in range(k) if b[c + 1] > b[c]]
+
+
 class SubBatches:
     def __init__(self, device, n_envs, k, unit=64):
-        units = (n_envs + unit - 1) // unit
-        k = max(1, min(int(k), units))
-        self.k = k
-        b = [min(n_envs, (units * c // k) * unit) for c in range(k + 1)]
-        b[k] = n_envs
-        self.ranges = [(b[c], b[c + 1]) for c in range(k) if b[c + 1] > b[c]]
+        self.ranges = sub_batch_ranges(n_envs, k, unit)
+        self.k = len(self.ranges)
         self.device = device
         self.streams = [torch.cuda.Stream(device=device) for _ in self.ranges]
         self.pending = False

@@ -145,3 +145,18 @@ def test_host_unpack_expands_packed_records(P, cells, n, threads):
     assert rc == 0
     np.testing.assert_array_equal(out, obs)
 
+
+
+def test_sub_batch_ranges_cover_the_batch_on_aligned_boundaries():
+    """pipeline.sub_batch_ranges: the sub-batches of BatchedDMFB / BatchedMEDA(sub_batches=K) partition [0, N), start on
+    multiples of 64 envs (16-byte aligned observation rows for any row length, whole step-kernel tiles) and never
+    outnumber the 64-env units."""
+    import importlib
+    pipe = importlib.import_module("marl-dmfb_b200.pipeline")
+    for n in (1, 63, 64, 65, 1000, 4096, 65536, 65537):
+        for k in (1, 2, 3, 4, 8, 5000):
+            r = pipe.sub_batch_ranges(n, k)
+            assert r[0][0] == 0 and r[-1][1] == n and len(r) <= max(1, min(k, (n + 63) // 64))
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:])) and all(hi > lo for lo, hi in r)
+            assert all(lo % 64 == 0 for lo, _ in r)
+    assert pipe.sub_batch_ranges(65536, 4) == [(0, 16384), (16384, 32768), (32768, 49152), (49152, 65536)]
