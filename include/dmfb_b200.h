@@ -13,8 +13,12 @@
  * Conventions
  *  - Plain C: pointers and sizes only, no torch / C++ types.
  *  - Every buffer is allocated and owned by the caller (device memory unless
- *    the function name says _host); the library keeps no global state, never
- *    allocates behind the caller's back (except the explicit dmfb_host_* handle
+ *    the function name says _host); the library keeps no state about env
+ *    batches (what it does keep per process: a launch counter, a thread-local
+ *    error string, the one-time cudaFuncSetAttribute bookkeeping of its kernels
+ *    and the tuning knobs DMFB_TILE_ENVS / DMFB_NO_PDL / MEDA_WARP_ENVS /
+ *    MEDA_WARPS_PER_CTA read once from the environment), never allocates behind
+ *    the caller's back (except the explicit dmfb_host_* / meda_host_* handle
  *    API) and never frees caller memory.
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *    Calls on one env batch are ordered by that stream; the library is

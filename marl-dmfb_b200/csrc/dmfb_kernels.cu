@@ -250,7 +250,8 @@ __host__ __device__ constexpr int cta_threads(int E, int G) { return ((E + 32 / 
 // i).  Two flavours, chosen by A alone (so every kernel instance draws the same task for the same key):
 //   A == 10  one attempt per WARP and round: lane = point, the 190 pair tests by shuffles with early exit;
 //   else     one attempt per lane GROUP, points exchanged by shuffles (32/G per round).
-constexpr uint32_t kTaskReady = 0x80000000u;   // dmfb_state_t.next_cursor: next_task holds the next episode's task
+constexpr uint32_t kTaskReady = 0x80000000u;
+constexpr uint32_t kStepNoRunAhead = 0x80000000u;   // internal step flag: the run-ahead search is a kernel of its own   // dmfb_state_t.next_cursor: next_task holds the next episode's task
 
 template <int G>
 __device__ __forceinline__ int attempts_per_round(int A) { return A == 10 ? 1 : Group<G>::kPerWarp; }
@@ -813,7 +814,7 @@ template <int G, int A_T, bool DEG_T>
 __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const Group<G>& g, int A,
                                                  int64_t n, size_t ja, bool env_on, bool lane_on, LaneIn in,
                                                  const double* __restrict__ u, uint64_t seed, uint32_t flags,
-                                                 int32_t* status_flag, CoordSets<A_T>& cs)
+                                                 int32_t* status_flag, CoordSets<A_T>& cs, const uint32_t* env_bits)
 {
     const int W = cfg.width, Lc = cfg.length;
     const uint32_t all_mask = (A >= 32) ? 0xFFFFFFFFu : ((1u << A) - 1u);
@@ -825,8 +826,7 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
         const uint32_t cell = (d & 255u) * (uint32_t)Lc + ((d >> 8) & 255u);
         // a clear bit in the (L2-sized) degraded-cell map means health == 1.0 exactly: no gather from the big array
         bool degraded = true;
-        if (st.health_bits)
-            degraded = (st.health_bits[(size_t)n * health_bit_words(cfg) + (cell >> 5)] >> (cell & 31u)) & 1u;
+        if (env_bits) degraded = (env_bits[cell >> 5] >> (cell & 31u)) & 1u;
         if (degraded) prob = st.health[(size_t)n * W * Lc + cell];
     }
     const int sc_in = g.get(in.sc_in, 0);
@@ -1132,7 +1132,12 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     }
 
     CoordSets<A_T> cs(S.sets, env_on ? e : 0);
-    const LaneOut o = dmfb_dynamics<G, A_T, DEG_T>(cfg, st, g, A, n, ja, env_on, lane_on, in, u, seed, flags, out.status, cs);
+    // degraded-cell bit map of this lane's env.  (Staging the maps of a warp's envs in shared memory with one coalesced
+    // load was measured and dropped: C3 47.3 -> 48.4 us fresh, 64.5 -> 71.9 us with every cell degraded.)
+    const uint32_t* env_bits = nullptr;
+    if (DEG_T && st.health_bits && st.health) env_bits = st.health_bits + (size_t)(env_on ? n : 0) * health_bit_words(cfg);
+    const LaneOut o = dmfb_dynamics<G, A_T, DEG_T>(cfg, st, g, A, n, ja, env_on, lane_on, in, u, seed, flags, out.status, cs,
+                                                   env_bits);
     if constexpr (A_T == 10) {
         // the paint reads the current positions from the sets: an env that was just reset has new ones
         if ((flags & DMFB_STEP_AUTO_RESET) && __any_sync(kFull, o.do_reset)) {
@@ -1166,7 +1171,10 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
         paint_agent<FOV_T, A_T>(cfg, L, S, agent, g.i, word, lane_on && !o.frozen, [&](int j) { return g.get(word, j); },
                                 cs, env_blocks);
     const bool in_flight = store_tile_issue(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
-    if (flags & DMFB_STEP_AUTO_RESET) run_ahead<G>(cfg, st, g, A, seed, n, ja, env_on, lane_on, o);
+    if (flags & DMFB_STEP_AUTO_RESET) {
+        if (!(flags & kStepNoRunAhead)) run_ahead<G>(cfg, st, g, A, seed, n, ja, env_on, lane_on, o);
+        else if (leader && o.cursor_dirty && st.next_cursor) st.next_cursor[n] = o.cursor;
+    }
     if (in_flight) tma_store_wait_read_all();
 }
 
@@ -1309,6 +1317,33 @@ dmfb_flush_usage_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state
     if ((threadIdx.x & 31) == 0) st.usage_log_len[n] = 0;
 }
 
+// --------------------------------------------------------------- task search --
+// Run-ahead task search for 10 droplets as a kernel of its own, launched by dmfb_step right after a fused auto-reset
+// step: one warp per env; envs whose next task is known leave after one load, the others examine up to `rounds` attempts
+// (one attempt per warp round, sample_rounds_warp) and park an accepted task in next_task.  Whole-set rejection at 1.4 %
+// acceptance (10 droplets, 20x20) costs ~30 % of the step kernel's instructions wherever it runs; inside the step kernel
+// the warps that search also delay their CTAs (barrier, tail of the launch: C2 37 -> 75 us with staggered resets), here
+// every warp does the same bounded amount of work and the kernel overlaps the step kernels of the other sub-batches.
+__global__ void __launch_bounds__(256)
+dmfb_task_search_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, uint64_t seed, uint32_t rounds)
+{
+    const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= st.n_envs) return;
+    const Group<32> g((int)threadIdx.x);
+    uint32_t cur = 0;
+    if (g.lane == 0) cur = st.next_cursor[n];
+    cur = __shfl_sync(kFull, cur, 0);
+    if ((cur & kTaskReady) || cur >= kMaxSamplerRounds) return;
+    uint32_t epi = 0;
+    if (g.lane == 0 && st.episode) epi = st.episode[n] + 1u;
+    epi = __shfl_sync(kFull, epi, 0);
+    uint32_t task = 0;
+    bool hit = false;
+    const uint32_t used = sample_rounds_warp<32, 10>(cfg, g, layout_stream(seed, cfg.env_base + n, epi), cur, rounds, 0, task, hit);
+    if (hit && g.lane < 10) st.next_task[(size_t)n * 10 + g.lane] = task;
+    if (g.lane == 0) st.next_cursor[n] = hit ? kTaskReady : cur + used;
+}
+
 // ---------------------------------------------------------- health bit map --
 // Rebuilds dmfb_state_t.health_bits from health (bit k of an env = health[k] != 1.0): one warp per env.
 __global__ void __launch_bounds__(128)
@@ -1374,10 +1409,8 @@ int tile_envs_for(const dmfb_cfg_t& cfg, int G)
     int max_envs = (kMaxThreads / 32) * per_warp;
     const int cap = G <= 4 ? 16 : (G == 10 ? 8 : 8 * per_warp);   // measured: C1 best with 16 envs, C2/C3 with 8 envs per CTA
     if (cap >= 16 / gcd_int(16, row) && cap < max_envs) max_envs = cap;
-    if (const char* ev = getenv("DMFB_TILE_ENVS")) {
-        const int v = atoi(ev);
-        if (v > 0 && cta_threads(v, G) <= kMaxThreads) return v;
-    }
+    static const int forced = getenv("DMFB_TILE_ENVS") ? atoi(getenv("DMFB_TILE_ENVS")) : 0;   // tuning knob, read once
+    if (forced > 0 && cta_threads(forced, G) <= kMaxThreads) return forced;
     return pick_tile_envs(row, 40 * 1024, max_envs);
 }
 
@@ -1600,12 +1633,28 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
     const int G = group_size_for(cfg->n_agents);
     const int E = tile_envs_for(*cfg, G);
     const TileLayout L(*cfg, E);
+    // 10 droplets with fused auto-reset: the run-ahead task search is a second, small kernel (dmfb_task_search_kernel)
+    static const bool search_in_step = getenv("DMFB_SEARCH_IN_STEP") != nullptr;   // experiment knob
+    // ... where whole-set rejection is expensive: the expected number of conflicting pairs among the 2A points,
+    // C(2A,2) * 9 / (W*L), is 4.3 on a 20x20 chip (1.4 % of the attempts accepted) and 0.7 on 50x50 (50 %), where the
+    // few attempts cost less inside the step kernel than a second launch does
+    const double conflicts = 0.5 * (2.0 * cfg->n_agents) * (2.0 * cfg->n_agents - 1.0) * 9.0 / ((double)cfg->width * cfg->length);
+    const bool search_kernel = (flags & DMFB_STEP_AUTO_RESET) && cfg->n_agents == 10 && conflicts > 2.8 && state->next_task &&
+                               state->next_cursor && !search_in_step;
+    flags &= ~kStepNoRunAhead;
+    if (search_kernel) flags |= kStepNoRunAhead;
     StepLaunch job{cfg, state, actions, action_elem_size, u_inject, seed, flags, out, static_cast<cudaStream_t>(stream),
                    E, (state->n_envs + E - 1) / E, L.total};
     rc = dispatch(cfg->obs_version == DMFB_OBS_V01 ? 0 : cfg->fov, G, job);   // v0_1: generic instance only
     if (rc) return rc;
     g_launches.fetch_add(1);
     DMFB_CUDA_TRY(cudaGetLastError());
+    if (search_kernel) {
+        // 16 attempts per open env and step: a search of 70 attempts on average is over ~5 steps after the reset
+        dmfb_task_search_kernel<<<(state->n_envs + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, *state, seed, 16u);
+        g_launches.fetch_add(1);
+        DMFB_CUDA_TRY(cudaGetLastError());
+    }
     return DMFB_OK;  // DMFB_STEP_AUTO_RESET is fused into the step kernel
 }
 
