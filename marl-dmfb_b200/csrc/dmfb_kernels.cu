@@ -1327,6 +1327,10 @@ dmfb_flush_usage_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state
 __global__ void __launch_bounds__(256)
 dmfb_task_search_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, uint64_t seed, uint32_t rounds)
 {
+    // the next step kernel of the stream may start its prologue now; this kernel's own loads wait for the step kernel
+    // in front of it (programmatic dependent launch on both sides)
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (n >= st.n_envs) return;
     const Group<32> g((int)threadIdx.x);
@@ -1651,9 +1655,20 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
     DMFB_CUDA_TRY(cudaGetLastError());
     if (search_kernel) {
         // 16 attempts per open env and step: a search of 70 attempts on average is over ~5 steps after the reset
-        dmfb_task_search_kernel<<<(state->n_envs + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(*cfg, *state, seed, 16u);
+        static const int rounds_knob = getenv("DMFB_SEARCH_ROUNDS") ? atoi(getenv("DMFB_SEARCH_ROUNDS")) : 0;   // tuning knob
+        static const bool no_pdl = getenv("DMFB_NO_PDL") != nullptr;
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3((unsigned)((state->n_envs + 7) / 8));
+        lc.blockDim = dim3(256);
+        lc.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = attr;
+        lc.numAttrs = no_pdl ? 0 : 1;
+        DMFB_CUDA_TRY(cudaLaunchKernelEx(&lc, dmfb_task_search_kernel, *cfg, *state, seed,
+                                         (uint32_t)(rounds_knob > 0 ? rounds_knob : 16)));
         g_launches.fetch_add(1);
-        DMFB_CUDA_TRY(cudaGetLastError());
     }
     return DMFB_OK;  // DMFB_STEP_AUTO_RESET is fused into the step kernel
 }
