@@ -11,5 +11,9 @@ for c in "$@"; do
   python tools/prof_step.py $cfg $steps $mode > gpurun_out/plain_$c.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:dmfb_step_kernel -s $skip -c 2 \
       -f -o gpurun_out/${tag}_step_$c python tools/prof_step.py $cfg $steps $mode > gpurun_out/ncu_$c.log 2>&1
-  echo "$c rc=$?"
+  rc=$?
+  # summarise on the box (gpurun brings back at most 64 MiB): text summary kept, report dropped unless KEEP_REP=1
+  python tools/ncu_summary.py gpurun_out/${tag}_step_$c.ncu-rep > gpurun_out/${tag}_step_${c}_ncu_full.txt 2>/dev/null
+  [ "${KEEP_REP:-0}" = "1" ] || rm -f gpurun_out/${tag}_step_$c.ncu-rep
+  echo "$c rc=$rc"
 done
