@@ -72,7 +72,7 @@ enum dmfb_status {
 #define DMFB_STEP_AUTO_RESET 4u    /* vectorised rollouts: envs that terminate in this step (all done or step
                                       limit) get DMFBenv.reset(new=False) right after it; their obs rows then hold
                                       the first observation of the new episode, reward/done/info those of the
-                                      finished step */
+                                      finished step.  Bit 31 of the flags is reserved for the library. */
 
 /* ------------------------------------------------------------------ DMFB -- */
 
@@ -128,8 +128,9 @@ typedef struct dmfb_state {
     /* Optional (both NULL = off) task prefetch for DMFB_STEP_AUTO_RESET.  _Generate_Start_End redraws the whole point set
      * until it is legal (dmfb.py:212-224), a geometric number of attempts whose tail would keep the whole launch waiting
      * for the unluckiest of the envs that reset in a step.  Attempt k of (seed, env, episode) is a pure function, so the
-     * search for the NEXT episode's task can run ahead: every step examines at most one round of attempts per warp for
-     * an env whose next task is not known yet and parks the first accepted one here; the reset then only picks it up
+     * search for the NEXT episode's task can run ahead: every step examines a bounded number of attempts for envs
+     * whose next task is not known yet (at the end of the step kernel, or, for dense 10-droplet chips, in a second
+     * kernel that dmfb_step launches behind it) and parks the first accepted one here; the reset then only picks it up
      * (or finishes the search where it stopped).  The task drawn is the same first accepted attempt either way. */
     uint32_t* next_task;    /* [N,A] packed x | y<<8 | goal_x<<16 | goal_y<<24 of the next episode's task */
     uint32_t* next_cursor;  /* [N] zero-initialised: attempts already examined; bit 31 = next_task is valid */

@@ -133,7 +133,7 @@ enum : uint32_t { kStreamMove = 1, kStreamLayout = 2, kStreamDegrade = 3, kStrea
 
 // The reference's task / obstacle generators redraw until the draw is legal, i.e. for ever when the requested density
 // cannot be placed (dmfb.py:212-224,246-250, meda.py:213-233).  A kernel that never ends takes the GPU with it, so the
-// device generators abort the launch (CUDA error, reported through the return code) after this many rounds.
+// device generators give up after this many rounds: they keep the previous layout and raise DMFB_STATUS_SAMPLER_GAVE_UP.
 constexpr uint32_t kMaxSamplerRounds = 1u << 22;
 
 // splitmix64 finaliser (Steele/Lea/Flood 2014): cheap counter-based generator for the task sampler

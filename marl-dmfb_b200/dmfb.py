@@ -87,8 +87,8 @@ class BatchedDMFB:
         self._usage_log = bool(usage_log) and track_usage
         self.usage_log = z(N, self.max_step, A, dtype=torch.int16) if self._usage_log else None
         self.usage_log_len = z(N, dtype=torch.int32) if self._usage_log else None
-        # task prefetch for auto_reset (dmfb_state_t.next_task): the search for the next episode's task runs ahead, one
-        # round of attempts per warp and step; the tasks drawn are the same with or without it
+        # task prefetch for auto_reset (dmfb_state_t.next_task): the search for the next episode's task runs ahead, a
+        # bounded number of attempts per step; the tasks drawn are the same with or without it
         self._prefetch = bool(task_prefetch)
         self.next_task = z(N, A, dtype=torch.int32) if self._prefetch else None
         self.next_cursor = z(N, dtype=torch.int32) if self._prefetch else None
