@@ -772,6 +772,7 @@ struct LaneIn {
     uint32_t episode;   // leader lane only
     int frozen_i;       // leader lane only
     uint32_t next_cur;  // leader lane only: task-prefetch cursor (dmfb_state_t.next_cursor)
+    int log_len;        // leader lane only: entries in the env's usage log (DEG only)
 };
 
 struct LaneOut {
@@ -792,7 +793,7 @@ __device__ __forceinline__ LaneIn load_lane_inputs(const dmfb_state_t& st, const
                                                    bool lane_on, bool leader)
 {
     LaneIn in;
-    in.d = 0; in.a = 0; in.draw = 0.0; in.sc_in = 0; in.cum_in = 0; in.episode = 0; in.frozen_i = 0; in.next_cur = 0;
+    in.d = 0; in.a = 0; in.draw = 0.0; in.sc_in = 0; in.cum_in = 0; in.episode = 0; in.frozen_i = 0; in.next_cur = 0; in.log_len = 0;
     if (lane_on) {
         in.d = reinterpret_cast<const uint32_t*>(st.drop)[ja];
         in.a = load_action(actions, aes, ja);
@@ -804,6 +805,8 @@ __device__ __forceinline__ LaneIn load_lane_inputs(const dmfb_state_t& st, const
         if (st.episode) in.episode = st.episode[n];
         if (flags & DMFB_STEP_FREEZE_TERM) in.frozen_i = st.terminated[n];
         if ((flags & DMFB_STEP_AUTO_RESET) && st.next_cursor) in.next_cur = st.next_cursor[n];
+        // loaded here, with the other inputs, instead of where it is used: one dependent round trip less per step
+        if (DEG_T && st.usage && st.usage_log_len != nullptr) in.log_len = st.usage_log_len[n];
     }
     return in;
 }
@@ -954,9 +957,7 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
         const bool add = lane_on && !frozen && !post_done;
         bool logged = false;
         if (st.usage_log != nullptr && st.usage_log_len != nullptr) {
-            int len = 0;
-            if (env_on && g.i == 0 && !frozen) len = st.usage_log_len[n];
-            len = g.get(len, 0);
+            const int len = g.get(in.log_len, 0);
             logged = len < st.usage_log_cap;                       // a full log falls back to direct increments
             o.log_len = len + (logged ? 1 : 0);
             if (logged && lane_on && !frozen) {
@@ -966,9 +967,7 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
         }
         if (add && !logged) atomicAdd(st.usage + ((size_t)n * W + nx) * Lc + ny, 1u);   // result unused -> RED.ADD
     } else if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage && st.usage_log != nullptr && st.usage_log_len != nullptr) {
-        int len = 0;                                               // record=False: a fused reset still replays the log
-        if (env_on && g.i == 0) len = st.usage_log_len[n];
-        o.log_len = g.get(len, 0);
+        o.log_len = g.get(in.log_len, 0);                          // record=False: a fused reset still replays the log
     }
 
     // ---- fused auto-reset: DMFBenv.reset(new=False) (:589-597) for envs that just terminated -------
@@ -1115,6 +1114,15 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
         zero_tile(L, S, tid, (int)blockDim.x);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const LaneIn in = load_lane_inputs<DEG_T>(st, actions, aes, u, flags, n, ja, lane_on, leader);
+#ifndef DMFB_NO_BITS_PREFETCH
+    if (DEG_T && st.health_bits && st.health && lane_on) {
+        // the droplet's bit lies somewhere in the env's map (a few 128-byte lines): ask for those lines together with
+        // the inputs, so that the lookup - whose address needs the droplet word - finds them close by
+        const int hb_bytes = health_bit_words(cfg) * 4;
+        const char* hb = reinterpret_cast<const char*>(st.health_bits) + (size_t)n * hb_bytes;
+        for (int k = g.i * 128; k < hb_bytes; k += A * 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(hb + k));
+    }
+#endif
     if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) {
         // An env on its last step before the limit is reset in this launch for certain: updateHealth will then scan its
         // counters (and replay its usage log), a chain of dependent DRAM round trips at the very end of the CTA - the

@@ -414,7 +414,7 @@ struct DropIn {
 };
 
 __device__ __forceinline__ DropIn meda_load_inputs(const meda_state_t& st, const void* __restrict__ actions, int aes,
-                                                   uint32_t flags, int64_t n0, int EW, int A)
+                                                   uint32_t flags, int64_t n0, int EW, int A, int cfg_cells)
 {
     const int lane = threadIdx.x & 31;
     DropIn in;
@@ -431,6 +431,13 @@ __device__ __forceinline__ DropIn meda_load_inputs(const meda_state_t& st, const
         in.sc0 = st.step_count[n];
         in.frozen = (flags & DMFB_STEP_FREEZE_TERM) && st.terminated[n];
         if (st.usage_log_len) in.log_len = st.usage_log_len[n];
+    }
+    if (st.health_bits != nullptr && st.health != nullptr) {
+        // the bits under a droplet lie somewhere in the env's degraded-cell map (a few 128-byte lines): ask for those
+        // lines together with the inputs, so that the lookups - whose addresses need the droplet word - find them in L1
+        const int hb_bytes = ((cfg_cells + 31) >> 5) * 4;
+        const char* hb = reinterpret_cast<const char*>(st.health_bits) + (size_t)n0 * hb_bytes;
+        for (int k = lane * 128; k < ev * hb_bytes; k += 32 * 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(hb + k));
     }
     return in;
 }
@@ -456,8 +463,10 @@ meda_step_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st, 
     const int grp = blockIdx.x * wpc + warp;
     if (grp >= n_groups) return;                              // no CTA-wide barrier below
     {
-        // loads first (lane = droplet), so that their latency overlaps the zero fill of the tile
-        const DropIn in = meda_load_inputs(st, actions, aes, flags, (int64_t)grp * EW, EW, A);
+        // loads first (lane = droplet), so that their latency overlaps the zero fill of the tile.  (Programmatic
+        // dependent launch - zero fill before griddepcontrol.wait, loads after it - was measured and dropped: the
+        // exposed load latency costs more than the overlapped prologue saves, 63.1 -> 64.4 us as 4 sub-batches.)
+        const DropIn in = meda_load_inputs(st, actions, aes, flags, (int64_t)grp * EW, EW, A, cells);
         {
             uint4* t4 = reinterpret_cast<uint4*>(region);
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
