@@ -927,7 +927,7 @@ int meda_launch_step_t(const meda_cfg_t* cfg, const meda_state_t* st, const void
                        uint64_t seed, uint32_t flags, const uint8_t* set_order, const meda_out_t* out, void* stream)
 {
     const int EW = meda_warp_envs(*cfg);
-    int wpc = 2;   // small CTAs pack the shared memory of an SM best (measured: 2 warps < 4 < 8)
+    int wpc = 1;   // small CTAs pack the shared memory of an SM best (measured: 1 warp < 2 < 4 < 8; base obs 66.3 -> 63.5 us)
     static const int forced_wpc = getenv("MEDA_WARPS_PER_CTA") ? atoi(getenv("MEDA_WARPS_PER_CTA")) : 0;   // tuning knob
     if (forced_wpc >= 1 && forced_wpc <= kThreads / 32) wpc = forced_wpc;
     while (wpc > 1 && StepLayout(*cfg, EW, wpc).total > 200u * 1024u) wpc >>= 1;
