@@ -10,13 +10,16 @@ import numpy as np
 from . import _native as nat
 
 
-def gpu_cpu_affinity(device):
-    """CPUs of the NUMA node GPU `device` hangs off (`nvidia-smi topo -m`, column "CPU Affinity"), or None."""
-    import subprocess
-    try:
-        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=10).stdout
-    except Exception:
-        return None
+def gpu_cpu_affinity(device, topo_text=None):
+    """CPUs of the NUMA node GPU `device` hangs off (`nvidia-smi topo -m`, column "CPU Affinity"), or None.
+    `topo_text`: the command's output, if the caller already has it."""
+    out = topo_text
+    if out is None:
+        import subprocess
+        try:
+            out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=10).stdout
+        except Exception:
+            return None
     import re
     out = re.sub(r"\x1b\[[0-9;]*m", "", out)                 # the header row is underlined with ANSI codes
     lines = [ln for ln in out.splitlines() if ln.strip()]

@@ -160,3 +160,17 @@ def test_sub_batch_ranges_cover_the_batch_on_aligned_boundaries():
             assert all(a[1] == b[0] for a, b in zip(r, r[1:])) and all(hi > lo for lo, hi in r)
             assert all(lo % 64 == 0 for lo, _ in r)
     assert pipe.sub_batch_ranges(65536, 4) == [(0, 16384), (16384, 32768), (32768, 49152), (49152, 65536)]
+
+
+def test_gpu_cpu_affinity_parses_nvidia_smi_topo():
+    """host.gpu_cpu_affinity: the "CPU Affinity" column of `nvidia-smi topo -m` (ANSI-underlined header, tab separated),
+    used by bench.py to keep each rank's pinned buffers and unpack threads on its GPU's NUMA node."""
+    import importlib
+    host = importlib.import_module("marl-dmfb_b200.host")
+    one = "\x1b[4m\tGPU0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\x1b[0m\nGPU0\t X \t0-15\t0\t\tN/A\n\nLegend:\n\n  X    = Self\n"
+    assert host.gpu_cpu_affinity(0, one) == set(range(16)) and host.gpu_cpu_affinity(1, one) is None
+    two = ("\x1b[4m\tGPU0\tGPU1\tNIC0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\x1b[0m\n"
+           "GPU0\t X \tNV18\tPIX\t0-55,112-167\t0\t\tN/A\nGPU1\tNV18\t X \tSYS\t56-111,168-223\t1\t\tN/A\nNIC0\tPIX\tSYS\t X \n")
+    assert host.gpu_cpu_affinity(0, two) == set(range(0, 56)) | set(range(112, 168))
+    assert min(host.gpu_cpu_affinity(1, two)) == 56 and len(host.gpu_cpu_affinity(1, two)) == 112
+    assert host.gpu_cpu_affinity(0, "no such table") is None and host.gpu_cpu_affinity(0, "") is None

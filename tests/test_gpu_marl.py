@@ -110,3 +110,26 @@ def test_meda_training_config4_rollout_and_updates():
     assert np.isfinite(losses).all() and not torch.equal(w0, learner.eval_rnn.conv2.weight)
     ph = timer.summary()
     assert ph["env_step"] > 0 and ph["policy_forward"] > 0 and "grad_allreduce" in ph
+
+
+def test_rollout_over_a_sub_batched_env_equals_the_single_launch_env():
+    """The lock-step rollout joins after every step (the policy needs all observations), so an env stepped as K
+    sub-batches on K streams (pipeline.py) must hand the worker exactly the episodes of the single-launch env."""
+    P = importlib.import_module("marl-dmfb_b200")
+    dev = torch.device("cuda:0")
+    N, A, n_act = 600, 4, 5
+    eps = []
+    for K in (1, 3):
+        env = P.BatchedDMFB(N, 10, 10, A, fov=9, device=dev, seed=11, sub_batches=K)
+        info = env.get_env_info()
+        learner = P.VDNLearner(info["obs_shape"], A, n_act, dev, seed=0)
+        agents = P.BatchedAgents(learner.eval_rnn, A, n_act, dev, seed=1)
+        worker = P.BatchedRolloutWorker(env, agents, epsilon=0.5, anneal_steps=1000)
+        ep, stats = worker.generate_episodes()
+        torch.cuda.synchronize()
+        eps.append((ep, stats))
+    (a, sa), (b, sb) = eps
+    for name in a._FIELDS:
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
