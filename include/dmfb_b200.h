@@ -73,6 +73,12 @@ enum dmfb_status {
                                       limit) get DMFBenv.reset(new=False) right after it; their obs rows then hold
                                       the first observation of the new episode, reward/done/info those of the
                                       finished step.  Bit 31 of the flags is reserved for the library. */
+#define DMFB_STEP_SKIP_TASK_SEARCH 8u /* with DMFB_STEP_AUTO_RESET on dense 10-droplet chips (dmfb_state_t.next_task): this
+                                      call does not launch the run-ahead task search kernel behind the step.  A caller
+                                      that launches it every P-th step only passes DMFB_STEP_SEARCH_SHARE(P) on that
+                                      step - P times the attempts per open search - and this flag on the others; the
+                                      tasks drawn do not depend on when the search runs.  Ignored elsewhere. */
+#define DMFB_STEP_SEARCH_SHARE(p) (((uint32_t)(p) & 0xFFu) << 8)
 
 /* ------------------------------------------------------------------ DMFB -- */
 

@@ -13,6 +13,12 @@ DMFB_L2_WORDS = 12
 STEP_RECORD_USAGE = 1
 STEP_FREEZE_TERM = 2
 STEP_AUTO_RESET = 4
+STEP_SKIP_TASK_SEARCH = 8
+
+
+def step_search_share(p):
+    return (int(p) & 0xFF) << 8
+
 STATUS_ILLEGAL_ACTION = 1
 STATUS_SAMPLER_GAVE_UP = 2
 

@@ -305,6 +305,10 @@ __device__ __forceinline__ uint32_t sample_rounds_warp(const dmfb_cfg_t& cfg, co
             if (q >= P) q -= P;
             const uint32_t other = __shfl_sync(kFull, cell, on ? q : p);
             bad = __any_sync(kFull, on && (__vabsdiffu4(cell, other) & 0xFEFEu) == 0u);   // |dx| <= 1 && |dy| <= 1
+#ifdef DMFB_WHATIF_SEARCH_FREE
+            bad = false;
+            break;
+#endif
         }
         if (bad) continue;
         // accepted: droplet i = start (point 2i) | goal (point 2i+1) << 16
@@ -745,14 +749,117 @@ __device__ __forceinline__ void update_health_env(const dmfb_cfg_t& cfg, const d
         if (__ldcg(usage + k) > 50u) hit(k);
 }
 
+// Log replay + updateHealth of env n in ONE pass over the counters, through a histogram in shared memory: `hist`
+// (16-bit counts, two cells per word; all zero on entry and on exit) is the step kernel's not-yet-painted tile.  The
+// env's log entries are counted with shared-memory atomics, then every thread adds the histogram to four counters per
+// load, applies the threshold (usage > 50 -> health *= degrade, usage = 0; dmfb.py:465-471) and writes the four counters
+// back where something changed.  Replaying the log with one global RED per entry instead - 2,000 per env on a 50x50
+// chip with 10 droplets, 660 K scattered atomics per step of 64K staggered envs - cost 12 of C3's 53 us per step
+// (gpurun_out/s3_c3diag2.txt: 41.3 us with updateHealth compiled out).  An episode adds at most one count per cell and
+// step, so 16 bits are enough for any usage_log_cap <= 65,535.
+__device__ __forceinline__ void update_health_env_hist(const dmfb_cfg_t& cfg, const dmfb_state_t& st, int64_t n, int tid,
+                                                       int nthreads, uint32_t* hist, int log_len)
+{
+    const int A = cfg.n_agents, Lc = cfg.length, cells = cfg.width * cfg.length;
+    const uint16_t* log = st.usage_log + (size_t)n * st.usage_log_cap * A;
+    const int total = min(log_len, st.usage_log_cap) * A;
+    auto count = [&](uint32_t c) {
+        if (c != 0xFFFFu) {
+            const uint32_t k = (c & 255u) * (uint32_t)Lc + (c >> 8);
+            atomicAdd(hist + (k >> 1), 1u << (16u * (k & 1u)));
+        }
+    };
+    auto count2 = [&](uint32_t w) {
+        count(w & 0xFFFFu);
+        count(w >> 16);
+    };
+    int done = 0;
+    if ((reinterpret_cast<uintptr_t>(log) & 15u) == 0) {
+        const uint4* log4 = reinterpret_cast<const uint4*>(log);
+        const int n4 = total >> 3;
+        for (int base = 0; base < n4; base += 2 * nthreads) {
+            const int k0 = base + tid, k1 = k0 + nthreads;
+            const uint4 none = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            const uint4 v0 = k0 < n4 ? __ldcg(log4 + k0) : none, v1 = k1 < n4 ? __ldcg(log4 + k1) : none;
+            count2(v0.x); count2(v0.y); count2(v0.z); count2(v0.w);
+            count2(v1.x); count2(v1.y); count2(v1.z); count2(v1.w);
+        }
+        done = n4 << 3;
+    }
+    for (int k = done + tid; k < total; k += nthreads) count(log[k]);
+    __syncthreads();
+
+    uint32_t* usage = st.usage + (size_t)n * cells;
+    double* health = st.health ? st.health + (size_t)n * cells : nullptr;
+    const double* degrade = st.degrade ? st.degrade + (size_t)n * cells : nullptr;
+    uint32_t* bits = st.health_bits ? st.health_bits + (size_t)n * health_bit_words(cfg) : nullptr;
+    auto settle = [&](uint32_t sum, int k) -> uint32_t {     // one cell: new counter value
+        if (sum <= 50u) return sum;
+        if (health) {
+            const double h = health[k] * (degrade ? degrade[k] : 1.0);
+            health[k] = h;
+            if (bits && h != 1.0) atomicOr(bits + (k >> 5), 1u << (k & 31));
+        }
+        return 0u;
+    };
+    int scanned = 0;
+    if ((reinterpret_cast<uintptr_t>(usage) & 15u) == 0) {
+        uint4* u4 = reinterpret_cast<uint4*>(usage);
+        uint2* h2 = reinterpret_cast<uint2*>(hist);
+        const int n4 = cells >> 2;
+        for (int base = 0; base < n4; base += 2 * nthreads) {
+            const int k0 = base + tid, k1 = k0 + nthreads;
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+            const uint4 a = k0 < n4 ? __ldcg(u4 + k0) : zero, b = k1 < n4 ? __ldcg(u4 + k1) : zero;
+            auto fold4 = [&](int k4, const uint4& u) {
+                if (k4 >= n4) return;
+                const uint2 h = h2[k4];
+                if ((h.x | h.y) == 0u && u.x <= 50u && u.y <= 50u && u.z <= 50u && u.w <= 50u) return;   // untouched
+                h2[k4] = make_uint2(0u, 0u);
+                const int k = 4 * k4;
+                uint4 o;
+                o.x = settle(u.x + (h.x & 0xFFFFu), k);
+                o.y = settle(u.y + (h.x >> 16), k + 1);
+                o.z = settle(u.z + (h.y & 0xFFFFu), k + 2);
+                o.w = settle(u.w + (h.y >> 16), k + 3);
+                u4[k4] = o;
+            };
+            fold4(k0, a);
+            fold4(k1, b);
+        }
+        scanned = n4 << 2;
+    }
+    for (int k = scanned + tid; k < cells; k += nthreads) {
+        const uint32_t h = (hist[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+        const uint32_t u = __ldcg(usage + k);
+        if (h == 0u && u <= 50u) continue;
+        usage[k] = settle(u + h, k);
+    }
+    __syncthreads();
+    for (int k = scanned + tid; k < cells; k += nthreads) hist[k >> 1] = 0u;   // the few words of the tail cells
+    if (tid == 0) st.usage_log_len[n] = 0;
+    __syncthreads();
+}
+
 // updateHealth for the envs of the tile flagged kFlagNewTask; whole CTA cooperates.  FUSED: inside a step launch, where
 // this is the tail of the CTA (and, for the last CTAs, of the launch): the log lengths come from shared memory
-// (S.loglen) instead of a dependent global read.
+// (S.loglen) instead of a dependent global read, and the tile - zero-filled, not painted yet - serves as the histogram
+// of update_health_env_hist when the chip fits (two cells per word).
 template <bool FUSED = false>
 __device__ __forceinline__ void update_health_flagged(const dmfb_cfg_t& cfg, const dmfb_state_t& st, const TileSmem& S,
-                                                      int64_t n0, int e_valid)
+                                                      int64_t n0, int e_valid, uint32_t tile_bytes = 0)
 {
-    if (st.usage_log != nullptr && st.usage_log_len != nullptr) {   // the counters are read below: fold the log in first
+    const bool logged = st.usage_log != nullptr && st.usage_log_len != nullptr;
+#ifndef DMFB_UPDATE_HEALTH_ATOMICS
+    if (FUSED && logged && (uint32_t)((cfg.width * cfg.length + 1) / 2) * 4u <= tile_bytes && st.usage_log_cap <= 65535) {
+        for (int e = 0; e < e_valid; ++e)
+            if (S.flag[e] & kFlagNewTask)
+                update_health_env_hist(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x,
+                                       reinterpret_cast<uint32_t*>(S.tile), S.loglen[e]);
+        return;
+    }
+#endif
+    if (logged) {   // the counters are read below: fold the log in first
         for (int e = 0; e < e_valid; ++e)
             if (S.flag[e] & kFlagNewTask)
                 replay_usage_log(cfg, st, n0 + e, (int)threadIdx.x, (int)blockDim.x, FUSED ? S.loglen[e] : -1);
@@ -1083,8 +1190,11 @@ __device__ __forceinline__ void write_avail(const dmfb_cfg_t& cfg, const dmfb_ou
 
 // A_T / E_T: compile-time droplet count and tile size for the shipped configs (0 = run-time values).
 // DEG_T = false strips the degradation path (health / usage / draws) when the state has none.
+// The degrading instances of the shipped tiles may use the 72 registers that their shared-memory residency leaves free
+// (9 CTAs of 96 threads, 13 of 64): left alone, ptxas settled on 56 and spilled a dozen values on the hot path.
 template <int FOV_T, int G, int A_T, int E_T, bool DEG_T>
-__global__ void __launch_bounds__(E_T ? cta_threads(E_T, G) : kMaxThreads)
+__global__ void __launch_bounds__(E_T ? cta_threads(E_T, G) : kMaxThreads,
+                                  (E_T && DEG_T) ? 65536 / (72 * cta_threads(E_T ? E_T : 1, G)) : 0)
 dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, const void* __restrict__ actions,
                  int aes, const double* __restrict__ u, uint64_t seed, uint32_t flags, const dmfb_out_t out, int E_rt)
 {
@@ -1125,6 +1235,7 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
         for (int k = g.i * 128; k < hb_bytes; k += A * 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(hb + k));
     }
 #endif
+#ifndef DMFB_WHATIF_NO_RESET_PREFETCH
     if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) {
         // An env on its last step before the limit is reset in this launch for certain: updateHealth will then scan its
         // counters (and replay its usage log), a chain of dependent DRAM round trips at the very end of the CTA - the
@@ -1140,6 +1251,7 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
             }
         }
     }
+#endif
 
     CoordSets<A_T> cs(S.sets, env_on ? e : 0);
     // degraded-cell bit map of this lane's env.  (Staging the maps of a warp's envs in shared memory with one coalesced
@@ -1168,7 +1280,11 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
     write_avail(cfg, out, A, n0, e_valid, any_frozen, tid, (int)blockDim.x, agent, lane_on, o.frozen);
     if (DEG_T && (flags & DMFB_STEP_AUTO_RESET) && st.usage) {
         // rare: only tiles in which an env was just reset scan its electrodes (updateHealth, dmfb.py:465-471)
-        if (__syncthreads_or(o.do_reset)) update_health_flagged<true>(cfg, st, S, n0, e_valid);
+#ifndef DMFB_WHATIF_NO_UPDATE_HEALTH
+        if (__syncthreads_or(o.do_reset)) update_health_flagged<true>(cfg, st, S, n0, e_valid, L.tile_bytes);
+#else
+        if (leader && o.do_reset && st.usage_log_len) st.usage_log_len[n] = 0;   // timing experiment
+#endif
     }
 
     const uint32_t word = o.word;
@@ -1182,6 +1298,9 @@ dmfb_step_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, 
                                 cs, env_blocks);
     const bool in_flight = store_tile_issue(out.obs + (size_t)n0 * A * L.D, S.tile, (uint32_t)(e_valid * A * L.D));
     if (flags & DMFB_STEP_AUTO_RESET) {
+#ifdef DMFB_WHATIF_NO_RUNAHEAD
+        flags |= kStepNoRunAhead;
+#endif
         if (!(flags & kStepNoRunAhead)) run_ahead<G>(cfg, st, g, A, seed, n, ja, env_on, lane_on, o);
         else if (leader && o.cursor_dirty && st.next_cursor) st.next_cursor[n] = o.cursor;
     }
@@ -1329,33 +1448,135 @@ dmfb_flush_usage_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state
 
 // --------------------------------------------------------------- task search --
 // Run-ahead task search for 10 droplets as a kernel of its own, launched by dmfb_step right after a fused auto-reset
-// step: one warp per env; envs whose next task is known leave after one load, the others examine up to `rounds` attempts
-// (one attempt per warp round, sample_rounds_warp) and park an accepted task in next_task.  Whole-set rejection at 1.4 %
-// acceptance (10 droplets, 20x20) costs ~30 % of the step kernel's instructions wherever it runs; inside the step kernel
-// the warps that search also delay their CTAs (barrier, tail of the launch: C2 37 -> 75 us with staggered resets), here
-// every warp does the same bounded amount of work and the kernel overlaps the step kernels of the other sub-batches.
-__global__ void __launch_bounds__(256)
+// step.  Whole-set rejection at 1.4 % acceptance (10 droplets, 20x20) costs ~30 % of the step kernel's instructions
+// when it runs inside the step kernel, where the warps that search also delay their CTAs (barrier, tail of the
+// launch: C2 37 -> 75 us with staggered resets); here every warp does the same bounded amount of work and the kernel
+// overlaps the step kernels of the other sub-batches.
+//
+// Grid: a CTA of 8 warps looks after kSearchEnvs = 128 consecutive envs.  Thread t reads the cursor of env t (coalesced),
+// the ~3 % of the envs whose next task is still unknown are compacted into a list in shared memory, and the warps
+// serve that list round-robin, one env per warp and turn; most CTAs have at most one turn per warp, a CTA without an
+// open search leaves after the one load.  (With one WARP per env - 8,192 CTAs per step of 64K envs that had next to
+// nothing to do - the launch itself cost 11 us per step: 45.4 us with every search finished at once against 34.1 us
+// with the same searches and the kernel not launched, gpurun_out/s3_diag.txt.  512 CTAs per step do not.)
+//
+// On chips of at most 30x30 cells a warp examines 32 CONSECUTIVE attempts at once, ONE PER LANE, against a private
+// bit board in shared memory (column `lane` of board[row][32]: no bank conflicts, no synchronisation): row x+1 holds,
+// at bit y+1, the cells within Chebyshev distance 1 of the points drawn so far, so a point is tested with one load and
+// one shift and added with three read-modify-writes - exactly the reference's "min pairwise squared distance > 2" rule
+// (dmfb.py:220), point by point.  The lowest accepted attempt of the 32 wins, which is the attempt the one-per-warp
+// flavour (sample_rounds_warp: same counters, same cells) would have stopped at: the tasks are the same whoever
+// searches.  ~22 instructions per attempt instead of ~55, and 32 attempts in the latency of 16.
+constexpr int kBoardRows = 32;                                   // W + 2 rows, W <= 30
+constexpr int kSearchEnvs = 128;                                 // envs per CTA of the search kernel
+constexpr int kSearchWarps = 8;
+__device__ __forceinline__ uint32_t attempt_cell(uint64_t z, uint32_t W, uint32_t Lc)
+{
+    return __umulhi((uint32_t)z, W) | (__umulhi((uint32_t)(z >> 32), Lc) << 8);
+}
+
+// 32 * ceil(rounds / 32) attempts of env n from attempt `cur` on, one per lane.  `col` = this lane's board column.
+__device__ __forceinline__ void search_env_lanewise(const dmfb_cfg_t& cfg, const dmfb_state_t& st, uint64_t base, int64_t n,
+                                                    uint32_t cur, uint32_t rounds, uint32_t* col, int lane)
+{
+    constexpr uint64_t kPhi = 0x9E3779B97F4A7C15ull;
+    constexpr int P = 20;
+    const uint32_t W = (uint32_t)cfg.width, Lc = (uint32_t)cfg.length;
+    const uint32_t batches = (rounds + 31u) / 32u;
+    for (uint32_t b = 0; b < batches; ++b, cur += 32u) {
+        const uint64_t ctr = base + (uint64_t)(cur + (uint32_t)lane) * (uint64_t)P * kPhi;
+        for (uint32_t r = 0; r < W + 2u; ++r) col[r * 32u] = 0u;
+        bool alive = true;
+#pragma unroll 1
+        for (int p = 0; p < P; p += 4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint64_t z = mix64(ctr + (uint64_t)(p + q + 1) * kPhi);
+                const uint32_t x = __umulhi((uint32_t)z, W), y = __umulhi((uint32_t)(z >> 32), Lc);
+                if (alive) {
+                    uint32_t* row = col + x * 32u;                // rows x, x+1, x+2 = cells x-1, x, x+1
+                    const uint32_t mid = row[32];
+                    if ((mid >> (y + 1u)) & 1u) {
+                        alive = false;
+                    } else {
+                        const uint32_t m = 7u << y;               // cells y-1, y, y+1 at bits y .. y+2
+                        row[0] |= m;
+                        row[32] = mid | m;
+                        row[64] |= m;
+                    }
+                }
+            }
+#ifdef DMFB_WHATIF_SEARCH_FREE
+            alive = true;                                         // timing experiment: every search ends at once
+            break;
+#endif
+            if (!__any_sync(kFull, alive)) break;
+        }
+        const unsigned ok = __ballot_sync(kFull, alive);
+        if (ok) {
+            const uint64_t cw = base + (uint64_t)(cur + (uint32_t)(__ffs(ok) - 1)) * (uint64_t)P * kPhi;
+            if (lane < 10) {
+                const uint32_t s = attempt_cell(mix64(cw + (uint64_t)(2 * lane + 1) * kPhi), W, Lc);
+                const uint32_t t = attempt_cell(mix64(cw + (uint64_t)(2 * lane + 2) * kPhi), W, Lc);
+                st.next_task[(size_t)n * 10 + lane] = s | (t << 16);
+            }
+            if (lane == 0) st.next_cursor[n] = kTaskReady;
+            return;
+        }
+    }
+    if (lane == 0) st.next_cursor[n] = cur;
+}
+
+__global__ void __launch_bounds__(kSearchWarps * 32)
 dmfb_task_search_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st, uint64_t seed, uint32_t rounds)
 {
+    __shared__ uint32_t board[kSearchWarps][kBoardRows][32];
+    __shared__ uint32_t open_cur[kSearchEnvs];
+    __shared__ uint8_t open_env[kSearchEnvs];
+    __shared__ int n_open;
     // the next step kernel of the stream may start its prologue now; this kernel's own loads wait for the step kernel
     // in front of it (programmatic dependent launch on both sides)
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (n >= st.n_envs) return;
-    const Group<32> g((int)threadIdx.x);
-    uint32_t cur = 0;
-    if (g.lane == 0) cur = st.next_cursor[n];
-    cur = __shfl_sync(kFull, cur, 0);
-    if ((cur & kTaskReady) || cur >= kMaxSamplerRounds) return;
-    uint32_t epi = 0;
-    if (g.lane == 0 && st.episode) epi = st.episode[n] + 1u;
-    epi = __shfl_sync(kFull, epi, 0);
-    uint32_t task = 0;
-    bool hit = false;
-    const uint32_t used = sample_rounds_warp<32, 10>(cfg, g, layout_stream(seed, cfg.env_base + n, epi), cur, rounds, 0, task, hit);
-    if (hit && g.lane < 10) st.next_task[(size_t)n * 10 + g.lane] = task;
-    if (g.lane == 0) st.next_cursor[n] = hit ? kTaskReady : cur + used;
+    const int tid = (int)threadIdx.x, warp = tid >> 5;
+    const Group<32> g(tid);
+    const int64_t n0 = (int64_t)blockIdx.x * kSearchEnvs;
+    if (tid == 0) n_open = 0;
+    __syncthreads();
+    if (tid < kSearchEnvs) {                                      // warps 0-3: one env per thread
+        uint32_t cur = kTaskReady;
+        if (n0 + tid < st.n_envs) cur = st.next_cursor[n0 + tid];
+        const bool open = !(cur & kTaskReady) && cur < kMaxSamplerRounds;
+        const unsigned m = __ballot_sync(kFull, open);
+        int at = 0;
+        if (g.lane == 0 && m) at = atomicAdd(&n_open, __popc(m));
+        at = __shfl_sync(kFull, at, 0) + __popc(m & ((1u << g.lane) - 1u));
+        if (open) {
+            open_env[at] = (uint8_t)tid;
+            open_cur[at] = cur;
+        }
+    }
+    __syncthreads();
+    const int todo = n_open;
+    for (int k = warp; k < todo; k += kSearchWarps) {
+        const int64_t n = n0 + open_env[k];
+        const uint32_t cur = open_cur[k];
+        uint32_t epi = 0;
+        if (g.lane == 0 && st.episode) epi = st.episode[n] + 1u;
+        epi = __shfl_sync(kFull, epi, 0);
+        const uint64_t base = layout_stream(seed, cfg.env_base + n, epi);
+#ifndef DMFB_SEARCH_WARPWISE
+        if (cfg.width <= kBoardRows - 2 && cfg.length <= 30) {
+            search_env_lanewise(cfg, st, base, n, cur, rounds, &board[warp][0][g.lane], g.lane);
+            continue;
+        }
+#endif
+        uint32_t task = 0;
+        bool hit = false;
+        const uint32_t used = sample_rounds_warp<32, 10>(cfg, g, base, cur, rounds, 0, task, hit);
+        if (hit && g.lane < 10) st.next_task[(size_t)n * 10 + g.lane] = task;
+        if (g.lane == 0) st.next_cursor[n] = hit ? kTaskReady : cur + used;
+    }
 }
 
 // ---------------------------------------------------------- health bit map --
@@ -1656,7 +1877,9 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
     const double conflicts = 0.5 * (2.0 * cfg->n_agents) * (2.0 * cfg->n_agents - 1.0) * 9.0 / ((double)cfg->width * cfg->length);
     const bool search_kernel = (flags & DMFB_STEP_AUTO_RESET) && cfg->n_agents == 10 && conflicts > 2.8 && state->next_task &&
                                state->next_cursor && !search_in_step;
-    flags &= ~kStepNoRunAhead;
+    const bool skip_search_once = (flags & DMFB_STEP_SKIP_TASK_SEARCH) != 0u;
+    const uint32_t search_share = ((flags >> 8) & 0xFFu) ? ((flags >> 8) & 0xFFu) : 1u;
+    flags &= ~(kStepNoRunAhead | DMFB_STEP_SKIP_TASK_SEARCH | DMFB_STEP_SEARCH_SHARE(0xFF));
     if (search_kernel) flags |= kStepNoRunAhead;
     StepLaunch job{cfg, state, actions, action_elem_size, u_inject, seed, flags, out, static_cast<cudaStream_t>(stream),
                    E, (state->n_envs + E - 1) / E, L.total};
@@ -1664,13 +1887,15 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
     if (rc) return rc;
     g_launches.fetch_add(1);
     DMFB_CUDA_TRY(cudaGetLastError());
-    if (search_kernel) {
-        // 16 attempts per open env and step: a search of 70 attempts on average is over ~5 steps after the reset
+    static const bool skip_search = getenv("DMFB_WHATIF_SKIP_SEARCH") != nullptr;   // timing experiment
+    if (search_kernel && !skip_search && !skip_search_once) {
+        // 32 attempts per open env and step (one per lane): a search of 70 attempts on average is over ~3 steps after
+        // the reset; a caller that launches the search every P-th step only asks for P times as many
         static const int rounds_knob = getenv("DMFB_SEARCH_ROUNDS") ? atoi(getenv("DMFB_SEARCH_ROUNDS")) : 0;   // tuning knob
         static const bool no_pdl = getenv("DMFB_NO_PDL") != nullptr;
         cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3((unsigned)((state->n_envs + 7) / 8));
-        lc.blockDim = dim3(256);
+        lc.gridDim = dim3((unsigned)((state->n_envs + kSearchEnvs - 1) / kSearchEnvs));
+        lc.blockDim = dim3(kSearchWarps * 32);
         lc.stream = static_cast<cudaStream_t>(stream);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1678,7 +1903,7 @@ int dmfb_step(const dmfb_cfg_t* cfg, const dmfb_state_t* state, const void* acti
         lc.attrs = attr;
         lc.numAttrs = no_pdl ? 0 : 1;
         DMFB_CUDA_TRY(cudaLaunchKernelEx(&lc, dmfb_task_search_kernel, *cfg, *state, seed,
-                                         (uint32_t)(rounds_knob > 0 ? rounds_knob : 16)));
+                                         (uint32_t)(rounds_knob > 0 ? rounds_knob : 32) * search_share));
         g_launches.fetch_add(1);
     }
     return DMFB_OK;  // DMFB_STEP_AUTO_RESET is fused into the step kernel

@@ -9,6 +9,7 @@
 PyTorch is used only for device memory and streams.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -34,7 +35,7 @@ class BatchedDMFB:
     def __init__(self, n_envs, width, length, n_agents, n_blocks=0, fov=5, stall=True, b_degrade=False,
                  per_degrade=0.1, device="cuda", seed=0, env_base=0, track_usage=None, reward_f64=False,
                  degrade=None, layouts=None, block_layouts=None, obs_version=0, usage_log=True, task_prefetch=True,
-                 health_bitmap=True, sub_batches=1):
+                 health_bitmap=True, sub_batches=1, search_period=None):
         # sub_batches: K > 1 steps the batch as K sub-batches on K streams (pipeline.py): consecutive steps issued with
         # step(..., join=False) then overlap - the results are the same, env for env
         self.lib = nat.load()
@@ -90,6 +91,14 @@ class BatchedDMFB:
         # task prefetch for auto_reset (dmfb_state_t.next_task): the search for the next episode's task runs ahead, a
         # bounded number of attempts per step; the tasks drawn are the same with or without it
         self._prefetch = bool(task_prefetch)
+        # dense 10-droplet chips: the run-ahead search is a kernel behind the step (dmfb_step).  Launched behind every
+        # P-th step of a (sub-)batch only, with P times the attempts - sub-batch k in the steps with (step + k) % P == 0,
+        # so that a step of the whole batch carries about one search launch - it costs one extra kernel boundary per
+        # P steps instead of one per step; the tasks drawn are the same
+        if search_period is None:
+            search_period = int(os.environ.get("DMFB_SEARCH_PERIOD", "4"))
+        self._search_period = max(1, min(int(search_period), 255))
+        self._auto_steps = 0
         self.next_task = z(N, A, dtype=torch.int32) if self._prefetch else None
         self.next_cursor = z(N, dtype=torch.int32) if self._prefetch else None
         self.status = z(1, dtype=torch.int32)          # sticky DMFB_STATUS_* bits (illegal action, sampler gave up)
@@ -234,10 +243,19 @@ class BatchedDMFB:
         else:
             obs, o = out, self._make_out(out)
         self._sync_health()
+        P, t = self._search_period, self._auto_steps
+        if auto_reset:
+            self._auto_steps += 1
+
+        def search_flags(k):
+            if not auto_reset or P == 1:
+                return 0
+            return nat.step_search_share(P) if (t + k) % P == 0 else nat.STEP_SKIP_TASK_SEARCH
+
         if self._sub is None:
             with torch.cuda.device(self.device):
                 rc = self.lib.dmfb_step(C.byref(self.cfg), C.byref(self.state), _ptr(actions), actions.element_size(),
-                                        _ptr(draws_t), self.seed, flags, C.byref(o), self._stream())
+                                        _ptr(draws_t), self.seed, flags | search_flags(0), C.byref(o), self._stream())
             nat.check(rc, "dmfb_step")
         else:
             sub, es = self._sub, actions.element_size()
@@ -248,7 +266,7 @@ class BatchedDMFB:
                     rc = self.lib.dmfb_step(C.byref(self._sub_cfg[k]), C.byref(self._sub_state[k]),
                                             C.c_void_p(actions.data_ptr() + lo * self.A * es), es,
                                             None if draws_t is None else C.c_void_p(draws_t.data_ptr() + lo * self.A * 8),
-                                            self.seed, flags, C.byref(o_k), stream)
+                                            self.seed, flags | search_flags(k), C.byref(o_k), stream)
                     nat.check(rc, "dmfb_step")
             if join:
                 sub.join()

@@ -11,7 +11,7 @@ out=gpurun_out/${tag}_kernel_timings.txt
   done
   echo "== DMFB C3, fraction of degraded cells 0.3 / 1.0 (one launch per step)"
   for f in 0.3 1.0; do python tools/time_variant.py 50 50 10 9 1 1 65536 $f; done
-  for K in 1 4; do
+  for K in $([ -n "${SKIP_MEDA:-}" ] || echo 1 4); do
     echo "== MEDA C4 (30x60, 4 droplets, fov 19), sub_batches $K: obs version, degrade, usage counters, auto-reset"
     TK_SUB=$K python tools/time_meda.py 0 65536 0 0 0
     TK_SUB=$K python tools/time_meda.py 0 65536 0 0 1
