@@ -1468,7 +1468,10 @@ dmfb_flush_usage_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state
 // flavour (sample_rounds_warp: same counters, same cells) would have stopped at: the tasks are the same whoever
 // searches.  ~22 instructions per attempt instead of ~55, and 32 attempts in the latency of 16.
 constexpr int kBoardRows = 32;                                   // W + 2 rows, W <= 30
-constexpr int kSearchEnvs = 128;                                 // envs per CTA of the search kernel
+#ifndef DMFB_SEARCH_ENVS
+#define DMFB_SEARCH_ENVS 128
+#endif
+constexpr int kSearchEnvs = DMFB_SEARCH_ENVS;                                 // envs per CTA of the search kernel
 constexpr int kSearchWarps = 8;
 __device__ __forceinline__ uint32_t attempt_cell(uint64_t z, uint32_t W, uint32_t Lc)
 {

@@ -54,10 +54,12 @@ class CRNN(nn.Module):
         self.rnn = nn.GRUCell(self.out + 10, rnn_hidden_dim)
         self.fc1 = nn.Linear(rnn_hidden_dim, n_actions)
 
-    def forward(self, inputs, hidden_state):
+    def forward(self, inputs, hidden_state, channels_last=False):
         npix = self.input_dim[-1] - self.input_dim[-2]
         pixel, vec = inputs[:, :npix], inputs[:, npix:]
         pixel = pixel.reshape((-1,) + self.input_dim[:3])
+        if channels_last:
+            pixel = pixel.contiguous(memory_format=torch.channels_last)
         for conv in self.convs:
             pixel = F.relu(conv(pixel))
         pixel = pixel.reshape(-1, self.out)
@@ -157,8 +159,11 @@ _NO_TIMER = PhaseTimer(enabled=False)
 class BatchedAgents:
     """Agents.choose_action (agent/agent.py:22-48) for all N*A agents in one forward pass, on the device."""
 
-    def __init__(self, net, n_agents, n_actions, device, seed=0):
+    def __init__(self, net, n_agents, n_actions, device, seed=0, autocast_dtype=None):
+        # autocast_dtype (e.g. torch.bfloat16): the ROLLOUT's forward pass runs under torch.autocast with channels-last
+        # activations - an opt-in trade of the reference's fp32 action values for throughput (the learner stays fp32)
         self.net, self.n_agents, self.n_actions = net, n_agents, n_actions
+        self.autocast_dtype = autocast_dtype
         self.device = torch.device(device)
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(int(seed))
@@ -171,8 +176,15 @@ class BatchedAgents:
         """obs int8 [N,A,D], last_onehot [N,A,n_actions], hidden [N*A,H], avail [N,A,n_actions] (0/1).
         Returns actions int64 [N,A] and the new hidden state.  Padded rows (avail all zero) get action 0."""
         N, A = obs.shape[0], obs.shape[1]
-        inputs = torch.cat([obs.to(torch.float32), last_onehot.to(torch.float32)], dim=2).reshape(N * A, -1)
-        q, hidden = self.net(inputs, hidden)
+        if self.autocast_dtype is None:
+            inputs = torch.cat([obs.to(torch.float32), last_onehot.to(torch.float32)], dim=2).reshape(N * A, -1)
+            q, hidden = self.net(inputs, hidden)
+        else:
+            dt = self.autocast_dtype
+            inputs = torch.cat([obs.to(dt), last_onehot.to(dt)], dim=2).reshape(N * A, -1)
+            with torch.autocast("cuda", dtype=dt):
+                q, hidden = self.net(inputs, hidden.to(dt), channels_last=True)
+            q, hidden = q.float(), hidden.float()
         q = q.reshape(N, A, self.n_actions).masked_fill(avail == 0, float("-inf"))     # agent.py:43
         greedy = torch.argmax(torch.nan_to_num(q, neginf=-3.0e38), dim=2)
         # np.random.choice(avail_actions_ind) (agent.py:44-45): uniform over the available actions

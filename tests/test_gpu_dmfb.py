@@ -660,6 +660,39 @@ def test_task_prefetch_is_transparent(W, L, A, fov, nb):
     b.check()
 
 
+@pytest.mark.parametrize("W,L,period,sub", [(20, 20, 1, 1), (20, 20, 3, 1), (20, 20, 4, 4), (18, 32, 2, 1)])
+def test_task_search_kernel_is_transparent(W, L, period, sub):
+    """Dense 10-droplet chips: the run-ahead search is a kernel of its own behind the step (dmfb_task_search_kernel) -
+    32 attempts at once, one per lane, against bit boards in shared memory (chips of at most 30x30 cells; 18x32 takes
+    the one-attempt-per-warp flavour), launched behind every `search_period`-th step of a (sub-)batch only
+    (DMFB_STEP_SKIP_TASK_SEARCH / DMFB_STEP_SEARCH_SHARE).  Whoever finds it, the task of (seed, env, episode) is the
+    first accepted attempt: the trajectories equal those of an env without any prefetch, and the searches do finish
+    ahead of the resets."""
+    P = pkg()
+    N, A = 4096, 10
+    kw = dict(fov=9, device="cuda:0", seed=7)
+    a = P.BatchedDMFB(N, W, L, A, task_prefetch=True, search_period=period, sub_batches=sub, **kw)
+    b = P.BatchedDMFB(N, W, L, A, task_prefetch=False, **kw)
+    gen = torch.Generator(device="cuda:0").manual_seed(16)
+    picked_up = resets = 0
+    for t in range(2 * (W + L) + 30):
+        d = a.drop.to(torch.int32)
+        dx, dy = d[..., 2] - d[..., 0], d[..., 3] - d[..., 1]
+        toward = torch.where(dx.abs() >= dy.abs(), torch.where(dx > 0, 1, 2), torch.where(dy > 0, 4, 3))
+        rnd = torch.randint(0, 5, (N, A), device="cuda:0", generator=gen)
+        acts = torch.where(torch.rand(N, A, device="cuda:0", generator=gen) < 0.7, toward, rnd).to(torch.int8)
+        ready = a.next_cursor < 0                                   # bit 31: the next task is known before the step
+        oa, ra, _, ia = a.step(acts, auto_reset=True)
+        ob, rb, _, ib = b.step(acts, auto_reset=True)
+        picked_up += int((ready & ia["terminated"]).sum())
+        resets += int(ia["terminated"].sum())
+        assert torch.equal(a.drop, b.drop) and torch.equal(oa, ob) and torch.equal(ra, rb), f"t{t}"
+        assert torch.equal(a.episode, b.episode) and torch.equal(ia["terminated"], ib["terminated"])
+    assert resets >= N and picked_up > 0.9 * resets, (picked_up, resets)
+    a.check()
+    b.check()
+
+
 def test_task_generator_gives_up_recoverably_on_an_impossible_density():
     """8x8 with 9 droplets passes the reference's density check (dmfb.py:144-146) but 18 points that are pairwise not
     within one cell do not fit an 8x8 chip (at most 16 do): the reference would redraw for ever.  The device generator

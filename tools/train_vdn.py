@@ -51,6 +51,8 @@ def main():
     ap.add_argument("--train-time", type=int, default=None, help="learner updates per iteration")
     ap.add_argument("--anneal-steps", type=int, default=None)
     ap.add_argument("--tf32", action="store_true", help="TF32 matmuls / convolutions in the policy and learner")
+    ap.add_argument("--bf16-rollout", action="store_true",
+                    help="the rollout's policy forward under bf16 autocast, channels-last (the learner stays fp32)")
     ap.add_argument("--save-dir", default="")
     ap.add_argument("--json", default="", help="write the run summary (throughput, per-phase ms) to this file")
     args = ap.parse_args()
@@ -86,7 +88,8 @@ def main():
         learner = P.QMIXLearner(info["obs_shape"], info["n_agents"], info["n_actions"], state_dim, dev, **kw)
     else:
         learner = P.VDNLearner(info["obs_shape"], info["n_agents"], info["n_actions"], dev, **kw)
-    agents = P.BatchedAgents(learner.eval_rnn, info["n_agents"], info["n_actions"], dev, seed=100 + rank)
+    agents = P.BatchedAgents(learner.eval_rnn, info["n_agents"], info["n_actions"], dev, seed=100 + rank,
+                             autocast_dtype=torch.bfloat16 if args.bf16_rollout else None)
     worker = P.BatchedRolloutWorker(env, agents, anneal_steps=args.anneal_steps, record_state=qmix, timer=timer)
     T, A, D, NA = info["episode_limit"], info["n_agents"], info["obs_shape"][-1], info["n_actions"]
     buf = P.ReplayBufferGPU(max(args.buffer_size, args.envs), T, A, D, NA, dev, seed=200 + rank, state_dim=state_dim)
@@ -125,7 +128,7 @@ def main():
         "what": f"end-to-end {args.alg.upper()} training on GPU-resident {args.name} envs (tools/train_vdn.py)",
         "config": {"env": args.name, "chip": [args.width, args.length], "droplets": args.drop_num, "fov": args.fov,
                    "envs_per_gpu": args.envs, "gpus": world, "total_envs": args.envs * world, "episode_limit": T,
-                   "batch_size": args.batch_size, "train_time": args.train_time, "tf32": bool(args.tf32)},
+                   "batch_size": args.batch_size, "train_time": args.train_time, "tf32": bool(args.tf32), "bf16_rollout": bool(args.bf16_rollout)},
         "iters_timed": iters, "wall_s": wall,
         "env_steps_per_s_executed": world * live_steps / max(wall, 1e-9),
         "agent_steps_per_s_executed": world * live_steps * A / max(wall, 1e-9),
