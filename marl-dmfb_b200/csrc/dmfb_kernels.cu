@@ -1469,9 +1469,9 @@ dmfb_flush_usage_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state
 // searches.  ~22 instructions per attempt instead of ~55, and 32 attempts in the latency of 16.
 constexpr int kBoardRows = 32;                                   // W + 2 rows, W <= 30
 #ifndef DMFB_SEARCH_ENVS
-#define DMFB_SEARCH_ENVS 128
+#define DMFB_SEARCH_ENVS 64
 #endif
-constexpr int kSearchEnvs = DMFB_SEARCH_ENVS;                                 // envs per CTA of the search kernel
+constexpr int kSearchEnvs = DMFB_SEARCH_ENVS;                    // envs per CTA of the search kernel (128 / 64 / 32: 40.1 / 38.6 / 39.6 us)
 constexpr int kSearchWarps = 8;
 __device__ __forceinline__ uint32_t attempt_cell(uint64_t z, uint32_t W, uint32_t Lc)
 {
