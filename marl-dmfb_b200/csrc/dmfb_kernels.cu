@@ -1062,6 +1062,15 @@ __device__ __forceinline__ LaneOut dmfb_dynamics(const dmfb_cfg_t& cfg, const dm
     if (frozen) { o.done_mask = all_mask; o.success = 0; }
     o.term = (o.done_mask == all_mask) ? 1 : 0;
 
+#ifdef DMFB_HEALTH_PREFETCH_NEXT
+    // The next step's getMoveProb reads health at the cell the droplet stands on NOW: if that cell is degraded, ask L2
+    // for its line, so that the gather - a dependent access of the next step's warp - does not go to DRAM
+    if (have_prob && lane_on && env_bits && !frozen && !post_done) {
+        const uint32_t c2 = (uint32_t)nx * (uint32_t)Lc + (uint32_t)ny;
+        if ((env_bits[c2 >> 5] >> (c2 & 31u)) & 1u)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(st.health + (size_t)n * W * Lc + c2));
+    }
+#endif
     if (DEG_T && (flags & DMFB_STEP_RECORD_USAGE) && st.usage) {   // addUsage (:459-463): droplets not done after the move
         const bool add = lane_on && !frozen && !post_done;
         bool logged = false;
