@@ -693,6 +693,36 @@ def test_task_search_kernel_is_transparent(W, L, period, sub):
     b.check()
 
 
+@pytest.mark.parametrize("W,L,A,fov", [(10, 10, 4, 9), (20, 20, 10, 9), (12, 12, 6, 5), (18, 32, 10, 9)])
+def test_device_tasks_are_the_first_accepted_attempt_of_the_stated_stream(W, L, A, fov):
+    """The device generator against its numpy restatement (tests/layout_ref.py): the task of (seed, global env, episode)
+    is the first attempt of that stream whose 2A cells are pairwise more than one cell apart (dmfb.py:207-226) - after
+    an explicit reset (reset kernel), and after fused auto-resets whose tasks were found ahead of time by the run-ahead
+    search (inside the step kernel, or by dmfb_task_search_kernel with one attempt per lane / per warp)."""
+    import layout_ref
+    P = pkg()
+    N, base, seed = 768, 4000, 2024
+    env = P.BatchedDMFB(N, W, L, A, fov=fov, device="cuda:0", seed=seed, env_base=base)
+    env.reset()
+
+    def check(tag):
+        want, at = layout_ref.first_accepted_tasks(seed, base + np.arange(N), env.episode.cpu().numpy(), W, L, A)
+        assert np.array_equal(env.start.cpu().numpy(), want[:, :, :2]), tag
+        assert np.array_equal(env.drop.cpu().numpy()[:, :, 2:], want[:, :, 2:]), tag
+        return at
+
+    epi0 = env.episode.clone()
+    at = check("reset")
+    assert np.array_equal(env.drop.cpu().numpy()[:, :, :2], env.start.cpu().numpy())
+    assert at.max() > 3 * at.mean() > 0                      # a geometric number of attempts, not the first one
+    gen = torch.Generator(device="cuda:0").manual_seed(3)
+    for t in range(2 * (W + L) + 3):
+        env.step(torch.randint(0, 5, (N, A), device="cuda:0", generator=gen, dtype=torch.int8), auto_reset=True)
+    assert bool((env.episode > epi0).all())
+    check("fused auto-reset")
+    env.check()
+
+
 def test_task_generator_gives_up_recoverably_on_an_impossible_density():
     """8x8 with 9 droplets passes the reference's density check (dmfb.py:144-146) but 18 points that are pairwise not
     within one cell do not fit an 8x8 chip (at most 16 do): the reference would redraw for ever.  The device generator

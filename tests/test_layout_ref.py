@@ -1,0 +1,31 @@
+"""The numpy restatement of the device task generator (tests/layout_ref.py) obeys the reference's rule itself."""
+import numpy as np
+import pytest
+
+import layout_ref
+
+
+@pytest.mark.parametrize("W,L,A", [(10, 10, 4), (20, 20, 10), (9, 9, 2)])
+def test_restated_generator_obeys_generate_start_end(W, L, A):
+    """_Generate_Start_End (dmfb.py:207-226): 2A cells on the chip, min pairwise squared distance > 2; whole-set
+    rejection means a geometric number of attempts, and different (env, episode) keys give different tasks."""
+    n = 200
+    tasks, at = layout_ref.first_accepted_tasks(77, 10 + np.arange(n), 1 + np.arange(n) % 3, W, L, A)
+    pts = tasks.reshape(n, 2 * A, 2).astype(np.int64)          # (x, y) of start_0, goal_0, start_1, ...
+    assert pts[..., 0].max() < W and pts[..., 1].max() < L and pts.min() >= 0
+    d2 = ((pts[:, :, None, :] - pts[:, None, :, :]) ** 2).sum(-1)
+    d2[:, np.arange(2 * A), np.arange(2 * A)] = 99
+    assert d2.min() > 2                                        # dmfb.py:220
+    assert at.min() >= 0 and at.max() > at.mean()
+    again, at2 = layout_ref.first_accepted_tasks(77, 10 + np.arange(n), 1 + np.arange(n) % 3, W, L, A)
+    assert np.array_equal(tasks, again) and np.array_equal(at, at2)
+    other, _ = layout_ref.first_accepted_tasks(78, 10 + np.arange(n), 1 + np.arange(n) % 3, W, L, A)
+    assert (tasks != other).any(axis=(1, 2)).mean() > 0.95
+
+
+def test_mix64_known_answers():
+    """splitmix64's finaliser (Steele, Lea, Flood 2014): outputs of the reference implementation for state 0 -
+    mix64(k * 0x9E3779B97F4A7C15) for k = 1, 2, 3."""
+    with np.errstate(over="ignore"):
+        z = layout_ref.mix64(np.arange(1, 4, dtype=np.uint64) * layout_ref.PHI)
+    assert [int(v) for v in z] == [0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4, 0x06C45D188009454F]
