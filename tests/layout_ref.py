@@ -70,3 +70,41 @@ def first_accepted_tasks(seed, env, episode, W, L, A, max_attempts=100000):
             todo = todo[~ok]
         assert todo.size == 0, "density that cannot be placed within max_attempts"
         return out, at
+
+
+def meda_first_tasks(seed, env, episode, W, L, A, r=2, max_draws=100000):
+    """meda_generate_tasks (marl-dmfb_b200/csrc/meda_kernels.cu), the device form of refresh / addTask /
+    _genLegalDroplet (meda.py:161-185,213-233): ONE sequential splitmix64 stream per (seed, env, episode); every draw
+    is a centre (y from the low word against `width`, x from the high word against `length`, both in [r, dim-r-1]);
+    droplet i's start is redrawn while it is closer than 9 to an earlier start, its destination while it is closer
+    than 9 to an earlier destination or overlaps its own start.  uint8 [N, A, 4] = (x, y, goal_x, goal_y)."""
+    out = np.zeros((len(env), A, 4), np.uint8)
+    with np.errstate(over="ignore"):
+        for n, (e, ep) in enumerate(zip(np.asarray(env, np.uint64), np.asarray(episode, np.uint64))):
+            state = mix64((np.uint64(seed) ^ (PHI * np.uint64(STREAM_LAYOUT + 1))) + e * C_ENV + (ep << np.uint64(32)) * C_EPI)
+            draws = 0
+
+            def centre():
+                nonlocal state, draws
+                draws += 1
+                assert draws < max_draws
+                state = state + PHI
+                z = mix64(state)
+                y = r + ((int(z) & 0xFFFFFFFF) * (W - 2 * r) >> 32)
+                x = r + ((int(z) >> 32) * (L - 2 * r) >> 32)
+                return x, y
+
+            for i in range(A):
+                while True:
+                    sx, sy = centre()
+                    if all((sx - int(out[n, j, 0])) ** 2 + (sy - int(out[n, j, 1])) ** 2 >= 81 for j in range(i)):
+                        break
+                while True:
+                    tx, ty = centre()
+                    if any((tx - int(out[n, j, 2])) ** 2 + (ty - int(out[n, j, 3])) ** 2 < 81 for j in range(i)):
+                        continue
+                    if abs(tx - sx) <= 2 * r and abs(ty - sy) <= 2 * r:      # isDropletOverlap (meda.py:71-81)
+                        continue
+                    break
+                out[n, i] = (sx, sy, tx, ty)
+    return out

@@ -353,3 +353,26 @@ def test_meda_sub_batch_pipelining_is_transparent():
     assert torch.equal(a.episode, b.episode) and torch.equal(a.fails, b.fails) and torch.equal(a.status, b.status)
     assert torch.equal(a.health, b.health) and torch.equal(a.usage_counts(), b.usage_counts())
     assert int(a.episode.max()) > 1
+
+
+@pytest.mark.parametrize("W,L,A", [(30, 60, 4), (80, 80, 10)])
+def test_meda_device_tasks_equal_the_restated_generator(W, L, A):
+    """meda_generate_tasks against its numpy restatement (tests/layout_ref.py: refresh / addTask / _genLegalDroplet,
+    meda.py:161-185,213-233, on one sequential stream per (seed, global env, episode)): after a reset kernel and after
+    fused auto-resets inside the step kernel."""
+    import layout_ref
+    P = pkg()
+    N, base, seed = 256, 900, 31
+    env = P.BatchedMEDA(N, W, L, A, fov=19, device="cuda:0", seed=seed, env_base=base)
+    env.reset()
+    want = layout_ref.meda_first_tasks(seed, base + np.arange(N), env.episode.cpu().numpy(), W, L, A)
+    assert np.array_equal(env.drop.cpu().numpy(), want)
+    assert np.array_equal(env.start.cpu().numpy(), want[:, :, :2])
+    epi0 = env.episode.clone()
+    gen = torch.Generator(device="cuda:0").manual_seed(4)
+    for t in range(W + L + 2):
+        env.step(torch.randint(0, 9, (N, A), device="cuda:0", generator=gen, dtype=torch.int8), auto_reset=True)
+    assert bool((env.episode > epi0).all())
+    want = layout_ref.meda_first_tasks(seed, base + np.arange(N), env.episode.cpu().numpy(), W, L, A)
+    assert np.array_equal(env.start.cpu().numpy(), want[:, :, :2])
+    assert np.array_equal(env.drop.cpu().numpy()[:, :, 2:], want[:, :, 2:])

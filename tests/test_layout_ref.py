@@ -29,3 +29,17 @@ def test_mix64_known_answers():
     with np.errstate(over="ignore"):
         z = layout_ref.mix64(np.arange(1, 4, dtype=np.uint64) * layout_ref.PHI)
     assert [int(v) for v in z] == [0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4, 0x06C45D188009454F]
+
+
+def test_restated_meda_generator_obeys_gen_legal_droplet():
+    """meda.py:213-233: centres in [r, dim-r-1] (x against `length`, y against `width`), starts pairwise at least 9
+    apart, destinations too, and no destination overlapping its own start (|dx| <= 4 and |dy| <= 4)."""
+    W, L, A, r = 30, 60, 4, 2
+    t = layout_ref.meda_first_tasks(9, 100 + np.arange(64), 1 + np.arange(64) % 2, W, L, A).astype(np.int64)
+    for a, b in ((0, 1), (2, 3)):
+        assert t[..., a].min() >= r and t[..., a].max() <= L - r - 1          # x
+        assert t[..., b].min() >= r and t[..., b].max() <= W - r - 1          # y
+        d2 = (t[:, :, None, a] - t[:, None, :, a]) ** 2 + (t[:, :, None, b] - t[:, None, :, b]) ** 2
+        d2[:, np.arange(A), np.arange(A)] = 999
+        assert d2.min() >= 81
+    assert not ((np.abs(t[..., 2] - t[..., 0]) <= 2 * r) & (np.abs(t[..., 3] - t[..., 1]) <= 2 * r)).any()
