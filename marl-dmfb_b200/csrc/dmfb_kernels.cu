@@ -1420,7 +1420,7 @@ dmfb_reset_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state_t st,
                             dg = degrade_in[(size_t)nn * cells + k];
                         } else if (cfg.b_degrade) {  // _random_health_statue (dmfb.py:157-164)
                             const uint4 r = env_random(seed, kStreamDegrade, cfg.env_base + nn, episode, (uint32_t)k, 0u);
-                            dg = u53(r.x, r.y) * 0.4 + 0.6;
+                            dg = __dadd_rn(__dmul_rn(u53(r.x, r.y), 0.4), 0.6);   // rand * 0.4 + 0.6 as two roundings, like NumPy (no FMA)
                             if (u53(r.z, r.w) < 1.0 - cfg.per_degrade) dg = 1.0;
                         }
                         degrade[k] = dg;

@@ -715,7 +715,7 @@ meda_reset_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_t st,
                         if (degrade_in) dg = degrade_in[(size_t)n * cells + k];
                         else if (cfg.b_degrade) {
                             const uint4 r = env_random(seed, kStreamDegrade, cfg.env_base + n, episode, (uint32_t)k, 0u);
-                            dg = u53(r.x, r.y) * 0.4 + 0.6;
+                            dg = __dadd_rn(__dmul_rn(u53(r.x, r.y), 0.4), 0.6);   // rand * 0.4 + 0.6 as two roundings, like NumPy (no FMA)
                             if (u53(r.z, r.w) < 1.0 - cfg.per_degrade) dg = 1.0;
                         }
                         st.degrade[(size_t)n * cells + k] = dg;

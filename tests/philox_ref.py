@@ -33,3 +33,22 @@ def move_draws(seed, env, episode, step, n_agents):
     z = np.zeros_like(env + agent)
     x, y, _, _ = philox4x32_10(((env & MASK) + z, episode + z, step + z, agent + z), (np.uint64(key0) + z, key1 + z))
     return ((x >> np.uint64(5)).astype(np.float64) * 67108864.0 + (y >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
+
+
+STREAM_DEGRADE = 3
+
+
+def degrade_matrix(seed, env, episode, cells, per_degrade):
+    """float64 [N, cells]: the device form of _random_health_statue (dmfb.py:157-164, meda.py:494-504) - cell k of global
+    env `env[n]` draws Philox(counter = env, episode, k, 0; stream 3): degrade = u53(x, y) * 0.4 + 0.6 (two roundings, as
+    NumPy computes rand * 0.4 + 0.6), set to 1.0 where u53(z, w) < 1 - per_degrade."""
+    env = np.asarray(env, np.uint64)[:, None]
+    episode = np.asarray(episode, np.uint64)[:, None]
+    k = np.arange(cells, dtype=np.uint64)[None, :]
+    key0 = (seed & 0xFFFFFFFF) ^ ((STREAM_DEGRADE * 0x85EBCA6B) & 0xFFFFFFFF)
+    key1 = (np.uint64((seed >> 32) & 0xFFFFFFFF) ^ (env >> np.uint64(32))) & MASK
+    z = np.zeros_like(env + k)
+    x, y, zz, w = philox4x32_10(((env & MASK) + z, episode + z, k + z, z), (np.uint64(key0) + z, key1 + z))
+    u53 = lambda a, b: ((a >> np.uint64(5)).astype(np.float64) * 67108864.0 + (b >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0  # noqa: E731
+    dg = u53(x, y) * 0.4 + 0.6
+    return np.where(u53(zz, w) < 1.0 - per_degrade, 1.0, dg)

@@ -723,6 +723,23 @@ def test_device_tasks_are_the_first_accepted_attempt_of_the_stated_stream(W, L, 
     env.check()
 
 
+def test_device_degrade_matrices_equal_the_restated_draws():
+    """_random_health_statue (dmfb.py:157-164) on the device, `reset(new=True)` without an injected matrix: cell k of
+    global env n draws Philox (stream 3) and degrade = rand * 0.4 + 0.6 in two roundings, 1.0 where the second draw is
+    below 1 - per_degrade - bit-equal to tests/philox_ref.degrade_matrix, so also independent of sharding."""
+    import philox_ref
+    P = pkg()
+    N, W, L, A, base, seed, per = 96, 12, 15, 4, 7000, (5 << 32) | 77, 0.3
+    env = P.BatchedDMFB(N, W, L, A, fov=5, b_degrade=True, per_degrade=per, device="cuda:0", seed=seed, env_base=base)
+    env.reset(new=True)
+    want = philox_ref.degrade_matrix(seed, base + np.arange(N), env.episode.cpu().numpy(), W * L, per)
+    got = env.degrade.cpu().numpy().reshape(N, W * L)
+    assert np.array_equal(got, want)
+    frac_one = float((got == 1.0).mean())
+    assert abs(frac_one - (1 - per)) < 0.02 and got.min() >= 0.6 and got[got < 1.0].max() < 1.0
+    assert float(env.health.min()) == 1.0 and int(env.usage_counts().max()) == 0     # refresh(new): a fresh chip
+
+
 def test_task_generator_gives_up_recoverably_on_an_impossible_density():
     """8x8 with 9 droplets passes the reference's density check (dmfb.py:144-146) but 18 points that are pairwise not
     within one cell do not fit an 8x8 chip (at most 16 do): the reference would redraw for ever.  The device generator

@@ -376,3 +376,17 @@ def test_meda_device_tasks_equal_the_restated_generator(W, L, A):
     want = layout_ref.meda_first_tasks(seed, base + np.arange(N), env.episode.cpu().numpy(), W, L, A)
     assert np.array_equal(env.start.cpu().numpy(), want[:, :, :2])
     assert np.array_equal(env.drop.cpu().numpy()[:, :, 2:], want[:, :, 2:])
+
+
+def test_meda_device_degrade_matrix_equals_the_restated_draws():
+    """MEDAEnv.__init__'s degradation factors (meda.py:494-504) drawn on the device (`reset(new_chip=True)`): bit-equal
+    to tests/philox_ref.degrade_matrix (rand * 0.4 + 0.6 in two roundings; 1.0 where rand2 < 1 - per_degrade)."""
+    import philox_ref
+    P = pkg()
+    N, W, L, A, base, seed, per = 48, 30, 60, 4, 300, 99, 0.5
+    env = P.BatchedMEDA(N, W, L, A, fov=19, b_degrade=True, per_degrade=per, device="cuda:0", seed=seed, env_base=base)
+    env.reset(new_chip=True)
+    want = philox_ref.degrade_matrix(seed, base + np.arange(N), env.episode.cpu().numpy(), W * L, per)
+    got = env.degrade.cpu().numpy().reshape(N, W * L)
+    assert np.array_equal(got, want)
+    assert abs(float((got == 1.0).mean()) - (1 - per)) < 0.02 and got.min() >= 0.6
