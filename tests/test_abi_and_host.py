@@ -46,6 +46,20 @@ def test_ctypes_mirrors_match_c_layout(P, tmp_path):
     assert got == want
 
 
+def test_step_flags_match_the_header(P, tmp_path):
+    """The Python layer's step flags are the header's macros (compiled, not parsed)."""
+    src = tmp_path / "fl.c"
+    src.write_text('#include <stdio.h>\n#include <stdint.h>\n#include "dmfb_b200.h"\nint main(){printf("%u %u %u %u %u\\n",'
+                   'DMFB_STEP_RECORD_USAGE,DMFB_STEP_FREEZE_TERM,DMFB_STEP_AUTO_RESET,DMFB_STEP_SKIP_TASK_SEARCH,'
+                   'DMFB_STEP_SEARCH_SHARE(5));return 0;}\n')
+    exe = tmp_path / "fl"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    n = P._native
+    assert got == [n.STEP_RECORD_USAGE, n.STEP_FREEZE_TERM, n.STEP_AUTO_RESET, n.STEP_SKIP_TASK_SEARCH, n.step_search_share(5)]
+    assert len({*got[:4]}) == 4 and not (got[4] & sum(got[:4])) and got[4] < (1 << 31)     # disjoint bits, bit 31 free
+
+
 def _py_dir(d, dim, fov):
     hf = fov // 2
     if abs(d) > hf:  # the reference expression, evaluated by python itself (banker's round on float64)
