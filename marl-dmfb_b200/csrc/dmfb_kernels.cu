@@ -1475,7 +1475,7 @@ dmfb_flush_usage_kernel(const __grid_constant__ dmfb_cfg_t cfg, const dmfb_state
 // one shift and added with three read-modify-writes - exactly the reference's "min pairwise squared distance > 2" rule
 // (dmfb.py:220), point by point.  The lowest accepted attempt of the 32 wins, which is the attempt the one-per-warp
 // flavour (sample_rounds_warp: same counters, same cells) would have stopped at: the tasks are the same whoever
-// searches.  ~22 instructions per attempt instead of ~55, and 32 attempts in the latency of 16.
+// searches.  ~30 instructions per attempt instead of ~55, and 32 attempts in the latency of 16.
 constexpr int kBoardRows = 32;                                   // W + 2 rows, W <= 30
 #ifndef DMFB_SEARCH_ENVS
 #define DMFB_SEARCH_ENVS 64
