@@ -791,7 +791,7 @@ meda_reset_list_kernel(const __grid_constant__ meda_cfg_t cfg, const meda_state_
                        const uint8_t* __restrict__ set_order, int8_t* __restrict__ obs)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int A = cfg.n_agents, D = cfg.obs_dim, cells = cfg.width * cfg.length;
+    const int A = cfg.n_agents, D = cfg.obs_dim;
     const int tid = (int)threadIdx.x, nthreads = (int)blockDim.x;
     const uint32_t region_bytes = (((uint32_t)(A * D) + 15u) & ~15u) + 16u;
     int8_t* const region = reinterpret_cast<int8_t*>(smem_raw);
