@@ -108,3 +108,35 @@ def meda_first_tasks(seed, env, episode, W, L, A, r=2, max_draws=100000):
                     break
                 out[n, i] = (sx, sy, tx, ty)
     return out
+
+
+STREAM_BLOCKS = 4
+
+
+def first_blocks(seed, env, episode, tasks, W, L, n_blocks, max_draws=100000):
+    """generate_blocks (marl-dmfb_b200/csrc/dmfb_kernels.cu), the device form of GenRandomBlocks (dmfb.py:228-251): one
+    sequential splitmix64 stream per (seed, env, episode); every draw is the (x_min, y_min) of a 2x2 block, uniform in
+    [0, W-4] x [0, L-4]; it is redrawn while the block covers a start or goal cell of the env's task `tasks[n]`
+    (uint8 [A, 4] = x, y, goal_x, goal_y) or overlaps / touches an earlier block (isBlockOverlap, dmfb.py:56-69).
+    uint8 [N, n_blocks, 2]."""
+    out = np.zeros((len(env), n_blocks, 2), np.uint8)
+    with np.errstate(over="ignore"):
+        for n, (e, ep) in enumerate(zip(np.asarray(env, np.uint64), np.asarray(episode, np.uint64))):
+            state = mix64((np.uint64(seed) ^ (PHI * np.uint64(STREAM_BLOCKS + 1))) + e * C_ENV + (ep << np.uint64(32)) * C_EPI)
+            cells = [(int(t[0]), int(t[1])) for t in tasks[n]] + [(int(t[2]), int(t[3])) for t in tasks[n]]
+            draws = 0
+            for b in range(n_blocks):
+                while True:
+                    draws += 1
+                    assert draws < max_draws
+                    state = state + PHI
+                    z = int(mix64(state))
+                    x, y = ((z & 0xFFFFFFFF) * (W - 3)) >> 32, ((z >> 32) * (L - 3)) >> 32
+                    if any(0 <= cx - x <= 1 and 0 <= cy - y <= 1 for cx, cy in cells):
+                        continue
+                    if any(not (x > int(out[n, k, 0]) + 1 or int(out[n, k, 0]) > x + 1) and
+                           not (y > int(out[n, k, 1]) + 1 or int(out[n, k, 1]) > y + 1) for k in range(b)):
+                        continue
+                    out[n, b] = (x, y)
+                    break
+    return out

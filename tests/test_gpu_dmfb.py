@@ -740,6 +740,32 @@ def test_device_degrade_matrices_equal_the_restated_draws():
     assert float(env.health.min()) == 1.0 and int(env.usage_counts().max()) == 0     # refresh(new): a fresh chip
 
 
+def test_device_blocks_equal_the_restated_generator():
+    """GenRandomBlocks (dmfb.py:228-251) on the device against tests/layout_ref.first_blocks: the obstacles of (seed,
+    global env, episode) are drawn from their own sequential stream and redrawn while they cover a start / goal cell of
+    the env's new task or touch an earlier block - after a reset kernel and after fused auto-resets."""
+    import layout_ref
+    P = pkg()
+    N, W, L, A, nb, base, seed = 256, 14, 14, 4, 5, 123, 808
+    env = P.BatchedDMFB(N, W, L, A, nb, fov=7, device="cuda:0", seed=seed, env_base=base)
+    env.reset()
+
+    def check(tag):
+        epi = env.episode.cpu().numpy()
+        tasks, _ = layout_ref.first_accepted_tasks(seed, base + np.arange(N), epi, W, L, A)
+        assert np.array_equal(env.start.cpu().numpy(), tasks[:, :, :2]), tag
+        want = layout_ref.first_blocks(seed, base + np.arange(N), epi, tasks, W, L, nb)
+        assert np.array_equal(env.blocks.cpu().numpy(), want), tag
+
+    check("reset")
+    epi0 = env.episode.clone()
+    gen = torch.Generator(device="cuda:0").manual_seed(8)
+    for t in range(2 * (W + L) + 2):
+        env.step(torch.randint(0, 5, (N, A), device="cuda:0", generator=gen, dtype=torch.int8), auto_reset=True)
+    assert bool((env.episode > epi0).all())
+    check("fused auto-reset")
+
+
 def test_task_generator_gives_up_recoverably_on_an_impossible_density():
     """8x8 with 9 droplets passes the reference's density check (dmfb.py:144-146) but 18 points that are pairwise not
     within one cell do not fit an 8x8 chip (at most 16 do): the reference would redraw for ever.  The device generator

@@ -43,3 +43,20 @@ def test_restated_meda_generator_obeys_gen_legal_droplet():
         d2[:, np.arange(A), np.arange(A)] = 999
         assert d2.min() >= 81
     assert not ((np.abs(t[..., 2] - t[..., 0]) <= 2 * r) & (np.abs(t[..., 3] - t[..., 1]) <= 2 * r)).any()
+
+
+def test_restated_block_generator_obeys_gen_random_blocks():
+    """dmfb.py:228-251: 2x2 blocks inside the chip that cover no start / goal cell and keep a free cell between them."""
+    W, L, A, nb, n = 14, 14, 4, 5, 64
+    tasks, _ = layout_ref.first_accepted_tasks(3, np.arange(n), np.ones(n), W, L, A)
+    blocks = layout_ref.first_blocks(3, np.arange(n), np.ones(n), tasks, W, L, nb).astype(np.int64)
+    assert blocks.min() >= 0 and blocks[..., 0].max() <= W - 4 and blocks[..., 1].max() <= L - 4
+    pts = tasks.reshape(n, 2 * A, 2).astype(np.int64)
+    dx = pts[:, None, :, 0] - blocks[:, :, None, 0]
+    dy = pts[:, None, :, 1] - blocks[:, :, None, 1]
+    assert not ((dx >= 0) & (dx <= 1) & (dy >= 0) & (dy <= 1)).any()
+    bx = np.abs(blocks[:, :, None, 0] - blocks[:, None, :, 0])
+    by = np.abs(blocks[:, :, None, 1] - blocks[:, None, :, 1])
+    touch = (bx <= 1) & (by <= 1)
+    touch[:, np.arange(nb), np.arange(nb)] = False
+    assert not touch.any()
