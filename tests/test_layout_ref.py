@@ -46,7 +46,7 @@ def test_restated_meda_generator_obeys_gen_legal_droplet():
 
 
 def test_restated_block_generator_obeys_gen_random_blocks():
-    """dmfb.py:228-251: 2x2 blocks inside the chip that cover no start / goal cell and keep a free cell between them."""
+    """dmfb.py:228-251: 2x2 blocks inside the chip that cover no start / goal cell and do not overlap each other."""
     W, L, A, nb, n = 14, 14, 4, 5, 64
     tasks, _ = layout_ref.first_accepted_tasks(3, np.arange(n), np.ones(n), W, L, A)
     blocks = layout_ref.first_blocks(3, np.arange(n), np.ones(n), tasks, W, L, nb).astype(np.int64)
